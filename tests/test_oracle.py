@@ -1,0 +1,195 @@
+"""CPU tests of the oracle (oracle/): NLP restatement, derivatives, Newton step, solves.
+
+The reference ships no golden vectors (parity unpinned), so the oracle is pinned
+to (i) the independent NumPy restatement of the NLP in oracle/nlp_numpy.py + finite differences,
+(ii) a dense NumPy solve of the same KKT system, (iii) SciPy SLSQP KKT points.
+"""
+import numpy as np
+import pytest
+
+from oracle.nlp_numpy import UnicycleNLP, euler_plant, shift_warm_start, synthetic_instances
+from oracle.oracle_lib import Oracle
+
+CFGS = [(1, 6, 0.25), (2, 5, 0.1), (3, 4, 0.05), (6, 3, 0.3)]
+
+
+def _ccs_to_dense(cp, ri, vals, nrow, ncol):
+    A = np.zeros((nrow, ncol))
+    for c in range(ncol):
+        for e in range(cp[c], cp[c + 1]):
+            A[ri[e], c] = vals[e]
+    return A
+
+
+@pytest.mark.parametrize("Nr,N,T", CFGS)
+def test_eval_matches_numpy_restatement(Nr, N, T):
+    rng = np.random.default_rng(Nr * 100 + N)
+    o, nlp = Oracle(Nr, N, T), UnicycleNLP(Nr, N, T)
+    assert (o.n, o.mg) == (nlp.n, nlp.mg)
+    assert o.nnz_jac == 3 * Nr + N * (11 * Nr + 4 * nlp.M)
+    assert o.nnz_hess == N * (6 * Nr + 2 * nlp.M)
+    w, p, lam = rng.normal(size=o.n), rng.normal(size=6 * Nr), rng.normal(size=o.mg)
+    e = o.eval(w, p, lam)
+    assert np.isclose(e["f"], nlp.f(w, p), rtol=1e-13)
+    np.testing.assert_allclose(e["grad"], nlp.grad_f(w, p), rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(e["g"], nlp.g(w, p), rtol=1e-13, atol=1e-13)
+    J = _ccs_to_dense(*o.jac_pattern(), e["jac"], o.mg, o.n)
+    np.testing.assert_allclose(J, nlp.jac_g(w, p), rtol=1e-13, atol=1e-13)
+    H = _ccs_to_dense(*o.hess_pattern(), e["hess"], o.n, o.n)
+    np.testing.assert_allclose(H, np.tril(nlp.hess_lag(w, p, lam)), rtol=1e-12, atol=1e-12)
+    # CCS row indices sorted within each column, as CasADi emits them
+    cp, ri = o.jac_pattern()
+    for c in range(o.n):
+        assert np.all(np.diff(ri[cp[c]:cp[c + 1]]) > 0)
+
+
+@pytest.mark.parametrize("Nr,N,T", CFGS[:3])
+def test_derivatives_vs_finite_differences(Nr, N, T):
+    rng = np.random.default_rng(7)
+    o = Oracle(Nr, N, T)
+    w, p, lam = rng.normal(size=o.n), rng.normal(size=6 * Nr), rng.normal(size=o.mg)
+    e = o.eval(w, p, lam)
+    J = _ccs_to_dense(*o.jac_pattern(), e["jac"], o.mg, o.n)
+    Hl = _ccs_to_dense(*o.hess_pattern(), e["hess"], o.n, o.n)
+    H = Hl + np.tril(Hl, -1).T
+    h = 1e-6
+    Jfd, Hfd, gfd = np.zeros_like(J), np.zeros_like(H), np.zeros(o.n)
+    for i in range(o.n):
+        d = np.zeros(o.n); d[i] = h
+        ep, em = o.eval(w + d, p, lam, False, False), o.eval(w - d, p, lam, False, False)
+        Jfd[:, i] = (ep["g"] - em["g"]) / (2 * h)
+        gfd[i] = (ep["f"] - em["f"]) / (2 * h)
+        jp = _ccs_to_dense(*o.jac_pattern(), o.eval(w + d, p)["jac"], o.mg, o.n)
+        jm = _ccs_to_dense(*o.jac_pattern(), o.eval(w - d, p)["jac"], o.mg, o.n)
+        Hfd[:, i] = (ep["grad"] - em["grad"]) / (2 * h) + (jp - jm).T @ lam / (2 * h)
+    np.testing.assert_allclose(J, Jfd, atol=1e-7)
+    np.testing.assert_allclose(e["grad"], gfd, atol=1e-6)
+    np.testing.assert_allclose(H, Hfd, atol=1e-6)
+
+
+def test_shift_and_plant_follow_reference_quirks():
+    """u0=[u[1:];u[-1]] (six...py:160-169) and X0=[X[1:];X[N-1]] -- row N-1, not N (:465)."""
+    o, nlp = Oracle(2, 4, 0.1), UnicycleNLP(2, 4, 0.1)
+    w = np.arange(o.n, dtype=float)
+    out = o.shift(w)
+    np.testing.assert_array_equal(out, shift_warm_start(nlp, w))
+    X, U = nlp.split(out)
+    Xp, Up = nlp.split(w)
+    np.testing.assert_array_equal(X[-1], Xp[nlp.N - 1])
+    np.testing.assert_array_equal(U[-1], Up[-1])
+    st, u = np.array([0.1, 0.2, 0.3, -1, 2, 1.0]), np.array([0.2, 1.0, -0.1, 0.5])
+    np.testing.assert_allclose(o.plant(st, u), euler_plant(nlp, st, u), rtol=1e-15)
+
+
+@pytest.mark.parametrize("Nr,N,T", [(2, 5, 0.1), (3, 4, 0.3), (6, 3, 0.3)])
+def test_riccati_newton_step_equals_dense_kkt_solve(Nr, N, T):
+    rng = np.random.default_rng(Nr)
+    o, nlp = Oracle(Nr, N, T), UnicycleNLP(Nr, N, T)
+    lbx, ubx, lbg, ubg = o.bounds(0.3, 0.22, 2.84)
+    w, p = rng.normal(size=o.n), rng.normal(size=6 * Nr)
+    lam = 0.05 * rng.normal(size=o.mg)
+    sx, ss = rng.uniform(1, 3, o.n), rng.uniform(0.5, 2, o.mg)
+    gx, gs, rg = rng.normal(size=o.n), rng.normal(size=o.mg), rng.normal(size=o.mg)
+    delta = 0.01
+    rc, dx, ds, yl = o.kkt_step(p, lbg, ubg, w, lam, 1.0, sx, ss, delta, gx, gs, rg)
+    assert rc == 0
+    H = nlp.hess_lag(w, p, lam) + np.diag(sx + delta)
+    J = nlp.jac_g(w, p)
+    ineq = lbg != ubg
+    E = np.where(ineq, 1.0 / (ss + delta), 0.0)
+    K = np.block([[H, J.T], [J, -np.diag(E)]])
+    rhs = np.concatenate([-gx, -rg - E * np.where(ineq, gs, 0.0)])
+    sol = np.linalg.solve(K, rhs)
+    ev = np.linalg.eigvalsh(K)
+    assert (ev > 0).sum() == o.n            # inertia (n, mg, 0): Riccati pivots all positive
+    np.testing.assert_allclose(dx, sol[:o.n], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(yl, sol[o.n:], rtol=1e-8, atol=1e-8)
+    np.testing.assert_allclose(ds[ineq], (J @ dx + rg)[ineq], rtol=1e-9, atol=1e-9)
+    # and a wrong-inertia system is reported, not solved
+    rc2, *_ = o.kkt_step(p, lbg, ubg, w, 40 * lam, 1.0, 0 * sx, ss, 0.0, gx, gs, rg)
+    H2 = nlp.hess_lag(w, p, 40 * lam)
+    K2 = np.block([[H2, J.T], [J, -np.diag(E)]])
+    if (np.linalg.eigvalsh(K2) > 1e-9).sum() != o.n:
+        assert rc2 == 1
+
+
+def _kkt_check(o, nlp, r, p, lbx, ubx, lbg, ubg, tol=1e-6):
+    x, lx, lg = r["x"], r["lam_x"], r["lam_g"]
+    g = nlp.g(x, p)
+    stat = nlp.grad_f(x, p) + nlp.jac_g(x, p).T @ lg + lx
+    assert np.abs(stat).max() < tol
+    assert np.all(g >= lbg - tol) and np.all(g <= ubg + tol)
+    assert np.all(x >= lbx - tol) and np.all(x <= ubx + tol)
+    ineq = lbg != ubg
+    # CasADi sign convention: lam < 0 on an active lower bound
+    if ineq.any():
+        assert np.all(lg[ineq] <= tol)
+        assert np.abs(lg[ineq] * (g[ineq] - lbg[ineq])).max() < tol
+
+
+def test_single_robot_solve_is_the_slsqp_kkt_point():
+    """C-1 (casadi_test.py:34-39,115-117): oracle optimum == SciPy SLSQP optimum (uni-modal case)."""
+    from scipy.optimize import Bounds, minimize
+    o, nlp = Oracle(1, 25, 0.25), UnicycleNLP(1, 25, 0.25)
+    lbx, ubx, lbg, ubg = o.bounds(0.3, 0.22, 2.84)
+    p = np.array([0, 0, 0, 2.5, 2.0, 1.57])
+    w0 = o.cold_start(p[:3])
+    r = o.solve(w0, p, lbx, ubx, lbg, ubg)
+    assert r["status"] == 0
+    _kkt_check(o, nlp, r, p, lbx, ubx, lbg, ubg)
+    res = minimize(lambda w: nlp.f(w, p), w0, jac=lambda w: nlp.grad_f(w, p), method="SLSQP",
+                   bounds=Bounds(lbx, ubx),
+                   constraints=[dict(type="eq", fun=lambda w: nlp.g(w, p), jac=lambda w: nlp.jac_g(w, p))],
+                   options=dict(maxiter=500, ftol=1e-12))
+    assert abs(res.fun - r["f"]) / r["f"] < 1e-6
+    assert np.abs(res.x - r["x"])[o.ns * 26:].max() < 1e-3      # SLSQP stalls early; see from-oracle polish
+    res2 = minimize(lambda w: nlp.f(w, p), r["x"], jac=lambda w: nlp.grad_f(w, p), method="SLSQP",
+                    bounds=Bounds(lbx, ubx),
+                    constraints=[dict(type="eq", fun=lambda w: nlp.g(w, p), jac=lambda w: nlp.jac_g(w, p))],
+                    options=dict(maxiter=200, ftol=1e-14))
+    assert np.abs(res2.x - r["x"]).max() < 1e-6
+    assert abs(res2.fun - r["f"]) / r["f"] < 1e-8
+
+
+def test_six_robot_hexagon_kkt_and_collision_free(hexagon_p):
+    o, nlp = Oracle(6, 20, 0.3), UnicycleNLP(6, 20, 0.3)
+    lbx, ubx, lbg, ubg = o.bounds(0.3, 0.22, 2.84)
+    r = o.solve(o.cold_start(hexagon_p[:18]), hexagon_p, lbx, ubx, lbg, ubg)
+    assert r["status"] == 0 and r["stats"][0] <= 1e-8
+    _kkt_check(o, nlp, r, hexagon_p, lbx, ubx, lbg, ubg)
+    d2 = r["g"].reshape(21, 33)[1:, 18:]
+    assert d2.min() >= 0.09 - 1e-6
+
+
+def test_synthetic_batch_all_converge():
+    o, nlp = Oracle(6, 20, 0.3), UnicycleNLP(6, 20, 0.3)
+    lbx, ubx, lbg, ubg = o.bounds(0.3, 0.22, 2.84)
+    P = synthetic_instances(16)
+    x0 = np.stack([o.cold_start(q[:18]) for q in P])
+    rb = o.solve_batch(x0, P, lbx, ubx, lbg, ubg, want_duals=True)
+    assert np.all(rb["status"] == 0)
+    for b in range(0, 16, 5):
+        r = {k: rb[k][b] for k in ("x", "lam_x", "lam_g")}
+        _kkt_check(o, nlp, r, P[b], lbx, ubx, lbg, ubg)
+
+
+def test_infeasible_start_exits_in_bounded_time():
+    """Family A's first step: all robots at the origin (centralized_six...py:361-362)."""
+    o = Oracle(2, 10, 0.1, max_iter=300)
+    lbx, ubx, lbg, ubg = o.bounds(0.25, 0.22, 2.84)
+    p = np.array([0, 0, 0, 0, 0, 0, 1, 1, 0.785, -1, -1, -2.356])
+    r = o.solve(o.cold_start(p[:6]), p, lbx, ubx, lbg, ubg)
+    assert r["status"] in (2, 3, 4)
+    assert np.all(np.isfinite(r["x"]))
+
+
+def test_api_errors():
+    o = Oracle(2, 3, 0.1)
+    lbx, ubx, lbg, ubg = o.bounds(0.25, 0.22, 2.84)
+    p = np.array([0, 0, 0, 1, 0, 0, 1, 1, 0, 0, 1, 0.0])
+    bad = lbx.copy(); bad[0] = 20
+    with pytest.raises(ValueError):
+        o.solve(o.cold_start(p[:6]), p, bad, ubx, lbg, ubg)
+    bad = ubg.copy(); bad[0] = 1.0
+    with pytest.raises(ValueError):
+        o.solve(o.cold_start(p[:6]), p, lbx, ubx, lbg, bad)
