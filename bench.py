@@ -1,0 +1,245 @@
+#!/usr/bin/env python
+"""bench.py -- 6-robot, N=20 NMPC solves/sec on B200 (BASELINE.json metric), one JSON line.
+
+  python bench.py --gpus 1 --steps K --warmup W          (N>1: launched by torch.distributed.run)
+  python bench.py --impl reference ...                    CPU arm: the restated IPOPT path on host cores
+
+A step = one cold-start solve (X_k = start, U = 0; centralized_six_robots_implementation.py:398-400)
+of a batch of synthetic start/goal instances (SURVEY.md 8d recipe).  Instances are independent, so
+ranks shard them with no collective on the data path ("weak": 8192 instances per GPU = 65536 / 8).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NR, NH, T, DMIN, VMAX, WMAX = 6, 20, 0.3, 0.3, 0.22, 2.84      # sixth_scenario.py:127-135, N overridden to 20
+PER_GPU = 8192
+ALG_BYTES_PER_SOLVE = 15728       # p + w0 in, x + f + g out
+F_FACT, F_SOLVE, F_EVAL = 1100160, 92160, 14700   # SURVEY.md 8d dense-stage FP64 flop counts @ Nr=6, N=20
+
+
+def synthetic(B, seed):
+    from oracle.nlp_numpy import synthetic_instances
+    cache = os.path.join(ROOT, "gpurun_out", "synth_%d_%d.npy" % (B, seed))
+    if os.path.exists(cache):
+        return np.load(cache)
+    P = synthetic_instances(B, NR, seed)
+    try:
+        os.makedirs(os.path.dirname(cache), exist_ok=True)
+        np.save(cache, P)
+    except OSError:
+        pass
+    return P
+
+
+class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.sm_max = index, False, [], set(), None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+            while not self.stop_flag:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.05)
+        except Exception as e:      # no NVML: report what we have
+            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons)}
+
+
+def cpu_arm(P, nthreads, budget_s=20.0):
+    """Restated IPOPT path (oracle/, 'port') on the host cores, bounded sample of the same workload."""
+    from oracle.oracle_lib import Oracle
+    o = Oracle(NR, NH, T)
+    lbx, ubx, lbg, ubg = o.bounds(DMIN, VMAX, WMAX)
+    n = 0
+    t0 = time.perf_counter()
+    chunk = max(2 * nthreads, 16)
+    iters = []
+    while n < len(P) and time.perf_counter() - t0 < budget_s:
+        Pi = P[n:n + chunk]
+        x0 = np.stack([o.cold_start(q[:3 * NR]) for q in Pi])
+        r = o.solve_batch(x0, Pi, lbx, ubx, lbg, ubg, nthreads=nthreads)
+        iters.append(r["iters"])
+        n += len(Pi)
+    dt = time.perf_counter() - t0
+    return n / dt, n, dt, float(np.concatenate(iters).mean())
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--per-gpu", type=int, default=PER_GPU)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    ncores = os.cpu_count() or 1
+    config = {"workload": "6-robot N=20 cold-start NMPC (sixth_scenario.py constants), %d synthetic start/goal instances per GPU "
+                          "(65536 over 8 GPUs), rng seed 20261018+rank" % a.per_gpu,
+              "Nr": NR, "N": NH, "T": T, "dmin": DMIN, "batch_per_gpu": a.per_gpu, "l2": "flushed between timed steps (512 MiB write)"}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        P = synthetic(512, 20261018)
+        per_step = []
+        tot_n = tot_t = 0
+        mean_it = 0.0
+        for s in range(a.warmup + a.steps):
+            v, n, dt, mean_it = cpu_arm(P, ncores, budget_s=8.0 if s >= a.warmup else 2.0)
+            if s >= a.warmup:
+                per_step.append(dt); tot_n += n; tot_t += dt
+        val = tot_n / tot_t
+        line = {"impl": "reference", "metric": "6-robot N=20 NMPC solves/sec", "value": val, "unit": "solves/s", "n_gpus": a.gpus,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * float(np.mean(per_step)), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": "solves/s", "cores": ncores, "kind": "port",
+                                 "sample": "%d cold-start instances of the same workload per step (~8 s), restated IPOPT "
+                                           "(oracle/nmpc_oracle.c, OpenMP); CasADi/IPOPT are not installable here" % (tot_n // max(1, a.steps)),
+                                 "mean_iters": mean_it},
+                "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    B = a.per_gpu
+    P = synthetic(B, 20261018 + rank)
+    prob = pkg.Problem(NR, NH, T)
+    lbx, ubx, lbg, ubg = prob.bounds(DMIN, VMAX, WMAX)
+    x0 = prob.cold_start(P[:, :3 * NR])
+    t = lambda v: torch.as_tensor(np.ascontiguousarray(v), dtype=torch.float64, device=dev)
+    d_x0, d_p, d_lbx, d_ubx, d_lbg, d_ubg = t(x0), t(P), t(lbx), t(ubx), t(lbg), t(ubg)
+    out = {}
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        prob.solve(d_x0, d_p, d_lbx, d_ubx, d_lbg, d_ubg, want=("f", "g", "stats"), out=out)
+
+    for _ in range(a.warmup):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = prob.launch_count()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(a.steps):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); step(); e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+    launches = prob.launch_count() - launches0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    tot_ms = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot_ms, op=dist.ReduceOp.MAX)
+    tot_ms = tot_ms.item()
+    st = out["status"].cpu().numpy()
+    stats = out["stats"].cpu().numpy()
+    iters = out["iters"].cpu().numpy()
+    solved = float((st == 0).mean())
+
+    # ---- end to end through the host-buffer C-ABI call (pinned inputs, H2D + solve + D2H of x, status, iters) ----
+    pin = lambda v: torch.as_tensor(np.ascontiguousarray(v), dtype=torch.float64).pin_memory().numpy()
+    h_x0, h_p = pin(x0), pin(P)
+    h_out = {"x": torch.empty((B, prob.n), dtype=torch.float64).pin_memory().numpy(),
+             "status": torch.empty(B, dtype=torch.int32).pin_memory().numpy(),
+             "iters": torch.empty(B, dtype=torch.int32).pin_memory().numpy()}
+    prob.solve_host(h_x0, h_p, lbx, ubx, lbg, ubg, want=(), out=h_out)      # warm-up (allocates the staging buffers)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.e2e_steps):
+        prob.solve_host(h_x0, h_p, lbx, ubx, lbg, ubg, want=(), out=h_out)
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    h2d = 8 * (h_x0.size + h_p.size + 2 * lbx.size + 2 * lbg.size)
+    d2h = 8 * h_out["x"].size + 4 * 2 * B
+    e2e_val = world * B * a.e2e_steps / e2e_s.item()
+
+    if rank != 0:
+        return
+    value = world * B * a.steps / (tot_ms * 1e-3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    per_gpu_solves = B * a.steps / (tot_ms * 1e-3)
+    ach_gbs = per_gpu_solves * ALG_BYTES_PER_SOLVE / 1e9
+    import ctypes
+    tf = ctypes.c_double(0.0)
+    pkg.lib().nmpc_probe_fp64(ctypes.byref(tf))
+    flops_per_solve = float((stats[:, 8] * F_FACT + iters * (F_SOLVE + F_EVAL)).mean())
+    ach_tf = per_gpu_solves * flops_per_solve / 1e12
+    cpu_val, cpu_n, cpu_dt, cpu_it = cpu_arm(synthetic(512, 20261018), ncores, budget_s=15.0)
+    line = {
+        "metric": "6-robot N=20 NMPC solves/sec", "value": value, "unit": "solves/s", "n_gpus": world, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": tot_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": config,
+        "solved_frac": solved, "mean_ip_iters": float(iters.mean()), "mean_factorisations": float(stats[:, 8].mean()),
+        "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                     "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                     "note": "solve_kernel is FP64-pipe/latency bound, not HBM bound (SURVEY.md 8d); see fp64"},
+        "fp64": {"achieved_tflops": ach_tf, "peak_tflops": tf.value, "frac": ach_tf / tf.value if tf.value else None,
+                 "flops_per_solve": flops_per_solve, "peak_source": "nmpc_probe_fp64 (DFMA microbenchmark, this run)"},
+        "cpu_baseline": {"value": cpu_val, "unit": "solves/s", "cores": ncores, "kind": "port",
+                         "sample": "%d cold-start instances of the same workload in %.1f s, restated IPOPT (oracle/), OpenMP" % (cpu_n, cpu_dt),
+                         "mean_iters": cpu_it},
+        "e2e": {"value": e2e_val, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches, "clocks": sampler.summary(),
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

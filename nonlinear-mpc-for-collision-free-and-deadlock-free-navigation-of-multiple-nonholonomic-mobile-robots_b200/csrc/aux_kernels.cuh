@@ -1,0 +1,161 @@
+// Streaming kernels either side of the solver:
+//   K1  eval_kernel   -- stand-alone f, grad f, g, CCS values of dg/dw and of hess(f + lam'g)
+//                        (what CasADi's AD sweeps hand IPOPT; NLP of
+//                        centralized_six_robots_implementation.py:207-331).  One CTA per point:
+//                        w, lam_g, p are loaded coalesced into shared memory, every robot-stage /
+//                        pair-stage thread scatters its entries into a shared-memory image of the
+//                        output record, and the record is written back with coalesced stores.
+//   K4  shift_kernel  -- warm-start shift of the MPC loop (shift() :160-169 and the X0 line :465)
+//       plant_kernel  -- Euler plant (casadi_test.py:17-26)
+//       prep_bounds_kernel -- flat lbx/ubx/lbg/ubg (:349-352) -> relaxed stage-layout rows
+#pragma once
+#include "bounds_prep.cuh"
+#include "nmpc_internal.h"
+
+// position tables built on the host at nmpc_create (device int arrays)
+struct NmpcEvalTables {
+    const int *jac_rs;   // [N*Nr*11]  CCS slot of each Jacobian entry of robot-stage (k,i)
+    const int *jac_ps;   // [N*M*4]    ... of pair-stage (k,q)
+    const int *hes_rs;   // [N*Nr*6]
+    const int *hes_ps;   // [N*M*2]
+    const int *jac_init; // [ns]       slots of the identity block of the initial-condition rows
+};
+
+__global__ void __launch_bounds__(256) eval_kernel(int Nr, int N, double T, double Q0, double Q1, double Q2, double R0,
+                                                   double R1, int B, const double *__restrict__ w, const double *__restrict__ p,
+                                                   const double *__restrict__ lam, double *__restrict__ f, double *__restrict__ grad,
+                                                   double *__restrict__ g, double *__restrict__ jac, double *__restrict__ hess,
+                                                   NmpcEvalTables tb)
+{
+    extern __shared__ double sh[];
+    const int ns = 3 * Nr, nc = 2 * Nr, M = Nr * (Nr - 1) / 2, S = N + 1, blk = ns + M;
+    const int n = ns * S + nc * N, mg = S * blk, nX = ns * S;
+    const int nj = 3 * Nr + N * (11 * Nr + 4 * M), nh = N * (6 * Nr + 2 * M);
+    double *sw = sh, *sl = sw + n, *sp = sl + mg, *sgrad = sp + 2 * ns, *sg = sgrad + n, *sj = sg + mg, *shs = sj + nj,
+           *sred = shs + nh;
+    const double Qw[3] = {Q0, Q1, Q2}, Rw[2] = {R0, R1};
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        const double *wb = w + (size_t)b * n;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) sw[i] = wb[i];
+        for (int i = threadIdx.x; i < 2 * ns; i += blockDim.x) sp[i] = p[(size_t)b * 2 * ns + i];
+        if (lam) for (int i = threadIdx.x; i < mg; i += blockDim.x) sl[i] = lam[(size_t)b * mg + i];
+        __syncthreads();
+        double facc = 0.0;
+        // robot-stage work items, then pair-stage items, then the initial block
+        const int nRS = N * Nr, nPS = N * M;
+        for (int it = threadIdx.x; it < nRS + nPS + ns + M + ns; it += blockDim.x) {
+            if (it < nRS) {
+                const int k = it / Nr, i = it % Nr, r0 = (k + 1) * blk + 3 * i;
+                const int ix = k * ns + 3 * i, iu = nX + k * nc + 2 * i;
+                const double x = sw[ix], y = sw[ix + 1], th = sw[ix + 2], v = sw[iu], om = sw[iu + 1];
+                double s_, c_;
+                sincos(th, &s_, &c_);
+                const double ex = x - sp[ns + 3 * i], ey = y - sp[ns + 3 * i + 1], et = th - sp[ns + 3 * i + 2];
+                facc += Qw[0] * ex * ex + Qw[1] * ey * ey + Qw[2] * et * et + Rw[0] * v * v + Rw[1] * om * om;
+                sgrad[ix] = 2 * Qw[0] * ex; sgrad[ix + 1] = 2 * Qw[1] * ey; sgrad[ix + 2] = 2 * Qw[2] * et;
+                sgrad[iu] = 2 * Rw[0] * v; sgrad[iu + 1] = 2 * Rw[1] * om;
+                sg[r0] = sw[ix + ns] - (x + T * v * c_);
+                sg[r0 + 1] = sw[ix + ns + 1] - (y + T * v * s_);
+                sg[r0 + 2] = sw[ix + ns + 2] - (th + T * om);
+                const int *js = tb.jac_rs + (size_t)it * 11;
+                sj[js[0]] = 1.0; sj[js[1]] = -1.0; sj[js[2]] = T * v * s_; sj[js[3]] = -T * c_;
+                sj[js[4]] = 1.0; sj[js[5]] = -1.0; sj[js[6]] = -T * v * c_; sj[js[7]] = -T * s_;
+                sj[js[8]] = 1.0; sj[js[9]] = -1.0; sj[js[10]] = -T;
+                if (lam && hess) {
+                    const double lx = sl[r0], ly = sl[r0 + 1];
+                    double sm2 = 0.0;
+                    for (int j = 0; j < Nr; j++) {
+                        if (j == i) continue;
+                        const int a = i < j ? i : j, c2 = i < j ? j : i;
+                        sm2 += 2.0 * sl[(k + 1) * blk + ns + a * (2 * Nr - a - 1) / 2 + (c2 - a - 1)];
+                    }
+                    const int *hs = tb.hes_rs + (size_t)it * 6;
+                    shs[hs[0]] = 2 * Qw[0] + sm2; shs[hs[1]] = 2 * Qw[1] + sm2;
+                    shs[hs[2]] = 2 * Qw[2] + T * v * (lx * c_ + ly * s_);
+                    shs[hs[3]] = T * (lx * s_ - ly * c_);
+                    shs[hs[4]] = 2 * Rw[0]; shs[hs[5]] = 2 * Rw[1];
+                }
+            } else if (it < nRS + nPS) {
+                const int e = it - nRS, k = e / M, q = e % M;
+                int a = 0, rem = q;
+                while (rem >= Nr - 1 - a) { rem -= Nr - 1 - a; a++; }
+                const int c2 = a + 1 + rem;
+                const double dx = sw[k * ns + 3 * a] - sw[k * ns + 3 * c2], dy = sw[k * ns + 3 * a + 1] - sw[k * ns + 3 * c2 + 1];
+                sg[(k + 1) * blk + ns + q] = dx * dx + dy * dy;
+                const int *js = tb.jac_ps + (size_t)e * 4;
+                sj[js[0]] = 2 * dx; sj[js[1]] = -2 * dx; sj[js[2]] = 2 * dy; sj[js[3]] = -2 * dy;
+                if (lam && hess) {
+                    const double mu = sl[(k + 1) * blk + ns + q];
+                    const int *hs = tb.hes_ps + (size_t)e * 2;
+                    shs[hs[0]] = -2 * mu; shs[hs[1]] = -2 * mu;
+                }
+            } else if (it < nRS + nPS + ns) {
+                const int r = it - nRS - nPS;
+                sg[r] = sw[r] - sp[r];
+                sj[tb.jac_init[r]] = 1.0;
+            } else if (it < nRS + nPS + ns + M) {
+                sg[ns + (it - nRS - nPS - ns)] = NMPC_DUMMY_ROW_VALUE;
+            } else {
+                sgrad[N * ns + (it - nRS - nPS - ns - M)] = 0.0;  // X_N is not in the cost
+            }
+        }
+        // block reduction of f
+        for (int m = 16; m > 0; m >>= 1) facc += __shfl_xor_sync(0xffffffffu, facc, m);
+        if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = facc;
+        __syncthreads();
+        if (threadIdx.x == 0 && f) {
+            double t = 0.0;
+            for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += sred[i];
+            f[b] = t;
+        }
+        if (grad) for (int i = threadIdx.x; i < n; i += blockDim.x) grad[(size_t)b * n + i] = sgrad[i];
+        if (g) for (int i = threadIdx.x; i < mg; i += blockDim.x) g[(size_t)b * mg + i] = sg[i];
+        if (jac) for (int i = threadIdx.x; i < nj; i += blockDim.x) jac[(size_t)b * nj + i] = sj[i];
+        if (hess && lam) for (int i = threadIdx.x; i < nh; i += blockDim.x) hess[(size_t)b * nh + i] = shs[i];
+        __syncthreads();
+    }
+}
+
+// u0 = [u[1:]; u[-1]]  and  X0 = [X[1:]; X[N-1]]   (row N-1, not N: the reference's quirk)
+__global__ void shift_kernel(int Nr, int N, long long total, const double *__restrict__ xp, double *__restrict__ xn)
+{
+    const int ns = 3 * Nr, nc = 2 * Nr, nX = ns * (N + 1), n = nX + nc * N;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long b = e / n;
+        const int j = (int)(e - b * n);
+        int src;
+        if (j < nX) { const int k = j / ns, c = j - k * ns; src = (k < N ? k + 1 : N - 1) * ns + c; }
+        else { const int k = (j - nX) / nc, c = (j - nX) - k * nc; src = nX + (k < N - 1 ? k + 1 : N - 1) * nc + c; }
+        xn[e] = xp[b * n + src];
+    }
+}
+
+__global__ void plant_kernel(int Nr, int N, double T, int B, const double *__restrict__ st, const double *__restrict__ xopt,
+                             double *__restrict__ out)
+{
+    const int ns = 3 * Nr, nc = 2 * Nr, nX = ns * (N + 1), n = nX + nc * N;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < B * Nr; e += gridDim.x * blockDim.x) {
+        const int b = e / Nr, i = e % Nr;
+        const double *s = st + (size_t)b * ns + 3 * i;
+        const double v = xopt[(size_t)b * n + nX + 2 * i], om = xopt[(size_t)b * n + nX + 2 * i + 1];
+        const double x = s[0], y = s[1], th = s[2];
+        double s_, c_;
+        sincos(th, &s_, &c_);
+        double *o = out + (size_t)b * ns + 3 * i;
+        o[0] = x + T * v * c_; o[1] = y + T * v * s_; o[2] = th + T * om;
+    }
+}
+
+__global__ void prep_bounds_kernel(int Nr, int N, double relax, int nb, const double *__restrict__ lbx, const double *__restrict__ ubx,
+                                   const double *__restrict__ lbg, const double *__restrict__ ubg, double *__restrict__ rows, int *err)
+{
+    const int S = N + 1, ns = 3 * Nr, nc = 2 * Nr, M = Nr * (Nr - 1) / 2;
+    const long long n = (long long)ns * S + (long long)nc * N, mg = (long long)S * (ns + M);
+    const long long total = (long long)nb * S * 32, bstride = (long long)NMPC_BR_COUNT * S * 32;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long b = e / (S * 32);
+        const int k = (int)((e / 32) % S), lane = (int)(e & 31);
+        int rc = nmpc_prep_bounds_elem(Nr, N, relax, lbx + b * n, ubx + b * n, lbg + b * mg, ubg + b * mg, k, lane, rows + b * bstride);
+        if (rc) atomicCAS(err, 0, rc);
+    }
+}

@@ -1,0 +1,52 @@
+// Stage-layout bound rows from the reference's flat lbx/ubx/lbg/ubg arrays
+// (centralized_six_robots_implementation.py:349-352), relaxed by IPOPT's bound_relax_factor.
+// One call per (bound set, stage k, lane); shared by prep_bounds_kernel and the CPU emulation.
+#pragma once
+#include "nmpc_internal.h"
+
+#ifndef NMPC_HD
+#ifdef __CUDACC__
+#define NMPC_HD __host__ __device__
+#else
+#define NMPC_HD
+#endif
+#endif
+#ifndef NMPC_INF
+#define NMPC_INF ((double)INFINITY)
+#endif
+
+NMPC_HD inline double nmpc_relax_lo(double v, double f) { return v > -NMPC_INF ? v - f * fmax(1.0, fabs(v)) : -NMPC_INF; }
+NMPC_HD inline double nmpc_relax_hi(double v, double f) { return v < NMPC_INF ? v + f * fmax(1.0, fabs(v)) : NMPC_INF; }
+
+// rows: [NMPC_BR_COUNT][S][32] of this bound set.  Returns 0 or a negative NMPC_E* code.
+NMPC_HD inline int nmpc_prep_bounds_elem(int Nr, int N, double relax, const double *lbx, const double *ubx,
+                                         const double *lbg, const double *ubg, int k, int lane, double *rows)
+{
+    const int ns = 3 * Nr, nc = 2 * Nr, nz = 5 * Nr, M = Nr * (Nr - 1) / 2, S = N + 1, blk = ns + M;
+    const long long rs = (long long)S * 32;
+    const int e = k * 32 + lane;
+    int err = 0;
+    double lo = -NMPC_INF, hi = NMPC_INF;
+    if (lane < ns) { lo = lbx[k * ns + lane]; hi = ubx[k * ns + lane]; }
+    else if (lane < nz && k < N) { lo = lbx[ns * S + k * nc + (lane - ns)]; hi = ubx[ns * S + k * nc + (lane - ns)]; }
+    if (!(lo <= hi)) err = NMPC_EBOUNDS;
+    else if (lo == hi) err = NMPC_ENOTSUP;  // fixed variables are not part of this path
+    rows[NMPC_BR_BL * rs + e] = nmpc_relax_lo(lo, relax);
+    rows[NMPC_BR_BU * rs + e] = nmpc_relax_hi(hi, relax);
+    double ce = 0.0;
+    if (lane < ns) {
+        double l = lbg[k * blk + lane], u = ubg[k * blk + lane];
+        if (!(l == u) || !(l > -NMPC_INF && l < NMPC_INF)) err = err ? err : NMPC_ENOTSUP;  // dynamics rows are equalities
+        ce = l;
+    }
+    rows[NMPC_BR_CE * rs + e] = ce;
+    double dl = -NMPC_INF, du = NMPC_INF;
+    if (lane < M) {
+        dl = lbg[k * blk + ns + lane]; du = ubg[k * blk + ns + lane];
+        if (!(dl <= du)) err = err ? err : NMPC_EBOUNDS;
+        else if (dl == du) err = err ? err : NMPC_ENOTSUP;  // equality on a distance row
+    }
+    rows[NMPC_BR_DL * rs + e] = nmpc_relax_lo(dl, relax);
+    rows[NMPC_BR_DU * rs + e] = nmpc_relax_hi(du, relax);
+    return err;
+}

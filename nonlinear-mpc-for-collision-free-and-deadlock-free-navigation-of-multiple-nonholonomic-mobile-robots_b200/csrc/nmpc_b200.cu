@@ -1,0 +1,430 @@
+// libnmpc_b200.so -- C-ABI (include/nmpc_b200.h) over the sm_100a kernels.
+// No CPU fallback: every entry point launches CUDA work or fails with NMPC_ECUDA.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "nmpc_b200.h"
+#include "warp_prims.cuh"
+#include "solver_body.cuh"
+#include "aux_kernels.cuh"
+
+#define SOLVE_WARPS 4
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CUDA_OK(call)                                                                                    \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return fail(NMPC_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+extern "C" const char *nmpc_last_error(void) { return g_err; }
+
+extern "C" void nmpc_default_opts(nmpc_opts *o)
+{
+    o->tol = 1e-8; o->max_iter = 2000; o->acceptable_tol = 1e-8; o->acceptable_iter = 15;
+    o->acceptable_obj_change_tol = 1e-6; o->dual_inf_tol = 1.0; o->constr_viol_tol = 1e-4; o->compl_inf_tol = 1e-4;
+    o->mu_init = 0.1; o->kappa_mu = 0.2; o->theta_mu = 1.5; o->barrier_tol_factor = 10.0; o->tau_min = 0.99;
+    o->bound_push = 0.01; o->bound_frac = 0.01; o->bound_relax_factor = 1e-8; o->bound_mult_init_val = 1.0;
+    o->constr_mult_init_max = 1e3; o->kappa_sigma = 1e10; o->kappa_d = 1e-5; o->nlp_scaling_max_gradient = 100.0;
+    o->max_soc = 4; o->max_resto_iter = 100;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the persistent solve kernel: one warp per instance, instances pulled from an atomic queue
+// ------------------------------------------------------------------------------------------------
+template <int NR>
+__global__ void __launch_bounds__(SOLVE_WARPS * 32) solve_kernel(const NmpcSolveParams P)
+{
+    extern __shared__ double smem[];
+    const int w = threadIdx.x >> 5;
+    double *sm = smem + (size_t)w * WarpSolver<NR>::SM_DOUBLES;
+    double *ws = P.ws + ((long long)blockIdx.x * SOLVE_WARPS + w) * P.ws_stride;
+    WarpSolver<NR> s(P, sm, ws);
+    for (;;) {
+        int inst = 0;
+        if ((threadIdx.x & 31) == 0) inst = atomicAdd(P.counter, 1);
+        inst = __shfl_sync(0xffffffffu, inst, 0);
+        if (inst >= P.B) break;
+        s.setup(inst);
+        s.run();
+        __syncwarp();
+    }
+}
+
+struct nmpc_handle {
+    nmpc_desc d;
+    nmpc_opts o;
+    int ns, nc, M, S, n, mg, np, nnzj, nnzh, sm_count, dev;
+    std::vector<int> jcol, jrow, hcol, hrow;  // CCS patterns (host)
+    int *d_tables;
+    NmpcEvalTables tb;
+    long long launches;
+    size_t ws_doubles_per_slot, solve_smem, eval_smem;
+    int ctas_per_sm;
+    // host-pointer API staging
+    char *d_buf;
+    size_t d_bytes;
+    cudaStream_t stream;
+};
+
+struct Trip { int r, c, tag; };
+
+static void build_tables(nmpc_handle *h, std::vector<int> &tab)
+{
+    const int Nr = h->d.Nr, N = h->d.N, ns = h->ns, nc = h->nc, M = h->M, blk = ns + M, nX = ns * h->S;
+    auto IX = [&](int k, int i, int c) { return k * ns + 3 * i + c; };
+    auto IU = [&](int k, int i, int c) { return nX + k * nc + 2 * i + c; };
+    std::vector<Trip> J, H;
+    int tag = 0;
+    // tags follow the layout of NmpcEvalTables: jac_rs | jac_ps | jac_init, then hes_rs | hes_ps
+    for (int k = 0; k < N; k++)
+        for (int i = 0; i < Nr; i++) {
+            const int b = (k + 1) * blk, rx = b + 3 * i, ry = rx + 1, rt = rx + 2;
+            const int rc[11][2] = {{rx, IX(k + 1, i, 0)}, {rx, IX(k, i, 0)}, {rx, IX(k, i, 2)}, {rx, IU(k, i, 0)},
+                                   {ry, IX(k + 1, i, 1)}, {ry, IX(k, i, 1)}, {ry, IX(k, i, 2)}, {ry, IU(k, i, 0)},
+                                   {rt, IX(k + 1, i, 2)}, {rt, IX(k, i, 2)}, {rt, IU(k, i, 1)}};
+            for (auto &e : rc) J.push_back({e[0], e[1], tag++});
+        }
+    std::vector<std::pair<int, int>> pairs;
+    for (int a = 0; a < Nr; a++)
+        for (int b = a + 1; b < Nr; b++) pairs.push_back({a, b});
+    for (int k = 0; k < N; k++)
+        for (int q = 0; q < M; q++) {
+            const int r = (k + 1) * blk + ns + q, i = pairs[q].first, j = pairs[q].second;
+            J.push_back({r, IX(k, i, 0), tag++}); J.push_back({r, IX(k, j, 0), tag++});
+            J.push_back({r, IX(k, i, 1), tag++}); J.push_back({r, IX(k, j, 1), tag++});
+        }
+    for (int r = 0; r < ns; r++) J.push_back({r, r, tag++});
+    int htag = 0;
+    for (int k = 0; k < N; k++)
+        for (int i = 0; i < Nr; i++) {
+            H.push_back({IX(k, i, 0), IX(k, i, 0), htag++}); H.push_back({IX(k, i, 1), IX(k, i, 1), htag++});
+            H.push_back({IX(k, i, 2), IX(k, i, 2), htag++}); H.push_back({IU(k, i, 0), IX(k, i, 2), htag++});
+            H.push_back({IU(k, i, 0), IU(k, i, 0), htag++}); H.push_back({IU(k, i, 1), IU(k, i, 1), htag++});
+        }
+    for (int k = 0; k < N; k++)
+        for (int q = 0; q < M; q++) {
+            H.push_back({IX(k, pairs[q].second, 0), IX(k, pairs[q].first, 0), htag++});
+            H.push_back({IX(k, pairs[q].second, 1), IX(k, pairs[q].first, 1), htag++});
+        }
+    auto cmp = [](const Trip &a, const Trip &b) { return a.c != b.c ? a.c < b.c : a.r < b.r; };
+    std::sort(J.begin(), J.end(), cmp);
+    std::sort(H.begin(), H.end(), cmp);
+    auto to_ccs = [&](const std::vector<Trip> &T, std::vector<int> &cp, std::vector<int> &ri, std::vector<int> &slot) {
+        cp.assign(h->n + 1, 0); ri.resize(T.size()); slot.resize(T.size());
+        for (size_t e = 0; e < T.size(); e++) { cp[T[e].c + 1]++; ri[e] = T[e].r; slot[T[e].tag] = (int)e; }
+        for (int c = 0; c < h->n; c++) cp[c + 1] += cp[c];
+    };
+    std::vector<int> js, hs;
+    to_ccs(J, h->jcol, h->jrow, js);
+    to_ccs(H, h->hcol, h->hrow, hs);
+    tab = js;
+    tab.insert(tab.end(), hs.begin(), hs.end());
+}
+
+template <int NR> static size_t slot_doubles(int N) { return (size_t)WarpSolver<NR>::ws_doubles(N); }
+template <int NR> static cudaError_t config_solve(nmpc_handle *h)
+{
+    h->solve_smem = (size_t)SOLVE_WARPS * WarpSolver<NR>::SM_DOUBLES * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(solve_kernel<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->solve_smem);
+    if (e != cudaSuccess) return e;
+    int nb = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, solve_kernel<NR>, SOLVE_WARPS * 32, h->solve_smem);
+    h->ctas_per_sm = nb > 0 ? nb : 1;
+    return e;
+}
+
+extern "C" int nmpc_create(const nmpc_desc *d, const nmpc_opts *o, nmpc_handle **out)
+{
+    if (!d || !out) return fail(NMPC_EINVAL, "nmpc_create: NULL argument");
+    if (d->N < 1 || !(d->T > 0)) return fail(NMPC_EINVAL, "nmpc_create: need N >= 1 and T > 0");
+    if (d->Nr < 1 || d->Nr > 6) return fail(NMPC_ENOTSUP, "nmpc_create: Nr = %d; the register-resident Riccati path covers 1..6 robots", d->Nr);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(NMPC_ECUDA, "nmpc_create: no CUDA device -- this library has no CPU fallback");
+    nmpc_handle *h = new nmpc_handle();
+    h->d = *d;
+    if (o) h->o = *o; else nmpc_default_opts(&h->o);
+    h->ns = 3 * d->Nr; h->nc = 2 * d->Nr; h->M = d->Nr * (d->Nr - 1) / 2; h->S = d->N + 1;
+    h->n = h->ns * h->S + h->nc * d->N; h->mg = h->S * (h->ns + h->M); h->np = 2 * h->ns;
+    h->nnzj = 3 * d->Nr + d->N * (11 * d->Nr + 4 * h->M); h->nnzh = d->N * (6 * d->Nr + 2 * h->M);
+    h->launches = 0; h->d_buf = nullptr; h->d_bytes = 0; h->stream = nullptr; h->d_tables = nullptr;
+    cudaGetDevice(&h->dev);
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->dev);
+    std::vector<int> tab;
+    build_tables(h, tab);
+    cudaError_t e = cudaMalloc(&h->d_tables, tab.size() * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_tables, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { delete h; return fail(NMPC_ECUDA, "nmpc_create: table upload failed: %s", cudaGetErrorString(e)); }
+    const int N = d->N, Nr = d->Nr, M = h->M;
+    h->tb.jac_rs = h->d_tables;
+    h->tb.jac_ps = h->tb.jac_rs + (size_t)N * Nr * 11;
+    h->tb.jac_init = h->tb.jac_ps + (size_t)N * M * 4;
+    h->tb.hes_rs = h->d_tables + h->nnzj;
+    h->tb.hes_ps = h->tb.hes_rs + (size_t)N * Nr * 6;
+    switch (Nr) {
+        case 1: h->ws_doubles_per_slot = slot_doubles<1>(N); e = config_solve<1>(h); break;
+        case 2: h->ws_doubles_per_slot = slot_doubles<2>(N); e = config_solve<2>(h); break;
+        case 3: h->ws_doubles_per_slot = slot_doubles<3>(N); e = config_solve<3>(h); break;
+        case 4: h->ws_doubles_per_slot = slot_doubles<4>(N); e = config_solve<4>(h); break;
+        case 5: h->ws_doubles_per_slot = slot_doubles<5>(N); e = config_solve<5>(h); break;
+        default: h->ws_doubles_per_slot = slot_doubles<6>(N); e = config_solve<6>(h); break;
+    }
+    if (e != cudaSuccess) { cudaFree(h->d_tables); delete h; return fail(NMPC_ECUDA, "nmpc_create: kernel configuration failed: %s", cudaGetErrorString(e)); }
+    h->eval_smem = (size_t)(2 * h->n + 2 * h->mg + 2 * h->ns + h->nnzj + h->nnzh + 32) * sizeof(double);
+    e = cudaFuncSetAttribute(eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->eval_smem);
+    if (e != cudaSuccess) { cudaFree(h->d_tables); delete h; return fail(NMPC_ENOTSUP, "nmpc_create: eval record (%zu B) exceeds shared memory: %s", h->eval_smem, cudaGetErrorString(e)); }
+    *out = h;
+    return 0;
+}
+
+extern "C" void nmpc_destroy(nmpc_handle *h)
+{
+    if (!h) return;
+    if (h->d_tables) cudaFree(h->d_tables);
+    if (h->d_buf) cudaFree(h->d_buf);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int nmpc_n(const nmpc_handle *h) { return h ? h->n : NMPC_EINVAL; }
+extern "C" int nmpc_mg(const nmpc_handle *h) { return h ? h->mg : NMPC_EINVAL; }
+extern "C" int nmpc_np(const nmpc_handle *h) { return h ? h->np : NMPC_EINVAL; }
+extern "C" int nmpc_nnz_jac(const nmpc_handle *h) { return h ? h->nnzj : NMPC_EINVAL; }
+extern "C" int nmpc_nnz_hess(const nmpc_handle *h) { return h ? h->nnzh : NMPC_EINVAL; }
+extern "C" long long nmpc_launch_count(const nmpc_handle *h) { return h ? h->launches : 0; }
+
+extern "C" int nmpc_jac_pattern(const nmpc_handle *h, int32_t *colptr, int32_t *rowidx)
+{
+    if (!h || !colptr || !rowidx) return fail(NMPC_EINVAL, "nmpc_jac_pattern: NULL argument");
+    memcpy(colptr, h->jcol.data(), sizeof(int) * (h->n + 1)); memcpy(rowidx, h->jrow.data(), sizeof(int) * h->nnzj);
+    return 0;
+}
+extern "C" int nmpc_hess_pattern(const nmpc_handle *h, int32_t *colptr, int32_t *rowidx)
+{
+    if (!h || !colptr || !rowidx) return fail(NMPC_EINVAL, "nmpc_hess_pattern: NULL argument");
+    memcpy(colptr, h->hcol.data(), sizeof(int) * (h->n + 1)); memcpy(rowidx, h->hrow.data(), sizeof(int) * h->nnzh);
+    return 0;
+}
+
+static int solve_grid(const nmpc_handle *h, int B)
+{
+    int need = (B + SOLVE_WARPS - 1) / SOLVE_WARPS, cap = h->sm_count * h->ctas_per_sm;
+    return need < cap ? (need > 0 ? need : 1) : cap;
+}
+static size_t bound_rows_bytes(const nmpc_handle *h, int nb) { return (size_t)nb * NMPC_BR_COUNT * h->S * 32 * sizeof(double); }
+static size_t ws_bytes_for(const nmpc_handle *h, int B, int nb)
+{
+    return 256 + bound_rows_bytes(h, nb) + (size_t)solve_grid(h, B) * SOLVE_WARPS * h->ws_doubles_per_slot * sizeof(double);
+}
+extern "C" size_t nmpc_workspace_bytes(const nmpc_handle *h, int B) { return h && B > 0 ? ws_bytes_for(h, B, 1) : 0; }
+extern "C" size_t nmpc_workspace_bytes_batched_bounds(const nmpc_handle *h, int B) { return h && B > 0 ? ws_bytes_for(h, B, B) : 0; }
+
+static int solve_impl(nmpc_handle *h, int B, const double *x0, const double *p, const double *lbx, const double *ubx,
+                      const double *lbg, const double *ubg, int bounds_batched, double *x, double *f, double *g,
+                      double *lam_x, double *lam_g, int32_t *status, int32_t *iters, double *stats, double *trace,
+                      int max_trace, void *workspace, size_t workspace_bytes, cudaStream_t st)
+{
+    if (!h || !x0 || !p || !lbx || !ubx || !lbg || !ubg || !x || !workspace) return fail(NMPC_EINVAL, "nmpc_solve: NULL argument");
+    if (B <= 0) return fail(NMPC_EINVAL, "nmpc_solve: B must be positive");
+    const int nb = bounds_batched ? B : 1;
+    const size_t need = ws_bytes_for(h, B, nb);
+    if (workspace_bytes < need) return fail(NMPC_ENOMEM, "nmpc_solve: workspace %zu B < %zu B required", workspace_bytes, need);
+    char *base = (char *)workspace;
+    int *counter = (int *)base, *berr = counter + 1;
+    double *brows = (double *)(base + 256);
+    double *slots = (double *)(base + 256 + bound_rows_bytes(h, nb));
+    CUDA_OK(cudaMemsetAsync(base, 0, 256, st));
+    {
+        long long total = (long long)nb * h->S * 32;
+        int blocks = (int)std::min<long long>((total + 255) / 256, 4096);
+        prep_bounds_kernel<<<blocks, 256, 0, st>>>(h->d.Nr, h->d.N, h->o.bound_relax_factor, nb, lbx, ubx, lbg, ubg, brows, berr);
+        h->launches++;
+    }
+    NmpcSolveParams P;
+    memset(&P, 0, sizeof P);
+    P.Nr = h->d.Nr; P.N = h->d.N; P.B = B; P.T = h->d.T;
+    memcpy(P.Q, h->d.Q, sizeof P.Q); memcpy(P.R, h->d.R, sizeof P.R);
+    P.o = h->o; P.x0 = x0; P.p = p; P.brows = brows;
+    P.bstride = bounds_batched ? (long long)NMPC_BR_COUNT * h->S * 32 : 0;
+    P.bound_err = berr; P.x = x; P.f = f; P.g = g; P.lam_x = lam_x; P.lam_g = lam_g; P.status = status; P.iters = iters;
+    P.stats = stats; P.trace = trace; P.max_trace = max_trace; P.ws = slots; P.ws_stride = (long long)h->ws_doubles_per_slot;
+    P.counter = counter;
+    const int grid = solve_grid(h, B);
+    switch (h->d.Nr) {
+        case 1: solve_kernel<1><<<grid, SOLVE_WARPS * 32, h->solve_smem, st>>>(P); break;
+        case 2: solve_kernel<2><<<grid, SOLVE_WARPS * 32, h->solve_smem, st>>>(P); break;
+        case 3: solve_kernel<3><<<grid, SOLVE_WARPS * 32, h->solve_smem, st>>>(P); break;
+        case 4: solve_kernel<4><<<grid, SOLVE_WARPS * 32, h->solve_smem, st>>>(P); break;
+        case 5: solve_kernel<5><<<grid, SOLVE_WARPS * 32, h->solve_smem, st>>>(P); break;
+        default: solve_kernel<6><<<grid, SOLVE_WARPS * 32, h->solve_smem, st>>>(P); break;
+    }
+    h->launches++;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int nmpc_solve(nmpc_handle *h, int B, const double *x0, const double *p, const double *lbx, const double *ubx,
+                          const double *lbg, const double *ubg, int bounds_batched, double *x, double *f, double *g,
+                          double *lam_x, double *lam_g, int32_t *status, int32_t *iters, double *stats, void *workspace,
+                          size_t workspace_bytes, void *stream)
+{
+    return solve_impl(h, B, x0, p, lbx, ubx, lbg, ubg, bounds_batched, x, f, g, lam_x, lam_g, status, iters, stats, nullptr, 0,
+                      workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// debugging / parity entry: same as nmpc_solve plus a per-iteration trace [B][max_trace][8]
+extern "C" int nmpc_solve_trace(nmpc_handle *h, int B, const double *x0, const double *p, const double *lbx, const double *ubx,
+                                const double *lbg, const double *ubg, int bounds_batched, double *x, double *f, double *g,
+                                double *lam_x, double *lam_g, int32_t *status, int32_t *iters, double *stats, double *trace,
+                                int max_trace, void *workspace, size_t workspace_bytes, void *stream)
+{
+    return solve_impl(h, B, x0, p, lbx, ubx, lbg, ubg, bounds_batched, x, f, g, lam_x, lam_g, status, iters, stats, trace, max_trace,
+                      workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+static size_t al(size_t v) { return (v + 255) & ~(size_t)255; }
+
+extern "C" int nmpc_solve_host(nmpc_handle *h, int B, const double *x0, const double *p, const double *lbx, const double *ubx,
+                               const double *lbg, const double *ubg, int bounds_batched, double *x, double *f, double *g,
+                               double *lam_x, double *lam_g, int32_t *status, int32_t *iters, double *stats)
+{
+    if (!h || !x0 || !p || !lbx || !ubx || !lbg || !ubg || !x) return fail(NMPC_EINVAL, "nmpc_solve_host: NULL argument");
+    if (B <= 0) return fail(NMPC_EINVAL, "nmpc_solve_host: B must be positive");
+    const int nb = bounds_batched ? B : 1;
+    const size_t n = h->n, mg = h->mg, np = h->np, D = sizeof(double);
+    const size_t o_x0 = 0, o_p = o_x0 + al(B * n * D), o_lbx = o_p + al(B * np * D), o_ubx = o_lbx + al(nb * n * D),
+                 o_lbg = o_ubx + al(nb * n * D), o_ubg = o_lbg + al(nb * mg * D), o_x = o_ubg + al(nb * mg * D),
+                 o_f = o_x + al(B * n * D), o_g = o_f + al(B * D), o_lx = o_g + al(B * mg * D), o_lg = o_lx + al(B * n * D),
+                 o_st = o_lg + al(B * mg * D), o_it = o_st + al(B * 4), o_stats = o_it + al(B * 4),
+                 o_ws = o_stats + al((size_t)B * NMPC_NSTATS * D);
+    const size_t wsb = ws_bytes_for(h, B, nb), total = o_ws + wsb;
+    if (!h->stream) CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    if (h->d_bytes < total) {
+        if (h->d_buf) cudaFree(h->d_buf);
+        h->d_buf = nullptr; h->d_bytes = 0;
+        CUDA_OK(cudaMalloc(&h->d_buf, total));
+        h->d_bytes = total;
+    }
+    char *b = h->d_buf;
+    cudaStream_t st = h->stream;
+    CUDA_OK(cudaMemcpyAsync(b + o_x0, x0, B * n * D, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(b + o_p, p, B * np * D, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(b + o_lbx, lbx, nb * n * D, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(b + o_ubx, ubx, nb * n * D, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(b + o_lbg, lbg, nb * mg * D, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(b + o_ubg, ubg, nb * mg * D, cudaMemcpyHostToDevice, st));
+    int rc = solve_impl(h, B, (double *)(b + o_x0), (double *)(b + o_p), (double *)(b + o_lbx), (double *)(b + o_ubx),
+                        (double *)(b + o_lbg), (double *)(b + o_ubg), bounds_batched, (double *)(b + o_x),
+                        f ? (double *)(b + o_f) : nullptr, g ? (double *)(b + o_g) : nullptr,
+                        lam_x ? (double *)(b + o_lx) : nullptr, lam_g ? (double *)(b + o_lg) : nullptr, (int32_t *)(b + o_st),
+                        iters ? (int32_t *)(b + o_it) : nullptr, stats ? (double *)(b + o_stats) : nullptr, nullptr, 0, b + o_ws,
+                        wsb, st);
+    if (rc) return rc;
+    CUDA_OK(cudaMemcpyAsync(x, b + o_x, B * n * D, cudaMemcpyDeviceToHost, st));
+    if (f) CUDA_OK(cudaMemcpyAsync(f, b + o_f, B * D, cudaMemcpyDeviceToHost, st));
+    if (g) CUDA_OK(cudaMemcpyAsync(g, b + o_g, B * mg * D, cudaMemcpyDeviceToHost, st));
+    if (lam_x) CUDA_OK(cudaMemcpyAsync(lam_x, b + o_lx, B * n * D, cudaMemcpyDeviceToHost, st));
+    if (lam_g) CUDA_OK(cudaMemcpyAsync(lam_g, b + o_lg, B * mg * D, cudaMemcpyDeviceToHost, st));
+    std::vector<int32_t> st_host;
+    int32_t *stp = status;
+    if (!stp) { st_host.resize(B); stp = st_host.data(); }
+    CUDA_OK(cudaMemcpyAsync(stp, b + o_st, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    if (iters) CUDA_OK(cudaMemcpyAsync(iters, b + o_it, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    if (stats) CUDA_OK(cudaMemcpyAsync(stats, b + o_stats, (size_t)B * NMPC_NSTATS * D, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    if (stp[0] < 0) return fail(stp[0], "nmpc_solve_host: bounds rejected (%s)", stp[0] == NMPC_EBOUNDS ? "lb > ub" : "fixed variable, non-equality dynamics row or equality distance row");
+    return 0;
+}
+
+extern "C" int nmpc_shift(nmpc_handle *h, int B, const double *x_prev, double *x0_next, void *stream)
+{
+    if (!h || !x_prev || !x0_next || B <= 0) return fail(NMPC_EINVAL, "nmpc_shift: bad argument");
+    if (x_prev == x0_next) return fail(NMPC_EINVAL, "nmpc_shift: in-place shift is not supported");
+    long long total = (long long)B * h->n;
+    int blocks = (int)std::min<long long>((total + 255) / 256, (long long)h->sm_count * 16);
+    shift_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(h->d.Nr, h->d.N, total, x_prev, x0_next);
+    h->launches++;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int nmpc_plant(nmpc_handle *h, int B, const double *state, const double *x_opt, double *state_next, void *stream)
+{
+    if (!h || !state || !x_opt || !state_next || B <= 0) return fail(NMPC_EINVAL, "nmpc_plant: bad argument");
+    int blocks = std::min((B * h->d.Nr + 255) / 256, h->sm_count * 16);
+    plant_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(h->d.Nr, h->d.N, h->d.T, B, state, x_opt, state_next);
+    h->launches++;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int nmpc_eval(nmpc_handle *h, int B, const double *w, const double *p, const double *lam_g, double *f, double *grad,
+                         double *g, double *jac, double *hess, void *stream)
+{
+    if (!h || !w || !p || B <= 0) return fail(NMPC_EINVAL, "nmpc_eval: bad argument");
+    if (hess && !lam_g) return fail(NMPC_EINVAL, "nmpc_eval: hess needs lam_g");
+    int per_sm = (int)std::max<size_t>(1, (size_t)(220 * 1024) / h->eval_smem);
+    int blocks = std::min(B, h->sm_count * per_sm);
+    eval_kernel<<<blocks, 256, h->eval_smem, (cudaStream_t)stream>>>(h->d.Nr, h->d.N, h->d.T, h->d.Q[0], h->d.Q[1], h->d.Q[2],
+                                                                       h->d.R[0], h->d.R[1], B, w, p, lam_g, f, grad, g, jac, hess, h->tb);
+    h->launches++;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64 FMA-pipe probe: the roofline denominator for the factorisation (MEASURED_PEAKS.json holds
+// only HBM and bf16 figures).  8 independent DFMA chains per thread, 148 x 8 CTAs of 256 threads.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dfma_probe_kernel(int iters, double *out)
+{
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    double r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (r == 123.456) out[0] = r;
+}
+
+extern "C" int nmpc_probe_fp64(double *tflops_out)
+{
+    if (!tflops_out) return fail(NMPC_EINVAL, "nmpc_probe_fp64: NULL argument");
+    int dev = 0, sms = 0;
+    CUDA_OK(cudaGetDevice(&dev));
+    CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    double *d = nullptr;
+    CUDA_OK(cudaMalloc(&d, 64));
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
+    const int iters = 1 << 16, grid = sms * 8;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        CUDA_OK(cudaEventRecord(e0));
+        dfma_probe_kernel<<<grid, 256>>>(iters, d);
+        CUDA_OK(cudaEventRecord(e1));
+        CUDA_OK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+        double tf = 2.0 * 8.0 * iters * 256.0 * grid / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    *tflops_out = best;
+    return 0;
+}

@@ -1,0 +1,927 @@
+// Warp-per-instance primal-dual interior-point solver for the Nr-robot unicycle NMPC NLP.
+//
+// Replaces, for one instance, everything behind the reference's
+//     sol = solver(x0=, p=, lbx=, ubx=, lbg=, ubg=)     centralized_six_robots_implementation.py:432
+// i.e. CasADi's derivative evaluation (K1), IPOPT's filter line-search interior-point iteration
+// (K2) and the MUMPS factorisation of the KKT system (K3, done here as a stage-wise Riccati
+// sweep).  NLP definition: same file :207-352 (cost :314, defects/distances :282-331, bounds
+// :349-352); algorithm: Waechter & Biegler 2006 with IPOPT's default options.
+//
+// Mapping: lane l of the warp owns variable l of the stage vector z_k = [X_k ; U_k]
+// (5 Nr <= 30 lanes), pair row q of an inequality block (lanes < M), and COLUMN l of the
+// (5Nr+1) x 5Nr bordered stage KKT matrix, which lives in registers.  Eliminating the control
+// block is a symmetric sweep: the pivot row is exchanged through shared memory, the rank-1
+// update is 5Nr+1 independent DFMAs per lane.  Iterates, steps and the Riccati factors stream
+// through a per-warp scratch area in global memory in [stage][32-lane] rows (256 B, coalesced).
+//
+// The file is written against the small `wp::` interface (warp_prims.cuh) so that the tests can
+// step the same source through a CPU fibre emulation of a warp (tests/emul/).
+#pragma once
+#include "nmpc_internal.h"
+
+#ifndef NMPC_INF
+#define NMPC_INF ((double)INFINITY)
+#endif
+
+template <int NR>
+struct WarpSolver {
+    static constexpr int NS = 3 * NR, NC = 2 * NR, NZ = 5 * NR, M = NR * (NR - 1) / 2;
+    static constexpr int LIN = NZ, NM = NZ + 1;
+    enum Row {
+        R_Z, R_ZL, R_ZU, R_DZ, R_DZ2, R_GX, R_YC, R_YTC, R_YTC2, R_RC, R_CSOC, R_COEF, R_LIN,
+        R_S, R_VL, R_VU, R_YD, R_DS, R_DS2, R_YTD, R_YTD2, R_DSOC, R_GXQ, R_GYQ, R_RD, R_DQ, R_GS,
+        R_COUNT
+    };
+    // shared-memory carve-up (doubles, per warp)
+    enum {
+        SM_COL = 0, SM_PB = 64, SM_ZB = SM_PB + 18 * 18, SM_DZB = SM_ZB + 32, SM_RCB = SM_DZB + 32,
+        SM_PRB = SM_RCB + 32, SM_CS = SM_PRB + 32, SM_SN = SM_CS + 8, SM_CA = SM_SN + 8, SM_CB = SM_CA + 8,
+        SM_TCS = SM_CB + 8, SM_TSN = SM_TCS + 8, SM_CRS = SM_TSN + 8, SM_THD = SM_CRS + 8,
+        SM_PXX = SM_THD + 8, SM_PYY = SM_PXX + 16, SM_PXY = SM_PYY + 16, SM_PHX = SM_PXY + 16,
+        SM_PHY = SM_PHX + 16, SM_FTH = SM_PHY + 16, SM_FPH = SM_FTH + 16, SM_MISC = SM_FPH + 16,
+        SM_DOUBLES = SM_MISC + 8
+    };
+    static NMPC_DEV long long ws_doubles(int N) { return ((long long)R_COUNT * (N + 1) + (long long)(N + 1) * NS) * 32; }
+
+    const NmpcSolveParams &P;
+    double *sm, *ws;
+    const double *BL, *BU, *CE, *DL, *DU;
+    int N, S, l, rob, comp, pi, pj, inst, fn;
+    bool isx, isu, isz, isq;
+    double T, df, xs_l, qw, x0bar_l, ny_nzb, nzb_cnt;
+    int n_reg, n_resto, n_soc, n_fact, n_ls;
+
+    NMPC_DEV WarpSolver(const NmpcSolveParams &p, double *smem, double *wsp) : P(p), sm(smem), ws(wsp) {}
+
+    NMPC_DEV double *row(int r, int k) const { return ws + ((long long)r * S + k) * 32; }
+    NMPC_DEV double *frow(int k, int i) const { return ws + ((long long)R_COUNT * S + (long long)k * NS + i) * 32; }
+    NMPC_DEV bool zvalid(int k) const { return l < (k < N ? NZ : NS); }
+    static NMPC_DEV int pairidx(int a, int b) { return a * (2 * NR - a - 1) / 2 + (b - a - 1); }
+    static NMPC_DEV bool fin(double v) { return v > -NMPC_INF && v < NMPC_INF; }
+
+    // ---------------------------------------------------------------------------------------
+    NMPC_DEV void setup(int instance)
+    {
+        inst = instance; N = P.N; S = N + 1; T = P.T; l = wp::lane();
+        isx = l < NS; isu = l >= NS && l < NZ; isz = l < NZ; isq = l < M;
+        rob = isx ? l / 3 : (isu ? (l - NS) / 2 : 0);
+        comp = isx ? l % 3 : (isu ? (l - NS) % 2 : 0);
+        pi = 0; pj = 0;
+        if (isq) {
+            int q = 0;
+            for (int a = 0; a < NR; a++)
+                for (int b = a + 1; b < NR; b++) { if (q == l) { pi = a; pj = b; } q++; }
+        }
+        const double *br = P.brows + (long long)inst * P.bstride;
+        BL = br + (long long)NMPC_BR_BL * S * 32; BU = br + (long long)NMPC_BR_BU * S * 32;
+        CE = br + (long long)NMPC_BR_CE * S * 32; DL = br + (long long)NMPC_BR_DL * S * 32;
+        DU = br + (long long)NMPC_BR_DU * S * 32;
+        const double *pp = P.p + (long long)inst * 2 * NS;
+        x0bar_l = isx ? pp[l] : 0.0;
+        xs_l = isx ? pp[NS + l] : 0.0;
+        qw = isx ? 2.0 * P.Q[comp] : (isu ? 2.0 * P.R[comp] : 0.0);
+        df = 1.0; fn = 0;
+        n_reg = n_resto = n_soc = n_fact = n_ls = 0;
+    }
+
+    NMPC_DEV double gradf(int k, double z) const { return (k < N && isz) ? qw * (z - xs_l) : 0.0; }
+
+    static NMPC_DEV double push_in(double x, double lo, double hi, double k1, double k2)
+    {
+        bool hl = lo > -NMPC_INF, hu = hi < NMPC_INF;
+        if (hl && hu) {
+            double pl = fmin(k1 * fmax(1.0, fabs(lo)), k2 * (hi - lo));
+            double pu = fmin(k1 * fmax(1.0, fabs(hi)), k2 * (hi - lo));
+            x = fmax(x, lo + pl); x = fmin(x, hi - pu);
+        } else if (hl) x = fmax(x, lo + k1 * fmax(1.0, fabs(lo)));
+        else if (hu) x = fmin(x, hi - k1 * fmax(1.0, fabs(hi)));
+        return x;
+    }
+
+    // starting point: objective scaling, push into bounds, slacks, bound multipliers
+    NMPC_DEV void init_point()
+    {
+        const double *x0 = P.x0 + (long long)inst * (NS * S + NC * N);
+        const nmpc_opts &o = P.o;
+        double gmax = 0.0;
+        for (int k = 0; k <= N; k++) {
+            double z = isx ? x0[k * NS + l] : ((isu && k < N) ? x0[NS * S + k * NC + (l - NS)] : 0.0);
+            gmax = fmax(gmax, fabs(gradf(k, z)));
+            row(R_Z, k)[l] = z;
+        }
+        gmax = wp::red_max(gmax);
+        df = gmax > o.nlp_scaling_max_gradient ? fmax(o.nlp_scaling_max_gradient / gmax, 1e-8) : 1.0;
+        double cnt_z = 0.0;
+        for (int k = 0; k <= N; k++) {
+            double lo = BL[k * 32 + l], hi = BU[k * 32 + l];
+            double z = push_in(row(R_Z, k)[l], lo, hi, o.bound_push, o.bound_frac);
+            row(R_Z, k)[l] = z;
+            bool hl = lo > -NMPC_INF, hu = hi < NMPC_INF;
+            row(R_ZL, k)[l] = hl ? o.bound_mult_init_val : 0.0;
+            row(R_ZU, k)[l] = hu ? o.bound_mult_init_val : 0.0;
+            cnt_z += (hl ? 1.0 : 0.0) + (hu ? 1.0 : 0.0);
+            row(R_YC, k)[l] = 0.0; row(R_YD, k)[l] = 0.0;
+            row(R_CSOC, k)[l] = 0.0; row(R_DSOC, k)[l] = 0.0;
+        }
+        wp::sync();
+        double cnt_y = isx ? (double)S : 0.0;
+        for (int b = 0; b <= N; b++) {
+            double s = 0.0, vl = 0.0, vu = 0.0;
+            if (isq) {
+                double lo = DL[b * 32 + l], hi = DU[b * 32 + l];
+                bool hl = lo > -NMPC_INF, hu = hi < NMPC_INF;
+                double dv = NMPC_DUMMY_ROW_VALUE;
+                if (b > 0) {
+                    const double *zr = row(R_Z, b - 1);
+                    double dx = zr[3 * pi] - zr[3 * pj], dy = zr[3 * pi + 1] - zr[3 * pj + 1];
+                    dv = dx * dx + dy * dy;
+                }
+                s = (hl || hu) ? push_in(dv, lo, hi, o.bound_push, o.bound_frac) : dv;
+                vl = hl ? o.bound_mult_init_val : 0.0; vu = hu ? o.bound_mult_init_val : 0.0;
+                cnt_z += (hl ? 1.0 : 0.0) + (hu ? 1.0 : 0.0);
+                cnt_y += (hl || hu) ? 1.0 : 0.0;
+            }
+            row(R_S, b)[l] = s; row(R_VL, b)[l] = vl; row(R_VU, b)[l] = vu;
+        }
+        nzb_cnt = wp::red_sum(cnt_z);
+        ny_nzb = wp::red_sum(cnt_y) + nzb_cnt;
+        wp::sync();
+    }
+
+    // ---------------------------------------------------------------------------------------
+    // residuals / merit quantities at the iterate (FULL) or at a trial point z + alpha dz
+    // ---------------------------------------------------------------------------------------
+    struct EvalOut { double pinf, viol, dinf, c0, cmu, ysum, zsum, theta, f, slog, sdamp; };
+
+    template <bool FULL>
+    NMPC_DEV void eval_pass(double mu, double alpha, int rdz, int rds, bool trial, bool socacc, double asoc, EvalOut &E)
+    {
+        const double kd = P.o.kappa_d;
+        double pinf = 0, viol = 0, dinf = 0, c0 = 0, cmu = 0, ysum = 0, zsum = 0, th = 0, fo = 0, slog = 0, sdamp = 0;
+        double *zb = sm + SM_ZB, *cs = sm + SM_CS, *sn = sm + SM_SN;
+        for (int k = 0; k <= N; k++) {
+            const bool zv = zvalid(k);
+            double zk = zv ? row(R_Z, k)[l] : 0.0;
+            if (trial && zv) zk += alpha * row(rdz, k)[l];
+            zb[l] = zk;
+            wp::sync();
+            if (k < N && l < NR) { double s_, c_; wp::sincos_(zb[3 * l + 2], &s_, &c_); cs[l] = c_; sn[l] = s_; }
+            wp::sync();
+            // ---- equality rows: block 0 (k == 0) and block k+1 ----
+            if (isx) {
+                if (k == 0) {
+                    double c = zk - x0bar_l - CE[l];
+                    pinf = fmax(pinf, fabs(c)); th += fabs(c); viol = fmax(viol, fabs(c));
+                    if (socacc) row(R_CSOC, 0)[l] = asoc * row(R_CSOC, 0)[l] + c;
+                }
+                if (k < N) {
+                    double zn = row(R_Z, k + 1)[l];
+                    if (trial) zn += alpha * row(rdz, k + 1)[l];
+                    double v = zb[NS + 2 * rob];
+                    double pred = comp == 0 ? zk + T * v * cs[rob] : (comp == 1 ? zk + T * v * sn[rob] : zk + T * zb[NS + 2 * rob + 1]);
+                    double c = zn - pred - CE[(k + 1) * 32 + l];
+                    pinf = fmax(pinf, fabs(c)); th += fabs(c); viol = fmax(viol, fabs(c));
+                    if (socacc) row(R_CSOC, k + 1)[l] = asoc * row(R_CSOC, k + 1)[l] + c;
+                }
+                if (FULL) ysum += fabs(row(R_YC, k)[l]);
+            }
+            // ---- inequality rows: block 0 (dummy rows) and block k+1 (distances on X_k) ----
+            if (M > 0 && isq) {
+                for (int pass = (k == 0 ? 0 : 1); pass < 2; pass++) {
+                    if (pass == 1 && k == N) break;
+                    const int b = pass == 0 ? 0 : k + 1;
+                    double lo = DL[b * 32 + l], hi = DU[b * 32 + l];
+                    bool hl = lo > -NMPC_INF, hu = hi < NMPC_INF;
+                    if (!(hl || hu)) continue;
+                    double dv = NMPC_DUMMY_ROW_VALUE;
+                    if (pass == 1) {
+                        double dx = zb[3 * pi] - zb[3 * pj], dy = zb[3 * pi + 1] - zb[3 * pj + 1];
+                        dv = dx * dx + dy * dy;
+                    }
+                    double s = row(R_S, b)[l];
+                    if (trial) s += alpha * row(rds, b)[l];
+                    double dms = dv - s;
+                    pinf = fmax(pinf, fabs(dms)); th += fabs(dms);
+                    viol = fmax(viol, fmax(lo - dv, dv - hi));
+                    if (socacc) row(R_DSOC, b)[l] = asoc * row(R_DSOC, b)[l] + dms;
+                    if (hl) slog += log(s - lo);
+                    if (hu) slog += log(hi - s);
+                    if (hl && !hu) sdamp += s - lo;
+                    if (hu && !hl) sdamp += hi - s;
+                    if (FULL) {
+                        double yd = row(R_YD, b)[l], vl = row(R_VL, b)[l], vu = row(R_VU, b)[l];
+                        ysum += fabs(yd);
+                        double t = -yd - vl + vu;
+                        if (hl && !hu) t += kd * mu;
+                        if (hu && !hl) t -= kd * mu;
+                        dinf = fmax(dinf, fabs(t));
+                        if (hl) { double u = (s - lo) * vl; c0 = fmax(c0, fabs(u)); cmu = fmax(cmu, fabs(u - mu)); zsum += fabs(vl); }
+                        if (hu) { double u = (hi - s) * vu; c0 = fmax(c0, fabs(u)); cmu = fmax(cmu, fabs(u - mu)); zsum += fabs(vu); }
+                    }
+                }
+            }
+            // ---- variable bounds, objective, stationarity of stage k ----
+            if (zv) {
+                double lo = BL[k * 32 + l], hi = BU[k * 32 + l];
+                bool hl = lo > -NMPC_INF, hu = hi < NMPC_INF;
+                if (hl) slog += log(zk - lo);
+                if (hu) slog += log(hi - zk);
+                if (hl && !hu) sdamp += zk - lo;
+                if (hu && !hl) sdamp += hi - zk;
+                if (k < N) { double e = zk - xs_l; fo += 0.5 * qw * e * e; }
+                if (FULL) {
+                    double zl = row(R_ZL, k)[l], zu = row(R_ZU, k)[l];
+                    double r = df * gradf(k, zk) - zl + zu;
+                    if (hl && !hu) r += kd * mu;
+                    if (hu && !hl) r -= kd * mu;
+                    if (isx) r += row(R_YC, k)[l];
+                    if (k < N) {
+                        const double *ycn = row(R_YC, k + 1);
+                        if (isx) {
+                            if (comp == 2) {
+                                double v = zb[NS + 2 * rob];
+                                r -= ycn[l] + (-T * v * sn[rob]) * ycn[3 * rob] + (T * v * cs[rob]) * ycn[3 * rob + 1];
+                            } else {
+                                r -= ycn[l];
+                                if (M > 0) {
+                                    const double *ydn = row(R_YD, k + 1);
+                                    NMPC_UNROLL
+                                    for (int j = 0; j < NR; j++) {
+                                        if (j == rob) continue;
+                                        int q = rob < j ? pairidx(rob, j) : pairidx(j, rob);
+                                        r += 2.0 * (zk - zb[3 * j + comp]) * ydn[q];
+                                    }
+                                }
+                            }
+                        } else {
+                            if (comp == 0) r -= T * (cs[rob] * ycn[3 * rob] + sn[rob] * ycn[3 * rob + 1]);
+                            else r -= T * ycn[3 * rob + 2];
+                        }
+                    }
+                    dinf = fmax(dinf, fabs(r));
+                    if (hl) { double u = (zk - lo) * zl; c0 = fmax(c0, fabs(u)); cmu = fmax(cmu, fabs(u - mu)); zsum += fabs(zl); }
+                    if (hu) { double u = (hi - zk) * zu; c0 = fmax(c0, fabs(u)); cmu = fmax(cmu, fabs(u - mu)); zsum += fabs(zu); }
+                }
+            }
+            wp::sync();
+        }
+        E.pinf = wp::red_max(pinf); E.theta = wp::red_sum(th); E.f = wp::red_sum(fo);
+        E.slog = wp::red_sum(slog); E.sdamp = wp::red_sum(sdamp); E.viol = wp::red_max(viol);
+        if (FULL) {
+            E.dinf = wp::red_max(dinf); E.c0 = wp::red_max(c0); E.cmu = wp::red_max(cmu);
+            E.ysum = wp::red_sum(ysum); E.zsum = wp::red_sum(zsum);
+        }
+    }
+
+    // ---------------------------------------------------------------------------------------
+    // barrier Hessian / gradient pieces of one variable or slack
+    //   MODE 0: primal-dual system;  1: least-squares multiplier estimate;  2: restoration
+    // ---------------------------------------------------------------------------------------
+    template <int MODE>
+    NMPC_DEV void sig_g(double v, double lo, double hi, double ml, double mu_, double mu, double g0, double &sig, double &g) const
+    {
+        bool hl = lo > -NMPC_INF, hu = hi < NMPC_INF;
+        if (MODE == 1) { sig = 1.0; g = g0 - ml + mu_; return; }
+        sig = 0.0; g = MODE == 0 ? g0 : 0.0;
+        if (hl) { double sl = v - lo; sig += MODE == 0 ? ml / sl : mu / (sl * sl); g -= mu / sl; }
+        if (hu) { double sl = hi - v; sig += MODE == 0 ? mu_ / sl : mu / (sl * sl); g += mu / sl; }
+        if (MODE == 0) {
+            if (hl && !hu) g += P.o.kappa_d * mu;
+            if (hu && !hl) g -= P.o.kappa_d * mu;
+        }
+    }
+
+    // inequality block b: condensed weights; writes the per-pair rows the forward pass needs
+    template <int MODE>
+    NMPC_DEV void ineq_block(int b, double mu, double delta, bool soc, const double *zb, double &pxx, double &pyy,
+                             double &pxy, double &phx, double &phy)
+    {
+        pxx = pyy = pxy = phx = phy = 0.0;
+        double gxq = 0, gyq = 0, rd = 0, Dq = 0, gs = 0;
+        double lo = DL[b * 32 + l], hi = DU[b * 32 + l];
+        if (lo > -NMPC_INF || hi < NMPC_INF) {
+            double dv = NMPC_DUMMY_ROW_VALUE;
+            if (b > 0) {
+                double dx = zb[3 * pi] - zb[3 * pj], dy = zb[3 * pi + 1] - zb[3 * pj + 1];
+                gxq = 2.0 * dx; gyq = 2.0 * dy; dv = dx * dx + dy * dy;
+            }
+            double s = row(R_S, b)[l], sigs;
+            sig_g<MODE>(s, lo, hi, row(R_VL, b)[l], row(R_VU, b)[l], mu, 0.0, sigs, gs);
+            rd = MODE == 1 ? 0.0 : (soc ? row(R_DSOC, b)[l] : dv - s);
+            Dq = sigs + delta;
+            double hq = Dq * rd + gs, mu2 = MODE == 0 ? 2.0 * row(R_YD, b)[l] : 0.0;
+            pxx = Dq * gxq * gxq + mu2; pyy = Dq * gyq * gyq + mu2; pxy = Dq * gxq * gyq;
+            phx = gxq * hq; phy = gyq * hq;
+        }
+        row(R_GXQ, b)[l] = gxq; row(R_GYQ, b)[l] = gyq; row(R_RD, b)[l] = rd; row(R_DQ, b)[l] = Dq; row(R_GS, b)[l] = gs;
+    }
+
+    // ---------------------------------------------------------------------------------------
+    // backward Riccati sweep (K3).  false = a control-block pivot was <= 0 (wrong inertia).
+    // ---------------------------------------------------------------------------------------
+    template <int MODE>
+    NMPC_DEV bool factor(double mu, double delta, bool soc)
+    {
+        const double zeta = MODE == 2 ? sqrt(mu) : 0.0;
+        double Mr[NM];
+        double *col = sm + SM_COL, *pb = sm + SM_PB, *zb = sm + SM_ZB, *rcb = sm + SM_RCB, *prb = sm + SM_PRB;
+        double *cs = sm + SM_CS, *sn = sm + SM_SN, *ca = sm + SM_CA, *cb = sm + SM_CB, *tcs = sm + SM_TCS,
+               *tsn = sm + SM_TSN, *crs = sm + SM_CRS, *thd = sm + SM_THD;
+        double *pxx = sm + SM_PXX, *pyy = sm + SM_PYY, *pxy = sm + SM_PXY, *phx = sm + SM_PHX, *phy = sm + SM_PHY;
+        n_fact++;
+        // terminal stage: X_N carries no cost and no distance rows, only its box
+        {
+            double sig = 0.0, gx = 0.0;
+            if (isx) sig_g<MODE>(row(R_Z, N)[l], BL[N * 32 + l], BU[N * 32 + l], row(R_ZL, N)[l], row(R_ZU, N)[l], mu, 0.0, sig, gx);
+            NMPC_UNROLL
+            for (int i = 0; i < NM; i++) Mr[i] = 0.0;
+            NMPC_UNROLL
+            for (int i = 0; i < NS; i++) Mr[i] = (isx && i == l) ? sig + delta + zeta : 0.0;
+            Mr[LIN] = isx ? gx : 0.0;
+            row(R_GX, N)[l] = isx ? gx : 0.0;
+            NMPC_UNROLL
+            for (int i = 0; i < NS; i++) frow(N, i)[l] = Mr[i];
+            row(R_LIN, N)[l] = Mr[LIN];
+        }
+        for (int k = N - 1; k >= 0; k--) {
+            wp::sync();
+            const double zk = isz ? row(R_Z, k)[l] : 0.0;
+            zb[l] = zk;
+            if (l < NR) {
+                const double *zr = row(R_Z, k);
+                double th = zr[3 * l + 2], v = zr[NS + 2 * l], s_, c_;
+                wp::sincos_(th, &s_, &c_);
+                cs[l] = c_; sn[l] = s_;
+                double a_ = -T * v * s_, b_ = T * v * c_, tc = T * c_, ts = T * s_;
+                ca[l] = a_; cb[l] = b_; tcs[l] = tc; tsn[l] = ts;
+                double *cf = row(R_COEF, k);
+                cf[l] = a_; cf[8 + l] = b_; cf[16 + l] = tc; cf[24 + l] = ts;
+                if (MODE == 0) {
+                    const double *yc = row(R_YC, k + 1);
+                    double lx = yc[3 * l], ly = yc[3 * l + 1];
+                    crs[l] = T * (lx * s_ - ly * c_); thd[l] = T * v * (lx * c_ + ly * s_);
+                } else { crs[l] = 0.0; thd[l] = 0.0; }
+            }
+            if (isx) {
+                NMPC_UNROLL
+                for (int i = 0; i < NS; i++) pb[i * NS + l] = Mr[i];
+            }
+            wp::sync();
+            // equality residual of block k+1 and the condensed inequality block k+1
+            if (isx) {
+                double rc = 0.0;
+                if (MODE != 1) {
+                    if (soc) rc = row(R_CSOC, k + 1)[l];
+                    else {
+                        double v = zb[NS + 2 * rob];
+                        double pred = comp == 0 ? zk + T * v * cs[rob] : (comp == 1 ? zk + T * v * sn[rob] : zk + T * zb[NS + 2 * rob + 1]);
+                        rc = row(R_Z, k + 1)[l] - pred - CE[(k + 1) * 32 + l];
+                    }
+                }
+                rcb[l] = rc; row(R_RC, k + 1)[l] = rc;
+            }
+            if (M > 0 && isq) {
+                double a0, a1, a2, a3, a4;
+                ineq_block<MODE>(k + 1, mu, delta, soc, zb, a0, a1, a2, a3, a4);
+                pxx[l] = a0; pyy[l] = a1; pxy[l] = a2; phx[l] = a3; phy[l] = a4;
+            }
+            wp::sync();
+            // pr = p_{k+1} + P_{k+1} r,  r = -rc
+            if (isx) {
+                double pr = Mr[LIN];
+                if (MODE != 1) {
+                    NMPC_UNROLL
+                    for (int i = 0; i < NS; i++) pr -= Mr[i] * rcb[i];
+                }
+                prb[l] = pr;
+            }
+            wp::sync();
+            // column l of [A B]:  al e_x + be e_y + ga e_theta of this lane's robot
+            double al = 0.0, be = 0.0, ga = 0.0;
+            if (isx) { if (comp == 0) al = 1.0; else if (comp == 1) be = 1.0; else { al = ca[rob]; be = cb[rob]; ga = 1.0; } }
+            else if (isu) { if (comp == 0) { al = tcs[rob]; be = tsn[rob]; } else ga = T; }
+            const int base = 3 * rob;
+            double W[NS];
+            NMPC_UNROLL
+            for (int r = 0; r < NS; r++) W[r] = al * pb[r * NS + base] + be * pb[r * NS + base + 1] + ga * pb[r * NS + base + 2];
+            const double wv = al * prb[base] + be * prb[base + 1] + ga * prb[base + 2];
+            NMPC_UNROLL
+            for (int i = 0; i < NR; i++) {
+                double Wx = W[3 * i], Wy = W[3 * i + 1], Wt = W[3 * i + 2];
+                Mr[3 * i] = Wx; Mr[3 * i + 1] = Wy; Mr[3 * i + 2] = Wt + ca[i] * Wx + cb[i] * Wy;
+                Mr[NS + 2 * i] = tcs[i] * Wx + tsn[i] * Wy; Mr[NS + 2 * i + 1] = T * Wt;
+            }
+            // stage Hessian and gradient
+            double sig = 0.0, gx = 0.0;
+            if (isz) sig_g<MODE>(zk, BL[k * 32 + l], BU[k * 32 + l], row(R_ZL, k)[l], row(R_ZU, k)[l], mu, df * gradf(k, zk), sig, gx);
+            row(R_GX, k)[l] = gx;
+            double dg = 0.0;
+            if (isz) {
+                dg = sig + delta + zeta;
+                if (MODE == 0) { dg += df * qw; if (isx && comp == 2) dg += thd[rob]; }
+            }
+            Mr[LIN] = isz ? wv + gx : 0.0;
+            NMPC_UNROLL
+            for (int r = 0; r < NZ; r++) Mr[r] += (r == l) ? dg : 0.0;
+            if (MODE == 0) {
+                NMPC_UNROLL
+                for (int i = 0; i < NR; i++) {
+                    if (l == 3 * i + 2) Mr[NS + 2 * i] += crs[i];
+                    if (l == NS + 2 * i) Mr[3 * i + 2] += crs[i];
+                }
+            }
+            if (M > 0 && isx && comp < 2) {
+                double ssame = 0.0, scross = 0.0, glin = 0.0;
+                NMPC_UNROLL
+                for (int j = 0; j < NR; j++) {
+                    if (j == rob) continue;
+                    int q = rob < j ? pairidx(rob, j) : pairidx(j, rob);
+                    double vs = comp == 0 ? pxx[q] : pyy[q], vc = pxy[q];
+                    double ph = comp == 0 ? phx[q] : phy[q];
+                    Mr[3 * j] -= comp == 0 ? vs : vc;
+                    Mr[3 * j + 1] -= comp == 0 ? vc : vs;
+                    ssame += vs; scross += vc; glin += rob < j ? ph : -ph;
+                }
+                NMPC_UNROLL
+                for (int j = 0; j < NR; j++)
+                    if (j == rob) { Mr[3 * j] += comp == 0 ? ssame : scross; Mr[3 * j + 1] += comp == 0 ? scross : ssame; }
+                Mr[LIN] += glin;
+            }
+            // symmetric sweep of the control pivots
+            NMPC_UNROLL
+            for (int j = NS; j < NZ; j++) {
+                double *buf = col + 32 * (j & 1);
+                if (isz) buf[l] = Mr[j];
+                if (l == j) buf[LIN] = Mr[LIN];
+                wp::sync();
+                const double d = buf[j];
+                if (!(d > 0.0) || !(d < NMPC_INF)) return false;
+                const double inv = 1.0 / d;
+                // lane j owns the pivot column: it becomes column/d (computed directly -- forming it as
+                // M - col*(1 - 1/d) cancels catastrophically when d ~ 1e13 on a saturated control)
+                const bool own = (l == j);
+                const double t = own ? -inv : Mr[j] * inv;
+                NMPC_UNROLL
+                for (int i = 0; i < NM; i++)
+                    if (i != j) Mr[i] = (own ? 0.0 : Mr[i]) - buf[i] * t;
+                Mr[j] = t;
+            }
+            if (isz) {
+                NMPC_UNROLL
+                for (int i = 0; i < NS; i++) frow(k, i)[l] = Mr[i];
+                row(R_LIN, k)[l] = Mr[LIN];
+            }
+        }
+        wp::sync();
+        if (isx) row(R_RC, 0)[l] = MODE == 1 ? 0.0 : (soc ? row(R_CSOC, 0)[l] : row(R_Z, 0)[l] - x0bar_l - CE[l]);
+        if (M > 0 && isq) { double a0, a1, a2, a3, a4; ineq_block<MODE>(0, mu, delta, soc, zb, a0, a1, a2, a3, a4); }
+        wp::sync();
+        return true;
+    }
+
+    // ---------------------------------------------------------------------------------------
+    // forward pass: steps, new multipliers, fraction-to-boundary step sizes, grad(phi)'d
+    // ---------------------------------------------------------------------------------------
+    struct StepInfo { double ap, az, gbd, tiny; };
+
+    NMPC_DEV void slack_step_terms(double v, double dv, double lo, double hi, double ml, double mu_, double mu, double tau,
+                                   double &ap, double &az) const
+    {
+        if (lo > -NMPC_INF) {
+            double sl = v - lo;
+            if (dv < 0.0) ap = fmin(ap, -tau * sl / dv);
+            double dm = mu / sl - ml - ml / sl * dv;
+            if (dm < 0.0) az = fmin(az, -tau * ml / dm);
+        }
+        if (hi < NMPC_INF) {
+            double sl = hi - v;
+            if (dv > 0.0) ap = fmin(ap, tau * sl / dv);
+            double dm = mu / sl - mu_ + mu_ / sl * dv;
+            if (dm < 0.0) az = fmin(az, -tau * mu_ / dm);
+        }
+    }
+
+    NMPC_DEV void forward(double mu, double tau, int rdz, int rds, int rytc, int rytd, StepInfo &si)
+    {
+        double ap = 1.0, az = 1.0, gbd = 0.0, tiny = 0.0;
+        double *dzb = sm + SM_DZB;
+        double dx = isx ? -row(R_RC, 0)[l] : 0.0;
+        if (M > 0 && isq) {
+            double rd = row(R_RD, 0)[l], Dq = row(R_DQ, 0)[l], gs = row(R_GS, 0)[l];
+            bool act = DL[l] > -NMPC_INF || DU[l] < NMPC_INF;
+            double ds = act ? rd : 0.0, ytd = act ? Dq * ds + gs : 0.0;
+            row(rds, 0)[l] = ds; row(rytd, 0)[l] = ytd;
+            if (act) {
+                double s = row(R_S, 0)[l];
+                slack_step_terms(s, ds, DL[l], DU[l], row(R_VL, 0)[l], row(R_VU, 0)[l], mu, tau, ap, az);
+                gbd += gs * ds; tiny = fmax(tiny, fabs(ds) / (1.0 + fabs(s)));
+            }
+        }
+        for (int k = 0; k <= N; k++) {
+            wp::sync();
+            if (isx) dzb[l] = dx;
+            wp::sync();
+            double acc = 0.0;
+            if (isz) {
+                acc = row(R_LIN, k)[l];
+                NMPC_UNROLL
+                for (int i = 0; i < NS; i++) acc += frow(k, i)[l] * dzb[i];
+            }
+            if (isx) row(rytc, k)[l] = -acc;
+            const double du = (isu && k < N) ? -acc : 0.0;
+            if (isu) dzb[l] = du;
+            const double dzl = isx ? dx : du;
+            row(rdz, k)[l] = dzl;
+            if (zvalid(k)) {
+                double z = row(R_Z, k)[l];
+                slack_step_terms(z, dzl, BL[k * 32 + l], BU[k * 32 + l], row(R_ZL, k)[l], row(R_ZU, k)[l], mu, tau, ap, az);
+                gbd += row(R_GX, k)[l] * dzl; tiny = fmax(tiny, fabs(dzl) / (1.0 + fabs(z)));
+            }
+            if (k < N) {
+                wp::sync();
+                double dn = 0.0;
+                if (isx) {
+                    const double *cf = row(R_COEF, k);
+                    double cA = comp == 0 ? cf[rob] : (comp == 1 ? cf[8 + rob] : 0.0);
+                    double cB = comp == 0 ? cf[16 + rob] : (comp == 1 ? cf[24 + rob] : T);
+                    dn = dzb[l] + cA * dzb[3 * rob + 2] + cB * dzb[NS + 2 * rob + (comp == 2 ? 1 : 0)] - row(R_RC, k + 1)[l];
+                }
+                if (M > 0 && isq) {
+                    const int b = k + 1;
+                    bool act = DL[b * 32 + l] > -NMPC_INF || DU[b * 32 + l] < NMPC_INF;
+                    double ds = 0.0, ytd = 0.0;
+                    if (act) {
+                        double gs = row(R_GS, b)[l];
+                        ds = row(R_GXQ, b)[l] * (dzb[3 * pi] - dzb[3 * pj]) + row(R_GYQ, b)[l] * (dzb[3 * pi + 1] - dzb[3 * pj + 1]) + row(R_RD, b)[l];
+                        ytd = row(R_DQ, b)[l] * ds + gs;
+                        double s = row(R_S, b)[l];
+                        slack_step_terms(s, ds, DL[b * 32 + l], DU[b * 32 + l], row(R_VL, b)[l], row(R_VU, b)[l], mu, tau, ap, az);
+                        gbd += gs * ds; tiny = fmax(tiny, fabs(ds) / (1.0 + fabs(s)));
+                    }
+                    row(rds, b)[l] = ds; row(rytd, b)[l] = ytd;
+                }
+                dx = dn;
+            }
+        }
+        si.ap = wp::red_min(ap); si.az = wp::red_min(az); si.gbd = wp::red_sum(gbd); si.tiny = wp::red_max(tiny);
+        wp::sync();
+    }
+
+    // ---------------------------------------------------------------------------------------
+    NMPC_DEV void accept(double alpha, double az, double mu, int rdz, int rds, int rytc, int rytd)
+    {
+        const double ks = P.o.kappa_sigma;
+        for (int k = 0; k <= N; k++) {
+            if (zvalid(k)) {
+                double z = row(R_Z, k)[l], dz = row(rdz, k)[l], lo = BL[k * 32 + l], hi = BU[k * 32 + l];
+                double zn = z + alpha * dz;
+                if (lo > -NMPC_INF) {
+                    double sl = z - lo, ml = row(R_ZL, k)[l];
+                    double m2 = ml + az * (mu / sl - ml - ml / sl * dz), s2 = zn - lo;
+                    row(R_ZL, k)[l] = fmax(fmin(m2, ks * mu / s2), mu / (ks * s2));
+                }
+                if (hi < NMPC_INF) {
+                    double sl = hi - z, mu_ = row(R_ZU, k)[l];
+                    double m2 = mu_ + az * (mu / sl - mu_ + mu_ / sl * dz), s2 = hi - zn;
+                    row(R_ZU, k)[l] = fmax(fmin(m2, ks * mu / s2), mu / (ks * s2));
+                }
+                row(R_Z, k)[l] = zn;
+            }
+            if (isx) { double y = row(R_YC, k)[l]; row(R_YC, k)[l] = y + alpha * (row(rytc, k)[l] - y); }
+            if (M > 0 && isq) {
+                double lo = DL[k * 32 + l], hi = DU[k * 32 + l];
+                if (lo > -NMPC_INF || hi < NMPC_INF) {
+                    double s = row(R_S, k)[l], ds = row(rds, k)[l], sn_ = s + alpha * ds;
+                    if (lo > -NMPC_INF) {
+                        double sl = s - lo, ml = row(R_VL, k)[l];
+                        double m2 = ml + az * (mu / sl - ml - ml / sl * ds), s2 = sn_ - lo;
+                        row(R_VL, k)[l] = fmax(fmin(m2, ks * mu / s2), mu / (ks * s2));
+                    }
+                    if (hi < NMPC_INF) {
+                        double sl = hi - s, mu_ = row(R_VU, k)[l];
+                        double m2 = mu_ + az * (mu / sl - mu_ + mu_ / sl * ds), s2 = hi - sn_;
+                        row(R_VU, k)[l] = fmax(fmin(m2, ks * mu / s2), mu / (ks * s2));
+                    }
+                    row(R_S, k)[l] = sn_;
+                    double y = row(R_YD, k)[l]; row(R_YD, k)[l] = y + alpha * (row(rytd, k)[l] - y);
+                }
+            }
+        }
+        wp::sync();
+    }
+
+    NMPC_DEV void accept_primal(double alpha, int rdz, int rds)
+    {
+        for (int k = 0; k <= N; k++) {
+            if (zvalid(k)) row(R_Z, k)[l] += alpha * row(rdz, k)[l];
+            if (M > 0 && isq && (DL[k * 32 + l] > -NMPC_INF || DU[k * 32 + l] < NMPC_INF)) row(R_S, k)[l] += alpha * row(rds, k)[l];
+        }
+        wp::sync();
+    }
+
+    // after the restoration fallback: equality multipliers reset, bound multipliers clipped
+    NMPC_DEV void resto_reset(double mu)
+    {
+        const double ks = P.o.kappa_sigma;
+        for (int k = 0; k <= N; k++) {
+            if (zvalid(k)) {
+                double z = row(R_Z, k)[l], lo = BL[k * 32 + l], hi = BU[k * 32 + l];
+                if (lo > -NMPC_INF) { double s2 = z - lo; row(R_ZL, k)[l] = fmax(fmin(row(R_ZL, k)[l], ks * mu / s2), mu / (ks * s2)); }
+                if (hi < NMPC_INF) { double s2 = hi - z; row(R_ZU, k)[l] = fmax(fmin(row(R_ZU, k)[l], ks * mu / s2), mu / (ks * s2)); }
+            }
+            row(R_YC, k)[l] = 0.0; row(R_YD, k)[l] = 0.0;
+            if (M > 0 && isq) {
+                double s = row(R_S, k)[l], lo = DL[k * 32 + l], hi = DU[k * 32 + l];
+                if (lo > -NMPC_INF) { double s2 = s - lo; row(R_VL, k)[l] = fmax(fmin(row(R_VL, k)[l], ks * mu / s2), mu / (ks * s2)); }
+                if (hi < NMPC_INF) { double s2 = hi - s; row(R_VU, k)[l] = fmax(fmin(row(R_VU, k)[l], ks * mu / s2), mu / (ks * s2)); }
+            }
+        }
+        wp::sync();
+    }
+
+    // copy the initial-residual rows into the SOC accumulators (c_soc := c, d_soc := d - s)
+    NMPC_DEV void soc_begin()
+    {
+        for (int k = 0; k <= N; k++) {
+            row(R_CSOC, k)[l] = isx ? row(R_RC, k)[l] : 0.0;
+            row(R_DSOC, k)[l] = (M > 0 && isq) ? row(R_RD, k)[l] : 0.0;
+        }
+        wp::sync();
+    }
+
+    // ---------------------------------------------------------------------------------------
+    // filter (kept in shared memory; lane 0 edits)
+    // ---------------------------------------------------------------------------------------
+    NMPC_DEV bool filter_ok(double th, double ph) const
+    {
+        const double *fth = sm + SM_FTH, *fph = sm + SM_FPH;
+        for (int i = 0; i < fn; i++)
+            if (!(th < fth[i] || ph < fph[i])) return false;
+        return true;
+    }
+    NMPC_DEV void filter_add(double th, double ph)
+    {
+        double *fth = sm + SM_FTH, *fph = sm + SM_FPH, *misc = sm + SM_MISC;
+        wp::sync();
+        if (l == 0) {
+            int m = 0;
+            for (int i = 0; i < fn; i++)
+                if (!(fth[i] >= th && fph[i] >= ph)) { fth[m] = fth[i]; fph[m] = fph[i]; m++; }
+            if (m == NMPC_FILTER_CAP) {
+                for (int i = 1; i < m; i++) { fth[i - 1] = fth[i]; fph[i - 1] = fph[i]; }
+                m--;
+            }
+            fth[m] = th; fph[m] = ph; m++;
+            misc[0] = (double)m;
+        }
+        wp::sync();
+        fn = (int)misc[0];
+    }
+    static NMPC_DEV bool cmp_le(double lhs, double rhs, double bas) { return lhs - rhs <= 10.0 * 2.220446049250313e-16 * fabs(bas); }
+
+    // ---------------------------------------------------------------------------------------
+    // outputs in the reference layout, multipliers in CasADi's sign convention
+    // ---------------------------------------------------------------------------------------
+    NMPC_DEV void write_outputs(int st, int iter, double E0, double pinf, double dinf, double c0, double mu)
+    {
+        const long long n = (long long)NS * S + (long long)NC * N, mg = (long long)S * (NS + M);
+        double *x = P.x + inst * n;
+        double *lx = P.lam_x ? P.lam_x + inst * n : nullptr;
+        double *g = P.g ? P.g + inst * mg : nullptr;
+        double *lg = P.lam_g ? P.lam_g + inst * mg : nullptr;
+        double *zb = sm + SM_ZB, *cs = sm + SM_CS, *sn = sm + SM_SN;
+        double fo = 0.0;
+        for (int k = 0; k <= N; k++) {
+            wp::sync();
+            const bool zv = zvalid(k);
+            double zk = zv ? row(R_Z, k)[l] : 0.0;
+            zb[l] = zk;
+            if (zv) {
+                long long idx = isx ? (long long)k * NS + l : (long long)NS * S + (long long)k * NC + (l - NS);
+                x[idx] = zk;
+                if (lx) lx[idx] = (row(R_ZU, k)[l] - row(R_ZL, k)[l]) / df;
+                if (k < N) { double e = zk - xs_l; fo += 0.5 * qw * e * e; }
+            }
+            wp::sync();
+            if (k < N && l < NR) { double s_, c_; wp::sincos_(zb[3 * l + 2], &s_, &c_); cs[l] = c_; sn[l] = s_; }
+            wp::sync();
+            if (isx) {
+                if (k == 0) {
+                    if (g) g[l] = zk - x0bar_l;
+                    if (lg) lg[l] = row(R_YC, 0)[l] / df;
+                }
+                if (k < N) {
+                    double v = zb[NS + 2 * rob];
+                    double pred = comp == 0 ? zk + T * v * cs[rob] : (comp == 1 ? zk + T * v * sn[rob] : zk + T * zb[NS + 2 * rob + 1]);
+                    if (g) g[(long long)(k + 1) * (NS + M) + l] = row(R_Z, k + 1)[l] - pred;
+                    if (lg) lg[(long long)(k + 1) * (NS + M) + l] = row(R_YC, k + 1)[l] / df;
+                }
+            }
+            if (M > 0 && isq) {
+                if (k == 0) {
+                    if (g) g[NS + l] = NMPC_DUMMY_ROW_VALUE;
+                    if (lg) lg[NS + l] = row(R_YD, 0)[l] / df;
+                }
+                if (k < N) {
+                    double dx = zb[3 * pi] - zb[3 * pj], dy = zb[3 * pi + 1] - zb[3 * pj + 1];
+                    if (g) g[(long long)(k + 1) * (NS + M) + NS + l] = dx * dx + dy * dy;
+                    if (lg) lg[(long long)(k + 1) * (NS + M) + NS + l] = row(R_YD, k + 1)[l] / df;
+                }
+            }
+        }
+        fo = wp::red_sum(fo);
+        if (l == 0) {
+            if (P.f) P.f[inst] = fo;
+            if (P.status) P.status[inst] = st;
+            if (P.iters) P.iters[inst] = iter;
+            if (P.stats) {
+                double *sp = P.stats + (long long)inst * NMPC_NSTATS;
+                sp[NMPC_ST_KKT_ERR] = E0; sp[NMPC_ST_PRIMAL_INF] = pinf; sp[NMPC_ST_DUAL_INF] = dinf; sp[NMPC_ST_COMPL] = c0;
+                sp[NMPC_ST_MU] = mu; sp[NMPC_ST_N_REG] = n_reg; sp[NMPC_ST_N_RESTO] = n_resto; sp[NMPC_ST_N_SOC] = n_soc;
+                sp[NMPC_ST_N_FACTOR] = n_fact; sp[NMPC_ST_N_LS] = n_ls;
+            }
+        }
+        wp::sync();
+    }
+
+    // trial-point acceptance test shared by the line search and the second-order correction
+    NMPC_DEV bool trial_ok(double th_t, double ph_t, double theta, double phi, double theta_max, double theta_min, double gbd,
+                           double alpha_test, bool ftype) const
+    {
+        if (!(fin(th_t) && fin(ph_t)) || !cmp_le(th_t, theta_max, theta)) return false;
+        bool ok;
+        if (ftype && theta <= theta_min) ok = cmp_le(ph_t - phi, 1e-8 * alpha_test * gbd, phi);
+        else ok = cmp_le(th_t, (1.0 - 1e-5) * theta, theta) || cmp_le(ph_t - phi, -1e-8 * theta, phi);
+        return ok && filter_ok(th_t, ph_t);
+    }
+
+    // ---------------------------------------------------------------------------------------
+    // K2: the interior-point iteration
+    // ---------------------------------------------------------------------------------------
+    NMPC_DEV void run()
+    {
+        const nmpc_opts &o = P.o;
+        if (P.bound_err && *P.bound_err) {  // bounds rejected by prep_bounds_kernel: report, do not solve
+            if (l == 0) { if (P.status) P.status[inst] = *P.bound_err; if (P.iters) P.iters[inst] = 0; }
+            return;
+        }
+        init_point();
+        // least-squares equality multipliers (W = 0, Sigma = I); discarded when too large
+        {
+            bool ok = factor<1>(0.0, 0.0, false);
+            StepInfo si;
+            if (ok) forward(0.0, 0.99, R_DZ, R_DS, R_YC, R_YD, si);
+            double ymax = 0.0;
+            for (int k = 0; k <= N; k++) ymax = fmax(ymax, fmax(isx ? fabs(row(R_YC, k)[l]) : 0.0, (M > 0 && isq) ? fabs(row(R_YD, k)[l]) : 0.0));
+            ymax = wp::red_max(ymax);
+            if (!ok || !(ymax <= o.constr_mult_init_max)) {
+                for (int k = 0; k <= N; k++) { row(R_YC, k)[l] = 0.0; row(R_YD, k)[l] = 0.0; }
+            }
+            wp::sync();
+        }
+        double mu = o.mu_init, tau = fmax(o.tau_min, 1.0 - mu);
+        double theta_max = -1.0, theta_min = -1.0, delta_last = 0.0, f_prev = 0.0;
+        int iter = 0, st = NMPC_MAX_ITER, n_acc = 0;
+        bool tiny_prev = false;
+        double E0 = 0.0;
+        const double mu_floor = fmin(o.tol, o.compl_inf_tol) / (o.barrier_tol_factor + 1.0);
+        EvalOut E;
+        E.dinf = E.c0 = E.cmu = E.ysum = E.zsum = 0.0;
+        for (;;) {
+            eval_pass<true>(mu, 0.0, 0, 0, false, false, 0.0, E);
+            const double smax = 100.0;
+            const double sd = fmax(smax, (E.ysum + E.zsum) / fmax(1.0, ny_nzb)) / smax;
+            const double sc = fmax(smax, E.zsum / fmax(1.0, nzb_cnt)) / smax;
+            for (int pass = 0;; pass++) {
+                E0 = fmax(fmax(E.dinf / sd, E.pinf), E.c0 / sc);
+                const double Emu = fmax(fmax(E.dinf / sd, E.pinf), E.cmu / sc);
+                if (pass == 0) {
+                    if (E0 <= o.tol && E.dinf / df <= o.dual_inf_tol && E.viol <= o.constr_viol_tol && E.c0 / df <= o.compl_inf_tol) { st = NMPC_SOLVED; goto finished; }
+                    bool acc = E0 <= o.acceptable_tol && E.dinf / df <= 1e10 && E.viol <= 1e-2 && E.c0 / df <= 1e-2 &&
+                               (iter == 0 || fabs(E.f - f_prev) / fmax(1.0, fabs(E.f)) <= o.acceptable_obj_change_tol);
+                    n_acc = acc ? n_acc + 1 : 0;
+                    if (n_acc >= o.acceptable_iter) { st = NMPC_ACCEPTABLE; goto finished; }
+                    if (iter >= o.max_iter) { st = NMPC_MAX_ITER; goto finished; }
+                }
+                if (!(Emu <= o.barrier_tol_factor * mu) && !(tiny_prev && pass == 0)) break;
+                const double nm = fmax(fmin(o.kappa_mu * mu, pow(mu, o.theta_mu)), mu_floor);
+                if (nm >= mu) break;
+                mu = nm; tau = fmax(o.tau_min, 1.0 - mu); fn = 0; tiny_prev = false;
+                eval_pass<true>(mu, 0.0, 0, 0, false, false, 0.0, E);
+            }
+            f_prev = E.f;
+            const double theta = E.theta;
+            const double phi = df * E.f - mu * E.slog + o.kappa_d * mu * E.sdamp;
+            if (theta_max < 0.0) { theta_max = 1e4 * fmax(1.0, theta); theta_min = 1e-4 * fmax(1.0, theta); }
+            double *tr = (P.trace && iter < P.max_trace) ? P.trace + ((long long)inst * P.max_trace + iter) * NMPC_NTRACE : nullptr;
+            if (tr && l == 0) { tr[0] = mu; tr[1] = E0; tr[2] = theta; tr[3] = E.f; tr[4] = tr[5] = tr[6] = tr[7] = 0.0; }
+            // ---- search direction with inertia correction ----
+            double delta = 0.0;
+            bool need_resto = false;
+            for (;;) {
+                if (factor<0>(mu, delta, false)) break;
+                if (delta == 0.0) delta = delta_last == 0.0 ? 1e-4 : fmax(1e-20, delta_last / 3.0);
+                else delta *= (delta_last == 0.0 || 1e5 * delta_last < delta) ? 100.0 : 8.0;
+                if (delta > 1e20) { need_resto = true; break; }
+            }
+            if (delta > 0.0 && !need_resto) { delta_last = delta; n_reg++; }
+            double alpha = 0.0, alpha_z = 0.0;
+            int ls_count = 0;
+            if (!need_resto) {
+                StepInfo si;
+                forward(mu, tau, R_DZ, R_DS, R_YTC, R_YTD, si);
+                const double gbd = si.gbd;
+                const bool tiny = si.tiny < 10.0 * 2.220446049250313e-16 && theta < 1e-4;
+                double amin = 1e-5;
+                if (gbd < 0.0) {
+                    amin = fmin(1e-5, 1e-8 * theta / (-gbd));
+                    if (theta <= theta_min) amin = fmin(amin, pow(theta, 1.1) / pow(-gbd, 2.3));
+                }
+                amin *= 0.05;
+                bool accepted = false, armijo_step = false, use_soc = false;
+                alpha = si.ap; alpha_z = si.az;
+                if (tiny) { accepted = true; tiny_prev = true; }
+                while (!accepted) {
+                    ls_count++;
+                    EvalOut Et;
+                    eval_pass<false>(mu, alpha, R_DZ, R_DS, true, false, 0.0, Et);
+                    const double th_t = Et.theta, ph_t = df * Et.f - mu * Et.slog + o.kappa_d * mu * Et.sdamp;
+                    const bool ftype = gbd < 0.0 && alpha * pow(-gbd, 2.3) > pow(theta, 1.1);
+                    if (trial_ok(th_t, ph_t, theta, phi, theta_max, theta_min, gbd, alpha, ftype)) {
+                        accepted = true; armijo_step = ftype && theta <= theta_min; break;
+                    }
+                    if (ls_count == 1 && th_t >= theta && o.max_soc > 0) {  // second-order correction
+                        double th_old = 0.0, th_tr = th_t, a_soc = alpha;
+                        int cnt = 0;
+                        soc_begin();
+                        int rz = R_DZ, rs = R_DS;  // direction whose trial point feeds the next correction
+                        while (cnt < o.max_soc && !accepted && (cnt == 0 || th_tr <= 0.99 * th_old)) {
+                            th_old = th_tr;
+                            EvalOut Ea;  // c_soc := a_soc c_soc + c(trial)
+                            eval_pass<false>(mu, a_soc, rz, rs, true, true, a_soc, Ea);
+                            n_soc++;
+                            if (!factor<0>(mu, delta, true)) break;
+                            StepInfo s2;
+                            forward(mu, tau, R_DZ2, R_DS2, R_YTC2, R_YTD2, s2);
+                            a_soc = s2.ap; rz = R_DZ2; rs = R_DS2;
+                            EvalOut E2;
+                            eval_pass<false>(mu, a_soc, R_DZ2, R_DS2, true, false, 0.0, E2);
+                            const double th2 = E2.theta, ph2 = df * E2.f - mu * E2.slog + o.kappa_d * mu * E2.sdamp;
+                            if (trial_ok(th2, ph2, theta, phi, theta_max, theta_min, gbd, alpha, ftype)) {
+                                accepted = true; armijo_step = ftype && theta <= theta_min; use_soc = true;
+                                alpha = a_soc; alpha_z = s2.az;
+                            } else { cnt++; th_tr = th2; }
+                        }
+                        if (accepted) break;
+                    }
+                    alpha *= 0.5;
+                    if (alpha < amin) break;
+                }
+                if (!accepted) need_resto = true;
+                else {
+                    if (!tiny && !armijo_step) filter_add((1.0 - 1e-5) * theta, phi - 1e-8 * theta);
+                    if (!tiny) tiny_prev = false;
+                    if (use_soc) accept(alpha, alpha_z, mu, R_DZ2, R_DS2, R_YTC2, R_YTD2);
+                    else accept(alpha, alpha_z, mu, R_DZ, R_DS, R_YTC, R_YTD);
+                }
+            }
+            if (need_resto) {
+                // bounded substitute for IPOPT's restoration phase (see oracle/nmpc_oracle.c)
+                n_resto++;
+                filter_add((1.0 - 1e-5) * theta, phi - 1e-8 * theta);
+                const double thR = theta;
+                bool ok = false;
+                for (int r_it = 0; r_it < o.max_resto_iter; r_it++) {
+                    EvalOut Er;
+                    eval_pass<false>(mu, 0.0, 0, 0, false, false, 0.0, Er);
+                    const double th = Er.theta;
+                    if (r_it > 0 && (th <= 0.9 * thR || th <= 1e-9) &&
+                        filter_ok(th, df * Er.f - mu * Er.slog + o.kappa_d * mu * Er.sdamp)) { ok = true; break; }
+                    if (!factor<2>(mu, 0.0, false)) break;
+                    StepInfo sr;
+                    forward(mu, tau, R_DZ, R_DS, R_YTC, R_YTD, sr);
+                    double a = sr.ap, th_t = th;
+                    bool got = false;
+                    while (a > 1e-12) {
+                        EvalOut Et;
+                        eval_pass<false>(mu, a, R_DZ, R_DS, true, false, 0.0, Et);
+                        th_t = Et.theta;
+                        if (th_t <= (1.0 - 1e-4 * a) * th) { got = true; break; }
+                        a *= 0.5;
+                    }
+                    if (!got) break;
+                    accept_primal(a, R_DZ, R_DS);
+                    if (th - th_t < 1e-14 * fmax(1.0, th)) break;
+                }
+                if (!ok) { st = NMPC_INFEASIBLE; iter++; goto finished; }
+                resto_reset(mu);
+                alpha = 0.0; alpha_z = 0.0;
+            }
+            n_ls += ls_count;
+            if (tr && l == 0) { tr[4] = alpha; tr[5] = alpha_z; tr[6] = delta; tr[7] = ls_count; }
+            iter++;
+        }
+    finished:
+        write_outputs(st, iter, E0, E.pinf, E.dinf, E.c0, mu);
+    }
+};

@@ -22,3 +22,10 @@ def hexagon_p():
     goal = -start.copy()
     goal[:, 2] = start[:, 2]
     return np.concatenate([start.ravel(), goal.ravel()])
+
+
+@pytest.fixture(scope="session")
+def pkg():
+    """The product package (ctypes over libnmpc_b200.so), imported under the alias nmpc_b200."""
+    import __graft_entry__ as ge
+    return ge.load_package()

@@ -1,0 +1,36 @@
+// Host implementation of the wp:: interface of csrc/warp_prims.cuh -- TEST INFRASTRUCTURE ONLY.
+// A warp is emulated by 32 ucontext fibres that run one after the other between warp-wide
+// synchronisation points, so csrc/solver_body.cuh (the product's device source) can be executed
+// and debugged on a CPU.  Running lanes strictly one after another also makes most missing
+// __syncwarp() bugs show up as wrong results (and `reverse` flips the lane order).
+#pragma once
+#include <math.h>
+#include <ucontext.h>
+
+#define NMPC_DEV inline
+#define NMPC_HD
+#define NMPC_UNROLL
+
+namespace wp {
+struct Emu {
+    ucontext_t main, ctx[32];
+    int cur;
+    bool done[32];
+    double xd[32];
+    int xi[32];
+    bool xb[32];
+};
+extern thread_local Emu *emu;
+inline int lane() { return emu->cur; }
+inline void sync() { swapcontext(&emu->ctx[emu->cur], &emu->main); }
+inline double shfl(double v, int src) { emu->xd[emu->cur] = v; sync(); double r = emu->xd[src & 31]; sync(); return r; }
+inline double shfl_xor(double v, int m) { return shfl(v, emu->cur ^ m); }
+inline int shfl_i(int v, int src) { emu->xi[emu->cur] = v; sync(); int r = emu->xi[src & 31]; sync(); return r; }
+inline bool any(bool p) { emu->xb[emu->cur] = p; sync(); bool r = false; for (int i = 0; i < 32; i++) r = r || emu->xb[i]; sync(); return r; }
+inline bool all(bool p) { emu->xb[emu->cur] = p; sync(); bool r = true; for (int i = 0; i < 32; i++) r = r && emu->xb[i]; sync(); return r; }
+inline int atomic_next(int *c) { return (*c)++; }
+inline void sincos_(double x, double *s, double *c) { ::sincos(x, s, c); }
+inline double red_sum(double v) { for (int m = 16; m > 0; m >>= 1) v += shfl_xor(v, m); return v; }
+inline double red_max(double v) { for (int m = 16; m > 0; m >>= 1) v = fmax(v, shfl_xor(v, m)); return v; }
+inline double red_min(double v) { for (int m = 16; m > 0; m >>= 1) v = fmin(v, shfl_xor(v, m)); return v; }
+}  // namespace wp

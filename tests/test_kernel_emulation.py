@@ -1,0 +1,60 @@
+"""The product's device source (csrc/solver_body.cuh) stepped through a CPU emulation of a warp
+(tests/emul/) and compared with the oracle: CPU-side evidence that the kernel's algorithm is the
+oracle's, iteration by iteration.  Test infrastructure only -- the product never runs this way."""
+import numpy as np
+import pytest
+
+from oracle.oracle_lib import Oracle
+from tests.emul.emul_lib import emu_solve
+
+CASES = [
+    (1, 25, 0.25, 0.3, [0, 0, 0, 2.5, 2.0, 1.57]),
+    (2, 10, 0.1, 0.25, [-1, -1, 0.785, 1, 1, 2.356, 1, 1, 0.785, -1, -1, -2.356]),
+    (3, 8, 0.3, 0.3, [-1, -1, 1.57, 0, -1, 1.57, 1, -1, 1.57, 1, 2, 0, 0, 1, 0, -1, 0.5, 0]),
+]
+
+
+@pytest.mark.parametrize("Nr,N,T,dmin,p", CASES)
+@pytest.mark.parametrize("reverse", [0, 1])
+def test_emulated_kernel_follows_the_oracle(Nr, N, T, dmin, p, reverse):
+    p = np.asarray(p, float)
+    o = Oracle(Nr, N, T)
+    lbx, ubx, lbg, ubg = o.bounds(dmin, 0.22, 2.84)
+    w0 = o.cold_start(p[:3 * Nr])
+    r = o.solve(w0, p, lbx, ubx, lbg, ubg, trace=True)
+    e = emu_solve(Nr, N, T, w0, p, lbx, ubx, lbg, ubg, trace=True, reverse=reverse)
+    assert e["rc"] == 0 and e["status"][0] == r["status"] == 0
+    assert abs(int(e["iters"][0]) - r["iters"]) <= 2
+    nX = 3 * Nr * (N + 1)
+    assert np.abs(e["x"][0] - r["x"])[nX:].max() <= 1e-7
+    assert abs(e["f"][0] - r["f"]) / r["f"] <= 1e-9
+    np.testing.assert_allclose(e["lam_g"][0], r["lam_g"], atol=1e-5)
+    m = min(int(e["iters"][0]), r["iters"]) - 3
+    # same barrier parameter, step sizes, regularisation and line-search counts along the way
+    np.testing.assert_allclose(e["trace"][0][:m, [0, 6, 7]], r["trace"][:m, [0, 6, 7]], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(e["trace"][0][:m, [2, 3, 4, 5]], r["trace"][:m, [2, 3, 4, 5]], rtol=1e-5, atol=1e-9)
+
+
+def test_emulated_kernel_six_robots_short_horizon():
+    Nr, N, T = 6, 6, 0.3
+    o = Oracle(Nr, N, T)
+    lbx, ubx, lbg, ubg = o.bounds(0.3, 0.22, 2.84)
+    s3 = np.sqrt(3) / 2
+    start = np.array([[s3, 0.5, -2.618], [0, 1, -1.571], [-s3, 0.5, -0.524], [-s3, -0.5, 0.524], [0, -1, 1.571], [s3, -0.5, 2.618]])
+    goal = -start.copy(); goal[:, 2] = start[:, 2]
+    p = np.concatenate([start.ravel(), goal.ravel()])
+    w0 = o.cold_start(p[:18])
+    r = o.solve(w0, p, lbx, ubx, lbg, ubg)
+    e = emu_solve(Nr, N, T, w0, p, lbx, ubx, lbg, ubg)
+    assert e["status"][0] == r["status"] == 0
+    assert np.abs(e["x"][0] - r["x"])[18 * 7:].max() <= 1e-6
+    assert int(e["stats"][0][8]) == int(r["stats"][8])      # same number of factorisations
+
+
+def test_emulated_kernel_rejects_bad_bounds():
+    o = Oracle(2, 3, 0.1)
+    lbx, ubx, lbg, ubg = o.bounds(0.25, 0.22, 2.84)
+    p = np.array([0, 0, 0, 1, 0, 0, 1, 1, 0, 0, 1, 0.0])
+    bad = lbx.copy(); bad[0] = 20.0
+    e = emu_solve(2, 3, 0.1, o.cold_start(p[:6]), p, bad, ubx, lbg, ubg)
+    assert e["rc"] == -2 and e["status"][0] == -2
