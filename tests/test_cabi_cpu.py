@@ -11,7 +11,7 @@ import pytest
 def test_library_exports_every_declared_symbol(pkg):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     hdr = open(os.path.join(root, "include", "nmpc_b200.h")).read()
-    declared = set(re.findall(r"\b(nmpc_[a-z_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(nmpc_[a-z0-9_]+)\s*\(", hdr))
     assert declared == set(pkg.SYMBOLS)
     L = ctypes.CDLL(pkg.LIB_PATH)
     for s in declared:
