@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -152,6 +153,9 @@ extern "C" int nmpc_create(const nmpc_desc *d, const nmpc_opts *o, nmpc_handle *
     if (!d || !out) return fail(NMPC_EINVAL, "nmpc_create: NULL argument");
     if (d->N < 1 || !(d->T > 0)) return fail(NMPC_EINVAL, "nmpc_create: need N >= 1 and T > 0");
     if (d->Nr < 1 || d->Nr > 6) return fail(NMPC_ENOTSUP, "nmpc_create: Nr = %d; the register-resident Riccati path covers 1..6 robots", d->Nr);
+    const bool dbg = getenv("NMPC_DEBUG") != nullptr;
+#define DBG(msg) do { if (dbg) { fprintf(stderr, "[nmpc_create] %s\n", msg); fflush(stderr); } } while (0)
+    DBG("enter");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(NMPC_ECUDA, "nmpc_create: no CUDA device -- this library has no CPU fallback");
@@ -162,13 +166,17 @@ extern "C" int nmpc_create(const nmpc_desc *d, const nmpc_opts *o, nmpc_handle *
     h->n = h->ns * h->S + h->nc * d->N; h->mg = h->S * (h->ns + h->M); h->np = 2 * h->ns;
     h->nnzj = 3 * d->Nr + d->N * (11 * d->Nr + 4 * h->M); h->nnzh = d->N * (6 * d->Nr + 2 * h->M);
     h->launches = 0; h->d_buf = nullptr; h->d_bytes = 0; h->stream = nullptr; h->d_tables = nullptr;
+    DBG("device count ok");
     cudaGetDevice(&h->dev);
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->dev);
     std::vector<int> tab;
+    DBG("build tables");
     build_tables(h, tab);
+    DBG("tables built");
     cudaError_t e = cudaMalloc(&h->d_tables, tab.size() * sizeof(int));
     if (e == cudaSuccess) e = cudaMemcpy(h->d_tables, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { delete h; return fail(NMPC_ECUDA, "nmpc_create: table upload failed: %s", cudaGetErrorString(e)); }
+    DBG("tables uploaded");
     const int N = d->N, Nr = d->Nr, M = h->M;
     h->tb.jac_rs = h->d_tables;
     h->tb.jac_ps = h->tb.jac_rs + (size_t)N * Nr * 11;
@@ -184,6 +192,7 @@ extern "C" int nmpc_create(const nmpc_desc *d, const nmpc_opts *o, nmpc_handle *
         default: h->ws_doubles_per_slot = slot_doubles<6>(N); e = config_solve<6>(h); break;
     }
     if (e != cudaSuccess) { cudaFree(h->d_tables); delete h; return fail(NMPC_ECUDA, "nmpc_create: kernel configuration failed: %s", cudaGetErrorString(e)); }
+    DBG("solve kernel configured");
     h->eval_smem = (size_t)(2 * h->n + 2 * h->mg + 2 * h->ns + h->nnzj + h->nnzh + 32) * sizeof(double);
     e = cudaFuncSetAttribute(eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->eval_smem);
     if (e != cudaSuccess) { cudaFree(h->d_tables); delete h; return fail(NMPC_ENOTSUP, "nmpc_create: eval record (%zu B) exceeds shared memory: %s", h->eval_smem, cudaGetErrorString(e)); }

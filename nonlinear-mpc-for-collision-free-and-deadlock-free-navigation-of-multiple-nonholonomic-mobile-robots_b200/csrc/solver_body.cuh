@@ -41,7 +41,7 @@ struct WarpSolver {
         SM_PHY = SM_PHX + 16, SM_FTH = SM_PHY + 16, SM_FPH = SM_FTH + 16, SM_MISC = SM_FPH + 16,
         SM_DOUBLES = SM_MISC + 8
     };
-    static NMPC_DEV long long ws_doubles(int N) { return ((long long)R_COUNT * (N + 1) + (long long)(N + 1) * NS) * 32; }
+    static NMPC_HD long long ws_doubles(int N) { return ((long long)R_COUNT * (N + 1) + (long long)(N + 1) * NS) * 32; }
 
     const NmpcSolveParams &P;
     double *sm, *ws;

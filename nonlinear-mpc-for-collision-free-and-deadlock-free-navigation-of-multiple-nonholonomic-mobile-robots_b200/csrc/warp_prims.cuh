@@ -6,6 +6,7 @@
 #include <math.h>
 
 #define NMPC_DEV __device__ __forceinline__
+#define NMPC_HD __host__ __device__
 #define NMPC_UNROLL _Pragma("unroll")
 
 namespace wp {
