@@ -15,6 +15,9 @@
 #include "aux_kernels.cuh"
 
 #define SOLVE_WARPS 4
+#ifndef SOLVE_MIN_CTAS
+#define SOLVE_MIN_CTAS 4   // 16 resident warps per SM (<= 128 registers per thread)
+#endif
 
 static thread_local char g_err[512] = "";
 static int fail(int code, const char *fmt, ...)
@@ -47,7 +50,7 @@ extern "C" void nmpc_default_opts(nmpc_opts *o)
 // the persistent solve kernel: one warp per instance, instances pulled from an atomic queue
 // ------------------------------------------------------------------------------------------------
 template <int NR>
-__global__ void __launch_bounds__(SOLVE_WARPS * 32) solve_kernel(const NmpcSolveParams P)
+__global__ void __launch_bounds__(SOLVE_WARPS * 32, SOLVE_MIN_CTAS) solve_kernel(const NmpcSolveParams P)
 {
     extern __shared__ double smem[];
     const int w = threadIdx.x >> 5;

@@ -23,19 +23,52 @@
 #define NMPC_INF ((double)INFINITY)
 #endif
 
+
+// Inside a noinline pass the solver object lives in local memory; shadow the members that the pass
+// uses with locals so they are loaded once, and re-derive the pointers with their address spaces
+// (shared / global) so the compiler emits LDS/LDG instead of generic loads.
+#define NMPC_LOCALS                                                                                   \
+    double *const sm = wp::shared_ptr(this->sm);                                                      \
+    double *const ws = wp::global_ptr(this->ws);                                                      \
+    const double *const BL = wp::global_ptr(this->BL), *const BU = wp::global_ptr(this->BU),           \
+                 *const CE = wp::global_ptr(this->CE), *const DL = wp::global_ptr(this->DL),           \
+                 *const DU = wp::global_ptr(this->DU);                                                 \
+    const int N = this->N, S = this->S, l = this->l, rob = this->rob, comp = this->comp,               \
+              pi = this->pi, pj = this->pj;                                                            \
+    const bool isx = this->isx, isu = this->isu, isz = this->isz, isq = this->isq;                     \
+    const double T = this->T, df = this->df, xs_l = this->xs_l, qw = this->qw, x0bar_l = this->x0bar_l; \
+    (void)sm; (void)ws; (void)BL; (void)BU; (void)CE; (void)DL; (void)DU; (void)N; (void)S; (void)l;   \
+    (void)rob; (void)comp; (void)pi; (void)pj; (void)isx; (void)isu; (void)isz; (void)isq; (void)T;    \
+    (void)df; (void)xs_l; (void)qw; (void)x0bar_l;                                                     \
+    auto row = [=](int r, int k) -> double * { return ws + ((long long)r * S + k) * 32; };            \
+    auto frow = [=](int k, int i) -> double * { return ws + ((long long)R_COUNT * S + (long long)k * NS + i) * 32; }; \
+    auto zvalid = [=](int k) -> bool { return l < (k < N ? NZ : NS); };                                \
+    auto gradf = [=](int k, double z) -> double { return (k < N && isz) ? qw * (z - xs_l) : 0.0; };    \
+    /* prefetch up to 16 scratch rows of stage k into L1: lane pair p takes the p-th row of `mask` */ \
+    auto prefetch_lane = [=](unsigned mask) -> int { return (int)wp::nth_set_bit(mask, l >> 1); };     \
+    auto prefetch_at = [=](int rid, int k) {                                                           \
+        if (rid >= 0 && rid < 32 && k >= 0 && k <= N) wp::prefetch(ws + ((long long)rid * S + k) * 32 + (l & 1) * 16); \
+    };                                                                                                 \
+    auto prefetch_rows = [=](unsigned mask, int k) { prefetch_at(prefetch_lane(mask), k); };           \
+    (void)prefetch_lane; (void)prefetch_at;                                                            \
+    (void)row; (void)frow; (void)zvalid; (void)gradf; (void)prefetch_rows;
+
+struct alignas(16) NmpcD2 { double x, y; };   // one 128-bit shared-memory load
+
 template <int NR>
 struct WarpSolver {
     static constexpr int NS = 3 * NR, NC = 2 * NR, NZ = 5 * NR, M = NR * (NR - 1) / 2;
     static constexpr int LIN = NZ, NM = NZ + 1;
     enum Row {
         R_Z, R_ZL, R_ZU, R_DZ, R_DZ2, R_GX, R_YC, R_YTC, R_YTC2, R_RC, R_CSOC, R_COEF, R_LIN,
-        R_S, R_VL, R_VU, R_YD, R_DS, R_DS2, R_YTD, R_YTD2, R_DSOC, R_GXQ, R_GYQ, R_RD, R_DQ, R_GS,
+        R_S, R_VL, R_VU, R_YD, R_DS, R_DS2, R_YTD, R_YTD2, R_DSOC, R_GXQ, R_GYQ, R_RD, R_DQ, R_GS, R_DG,
         R_COUNT
     };
     // shared-memory carve-up (doubles, per warp)
     enum {
-        SM_COL = 0, SM_PB = 64, SM_ZB = SM_PB + 18 * 18, SM_DZB = SM_ZB + 32, SM_RCB = SM_DZB + 32,
-        SM_PRB = SM_RCB + 32, SM_CS = SM_PRB + 32, SM_SN = SM_CS + 8, SM_CA = SM_SN + 8, SM_CB = SM_CA + 8,
+        PLD = NS + 3,  // leading dimension of the P broadcast buffer: 3Nr columns of P, the pr column, 2 zero columns
+        SM_COL = 0, SM_PB = 64, SM_ZB = SM_PB + 18 * 21, SM_DZB = SM_ZB + 32, SM_RCB = SM_DZB + 32,
+        SM_PRB = SM_RCB + 32, SM_HB = SM_PRB + 32, SM_CS = SM_HB + 32, SM_SN = SM_CS + 8, SM_CA = SM_SN + 8, SM_CB = SM_CA + 8,
         SM_TCS = SM_CB + 8, SM_TSN = SM_TCS + 8, SM_CRS = SM_TSN + 8, SM_THD = SM_CRS + 8,
         SM_PXX = SM_THD + 8, SM_PYY = SM_PXX + 16, SM_PXY = SM_PYY + 16, SM_PHX = SM_PXY + 16,
         SM_PHY = SM_PHX + 16, SM_FTH = SM_PHY + 16, SM_FPH = SM_FTH + 16, SM_MISC = SM_FPH + 16,
@@ -82,6 +115,8 @@ struct WarpSolver {
         qw = isx ? 2.0 * P.Q[comp] : (isu ? 2.0 * P.R[comp] : 0.0);
         df = 1.0; fn = 0;
         n_reg = n_resto = n_soc = n_fact = n_ls = 0;
+        for (int e = l; e < NS * PLD; e += 32) sm[SM_PB + e] = 0.0;
+        wp::sync();
     }
 
     NMPC_DEV double gradf(int k, double z) const { return (k < N && isz) ? qw * (z - xs_l) : 0.0; }
@@ -99,8 +134,9 @@ struct WarpSolver {
     }
 
     // starting point: objective scaling, push into bounds, slacks, bound multipliers
-    NMPC_DEV void init_point()
+    NMPC_PASS void init_point()
     {
+        NMPC_LOCALS
         const double *x0 = P.x0 + (long long)inst * (NS * S + NC * N);
         const nmpc_opts &o = P.o;
         double gmax = 0.0;
@@ -110,7 +146,7 @@ struct WarpSolver {
             row(R_Z, k)[l] = z;
         }
         gmax = wp::red_max(gmax);
-        df = gmax > o.nlp_scaling_max_gradient ? fmax(o.nlp_scaling_max_gradient / gmax, 1e-8) : 1.0;
+        this->df = gmax > o.nlp_scaling_max_gradient ? fmax(o.nlp_scaling_max_gradient / gmax, 1e-8) : 1.0;
         double cnt_z = 0.0;
         for (int k = 0; k <= N; k++) {
             double lo = BL[k * 32 + l], hi = BU[k * 32 + l];
@@ -154,12 +190,17 @@ struct WarpSolver {
     struct EvalOut { double pinf, viol, dinf, c0, cmu, ysum, zsum, theta, f, slog, sdamp; };
 
     template <bool FULL>
-    NMPC_DEV void eval_pass(double mu, double alpha, int rdz, int rds, bool trial, bool socacc, double asoc, EvalOut &E)
+    NMPC_PASS void eval_pass(double mu, double alpha, int rdz, int rds, bool trial, bool socacc, double asoc, EvalOut &E)
     {
+        NMPC_LOCALS
         const double kd = P.o.kappa_d;
         double pinf = 0, viol = 0, dinf = 0, c0 = 0, cmu = 0, ysum = 0, zsum = 0, th = 0, fo = 0, slog = 0, sdamp = 0;
         double *zb = sm + SM_ZB, *cs = sm + SM_CS, *sn = sm + SM_SN;
+        const int pf_a = prefetch_lane((1u << R_Z) | (FULL ? (1u << R_ZL | 1u << R_ZU | 1u << R_YC) : 0u) | (trial ? 1u << rdz : 0u) | (socacc ? (1u << R_CSOC) : 0u));
+        const int pf_b = prefetch_lane((1u << R_S) | (FULL ? (1u << R_VL | 1u << R_VU | 1u << R_YD) : 0u) | (trial ? 1u << rds : 0u) | (socacc ? (1u << R_DSOC) : 0u));
         for (int k = 0; k <= N; k++) {
+            prefetch_at(pf_a, k + 3);
+            prefetch_at(pf_b, k + 3);
             const bool zv = zvalid(k);
             double zk = zv ? row(R_Z, k)[l] : 0.0;
             if (trial && zv) zk += alpha * row(rdz, k)[l];
@@ -204,8 +245,8 @@ struct WarpSolver {
                     pinf = fmax(pinf, fabs(dms)); th += fabs(dms);
                     viol = fmax(viol, fmax(lo - dv, dv - hi));
                     if (socacc) row(R_DSOC, b)[l] = asoc * row(R_DSOC, b)[l] + dms;
-                    if (hl) slog += log(s - lo);
-                    if (hu) slog += log(hi - s);
+                    if (hl) slog += wp::log_(s - lo);
+                    if (hu) slog += wp::log_(hi - s);
                     if (hl && !hu) sdamp += s - lo;
                     if (hu && !hl) sdamp += hi - s;
                     if (FULL) {
@@ -224,8 +265,8 @@ struct WarpSolver {
             if (zv) {
                 double lo = BL[k * 32 + l], hi = BU[k * 32 + l];
                 bool hl = lo > -NMPC_INF, hu = hi < NMPC_INF;
-                if (hl) slog += log(zk - lo);
-                if (hu) slog += log(hi - zk);
+                if (hl) slog += wp::log_(zk - lo);
+                if (hu) slog += wp::log_(hi - zk);
                 if (hl && !hu) sdamp += zk - lo;
                 if (hu && !hl) sdamp += hi - zk;
                 if (k < N) { double e = zk - xs_l; fo += 0.5 * qw * e * e; }
@@ -278,23 +319,24 @@ struct WarpSolver {
     //   MODE 0: primal-dual system;  1: least-squares multiplier estimate;  2: restoration
     // ---------------------------------------------------------------------------------------
     template <int MODE>
-    NMPC_DEV void sig_g(double v, double lo, double hi, double ml, double mu_, double mu, double g0, double &sig, double &g) const
+    static NMPC_DEV void sig_g(double kd, double v, double lo, double hi, double ml, double mu_, double mu, double g0, double &sig, double &g)
     {
         bool hl = lo > -NMPC_INF, hu = hi < NMPC_INF;
         if (MODE == 1) { sig = 1.0; g = g0 - ml + mu_; return; }
         sig = 0.0; g = MODE == 0 ? g0 : 0.0;
-        if (hl) { double sl = v - lo; sig += MODE == 0 ? ml / sl : mu / (sl * sl); g -= mu / sl; }
-        if (hu) { double sl = hi - v; sig += MODE == 0 ? mu_ / sl : mu / (sl * sl); g += mu / sl; }
+        if (hl) { double r = wp::rcp_pos(v - lo); sig += MODE == 0 ? ml * r : mu * r * r; g -= mu * r; }
+        if (hu) { double r = wp::rcp_pos(hi - v); sig += MODE == 0 ? mu_ * r : mu * r * r; g += mu * r; }
         if (MODE == 0) {
-            if (hl && !hu) g += P.o.kappa_d * mu;
-            if (hu && !hl) g -= P.o.kappa_d * mu;
+            if (hl && !hu) g += kd * mu;
+            if (hu && !hl) g -= kd * mu;
         }
     }
 
     // inequality block b: condensed weights; writes the per-pair rows the forward pass needs
-    template <int MODE>
-    NMPC_DEV void ineq_block(int b, double mu, double delta, bool soc, const double *zb, double &pxx, double &pyy,
-                             double &pxy, double &phx, double &phy)
+    template <int MODE, class RowFn>
+    static NMPC_DEV void ineq_block(RowFn row, const double *DL, const double *DU, int l, int pi, int pj, double kd, int b, double mu,
+                                    double delta, bool soc, const double *zb, double &pxx, double &pyy, double &pxy, double &phx,
+                                    double &phy)
     {
         pxx = pyy = pxy = phx = phy = 0.0;
         double gxq = 0, gyq = 0, rd = 0, Dq = 0, gs = 0;
@@ -306,7 +348,7 @@ struct WarpSolver {
                 gxq = 2.0 * dx; gyq = 2.0 * dy; dv = dx * dx + dy * dy;
             }
             double s = row(R_S, b)[l], sigs;
-            sig_g<MODE>(s, lo, hi, row(R_VL, b)[l], row(R_VU, b)[l], mu, 0.0, sigs, gs);
+            sig_g<MODE>(kd, s, lo, hi, row(R_VL, b)[l], row(R_VU, b)[l], mu, 0.0, sigs, gs);
             rd = MODE == 1 ? 0.0 : (soc ? row(R_DSOC, b)[l] : dv - s);
             Dq = sigs + delta;
             double hq = Dq * rd + gs, mu2 = MODE == 0 ? 2.0 * row(R_YD, b)[l] : 0.0;
@@ -319,32 +361,56 @@ struct WarpSolver {
     // ---------------------------------------------------------------------------------------
     // backward Riccati sweep (K3).  false = a control-block pivot was <= 0 (wrong inertia).
     // ---------------------------------------------------------------------------------------
+    // backward Riccati sweep (K3).  false = a control-block pivot was <= 0 (wrong inertia).
+    //
+    // Lane l < 5Nr holds column l of the stage KKT matrix M = H + [A B]' P+ [A B]: its 3Nr state
+    // rows in X[] and its 2Nr control rows in U[]; lane 31 holds the linear term m as one more
+    // column.  The control block is eliminated by 2Nr symmetric sweeps inside a ROLLED loop: the
+    // pivot row is always U[0] (published through shared memory), and the control rows rotate by
+    // one register per step (the rotation is folded into the destination registers of the
+    // update, so it costs nothing).  A control column's state rows stay 0 until its own pivot
+    // (they equal the pivot row by symmetry), which makes the own-column update the same FMA.
+    // After the loop X[] holds P (state lanes), K' (control lanes) and p (lane 31); U[] of lane
+    // 31 holds the feed-forward term.
+    // ---------------------------------------------------------------------------------------
     template <int MODE>
-    NMPC_DEV bool factor(double mu, double delta, bool soc)
+    NMPC_PASS bool factor(double mu, double delta, bool soc)
     {
-        const double zeta = MODE == 2 ? sqrt(mu) : 0.0;
-        double Mr[NM];
-        double *col = sm + SM_COL, *pb = sm + SM_PB, *zb = sm + SM_ZB, *rcb = sm + SM_RCB, *prb = sm + SM_PRB;
+        NMPC_LOCALS
+        const double zeta = MODE == 2 ? sqrt(mu) : 0.0, kd = this->P.o.kappa_d;
+        const bool isL = (l == 31);
+        double X[NS], U[NC];
+        double plin = 0.0, dgx = 0.0;
+        double *col = sm + SM_COL, *pb = sm + SM_PB, *zb = sm + SM_ZB, *rcb = sm + SM_RCB, *prb = sm + SM_PRB, *hb = sm + SM_HB;
         double *cs = sm + SM_CS, *sn = sm + SM_SN, *ca = sm + SM_CA, *cb = sm + SM_CB, *tcs = sm + SM_TCS,
                *tsn = sm + SM_TSN, *crs = sm + SM_CRS, *thd = sm + SM_THD;
         double *pxx = sm + SM_PXX, *pyy = sm + SM_PYY, *pxy = sm + SM_PXY, *phx = sm + SM_PHX, *phy = sm + SM_PHY;
         n_fact++;
+        const int pf_a = prefetch_lane((1u << R_Z | 1u << R_ZL | 1u << R_ZU));
+        const int pf_b = prefetch_lane((1u << R_YC | 1u << R_S | 1u << R_VL | 1u << R_VU | 1u << R_YD) | (soc ? (1u << R_CSOC | 1u << R_DSOC) : 0u));
+        wp::sync();
         // terminal stage: X_N carries no cost and no distance rows, only its box
         {
             double sig = 0.0, gx = 0.0;
-            if (isx) sig_g<MODE>(row(R_Z, N)[l], BL[N * 32 + l], BU[N * 32 + l], row(R_ZL, N)[l], row(R_ZU, N)[l], mu, 0.0, sig, gx);
+            if (isx) sig_g<MODE>(kd, row(R_Z, N)[l], BL[N * 32 + l], BU[N * 32 + l], row(R_ZL, N)[l], row(R_ZU, N)[l], mu, 0.0, sig, gx);
+            hb[l] = isx ? gx : 0.0;
+            wp::sync();
             NMPC_UNROLL
-            for (int i = 0; i < NM; i++) Mr[i] = 0.0;
+            for (int i = 0; i < NS; i++) X[i] = isL ? hb[i] : 0.0;
+            dgx = isx ? sig + delta + zeta : 0.0;   // P_N = X + diag(dgx): the own-row diagonal is carried separately
             NMPC_UNROLL
-            for (int i = 0; i < NS; i++) Mr[i] = (isx && i == l) ? sig + delta + zeta : 0.0;
-            Mr[LIN] = isx ? gx : 0.0;
-            row(R_GX, N)[l] = isx ? gx : 0.0;
+            for (int u = 0; u < NC; u++) U[u] = 0.0;
+            plin = isx ? gx : 0.0;
+            row(R_GX, N)[l] = plin;
             NMPC_UNROLL
-            for (int i = 0; i < NS; i++) frow(N, i)[l] = Mr[i];
-            row(R_LIN, N)[l] = Mr[LIN];
+            for (int i = 0; i < NS; i++) frow(N, i)[l] = isz ? X[i] : 0.0;
+            row(R_LIN, N)[l] = plin; row(R_DG, N)[l] = dgx;
         }
+        NMPC_NOUNROLL
         for (int k = N - 1; k >= 0; k--) {
             wp::sync();
+            prefetch_at(pf_a, k - 1);
+            prefetch_at(pf_b, k);
             const double zk = isz ? row(R_Z, k)[l] : 0.0;
             zb[l] = zk;
             if (l < NR) {
@@ -364,7 +430,8 @@ struct WarpSolver {
             }
             if (isx) {
                 NMPC_UNROLL
-                for (int i = 0; i < NS; i++) pb[i * NS + l] = Mr[i];
+                for (int i = 0; i < NS; i++) pb[i * PLD + l] = X[i];
+                pb[l * PLD + l] += dgx;   // same lane wrote this element just above
             }
             wp::sync();
             // equality residual of block k+1 and the condensed inequality block k+1
@@ -382,54 +449,56 @@ struct WarpSolver {
             }
             if (M > 0 && isq) {
                 double a0, a1, a2, a3, a4;
-                ineq_block<MODE>(k + 1, mu, delta, soc, zb, a0, a1, a2, a3, a4);
+                ineq_block<MODE>(row, DL, DU, l, pi, pj, kd, k + 1, mu, delta, soc, zb, a0, a1, a2, a3, a4);
                 pxx[l] = a0; pyy[l] = a1; pxy[l] = a2; phx[l] = a3; phy[l] = a4;
             }
             wp::sync();
-            // pr = p_{k+1} + P_{k+1} r,  r = -rc
+            // pr = p_{k+1} + P_{k+1} r (r = -rc), published as one more column of pb for lane 31
             if (isx) {
-                double pr = Mr[LIN];
+                double pr = plin;
                 if (MODE != 1) {
                     NMPC_UNROLL
-                    for (int i = 0; i < NS; i++) pr -= Mr[i] * rcb[i];
+                    for (int i = 0; i < NS; i++) pr -= X[i] * rcb[i];
+                    pr -= dgx * rcb[l];
                 }
-                prb[l] = pr;
+                pb[l * PLD + NS] = pr;
             }
-            wp::sync();
-            // column l of [A B]:  al e_x + be e_y + ga e_theta of this lane's robot
-            double al = 0.0, be = 0.0, ga = 0.0;
-            if (isx) { if (comp == 0) al = 1.0; else if (comp == 1) be = 1.0; else { al = ca[rob]; be = cb[rob]; ga = 1.0; } }
-            else if (isu) { if (comp == 0) { al = tcs[rob]; be = tsn[rob]; } else ga = T; }
-            const int base = 3 * rob;
-            double W[NS];
-            NMPC_UNROLL
-            for (int r = 0; r < NS; r++) W[r] = al * pb[r * NS + base] + be * pb[r * NS + base + 1] + ga * pb[r * NS + base + 2];
-            const double wv = al * prb[base] + be * prb[base + 1] + ga * prb[base + 2];
-            NMPC_UNROLL
-            for (int i = 0; i < NR; i++) {
-                double Wx = W[3 * i], Wy = W[3 * i + 1], Wt = W[3 * i + 2];
-                Mr[3 * i] = Wx; Mr[3 * i + 1] = Wy; Mr[3 * i + 2] = Wt + ca[i] * Wx + cb[i] * Wy;
-                Mr[NS + 2 * i] = tcs[i] * Wx + tsn[i] * Wy; Mr[NS + 2 * i + 1] = T * Wt;
-            }
-            // stage Hessian and gradient
-            double sig = 0.0, gx = 0.0;
-            if (isz) sig_g<MODE>(zk, BL[k * 32 + l], BU[k * 32 + l], row(R_ZL, k)[l], row(R_ZU, k)[l], mu, df * gradf(k, zk), sig, gx);
-            row(R_GX, k)[l] = gx;
-            double dg = 0.0;
+            // stage gradient h_l (variable l) and diagonal curvature
+            double sig = 0.0, gx = 0.0, dg = 0.0;
             if (isz) {
+                sig_g<MODE>(kd, zk, BL[k * 32 + l], BU[k * 32 + l], row(R_ZL, k)[l], row(R_ZU, k)[l], mu, df * gradf(k, zk), sig, gx);
                 dg = sig + delta + zeta;
                 if (MODE == 0) { dg += df * qw; if (isx && comp == 2) dg += thd[rob]; }
             }
-            Mr[LIN] = isz ? wv + gx : 0.0;
-            NMPC_UNROLL
-            for (int r = 0; r < NZ; r++) Mr[r] += (r == l) ? dg : 0.0;
-            if (MODE == 0) {
+            row(R_GX, k)[l] = gx;
+            double hl_ = gx;
+            // column l of [A B]:  al e_x + be e_y + ga e_theta of this lane's robot (lane 31: the pr column)
+            double al = 0.0, be = 0.0, ga = 0.0;
+            int base = 3 * rob;
+            if (isx) { if (comp == 0) al = 1.0; else if (comp == 1) be = 1.0; else { al = ca[rob]; be = cb[rob]; ga = 1.0; } }
+            else if (isu) { if (comp == 0) { al = tcs[rob]; be = tsn[rob]; } else ga = T; }
+            else if (isL) { al = 1.0; base = NS; }
+            wp::sync();
+            {
+                double W[NS];
+                NMPC_UNROLL
+                for (int r0 = 0; r0 < NS; r0 += 6) {   // loads of six rows are issued together, then the FMAs
+                    double t0[6], t1[6], t2[6];
+                    NMPC_UNROLL
+                    for (int r = 0; r < 6; r++)
+                        if (r0 + r < NS) { const double *q = pb + (r0 + r) * PLD + base; t0[r] = q[0]; t1[r] = q[1]; t2[r] = q[2]; }
+                    NMPC_UNROLL
+                    for (int r = 0; r < 6; r++)
+                        if (r0 + r < NS) W[r0 + r] = al * t0[r] + be * t1[r] + ga * t2[r];
+                }
                 NMPC_UNROLL
                 for (int i = 0; i < NR; i++) {
-                    if (l == 3 * i + 2) Mr[NS + 2 * i] += crs[i];
-                    if (l == NS + 2 * i) Mr[3 * i + 2] += crs[i];
+                    double Wx = W[3 * i], Wy = W[3 * i + 1], Wt = W[3 * i + 2];
+                    X[3 * i] = Wx; X[3 * i + 1] = Wy; X[3 * i + 2] = Wt + ca[i] * Wx + cb[i] * Wy;
+                    U[2 * i] = tcs[i] * Wx + tsn[i] * Wy; U[2 * i + 1] = T * Wt;
                 }
             }
+            // collision curvature (state lanes, x/y rows) and gradient
             if (M > 0 && isx && comp < 2) {
                 double ssame = 0.0, scross = 0.0, glin = 0.0;
                 NMPC_UNROLL
@@ -438,43 +507,101 @@ struct WarpSolver {
                     int q = rob < j ? pairidx(rob, j) : pairidx(j, rob);
                     double vs = comp == 0 ? pxx[q] : pyy[q], vc = pxy[q];
                     double ph = comp == 0 ? phx[q] : phy[q];
-                    Mr[3 * j] -= comp == 0 ? vs : vc;
-                    Mr[3 * j + 1] -= comp == 0 ? vc : vs;
+                    X[3 * j] -= comp == 0 ? vs : vc;
+                    X[3 * j + 1] -= comp == 0 ? vc : vs;
                     ssame += vs; scross += vc; glin += rob < j ? ph : -ph;
                 }
                 NMPC_UNROLL
                 for (int j = 0; j < NR; j++)
-                    if (j == rob) { Mr[3 * j] += comp == 0 ? ssame : scross; Mr[3 * j + 1] += comp == 0 ? scross : ssame; }
-                Mr[LIN] += glin;
+                    if (j == rob) { X[3 * j] += comp == 0 ? ssame : scross; X[3 * j + 1] += comp == 0 ? scross : ssame; }
+                hl_ += glin;
             }
-            // symmetric sweep of the control pivots
+            hb[l] = isz ? hl_ : 0.0;
+            wp::sync();
+            // + diagonal (own row); lane 31 adds the gradient vector h; control lanes start their state rows at 0
             NMPC_UNROLL
-            for (int j = NS; j < NZ; j++) {
-                double *buf = col + 32 * (j & 1);
-                if (isz) buf[l] = Mr[j];
-                if (l == j) buf[LIN] = Mr[LIN];
-                wp::sync();
-                const double d = buf[j];
-                if (!(d > 0.0) || !(d < NMPC_INF)) return false;
-                const double inv = 1.0 / d;
-                // lane j owns the pivot column: it becomes column/d (computed directly -- forming it as
-                // M - col*(1 - 1/d) cancels catastrophically when d ~ 1e13 on a saturated control)
-                const bool own = (l == j);
-                const double t = own ? -inv : Mr[j] * inv;
+            for (int u = 0; u < NC; u++) U[u] += (NS + u == l) ? dg : 0.0;
+            dgx = isx ? dg : 0.0;
+            if (isL) {
                 NMPC_UNROLL
-                for (int i = 0; i < NM; i++)
-                    if (i != j) Mr[i] = (own ? 0.0 : Mr[i]) - buf[i] * t;
-                Mr[j] = t;
+                for (int r = 0; r < NS; r++) X[r] += hb[r];
+                NMPC_UNROLL
+                for (int u = 0; u < NC; u++) U[u] += hb[NS + u];
             }
-            if (isz) {
+            if (isu) {
                 NMPC_UNROLL
-                for (int i = 0; i < NS; i++) frow(k, i)[l] = Mr[i];
-                row(R_LIN, k)[l] = Mr[LIN];
+                for (int r = 0; r < NS; r++) X[r] = 0.0;
+            }
+            if (MODE == 0) {
+                NMPC_UNROLL
+                for (int i = 0; i < NR; i++)
+                    if (l == 3 * i + 2) U[2 * i] += crs[i];
+            }
+            // symmetric sweep of the control pivots (rolled).  The pivot row is U[0] of every lane; it is
+            // published in ROTATED order (slot NS + r holds control column (j + r) mod 2Nr), so the readers
+            // use compile-time offsets and the rows rotate through the registers for free.
+            const int ucol = l - NS;   // control column of this lane (if any)
+            NMPC_NOUNROLL
+            for (int j = 0; j < NC; j++) {
+                double *buf = col + 32 * (j & 1);
+                int slot = l;
+                if (isu) { slot = ucol - j; slot += slot < 0 ? NC : 0; slot += NS; }
+                if (isz) buf[slot] = U[0];
+                wp::sync();
+                const double d = buf[NS];
+                if (!(d > 0.0) || !(d < NMPC_INF)) return false;
+                const double inv = wp::rcp_pos(d);
+                const bool own = (ucol == j);
+                const double t = own ? -inv : U[0] * inv;
+                const double tx = (ucol > j && isu) ? 0.0 : t;
+                {   // state rows: the pivot row arrives in 128-bit loads, all issued before the FMAs
+                    const NmpcD2 *b2 = reinterpret_cast<const NmpcD2 *>(buf);
+                    NmpcD2 bx[NS / 2];
+                    NMPC_UNROLL
+                    for (int i = 0; i < NS / 2; i++) bx[i] = b2[i];
+                    NMPC_UNROLL
+                    for (int i = 0; i < NS / 2; i++) { X[2 * i] -= bx[i].x * tx; X[2 * i + 1] -= bx[i].y * tx; }
+                    if (NS & 1) X[NS - 1] -= buf[NS - 1] * tx;
+                }
+                if (own) {   // the pivot column becomes column / d: start its remaining rows from 0
+                    NMPC_UNROLL
+                    for (int r = 1; r < NC; r++) U[r] = 0.0;
+                }
+                {   // control rows (rotating): slots NS+1 .. NS+NC-1
+                    double bu[NC];
+                    if ((NS & 1) == 0) {
+                        const NmpcD2 *b2 = reinterpret_cast<const NmpcD2 *>(buf + NS);
+                        NMPC_UNROLL
+                        for (int r = 0; r < NC / 2; r++) { NmpcD2 v = b2[r]; bu[2 * r] = v.x; bu[2 * r + 1] = v.y; }
+                    } else {
+                        NMPC_UNROLL
+                        for (int r = 0; r < NC; r++) bu[r] = buf[NS + r];
+                    }
+                    NMPC_UNROLL
+                    for (int r = 1; r < NC; r++) U[r - 1] = U[r] - bu[r] * t;
+                }
+                U[NC - 1] = t;
+            }
+            // publish p_k / feed-forward (lane 31's column) and store the factors
+            wp::sync();
+            if (isL) {
+                NMPC_UNROLL
+                for (int i = 0; i < NS; i++) prb[i] = X[i];
+                NMPC_UNROLL
+                for (int u = 0; u < NC; u++) prb[NS + u] = U[u];
+            }
+            wp::sync();
+            if (isz) {
+                const double v = prb[l];
+                plin = v;
+                row(R_LIN, k)[l] = v; row(R_DG, k)[l] = dgx;
+                NMPC_UNROLL
+                for (int i = 0; i < NS; i++) frow(k, i)[l] = X[i];
             }
         }
         wp::sync();
         if (isx) row(R_RC, 0)[l] = MODE == 1 ? 0.0 : (soc ? row(R_CSOC, 0)[l] : row(R_Z, 0)[l] - x0bar_l - CE[l]);
-        if (M > 0 && isq) { double a0, a1, a2, a3, a4; ineq_block<MODE>(0, mu, delta, soc, zb, a0, a1, a2, a3, a4); }
+        if (M > 0 && isq) { double a0, a1, a2, a3, a4; ineq_block<MODE>(row, DL, DU, l, pi, pj, kd, 0, mu, delta, soc, zb, a0, a1, a2, a3, a4); }
         wp::sync();
         return true;
     }
@@ -484,26 +611,31 @@ struct WarpSolver {
     // ---------------------------------------------------------------------------------------
     struct StepInfo { double ap, az, gbd, tiny; };
 
-    NMPC_DEV void slack_step_terms(double v, double dv, double lo, double hi, double ml, double mu_, double mu, double tau,
-                                   double &ap, double &az) const
+    // fraction-to-boundary bookkeeping of one bounded quantity: rp = max(-dv/slack), rz = max(-dmult/mult);
+    // the step sizes are tau / max ratio (one division per pass instead of one per bound)
+    static NMPC_DEV void slack_step_terms(double v, double dv, double lo, double hi, double ml, double mu_, double mu, double &rp,
+                                          double &rz)
     {
         if (lo > -NMPC_INF) {
-            double sl = v - lo;
-            if (dv < 0.0) ap = fmin(ap, -tau * sl / dv);
-            double dm = mu / sl - ml - ml / sl * dv;
-            if (dm < 0.0) az = fmin(az, -tau * ml / dm);
+            double r = wp::rcp_pos(v - lo);
+            rp = fmax(rp, -dv * r);
+            double dm = mu * r - ml - ml * r * dv;
+            rz = fmax(rz, -dm * wp::rcp_pos(ml));
         }
         if (hi < NMPC_INF) {
-            double sl = hi - v;
-            if (dv > 0.0) ap = fmin(ap, tau * sl / dv);
-            double dm = mu / sl - mu_ + mu_ / sl * dv;
-            if (dm < 0.0) az = fmin(az, -tau * mu_ / dm);
+            double r = wp::rcp_pos(hi - v);
+            rp = fmax(rp, dv * r);
+            double dm = mu * r - mu_ + mu_ * r * dv;
+            rz = fmax(rz, -dm * wp::rcp_pos(mu_));
         }
     }
 
-    NMPC_DEV void forward(double mu, double tau, int rdz, int rds, int rytc, int rytd, StepInfo &si)
+    NMPC_PASS void forward(double mu, double tau, int rdz, int rds, int rytc, int rytd, StepInfo &si)
     {
-        double ap = 1.0, az = 1.0, gbd = 0.0, tiny = 0.0;
+        NMPC_LOCALS
+        double ap = 0.0, az = 0.0, gbd = 0.0, tiny = 0.0;   // max ratios, see slack_step_terms
+        const int pf_a = prefetch_lane((1u << R_LIN | 1u << R_Z | 1u << R_ZL | 1u << R_ZU | 1u << R_GX | 1u << R_COEF | 1u << R_DG));
+        const int pf_b = prefetch_lane((1u << R_RC | 1u << R_GXQ | 1u << R_GYQ | 1u << R_RD | 1u << R_DQ | 1u << R_GS | 1u << R_S | 1u << R_VL | 1u << R_VU));
         double *dzb = sm + SM_DZB;
         double dx = isx ? -row(R_RC, 0)[l] : 0.0;
         if (M > 0 && isq) {
@@ -513,19 +645,37 @@ struct WarpSolver {
             row(rds, 0)[l] = ds; row(rytd, 0)[l] = ytd;
             if (act) {
                 double s = row(R_S, 0)[l];
-                slack_step_terms(s, ds, DL[l], DU[l], row(R_VL, 0)[l], row(R_VU, 0)[l], mu, tau, ap, az);
+                slack_step_terms(s, ds, DL[l], DU[l], row(R_VL, 0)[l], row(R_VU, 0)[l], mu, ap, az);
                 gbd += gs * ds; tiny = fmax(tiny, fabs(ds) / (1.0 + fabs(s)));
             }
         }
         for (int k = 0; k <= N; k++) {
             wp::sync();
+            if (k + 2 <= N) {   // factor rows and vectors two stages ahead
+                wp::prefetch(frow(k + 2, l >> 1) + (l & 1) * 16);
+                if (NS > 16 && l < 2 * (NS - 16)) wp::prefetch(frow(k + 2, 16 + (l >> 1)) + (l & 1) * 16);
+                prefetch_at(pf_a, k + 2);
+                prefetch_at(pf_b, k + 3);
+            }
             if (isx) dzb[l] = dx;
             wp::sync();
             double acc = 0.0;
             if (isz) {
-                acc = row(R_LIN, k)[l];
+                double a0 = row(R_LIN, k)[l], a1 = isx ? row(R_DG, k)[l] * dzb[l] : 0.0, a2 = 0.0;
                 NMPC_UNROLL
-                for (int i = 0; i < NS; i++) acc += frow(k, i)[l] * dzb[i];
+                for (int i0 = 0; i0 < NS; i0 += 6) {   // six factor rows in flight, three accumulation chains
+                    double fv[6];
+                    NMPC_UNROLL
+                    for (int i = 0; i < 6; i++)
+                        if (i0 + i < NS) fv[i] = frow(k, i0 + i)[l];
+                    NMPC_UNROLL
+                    for (int i = 0; i < 6; i += 3) {
+                        if (i0 + i < NS) a0 += fv[i] * dzb[i0 + i];
+                        if (i0 + i + 1 < NS) a1 += fv[i + 1] * dzb[i0 + i + 1];
+                        if (i0 + i + 2 < NS) a2 += fv[i + 2] * dzb[i0 + i + 2];
+                    }
+                }
+                acc = a0 + (a1 + a2);
             }
             if (isx) row(rytc, k)[l] = -acc;
             const double du = (isu && k < N) ? -acc : 0.0;
@@ -534,7 +684,7 @@ struct WarpSolver {
             row(rdz, k)[l] = dzl;
             if (zvalid(k)) {
                 double z = row(R_Z, k)[l];
-                slack_step_terms(z, dzl, BL[k * 32 + l], BU[k * 32 + l], row(R_ZL, k)[l], row(R_ZU, k)[l], mu, tau, ap, az);
+                slack_step_terms(z, dzl, BL[k * 32 + l], BU[k * 32 + l], row(R_ZL, k)[l], row(R_ZU, k)[l], mu, ap, az);
                 gbd += row(R_GX, k)[l] * dzl; tiny = fmax(tiny, fabs(dzl) / (1.0 + fabs(z)));
             }
             if (k < N) {
@@ -555,7 +705,7 @@ struct WarpSolver {
                         ds = row(R_GXQ, b)[l] * (dzb[3 * pi] - dzb[3 * pj]) + row(R_GYQ, b)[l] * (dzb[3 * pi + 1] - dzb[3 * pj + 1]) + row(R_RD, b)[l];
                         ytd = row(R_DQ, b)[l] * ds + gs;
                         double s = row(R_S, b)[l];
-                        slack_step_terms(s, ds, DL[b * 32 + l], DU[b * 32 + l], row(R_VL, b)[l], row(R_VU, b)[l], mu, tau, ap, az);
+                        slack_step_terms(s, ds, DL[b * 32 + l], DU[b * 32 + l], row(R_VL, b)[l], row(R_VU, b)[l], mu, ap, az);
                         gbd += gs * ds; tiny = fmax(tiny, fabs(ds) / (1.0 + fabs(s)));
                     }
                     row(rds, b)[l] = ds; row(rytd, b)[l] = ytd;
@@ -563,28 +713,31 @@ struct WarpSolver {
                 dx = dn;
             }
         }
-        si.ap = wp::red_min(ap); si.az = wp::red_min(az); si.gbd = wp::red_sum(gbd); si.tiny = wp::red_max(tiny);
+        ap = wp::red_max(ap); az = wp::red_max(az);
+        si.ap = ap > tau ? tau / ap : 1.0; si.az = az > tau ? tau / az : 1.0;
+        si.gbd = wp::red_sum(gbd); si.tiny = wp::red_max(tiny);
         wp::sync();
     }
 
     // ---------------------------------------------------------------------------------------
-    NMPC_DEV void accept(double alpha, double az, double mu, int rdz, int rds, int rytc, int rytd)
+    NMPC_PASS void accept(double alpha, double az, double mu, int rdz, int rds, int rytc, int rytd)
     {
-        const double ks = P.o.kappa_sigma;
+        NMPC_LOCALS
+        const double ks = this->P.o.kappa_sigma, iks = 1.0 / ks;
+        // bound multiplier after the step, kept in the kappa_sigma corridor around mu / (new slack)
+        auto mult = [=](double m, double sl_old, double sl_new, double dv_signed) {
+            double r = wp::rcp_pos(sl_old), c = mu * wp::rcp_pos(sl_new);
+            double m2 = m + az * (mu * r - m + m * r * dv_signed);
+            return fmax(fmin(m2, ks * c), iks * c);
+        };
+        const int pf_a = prefetch_lane((1u << R_Z) | (1u << rdz) | (1u << R_ZL) | (1u << R_ZU) | (1u << R_YC) | (1u << rytc) | (1u << R_S) | (1u << rds) | (1u << R_VL) | (1u << R_VU) | (1u << R_YD) | (1u << rytd));
         for (int k = 0; k <= N; k++) {
+            prefetch_at(pf_a, k + 2);
             if (zvalid(k)) {
                 double z = row(R_Z, k)[l], dz = row(rdz, k)[l], lo = BL[k * 32 + l], hi = BU[k * 32 + l];
                 double zn = z + alpha * dz;
-                if (lo > -NMPC_INF) {
-                    double sl = z - lo, ml = row(R_ZL, k)[l];
-                    double m2 = ml + az * (mu / sl - ml - ml / sl * dz), s2 = zn - lo;
-                    row(R_ZL, k)[l] = fmax(fmin(m2, ks * mu / s2), mu / (ks * s2));
-                }
-                if (hi < NMPC_INF) {
-                    double sl = hi - z, mu_ = row(R_ZU, k)[l];
-                    double m2 = mu_ + az * (mu / sl - mu_ + mu_ / sl * dz), s2 = hi - zn;
-                    row(R_ZU, k)[l] = fmax(fmin(m2, ks * mu / s2), mu / (ks * s2));
-                }
+                if (lo > -NMPC_INF) row(R_ZL, k)[l] = mult(row(R_ZL, k)[l], z - lo, zn - lo, -dz);
+                if (hi < NMPC_INF) row(R_ZU, k)[l] = mult(row(R_ZU, k)[l], hi - z, hi - zn, dz);
                 row(R_Z, k)[l] = zn;
             }
             if (isx) { double y = row(R_YC, k)[l]; row(R_YC, k)[l] = y + alpha * (row(rytc, k)[l] - y); }
@@ -592,16 +745,8 @@ struct WarpSolver {
                 double lo = DL[k * 32 + l], hi = DU[k * 32 + l];
                 if (lo > -NMPC_INF || hi < NMPC_INF) {
                     double s = row(R_S, k)[l], ds = row(rds, k)[l], sn_ = s + alpha * ds;
-                    if (lo > -NMPC_INF) {
-                        double sl = s - lo, ml = row(R_VL, k)[l];
-                        double m2 = ml + az * (mu / sl - ml - ml / sl * ds), s2 = sn_ - lo;
-                        row(R_VL, k)[l] = fmax(fmin(m2, ks * mu / s2), mu / (ks * s2));
-                    }
-                    if (hi < NMPC_INF) {
-                        double sl = hi - s, mu_ = row(R_VU, k)[l];
-                        double m2 = mu_ + az * (mu / sl - mu_ + mu_ / sl * ds), s2 = hi - sn_;
-                        row(R_VU, k)[l] = fmax(fmin(m2, ks * mu / s2), mu / (ks * s2));
-                    }
+                    if (lo > -NMPC_INF) row(R_VL, k)[l] = mult(row(R_VL, k)[l], s - lo, sn_ - lo, -ds);
+                    if (hi < NMPC_INF) row(R_VU, k)[l] = mult(row(R_VU, k)[l], hi - s, hi - sn_, ds);
                     row(R_S, k)[l] = sn_;
                     double y = row(R_YD, k)[l]; row(R_YD, k)[l] = y + alpha * (row(rytd, k)[l] - y);
                 }
@@ -610,8 +755,9 @@ struct WarpSolver {
         wp::sync();
     }
 
-    NMPC_DEV void accept_primal(double alpha, int rdz, int rds)
+    NMPC_PASS void accept_primal(double alpha, int rdz, int rds)
     {
+        NMPC_LOCALS
         for (int k = 0; k <= N; k++) {
             if (zvalid(k)) row(R_Z, k)[l] += alpha * row(rdz, k)[l];
             if (M > 0 && isq && (DL[k * 32 + l] > -NMPC_INF || DU[k * 32 + l] < NMPC_INF)) row(R_S, k)[l] += alpha * row(rds, k)[l];
@@ -620,8 +766,9 @@ struct WarpSolver {
     }
 
     // after the restoration fallback: equality multipliers reset, bound multipliers clipped
-    NMPC_DEV void resto_reset(double mu)
+    NMPC_PASS void resto_reset(double mu)
     {
+        NMPC_LOCALS
         const double ks = P.o.kappa_sigma;
         for (int k = 0; k <= N; k++) {
             if (zvalid(k)) {
@@ -640,8 +787,9 @@ struct WarpSolver {
     }
 
     // copy the initial-residual rows into the SOC accumulators (c_soc := c, d_soc := d - s)
-    NMPC_DEV void soc_begin()
+    NMPC_PASS void soc_begin()
     {
+        NMPC_LOCALS
         for (int k = 0; k <= N; k++) {
             row(R_CSOC, k)[l] = isx ? row(R_RC, k)[l] : 0.0;
             row(R_DSOC, k)[l] = (M > 0 && isq) ? row(R_RD, k)[l] : 0.0;
@@ -659,8 +807,9 @@ struct WarpSolver {
             if (!(th < fth[i] || ph < fph[i])) return false;
         return true;
     }
-    NMPC_DEV void filter_add(double th, double ph)
+    NMPC_PASS void filter_add(double th, double ph)
     {
+        NMPC_LOCALS
         double *fth = sm + SM_FTH, *fph = sm + SM_FPH, *misc = sm + SM_MISC;
         wp::sync();
         if (l == 0) {
@@ -682,8 +831,9 @@ struct WarpSolver {
     // ---------------------------------------------------------------------------------------
     // outputs in the reference layout, multipliers in CasADi's sign convention
     // ---------------------------------------------------------------------------------------
-    NMPC_DEV void write_outputs(int st, int iter, double E0, double pinf, double dinf, double c0, double mu)
+    NMPC_PASS void write_outputs(int st, int iter, double E0, double pinf, double dinf, double c0, double mu)
     {
+        NMPC_LOCALS
         const long long n = (long long)NS * S + (long long)NC * N, mg = (long long)S * (NS + M);
         double *x = P.x + inst * n;
         double *lx = P.lam_x ? P.lam_x + inst * n : nullptr;

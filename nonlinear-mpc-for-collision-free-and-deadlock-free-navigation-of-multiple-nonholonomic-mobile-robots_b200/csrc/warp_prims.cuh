@@ -7,7 +7,9 @@
 
 #define NMPC_DEV __device__ __forceinline__
 #define NMPC_HD __host__ __device__
+#define NMPC_PASS __device__ __noinline__   // one copy of each solver pass: keeps the hot code inside the instruction cache
 #define NMPC_UNROLL _Pragma("unroll")
+#define NMPC_NOUNROLL _Pragma("unroll 1")
 
 namespace wp {
 NMPC_DEV int lane() { return threadIdx.x & 31; }
@@ -18,21 +20,44 @@ NMPC_DEV int shfl_i(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 NMPC_DEV bool any(bool p) { return __any_sync(0xffffffffu, p); }
 NMPC_DEV bool all(bool p) { return __all_sync(0xffffffffu, p); }
 NMPC_DEV int atomic_next(int *counter) { return atomicAdd(counter, 1); }
-NMPC_DEV void sincos_(double x, double *s, double *c) { sincos(x, s, c); }
+// address-space hints for pointers that travel through the solver object
+extern __shared__ double nmpc_dyn_smem[];
+NMPC_DEV double *shared_ptr(double *p) { return nmpc_dyn_smem + (p - (double *)nmpc_dyn_smem); }
+template <class Tp> NMPC_DEV Tp *global_ptr(Tp *p) { __builtin_assume(__isGlobal(p)); return p; }
+// reciprocal of a positive, finite, normal double: MUFU seed + two Newton steps (<= 1 ulp), no range checks
+NMPC_DEV double rcp_pos(double d)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    return fma(r, e, r);
+}
+// prefetch by touching: a real L1-allocating load whose result is never used (nothing waits on it)
+NMPC_DEV void prefetch(const void *p)
+{
+    double sink;
+    asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(sink) : "l"(p));
+}
+NMPC_DEV unsigned nth_set_bit(unsigned mask, int n) { return __fns(mask, 0, n + 1); }
+// one shared copy of the long math routines: keeps the passes small enough for the instruction cache
+__device__ __noinline__ void sincos_(double x, double *s, double *c) { sincos(x, s, c); }
+__device__ __noinline__ double log_(double x) { return log(x); }
 
-NMPC_DEV double red_sum(double v)
+__device__ __noinline__ double red_sum(double v)
 {
     NMPC_UNROLL
     for (int m = 16; m > 0; m >>= 1) v += shfl_xor(v, m);
     return v;
 }
-NMPC_DEV double red_max(double v)
+__device__ __noinline__ double red_max(double v)
 {
     NMPC_UNROLL
     for (int m = 16; m > 0; m >>= 1) v = fmax(v, shfl_xor(v, m));
     return v;
 }
-NMPC_DEV double red_min(double v)
+__device__ __noinline__ double red_min(double v)
 {
     NMPC_UNROLL
     for (int m = 16; m > 0; m >>= 1) v = fmin(v, shfl_xor(v, m));

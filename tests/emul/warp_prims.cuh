@@ -9,7 +9,9 @@
 
 #define NMPC_DEV inline
 #define NMPC_HD
+#define NMPC_PASS inline
 #define NMPC_UNROLL
+#define NMPC_NOUNROLL
 
 namespace wp {
 struct Emu {
@@ -29,6 +31,12 @@ inline int shfl_i(int v, int src) { emu->xi[emu->cur] = v; sync(); int r = emu->
 inline bool any(bool p) { emu->xb[emu->cur] = p; sync(); bool r = false; for (int i = 0; i < 32; i++) r = r || emu->xb[i]; sync(); return r; }
 inline bool all(bool p) { emu->xb[emu->cur] = p; sync(); bool r = true; for (int i = 0; i < 32; i++) r = r && emu->xb[i]; sync(); return r; }
 inline int atomic_next(int *c) { return (*c)++; }
+inline double *shared_ptr(double *p) { return p; }
+template <class Tp> inline Tp *global_ptr(Tp *p) { return p; }
+inline double rcp_pos(double d) { return 1.0 / d; }
+inline void prefetch(const void *) {}
+inline unsigned nth_set_bit(unsigned mask, int n) { for (unsigned b = 0; b < 32; b++) if (mask >> b & 1u) { if (n == 0) return b; n--; } return 0xffffffffu; }
+inline double log_(double x) { return ::log(x); }
 inline void sincos_(double x, double *s, double *c) { ::sincos(x, s, c); }
 inline double red_sum(double v) { for (int m = 16; m > 0; m >>= 1) v += shfl_xor(v, m); return v; }
 inline double red_max(double v) { for (int m = 16; m > 0; m >>= 1) v = fmax(v, shfl_xor(v, m)); return v; }
