@@ -110,7 +110,7 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        P = synthetic(512, 20261018)
+        P = synthetic(a.per_gpu, 20261018)
         per_step = []
         tot_n = tot_t = 0
         mean_it = 0.0
@@ -123,7 +123,7 @@ def main():
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * float(np.mean(per_step)), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": val, "unit": "solves/s", "cores": ncores, "kind": "port",
-                                 "sample": "%d cold-start instances of the same workload per step (~8 s), restated IPOPT "
+                                 "sample": "first %d cold-start instances of the same workload per step (~8 s), restated IPOPT "
                                            "(oracle/nmpc_oracle.c, OpenMP); CasADi/IPOPT are not installable here" % (tot_n // max(1, a.steps)),
                                  "mean_iters": mean_it},
                 "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -219,7 +219,7 @@ def main():
     pkg.lib().nmpc_probe_fp64(ctypes.byref(tf))
     flops_per_solve = float((stats[:, 8] * F_FACT + iters * (F_SOLVE + F_EVAL)).mean())
     ach_tf = per_gpu_solves * flops_per_solve / 1e12
-    cpu_val, cpu_n, cpu_dt, cpu_it = cpu_arm(synthetic(512, 20261018), ncores, budget_s=15.0)
+    cpu_val, cpu_n, cpu_dt, cpu_it = cpu_arm(P, ncores, budget_s=15.0)     # same instances as the GPU arm, bounded to ~15 s
     line = {
         "metric": "6-robot N=20 NMPC solves/sec", "value": value, "unit": "solves/s", "n_gpus": world, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": tot_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

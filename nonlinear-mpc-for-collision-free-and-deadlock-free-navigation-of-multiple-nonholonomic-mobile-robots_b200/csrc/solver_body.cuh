@@ -786,6 +786,44 @@ struct WarpSolver {
         wp::sync();
     }
 
+    // restoration candidate: forward rollout of the current controls (every equality row becomes zero) and
+    // slacks reset from the distances; written as a direction (R_DZ, R_DS) = candidate - iterate
+    NMPC_PASS void rollout_project()
+    {
+        NMPC_LOCALS
+        const nmpc_opts &o = this->P.o;
+        double *zb = sm + SM_ZB, *cs = sm + SM_CS, *sn = sm + SM_SN;
+        double zt = isx ? push_in(x0bar_l + CE[l], BL[l], BU[l], o.bound_push, o.bound_frac) : (isu ? row(R_Z, 0)[l] : 0.0);
+        for (int k = 0; k <= N; k++) {
+            const bool zv = zvalid(k);
+            row(R_DZ, k)[l] = zv ? zt - row(R_Z, k)[l] : 0.0;
+            zb[l] = zv ? zt : 0.0;
+            wp::sync();
+            if (k < N && l < NR) { double s_, c_; wp::sincos_(zb[3 * l + 2], &s_, &c_); cs[l] = c_; sn[l] = s_; }
+            if (M > 0 && isq) {
+                for (int pass = (k == 0 ? 0 : 1); pass < 2; pass++) {
+                    if (pass == 1 && k == N) break;
+                    const int b = pass == 0 ? 0 : k + 1;
+                    double lo = DL[b * 32 + l], hi = DU[b * 32 + l], dv = NMPC_DUMMY_ROW_VALUE;
+                    if (pass == 1) { double dx = zb[3 * pi] - zb[3 * pj], dy = zb[3 * pi + 1] - zb[3 * pj + 1]; dv = dx * dx + dy * dy; }
+                    bool act = lo > -NMPC_INF || hi < NMPC_INF;
+                    row(R_DS, b)[l] = act ? push_in(dv, lo, hi, o.bound_push, o.bound_frac) - row(R_S, b)[l] : 0.0;
+                }
+            }
+            wp::sync();
+            if (k < N) {
+                double zn = 0.0;
+                if (isx) {
+                    double v = zb[NS + 2 * rob];
+                    zn = comp == 0 ? zt + T * v * cs[rob] : (comp == 1 ? zt + T * v * sn[rob] : zt + T * zb[NS + 2 * rob + 1]);
+                    zn = push_in(zn + CE[(k + 1) * 32 + l], BL[(k + 1) * 32 + l], BU[(k + 1) * 32 + l], o.bound_push, o.bound_frac);
+                } else if (isu && k + 1 < N) zn = row(R_Z, k + 1)[l];
+                zt = zn;
+            }
+            wp::sync();
+        }
+    }
+
     // copy the initial-residual rows into the SOC accumulators (c_soc := c, d_soc := d - s)
     NMPC_PASS void soc_begin()
     {
@@ -1041,11 +1079,17 @@ struct WarpSolver {
                 filter_add((1.0 - 1e-5) * theta, phi - 1e-8 * theta);
                 const double thR = theta;
                 bool ok = false;
+                {   // first candidate: rollout projection onto the dynamics (see oracle/nmpc_oracle.c)
+                    rollout_project();
+                    EvalOut Ep;
+                    eval_pass<false>(mu, 1.0, R_DZ, R_DS, true, false, 0.0, Ep);
+                    if (Ep.theta < thR) accept_primal(1.0, R_DZ, R_DS);
+                }
                 for (int r_it = 0; r_it < o.max_resto_iter; r_it++) {
                     EvalOut Er;
                     eval_pass<false>(mu, 0.0, 0, 0, false, false, 0.0, Er);
                     const double th = Er.theta;
-                    if (r_it > 0 && (th <= 0.9 * thR || th <= 1e-9) &&
+                    if ((th <= 0.9 * thR || th <= 1e-9) &&
                         filter_ok(th, df * Er.f - mu * Er.slog + o.kappa_d * mu * Er.sdamp)) { ok = true; break; }
                     if (!factor<2>(mu, 0.0, false)) break;
                     StepInfo sr;

@@ -13,6 +13,7 @@
 #include <float.h>
 #include <math.h>
 #include <stdlib.h>
+#include <stdio.h>
 #include <string.h>
 #ifdef _OPENMP
 #include <omp.h>
@@ -1050,13 +1051,41 @@ static int solve_one(const orc_desc *d, const orc_opts *o, const double *x0, con
              * accepted on an Armijo test of theta alone, until theta <= 0.9 theta_R and the point
              * is acceptable to the filter; exits INFEASIBLE when no progress is possible. */
             n_resto++;
+            if (getenv("ORC_DEBUG")) fprintf(stderr, "enter resto iter %d theta %.3e mu %.3e delta %.3e ls %d alpha %.3e\n", iter, theta, mu, delta, ls_count, alpha);
             filter_add(&F, (1 - 1e-5) * theta, phi - 1e-8 * theta);
             double thR = theta, zeta = sqrt(mu); int ok = 0, r_it;
+            /* first candidate: project onto the dynamics by a forward rollout of the current controls
+             * (multiple shooting: X_0 = xbar0, X_{k+1} = X_k + T f(X_k,U_k) makes every equality row zero),
+             * slacks reset from the distances; only a colliding rollout leaves infeasibility behind */
+            {
+                memcpy(V.zt, V.z, sizeof(double) * nZ);
+                for (int j = 0; j < ns; j++) V.zt[j] = push_in(p[j] + C.ceq[j], C.zl[j], C.zu[j], o->bound_push, o->bound_frac);
+                for (int k = 0; k < N; k++) {
+                    const double *zk = V.zt + k * nz; double *zn = V.zt + (k + 1) * nz; const double *ce = C.ceq + (k + 1) * ns;
+                    for (int i = 0; i < D->Nr; i++) {
+                        double th = zk[3 * i + 2], v = zk[ns + 2 * i], om = zk[ns + 2 * i + 1];
+                        zn[3 * i] = zk[3 * i] + D->T * v * cos(th) + ce[3 * i];
+                        zn[3 * i + 1] = zk[3 * i + 1] + D->T * v * sin(th) + ce[3 * i + 1];
+                        zn[3 * i + 2] = th + D->T * om + ce[3 * i + 2];
+                        for (int cc = 0; cc < 3; cc++) {
+                            int e = (k + 1) * nz + 3 * i + cc;
+                            zn[3 * i + cc] = push_in(zn[3 * i + cc], C.zl[e], C.zu[e], o->bound_push, o->bound_frac);
+                        }
+                    }
+                }
+                eval_cons(&C, V.zt, V.ct, V.dvt);
+                for (int r = 0; r < nI; r++) V.st[r] = V.act[r] ? push_in(V.dvt[r], C.dl[r], C.du[r], o->bound_push, o->bound_frac) : V.dvt[r];
+                double th_p = theta_of(&C, &V, V.ct, V.dvt, V.st);
+                if (th_p < thR) {   /* keep the projected point as the start of the Newton restoration */
+                    memcpy(V.z, V.zt, sizeof(double) * nZ);
+                    for (int r = 0; r < nI; r++) if (V.act[r]) V.s[r] = V.st[r];
+                }
+            }
             for (r_it = 0; r_it < o->max_resto_iter; r_it++) {
                 eval_cons(&C, V.z, V.c, V.dv);
                 for (int r = 0; r < nI; r++) V.dms[r] = V.act[r] ? V.dv[r] - V.s[r] : 0;
                 double th = theta_of(&C, &V, V.c, V.dv, V.s);
-                if (r_it > 0 && (th <= 0.9 * thR || th <= 1e-9) && filter_ok(&F, th, barrier_of(&C, &V, V.z, V.s, mu))) { ok = 1; break; }
+                if ((th <= 0.9 * thR || th <= 1e-9) && filter_ok(&F, th, barrier_of(&C, &V, V.z, V.s, mu))) { ok = 1; break; }
                 for (int k = 0; k <= N; k++)
                     for (int j = 0; j < nz; j++) {
                         int e = k * nz + j; double sg = 0, gg = 0;
@@ -1086,6 +1115,7 @@ static int solve_one(const orc_desc *d, const orc_opts *o, const double *x0, con
                     if (th_t <= (1 - 1e-4 * a) * th) { got = 1; break; }
                     a *= 0.5;
                 }
+                if (getenv("ORC_DEBUG")) fprintf(stderr, "resto it %d th %.3e a %.3e got %d amax %.3e\n", r_it, th, a, got, alpha_primal_max(&C, &V, V.z, V.s, V.dz, V.ds, tau));
                 if (!got) break;
                 memcpy(V.z, V.zt, sizeof(double) * nZ);
                 for (int r = 0; r < nI; r++) if (V.act[r]) V.s[r] = V.st[r];
