@@ -98,6 +98,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--per-gpu", type=int, default=PER_GPU)
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--clone", type=int, default=-1, help="diagnostic: replicate one instance B times (all warps run in lockstep)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -142,6 +143,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     B = a.per_gpu
     P = synthetic(B, 20261018 + rank)
+    if a.clone >= 0:
+        P = np.repeat(P[a.clone:a.clone + 1], B, axis=0)
     prob = pkg.Problem(NR, NH, T)
     lbx, ubx, lbg, ubg = prob.bounds(DMIN, VMAX, WMAX)
     x0 = prob.cold_start(P[:, :3 * NR])

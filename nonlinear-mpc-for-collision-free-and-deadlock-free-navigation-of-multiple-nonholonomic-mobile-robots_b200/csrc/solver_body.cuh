@@ -189,6 +189,11 @@ struct WarpSolver {
     // ---------------------------------------------------------------------------------------
     struct EvalOut { double pinf, viol, dinf, c0, cmu, ysum, zsum, theta, f, slog, sdamp; };
 
+    // Rows of one stage / inequality block, loaded one stage ahead of their use (register software pipeline:
+    // the loads of stage k+1 are in flight while stage k is processed, so HBM latency is paid once per pass).
+    struct ZRows { double z, dz, lo, hi, zl, zu, yc, ce, csoc; };
+    struct QRows { double s, ds, lo, hi, yd, vl, vu, dsoc; };
+
     template <bool FULL>
     NMPC_PASS void eval_pass(double mu, double alpha, int rdz, int rds, bool trial, bool socacc, double asoc, EvalOut &E)
     {
@@ -196,14 +201,54 @@ struct WarpSolver {
         const double kd = P.o.kappa_d;
         double pinf = 0, viol = 0, dinf = 0, c0 = 0, cmu = 0, ysum = 0, zsum = 0, th = 0, fo = 0, slog = 0, sdamp = 0;
         double *zb = sm + SM_ZB, *cs = sm + SM_CS, *sn = sm + SM_SN;
-        const int pf_a = prefetch_lane((1u << R_Z) | (FULL ? (1u << R_ZL | 1u << R_ZU | 1u << R_YC) : 0u) | (trial ? 1u << rdz : 0u) | (socacc ? (1u << R_CSOC) : 0u));
-        const int pf_b = prefetch_lane((1u << R_S) | (FULL ? (1u << R_VL | 1u << R_VU | 1u << R_YD) : 0u) | (trial ? 1u << rds : 0u) | (socacc ? (1u << R_DSOC) : 0u));
+        auto load_z = [&](int k) {
+            ZRows r;
+            k = k < N ? k : N;
+            r.z = row(R_Z, k)[l]; r.dz = trial ? row(rdz, k)[l] : 0.0;
+            r.lo = BL[k * 32 + l]; r.hi = BU[k * 32 + l]; r.ce = CE[k * 32 + l];
+            r.zl = FULL ? row(R_ZL, k)[l] : 0.0; r.zu = FULL ? row(R_ZU, k)[l] : 0.0; r.yc = FULL ? row(R_YC, k)[l] : 0.0;
+            r.csoc = socacc ? row(R_CSOC, k)[l] : 0.0;
+            return r;
+        };
+        auto load_q = [&](int b) {
+            QRows r;
+            b = b < N ? b : N;
+            r.s = row(R_S, b)[l]; r.ds = trial ? row(rds, b)[l] : 0.0;
+            r.lo = DL[b * 32 + l]; r.hi = DU[b * 32 + l];
+            r.yd = FULL ? row(R_YD, b)[l] : 0.0; r.vl = FULL ? row(R_VL, b)[l] : 0.0; r.vu = FULL ? row(R_VU, b)[l] : 0.0;
+            r.dsoc = socacc ? row(R_DSOC, b)[l] : 0.0;
+            return r;
+        };
+        // one inequality row: residual, merit and (FULL) dual / complementarity terms
+        auto ineq_row = [&](int b, const QRows &q, double dv) {
+            const bool hl = q.lo > -NMPC_INF, hu = q.hi < NMPC_INF;
+            if (!(hl || hu)) return;
+            const double s = q.s + alpha * q.ds, dms = dv - s;
+            pinf = fmax(pinf, fabs(dms)); th += fabs(dms);
+            viol = fmax(viol, fmax(q.lo - dv, dv - q.hi));
+            if (socacc) row(R_DSOC, b)[l] = asoc * q.dsoc + dms;
+            if (hl) slog += wp::log_(s - q.lo);
+            if (hu) slog += wp::log_(q.hi - s);
+            if (hl && !hu) sdamp += s - q.lo;
+            if (hu && !hl) sdamp += q.hi - s;
+            if (FULL) {
+                ysum += fabs(q.yd);
+                double t = -q.yd - q.vl + q.vu;
+                if (hl && !hu) t += kd * mu;
+                if (hu && !hl) t -= kd * mu;
+                dinf = fmax(dinf, fabs(t));
+                if (hl) { double u = (s - q.lo) * q.vl; c0 = fmax(c0, fabs(u)); cmu = fmax(cmu, fabs(u - mu)); zsum += fabs(q.vl); }
+                if (hu) { double u = (q.hi - s) * q.vu; c0 = fmax(c0, fabs(u)); cmu = fmax(cmu, fabs(u - mu)); zsum += fabs(q.vu); }
+            }
+        };
+        ZRows zc = load_z(0), zn = load_z(1);
+        QRows qn = load_q(1);
+        if (M > 0 && isq) { QRows q0 = load_q(0); ineq_row(0, q0, NMPC_DUMMY_ROW_VALUE); }   // block 0: the dummy rows
         for (int k = 0; k <= N; k++) {
-            prefetch_at(pf_a, k + 3);
-            prefetch_at(pf_b, k + 3);
+            const ZRows zf = load_z(k + 2);          // in flight during this stage
+            const QRows qf = load_q(k + 2);
             const bool zv = zvalid(k);
-            double zk = zv ? row(R_Z, k)[l] : 0.0;
-            if (trial && zv) zk += alpha * row(rdz, k)[l];
+            const double zk = zv ? zc.z + alpha * zc.dz : 0.0;
             zb[l] = zk;
             wp::sync();
             if (k < N && l < NR) { double s_, c_; wp::sincos_(zb[3 * l + 2], &s_, &c_); cs[l] = c_; sn[l] = s_; }
@@ -211,59 +256,28 @@ struct WarpSolver {
             // ---- equality rows: block 0 (k == 0) and block k+1 ----
             if (isx) {
                 if (k == 0) {
-                    double c = zk - x0bar_l - CE[l];
+                    double c = zk - x0bar_l - zc.ce;
                     pinf = fmax(pinf, fabs(c)); th += fabs(c); viol = fmax(viol, fabs(c));
-                    if (socacc) row(R_CSOC, 0)[l] = asoc * row(R_CSOC, 0)[l] + c;
+                    if (socacc) row(R_CSOC, 0)[l] = asoc * zc.csoc + c;
                 }
                 if (k < N) {
-                    double zn = row(R_Z, k + 1)[l];
-                    if (trial) zn += alpha * row(rdz, k + 1)[l];
+                    double znx = zn.z + alpha * zn.dz;
                     double v = zb[NS + 2 * rob];
                     double pred = comp == 0 ? zk + T * v * cs[rob] : (comp == 1 ? zk + T * v * sn[rob] : zk + T * zb[NS + 2 * rob + 1]);
-                    double c = zn - pred - CE[(k + 1) * 32 + l];
+                    double c = znx - pred - zn.ce;
                     pinf = fmax(pinf, fabs(c)); th += fabs(c); viol = fmax(viol, fabs(c));
-                    if (socacc) row(R_CSOC, k + 1)[l] = asoc * row(R_CSOC, k + 1)[l] + c;
+                    if (socacc) row(R_CSOC, k + 1)[l] = asoc * zn.csoc + c;
                 }
-                if (FULL) ysum += fabs(row(R_YC, k)[l]);
+                if (FULL) ysum += fabs(zc.yc);
             }
-            // ---- inequality rows: block 0 (dummy rows) and block k+1 (distances on X_k) ----
-            if (M > 0 && isq) {
-                for (int pass = (k == 0 ? 0 : 1); pass < 2; pass++) {
-                    if (pass == 1 && k == N) break;
-                    const int b = pass == 0 ? 0 : k + 1;
-                    double lo = DL[b * 32 + l], hi = DU[b * 32 + l];
-                    bool hl = lo > -NMPC_INF, hu = hi < NMPC_INF;
-                    if (!(hl || hu)) continue;
-                    double dv = NMPC_DUMMY_ROW_VALUE;
-                    if (pass == 1) {
-                        double dx = zb[3 * pi] - zb[3 * pj], dy = zb[3 * pi + 1] - zb[3 * pj + 1];
-                        dv = dx * dx + dy * dy;
-                    }
-                    double s = row(R_S, b)[l];
-                    if (trial) s += alpha * row(rds, b)[l];
-                    double dms = dv - s;
-                    pinf = fmax(pinf, fabs(dms)); th += fabs(dms);
-                    viol = fmax(viol, fmax(lo - dv, dv - hi));
-                    if (socacc) row(R_DSOC, b)[l] = asoc * row(R_DSOC, b)[l] + dms;
-                    if (hl) slog += wp::log_(s - lo);
-                    if (hu) slog += wp::log_(hi - s);
-                    if (hl && !hu) sdamp += s - lo;
-                    if (hu && !hl) sdamp += hi - s;
-                    if (FULL) {
-                        double yd = row(R_YD, b)[l], vl = row(R_VL, b)[l], vu = row(R_VU, b)[l];
-                        ysum += fabs(yd);
-                        double t = -yd - vl + vu;
-                        if (hl && !hu) t += kd * mu;
-                        if (hu && !hl) t -= kd * mu;
-                        dinf = fmax(dinf, fabs(t));
-                        if (hl) { double u = (s - lo) * vl; c0 = fmax(c0, fabs(u)); cmu = fmax(cmu, fabs(u - mu)); zsum += fabs(vl); }
-                        if (hu) { double u = (hi - s) * vu; c0 = fmax(c0, fabs(u)); cmu = fmax(cmu, fabs(u - mu)); zsum += fabs(vu); }
-                    }
-                }
+            // ---- inequality block k+1 (distances on X_k) ----
+            if (M > 0 && isq && k < N) {
+                double dx = zb[3 * pi] - zb[3 * pj], dy = zb[3 * pi + 1] - zb[3 * pj + 1];
+                ineq_row(k + 1, qn, dx * dx + dy * dy);
             }
             // ---- variable bounds, objective, stationarity of stage k ----
             if (zv) {
-                double lo = BL[k * 32 + l], hi = BU[k * 32 + l];
+                const double lo = zc.lo, hi = zc.hi;
                 bool hl = lo > -NMPC_INF, hu = hi < NMPC_INF;
                 if (hl) slog += wp::log_(zk - lo);
                 if (hu) slog += wp::log_(hi - zk);
@@ -271,19 +285,19 @@ struct WarpSolver {
                 if (hu && !hl) sdamp += hi - zk;
                 if (k < N) { double e = zk - xs_l; fo += 0.5 * qw * e * e; }
                 if (FULL) {
-                    double zl = row(R_ZL, k)[l], zu = row(R_ZU, k)[l];
+                    const double zl = zc.zl, zu = zc.zu;
                     double r = df * gradf(k, zk) - zl + zu;
                     if (hl && !hu) r += kd * mu;
                     if (hu && !hl) r -= kd * mu;
-                    if (isx) r += row(R_YC, k)[l];
+                    if (isx) r += zc.yc;
                     if (k < N) {
                         const double *ycn = row(R_YC, k + 1);
                         if (isx) {
                             if (comp == 2) {
                                 double v = zb[NS + 2 * rob];
-                                r -= ycn[l] + (-T * v * sn[rob]) * ycn[3 * rob] + (T * v * cs[rob]) * ycn[3 * rob + 1];
+                                r -= zn.yc + (-T * v * sn[rob]) * ycn[3 * rob] + (T * v * cs[rob]) * ycn[3 * rob + 1];
                             } else {
-                                r -= ycn[l];
+                                r -= zn.yc;
                                 if (M > 0) {
                                     const double *ydn = row(R_YD, k + 1);
                                     NMPC_UNROLL
@@ -304,6 +318,7 @@ struct WarpSolver {
                     if (hu) { double u = (hi - zk) * zu; c0 = fmax(c0, fabs(u)); cmu = fmax(cmu, fabs(u - mu)); zsum += fabs(zu); }
                 }
             }
+            zc = zn; zn = zf; qn = qf;
             wp::sync();
         }
         E.pinf = wp::red_max(pinf); E.theta = wp::red_sum(th); E.f = wp::red_sum(fo);
@@ -409,8 +424,8 @@ struct WarpSolver {
         NMPC_NOUNROLL
         for (int k = N - 1; k >= 0; k--) {
             wp::sync();
-            prefetch_at(pf_a, k - 1);
-            prefetch_at(pf_b, k);
+            prefetch_at(pf_a, k - 2);
+            prefetch_at(pf_b, k - 1);
             const double zk = isz ? row(R_Z, k)[l] : 0.0;
             zb[l] = zk;
             if (l < NR) {
@@ -730,27 +745,34 @@ struct WarpSolver {
             double m2 = m + az * (mu * r - m + m * r * dv_signed);
             return fmax(fmin(m2, ks * c), iks * c);
         };
-        const int pf_a = prefetch_lane((1u << R_Z) | (1u << rdz) | (1u << R_ZL) | (1u << R_ZU) | (1u << R_YC) | (1u << rytc) | (1u << R_S) | (1u << rds) | (1u << R_VL) | (1u << R_VU) | (1u << R_YD) | (1u << rytd));
+        struct AR { double z, dz, lo, hi, zl, zu, yc, ytc, s, ds, dlo, dhi, vl, vu, yd, ytd; };
+        auto load = [&](int k) {   // all rows of stage / block k, issued together one stage ahead of their use
+            AR r;
+            k = k < N ? k : N;
+            r.z = row(R_Z, k)[l]; r.dz = row(rdz, k)[l]; r.lo = BL[k * 32 + l]; r.hi = BU[k * 32 + l];
+            r.zl = row(R_ZL, k)[l]; r.zu = row(R_ZU, k)[l]; r.yc = row(R_YC, k)[l]; r.ytc = row(rytc, k)[l];
+            r.s = row(R_S, k)[l]; r.ds = row(rds, k)[l]; r.dlo = DL[k * 32 + l]; r.dhi = DU[k * 32 + l];
+            r.vl = row(R_VL, k)[l]; r.vu = row(R_VU, k)[l]; r.yd = row(R_YD, k)[l]; r.ytd = row(rytd, k)[l];
+            return r;
+        };
+        AR c = load(0);
         for (int k = 0; k <= N; k++) {
-            prefetch_at(pf_a, k + 2);
+            const AR nx = load(k + 1);
             if (zvalid(k)) {
-                double z = row(R_Z, k)[l], dz = row(rdz, k)[l], lo = BL[k * 32 + l], hi = BU[k * 32 + l];
-                double zn = z + alpha * dz;
-                if (lo > -NMPC_INF) row(R_ZL, k)[l] = mult(row(R_ZL, k)[l], z - lo, zn - lo, -dz);
-                if (hi < NMPC_INF) row(R_ZU, k)[l] = mult(row(R_ZU, k)[l], hi - z, hi - zn, dz);
+                const double zn = c.z + alpha * c.dz;
+                if (c.lo > -NMPC_INF) row(R_ZL, k)[l] = mult(c.zl, c.z - c.lo, zn - c.lo, -c.dz);
+                if (c.hi < NMPC_INF) row(R_ZU, k)[l] = mult(c.zu, c.hi - c.z, c.hi - zn, c.dz);
                 row(R_Z, k)[l] = zn;
             }
-            if (isx) { double y = row(R_YC, k)[l]; row(R_YC, k)[l] = y + alpha * (row(rytc, k)[l] - y); }
-            if (M > 0 && isq) {
-                double lo = DL[k * 32 + l], hi = DU[k * 32 + l];
-                if (lo > -NMPC_INF || hi < NMPC_INF) {
-                    double s = row(R_S, k)[l], ds = row(rds, k)[l], sn_ = s + alpha * ds;
-                    if (lo > -NMPC_INF) row(R_VL, k)[l] = mult(row(R_VL, k)[l], s - lo, sn_ - lo, -ds);
-                    if (hi < NMPC_INF) row(R_VU, k)[l] = mult(row(R_VU, k)[l], hi - s, hi - sn_, ds);
-                    row(R_S, k)[l] = sn_;
-                    double y = row(R_YD, k)[l]; row(R_YD, k)[l] = y + alpha * (row(rytd, k)[l] - y);
-                }
+            if (isx) row(R_YC, k)[l] = c.yc + alpha * (c.ytc - c.yc);
+            if (M > 0 && isq && (c.dlo > -NMPC_INF || c.dhi < NMPC_INF)) {
+                const double sn_ = c.s + alpha * c.ds;
+                if (c.dlo > -NMPC_INF) row(R_VL, k)[l] = mult(c.vl, c.s - c.dlo, sn_ - c.dlo, -c.ds);
+                if (c.dhi < NMPC_INF) row(R_VU, k)[l] = mult(c.vu, c.dhi - c.s, c.dhi - sn_, c.ds);
+                row(R_S, k)[l] = sn_;
+                row(R_YD, k)[l] = c.yd + alpha * (c.ytd - c.yd);
             }
+            c = nx;
         }
         wp::sync();
     }

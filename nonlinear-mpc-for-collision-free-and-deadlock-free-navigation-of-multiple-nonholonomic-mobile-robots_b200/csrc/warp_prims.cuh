@@ -34,12 +34,8 @@ NMPC_DEV double rcp_pos(double d)
     e = fma(-d, r, 1.0);
     return fma(r, e, r);
 }
-// prefetch by touching: a real L1-allocating load whose result is never used (nothing waits on it)
-NMPC_DEV void prefetch(const void *p)
-{
-    double sink;
-    asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(sink) : "l"(p));
-}
+// L2 prefetch of a line that a later stage of the same pass will read (the per-warp scratch does not fit L1)
+NMPC_DEV void prefetch(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 NMPC_DEV unsigned nth_set_bit(unsigned mask, int n) { return __fns(mask, 0, n + 1); }
 // one shared copy of the long math routines: keeps the passes small enough for the instruction cache
 __device__ __noinline__ void sincos_(double x, double *s, double *c) { sincos(x, s, c); }
