@@ -206,6 +206,50 @@ def main():
     d2h = 8 * h_out["x"].size + 4 * 2 * B
     e2e_val = world * B * a.e2e_steps / e2e_s.item()
 
+    # ---- second timed mode: warm start = apply u0 through the Euler plant, shift, re-solve ----
+    xo = out["x"].clone()
+    d_p2 = d_p.clone()
+    d_p2[:, :3 * NR] = prob.plant(d_p[:, :3 * NR].contiguous(), xo)
+    d_x0w = prob.shift(xo)
+    outw = {}
+    prob.solve(d_x0w, d_p2, d_lbx, d_ubx, d_lbg, d_ubg, want=("stats",), out=outw)
+    torch.cuda.synchronize()
+    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    flush.fill_(1)
+    w0.record()
+    prob.solve(d_x0w, d_p2, d_lbx, d_ubx, d_lbg, d_ubg, want=("stats",), out=outw)
+    w1.record()
+    torch.cuda.synchronize()
+    warm_ms = torch.tensor([w0.elapsed_time(w1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(warm_ms, op=dist.ReduceOp.MAX)
+    warm = {"value": world * B / (warm_ms.item() * 1e-3), "unit": "solves/s", "mean_ip_iters": float(outw["iters"].double().mean().item()),
+            "solved_frac": float((outw["status"] == 0).double().mean().item()),
+            "note": "one MPC step later: Euler plant + reference shift as initial guess (the closed-loop regime)"}
+
+    # ---- p50 single-solve latency: hexagon swap (C-6 constants, N=20), closed loop, batch = 1, host buffers ----
+    lat = None
+    if rank == 0:
+        s3 = np.sqrt(3) / 2
+        st = np.array([[s3, 0.5, -2.618], [0, 1, -1.571], [-s3, 0.5, -0.524], [-s3, -0.5, 0.524], [0, -1, 1.571], [s3, -0.5, 2.618]])
+        st = st + 0.02 * np.sin(1.0 + 2.0 * np.arange(18)).reshape(6, 3)        # de-symmetrised (see tests/test_closed_loop.py)
+        goal = -st.copy(); goal[:, 2] = st[:, 2]
+        p1 = np.concatenate([st.ravel(), goal.ravel()])[None]
+        w1_ = prob.cold_start(p1[:, :18])
+        times, o1 = [], {}
+        for step in range(60):
+            t0 = time.perf_counter()
+            prob.solve_host(w1_, p1, lbx, ubx, lbg, ubg, want=(), out=o1)
+            times.append(time.perf_counter() - t0)
+            u0 = o1["x"][0, 18 * (NH + 1):18 * (NH + 1) + 12]
+            for i in range(6):
+                th = p1[0, 3 * i + 2]
+                p1[0, 3 * i] += T * u0[2 * i] * np.cos(th); p1[0, 3 * i + 1] += T * u0[2 * i] * np.sin(th); p1[0, 3 * i + 2] += T * u0[2 * i + 1]
+            X = o1["x"][0, :18 * (NH + 1)].reshape(NH + 1, 18); U = o1["x"][0, 18 * (NH + 1):].reshape(NH, 12)
+            w1_ = np.concatenate([np.concatenate([X[1:], X[NH - 1:NH]]).ravel(), np.concatenate([U[1:], U[-1:]]).ravel()])[None]
+        lat = {"p50_ms": 1e3 * float(np.median(times[1:])), "p95_ms": 1e3 * float(np.percentile(times[1:], 95)), "first_cold_ms": 1e3 * times[0],
+               "steps": 60, "note": "batch=1 closed loop through nmpc_solve_host (H2D of p and guess, solve, D2H of x), wall clock"}
+
     if rank != 0:
         return
     value = world * B * a.steps / (tot_ms * 1e-3)
@@ -237,6 +281,7 @@ def main():
                          "sample": "%d cold-start instances of the same workload in %.1f s, restated IPOPT (oracle/), OpenMP" % (cpu_n, cpu_dt),
                          "mean_iters": cpu_it},
         "e2e": {"value": e2e_val, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "warm_start": warm, "latency": lat,
         "gpu_launches": launches, "clocks": sampler.summary(),
     }
     print(json.dumps(line))
