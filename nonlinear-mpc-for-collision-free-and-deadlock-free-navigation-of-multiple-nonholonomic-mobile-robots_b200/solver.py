@@ -244,6 +244,43 @@ class Problem:
         return o
 
 
+def closed_loop(prob, P, lbx, ubx, lbg, ubg, steps, tol=1e-1, dmin=None):
+    """Batched closed-loop driver, device resident: the reference's loop body
+    (centralized_six_robots_implementation.py:416-465 with the Euler plant of casadi_test.py:17-26) for B
+    independent instances at once.  Per step: solve -> apply u_0 through the plant -> reference shift as the next
+    guess; instances whose ||x - xs|| <= tol stop moving (the loop guard at :416).  Returns a dict of CUDA tensors:
+    traj [steps+1,B,3Nr], u [steps,B,2Nr], status [steps,B], iters [steps,B], active [steps,B], min_dist [B]."""
+    torch = prob._torch()
+    B, ns, nc, N = P.shape[0], prob.ns, prob.nc, prob.N
+    p = P.clone()
+    x0 = torch.cat([p[:, :ns].repeat(1, N + 1), torch.zeros((B, nc * N), dtype=torch.float64, device=P.device)], dim=1).contiguous()
+    traj = torch.empty((steps + 1, B, ns), dtype=torch.float64, device=P.device)
+    us = torch.zeros((steps, B, nc), dtype=torch.float64, device=P.device)
+    st = torch.zeros((steps, B), dtype=torch.int32, device=P.device)
+    its = torch.zeros((steps, B), dtype=torch.int32, device=P.device)
+    act = torch.zeros((steps, B), dtype=torch.bool, device=P.device)
+    traj[0] = p[:, :ns]
+    out = {}
+    for t in range(steps):
+        active = (p[:, :ns] - p[:, ns:]).norm(dim=1) > tol
+        act[t] = active
+        prob.solve(x0, p, lbx, ubx, lbg, ubg, want=(), out=out)
+        u0 = out["x"][:, ns * (N + 1):ns * (N + 1) + nc]
+        nxt = prob.plant(p[:, :ns].contiguous(), out["x"])
+        p[:, :ns] = torch.where(active[:, None], nxt, p[:, :ns])
+        us[t] = torch.where(active[:, None], u0, torch.zeros_like(u0))
+        st[t], its[t] = out["status"], out["iters"]
+        x0 = prob.shift(out["x"])
+        traj[t + 1] = p[:, :ns]
+    res = dict(traj=traj, u=us, status=st, iters=its, active=act)
+    if prob.Nr > 1:
+        pos = traj.reshape(steps + 1, B, prob.Nr, 3)[..., :2]
+        d = (pos[:, :, :, None, :] - pos[:, :, None, :, :]).norm(dim=-1)
+        d = d + torch.eye(prob.Nr, device=P.device, dtype=torch.float64)[None, None] * 1e9
+        res["min_dist"] = d.amin(dim=(0, 2, 3))
+    return res
+
+
 class NlpSolver:
     """What nlpsol(...) returns: callable with the reference's keyword arguments (:432)."""
 

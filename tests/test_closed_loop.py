@@ -85,3 +85,24 @@ def test_gpu_symmetric_scenarios_same_cost(pkg, sid):
     assert pkg.mpc_loop.min_pair_distance(xx, Nr) >= dmin - 1e-6
     err = np.linalg.norm(xx - np.asarray(goal, float)[None], axis=1)
     assert err[-1] < err[0]
+
+
+@pytest.mark.gpu
+def test_batched_device_closed_loop_is_collision_and_deadlock_free(pkg):
+    """SURVEY.md 8f-1 at batch scale: 512 synthetic six-robot instances, 40 MPC steps on the device."""
+    import torch
+    from oracle.nlp_numpy import synthetic_instances
+    prob = pkg.Problem(6, 20, 0.3)
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device="cuda")
+    lbx, ubx, lbg, ubg = [t(a) for a in prob.bounds(0.3, 0.22, 2.84)]
+    P = t(synthetic_instances(512))
+    res = pkg.closed_loop(prob, P, lbx, ubx, lbg, ubg, steps=40, tol=1e-1)
+    torch.cuda.synchronize()
+    st = res["status"].cpu().numpy()
+    assert (st == 0).mean() >= 0.995, np.bincount(st.ravel(), minlength=5)
+    assert res["min_dist"].min().item() >= 0.3 - 1e-6                       # zero collisions over every run
+    err = (res["traj"] - P[None, :, 18:]).norm(dim=2).cpu().numpy()
+    assert np.all(err[-1] < err[0])                                          # every instance approaches its goal ...
+    moved = np.abs(res["u"].cpu().numpy()[-5:]).max(axis=(0, 2))
+    assert np.all((moved > 1e-3) | (err[-1] <= 1e-1))                        # ... and none is deadlocked short of it
+    assert res["iters"].double()[1:].mean().item() < 0.5 * res["iters"].double()[0].mean().item()   # warm starts pay off
