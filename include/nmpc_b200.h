@@ -33,7 +33,7 @@ extern "C" {
 #endif
 
 typedef struct nmpc_desc {
-    int Nr;        /* robots          (reference variable m,  ...six...py:199)  1..6 on the CUDA path */
+    int Nr;        /* robots          (reference variable m,  ...six...py:199)  1..10 on the CUDA path */
     int N;         /* horizon         (reference variable N,  :198)                                 */
     double T;      /* sampling period (:197)                                                        */
     double Q[3];   /* diag state weights   (1, 5, 0.1)   :252-259                                   */

@@ -18,13 +18,13 @@
 NMPC_HD inline double nmpc_relax_lo(double v, double f) { return v > -NMPC_INF ? v - f * fmax(1.0, fabs(v)) : -NMPC_INF; }
 NMPC_HD inline double nmpc_relax_hi(double v, double f) { return v < NMPC_INF ? v + f * fmax(1.0, fabs(v)) : NMPC_INF; }
 
-// rows: [NMPC_BR_COUNT][S][32] of this bound set.  Returns 0 or a negative NMPC_E* code.
+// rows: [NMPC_BR_COUNT][S][lw] of this bound set (lw = 32 or 64 lanes per instance).  Returns 0 or a negative NMPC_E* code.
 NMPC_HD inline int nmpc_prep_bounds_elem(int Nr, int N, double relax, const double *lbx, const double *ubx,
-                                         const double *lbg, const double *ubg, int k, int lane, double *rows)
+                                         const double *lbg, const double *ubg, int k, int lane, int lw, double *rows)
 {
     const int ns = 3 * Nr, nc = 2 * Nr, nz = 5 * Nr, M = Nr * (Nr - 1) / 2, S = N + 1, blk = ns + M;
-    const long long rs = (long long)S * 32;
-    const int e = k * 32 + lane;
+    const long long rs = (long long)S * lw;
+    const int e = k * lw + lane;
     int err = 0;
     double lo = -NMPC_INF, hi = NMPC_INF;
     if (lane < ns) { lo = lbx[k * ns + lane]; hi = ubx[k * ns + lane]; }

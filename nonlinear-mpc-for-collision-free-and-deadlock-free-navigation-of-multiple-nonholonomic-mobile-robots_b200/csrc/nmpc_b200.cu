@@ -49,22 +49,32 @@ extern "C" void nmpc_default_opts(nmpc_opts *o)
 // ------------------------------------------------------------------------------------------------
 // the persistent solve kernel: one warp per instance, instances pulled from an atomic queue
 // ------------------------------------------------------------------------------------------------
+// threads per CTA and instances ("teams") per CTA: one warp per instance up to 6 robots (4 per CTA);
+// 7..10 robots use the two-warp team (one instance per 64-thread CTA)
+template <int NR> struct SolveCfg {
+    static constexpr int LW = WarpSolver<NR>::LW;
+    static constexpr int THREADS = LW == 32 ? SOLVE_WARPS * 32 : 64;
+    static constexpr int TEAMS = THREADS / LW;
+    static constexpr int MIN_CTAS = LW == 32 ? SOLVE_MIN_CTAS : 1;
+};
+
 template <int NR>
-__global__ void __launch_bounds__(SOLVE_WARPS * 32, SOLVE_MIN_CTAS) solve_kernel(const NmpcSolveParams P)
+__global__ void __launch_bounds__(SolveCfg<NR>::THREADS, SolveCfg<NR>::MIN_CTAS) solve_kernel(const NmpcSolveParams P)
 {
     extern __shared__ double smem[];
-    const int w = threadIdx.x >> 5;
-    double *sm = smem + (size_t)w * WarpSolver<NR>::SM_DOUBLES;
-    double *ws = P.ws + ((long long)blockIdx.x * SOLVE_WARPS + w) * P.ws_stride;
+    constexpr int LW = SolveCfg<NR>::LW;
+    const int team = threadIdx.x / LW, tl = threadIdx.x & (LW - 1);
+    double *sm = smem + (size_t)team * WarpSolver<NR>::SM_DOUBLES;
+    double *ws = P.ws + ((long long)blockIdx.x * SolveCfg<NR>::TEAMS + team) * P.ws_stride;
     WarpSolver<NR> s(P, sm, ws);
     for (;;) {
-        int inst = 0;
-        if ((threadIdx.x & 31) == 0) inst = atomicAdd(P.counter, 1);
-        inst = __shfl_sync(0xffffffffu, inst, 0);
+        WarpSolver<NR>::tsync();
+        if (tl == 0) sm[WarpSolver<NR>::SM_MISC + 1] = (double)atomicAdd(P.counter, 1);
+        WarpSolver<NR>::tsync();
+        const int inst = (int)sm[WarpSolver<NR>::SM_MISC + 1];
         if (inst >= P.B) break;
         s.setup(inst);
         s.run();
-        __syncwarp();
     }
 }
 
@@ -77,7 +87,7 @@ struct nmpc_handle {
     NmpcEvalTables tb;
     long long launches;
     size_t ws_doubles_per_slot, solve_smem, eval_smem;
-    int ctas_per_sm;
+    int ctas_per_sm, lw, teams_per_cta, threads;
     // host-pointer API staging
     char *d_buf;
     size_t d_bytes;
@@ -142,11 +152,12 @@ static void build_tables(nmpc_handle *h, std::vector<int> &tab)
 template <int NR> static size_t slot_doubles(int N) { return (size_t)WarpSolver<NR>::ws_doubles(N); }
 template <int NR> static cudaError_t config_solve(nmpc_handle *h)
 {
-    h->solve_smem = (size_t)SOLVE_WARPS * WarpSolver<NR>::SM_DOUBLES * sizeof(double);
+    h->lw = SolveCfg<NR>::LW; h->teams_per_cta = SolveCfg<NR>::TEAMS; h->threads = SolveCfg<NR>::THREADS;
+    h->solve_smem = (size_t)SolveCfg<NR>::TEAMS * WarpSolver<NR>::SM_DOUBLES * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(solve_kernel<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->solve_smem);
     if (e != cudaSuccess) return e;
     int nb = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, solve_kernel<NR>, SOLVE_WARPS * 32, h->solve_smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, solve_kernel<NR>, SolveCfg<NR>::THREADS, h->solve_smem);
     h->ctas_per_sm = nb > 0 ? nb : 1;
     return e;
 }
@@ -155,7 +166,7 @@ extern "C" int nmpc_create(const nmpc_desc *d, const nmpc_opts *o, nmpc_handle *
 {
     if (!d || !out) return fail(NMPC_EINVAL, "nmpc_create: NULL argument");
     if (d->N < 1 || !(d->T > 0)) return fail(NMPC_EINVAL, "nmpc_create: need N >= 1 and T > 0");
-    if (d->Nr < 1 || d->Nr > 6) return fail(NMPC_ENOTSUP, "nmpc_create: Nr = %d; the register-resident Riccati path covers 1..6 robots", d->Nr);
+    if (d->Nr < 1 || d->Nr > 10) return fail(NMPC_ENOTSUP, "nmpc_create: Nr = %d; the lane-per-column Riccati path covers 1..10 robots", d->Nr);
     const bool dbg = getenv("NMPC_DEBUG") != nullptr;
 #define DBG(msg) do { if (dbg) { fprintf(stderr, "[nmpc_create] %s\n", msg); fflush(stderr); } } while (0)
     DBG("enter");
@@ -192,7 +203,11 @@ extern "C" int nmpc_create(const nmpc_desc *d, const nmpc_opts *o, nmpc_handle *
         case 3: h->ws_doubles_per_slot = slot_doubles<3>(N); e = config_solve<3>(h); break;
         case 4: h->ws_doubles_per_slot = slot_doubles<4>(N); e = config_solve<4>(h); break;
         case 5: h->ws_doubles_per_slot = slot_doubles<5>(N); e = config_solve<5>(h); break;
-        default: h->ws_doubles_per_slot = slot_doubles<6>(N); e = config_solve<6>(h); break;
+        case 6: h->ws_doubles_per_slot = slot_doubles<6>(N); e = config_solve<6>(h); break;
+        case 7: h->ws_doubles_per_slot = slot_doubles<7>(N); e = config_solve<7>(h); break;
+        case 8: h->ws_doubles_per_slot = slot_doubles<8>(N); e = config_solve<8>(h); break;
+        case 9: h->ws_doubles_per_slot = slot_doubles<9>(N); e = config_solve<9>(h); break;
+        default: h->ws_doubles_per_slot = slot_doubles<10>(N); e = config_solve<10>(h); break;
     }
     if (e != cudaSuccess) { cudaFree(h->d_tables); delete h; return fail(NMPC_ECUDA, "nmpc_create: kernel configuration failed: %s", cudaGetErrorString(e)); }
     DBG("solve kernel configured");
@@ -234,13 +249,13 @@ extern "C" int nmpc_hess_pattern(const nmpc_handle *h, int32_t *colptr, int32_t 
 
 static int solve_grid(const nmpc_handle *h, int B)
 {
-    int need = (B + SOLVE_WARPS - 1) / SOLVE_WARPS, cap = h->sm_count * h->ctas_per_sm;
+    int need = (B + h->teams_per_cta - 1) / h->teams_per_cta, cap = h->sm_count * h->ctas_per_sm;
     return need < cap ? (need > 0 ? need : 1) : cap;
 }
-static size_t bound_rows_bytes(const nmpc_handle *h, int nb) { return (size_t)nb * NMPC_BR_COUNT * h->S * 32 * sizeof(double); }
+static size_t bound_rows_bytes(const nmpc_handle *h, int nb) { return (size_t)nb * NMPC_BR_COUNT * h->S * h->lw * sizeof(double); }
 static size_t ws_bytes_for(const nmpc_handle *h, int B, int nb)
 {
-    return 256 + bound_rows_bytes(h, nb) + (size_t)solve_grid(h, B) * SOLVE_WARPS * h->ws_doubles_per_slot * sizeof(double);
+    return 256 + bound_rows_bytes(h, nb) + (size_t)solve_grid(h, B) * h->teams_per_cta * h->ws_doubles_per_slot * sizeof(double);
 }
 extern "C" size_t nmpc_workspace_bytes(const nmpc_handle *h, int B) { return h && B > 0 ? ws_bytes_for(h, B, 1) : 0; }
 extern "C" size_t nmpc_workspace_bytes_batched_bounds(const nmpc_handle *h, int B) { return h && B > 0 ? ws_bytes_for(h, B, B) : 0; }
@@ -261,9 +276,9 @@ static int solve_impl(nmpc_handle *h, int B, const double *x0, const double *p, 
     double *slots = (double *)(base + 256 + bound_rows_bytes(h, nb));
     CUDA_OK(cudaMemsetAsync(base, 0, 256, st));
     {
-        long long total = (long long)nb * h->S * 32;
+        long long total = (long long)nb * h->S * h->lw;
         int blocks = (int)std::min<long long>((total + 255) / 256, 4096);
-        prep_bounds_kernel<<<blocks, 256, 0, st>>>(h->d.Nr, h->d.N, h->o.bound_relax_factor, nb, lbx, ubx, lbg, ubg, brows, berr);
+        prep_bounds_kernel<<<blocks, 256, 0, st>>>(h->d.Nr, h->d.N, h->o.bound_relax_factor, nb, h->lw, lbx, ubx, lbg, ubg, brows, berr);
         h->launches++;
     }
     NmpcSolveParams P;
@@ -271,18 +286,22 @@ static int solve_impl(nmpc_handle *h, int B, const double *x0, const double *p, 
     P.Nr = h->d.Nr; P.N = h->d.N; P.B = B; P.T = h->d.T;
     memcpy(P.Q, h->d.Q, sizeof P.Q); memcpy(P.R, h->d.R, sizeof P.R);
     P.o = h->o; P.x0 = x0; P.p = p; P.brows = brows;
-    P.bstride = bounds_batched ? (long long)NMPC_BR_COUNT * h->S * 32 : 0;
+    P.bstride = bounds_batched ? (long long)NMPC_BR_COUNT * h->S * h->lw : 0;
     P.bound_err = berr; P.x = x; P.f = f; P.g = g; P.lam_x = lam_x; P.lam_g = lam_g; P.status = status; P.iters = iters;
     P.stats = stats; P.trace = trace; P.max_trace = max_trace; P.ws = slots; P.ws_stride = (long long)h->ws_doubles_per_slot;
     P.counter = counter;
     const int grid = solve_grid(h, B);
     switch (h->d.Nr) {
-        case 1: solve_kernel<1><<<grid, SOLVE_WARPS * 32, h->solve_smem, st>>>(P); break;
-        case 2: solve_kernel<2><<<grid, SOLVE_WARPS * 32, h->solve_smem, st>>>(P); break;
-        case 3: solve_kernel<3><<<grid, SOLVE_WARPS * 32, h->solve_smem, st>>>(P); break;
-        case 4: solve_kernel<4><<<grid, SOLVE_WARPS * 32, h->solve_smem, st>>>(P); break;
-        case 5: solve_kernel<5><<<grid, SOLVE_WARPS * 32, h->solve_smem, st>>>(P); break;
-        default: solve_kernel<6><<<grid, SOLVE_WARPS * 32, h->solve_smem, st>>>(P); break;
+        case 1: solve_kernel<1><<<grid, h->threads, h->solve_smem, st>>>(P); break;
+        case 2: solve_kernel<2><<<grid, h->threads, h->solve_smem, st>>>(P); break;
+        case 3: solve_kernel<3><<<grid, h->threads, h->solve_smem, st>>>(P); break;
+        case 4: solve_kernel<4><<<grid, h->threads, h->solve_smem, st>>>(P); break;
+        case 5: solve_kernel<5><<<grid, h->threads, h->solve_smem, st>>>(P); break;
+        case 6: solve_kernel<6><<<grid, h->threads, h->solve_smem, st>>>(P); break;
+        case 7: solve_kernel<7><<<grid, h->threads, h->solve_smem, st>>>(P); break;
+        case 8: solve_kernel<8><<<grid, h->threads, h->solve_smem, st>>>(P); break;
+        case 9: solve_kernel<9><<<grid, h->threads, h->solve_smem, st>>>(P); break;
+        default: solve_kernel<10><<<grid, h->threads, h->solve_smem, st>>>(P); break;
     }
     h->launches++;
     CUDA_OK(cudaGetLastError());

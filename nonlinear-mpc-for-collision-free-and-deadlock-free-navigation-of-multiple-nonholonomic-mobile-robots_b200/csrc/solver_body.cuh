@@ -40,14 +40,14 @@
     (void)sm; (void)ws; (void)BL; (void)BU; (void)CE; (void)DL; (void)DU; (void)N; (void)S; (void)l;   \
     (void)rob; (void)comp; (void)pi; (void)pj; (void)isx; (void)isu; (void)isz; (void)isq; (void)T;    \
     (void)df; (void)xs_l; (void)qw; (void)x0bar_l;                                                     \
-    auto row = [=](int r, int k) -> double * { return ws + ((long long)r * S + k) * 32; };            \
-    auto frow = [=](int k, int i) -> double * { return ws + ((long long)R_COUNT * S + (long long)k * NS + i) * 32; }; \
+    auto row = [=](int r, int k) -> double * { return ws + ((long long)r * S + k) * LW; };            \
+    auto frow = [=](int k, int i) -> double * { return ws + ((long long)R_COUNT * S + (long long)k * NS + i) * LW; }; \
     auto zvalid = [=](int k) -> bool { return l < (k < N ? NZ : NS); };                                \
     auto gradf = [=](int k, double z) -> double { return (k < N && isz) ? qw * (z - xs_l) : 0.0; };    \
     /* prefetch up to 16 scratch rows of stage k into L1: lane pair p takes the p-th row of `mask` */ \
-    auto prefetch_lane = [=](unsigned mask) -> int { return (int)wp::nth_set_bit(mask, l >> 1); };     \
+    auto prefetch_lane = [=](unsigned mask) -> int { return (int)wp::nth_set_bit(mask, l / LPR); };     \
     auto prefetch_at = [=](int rid, int k) {                                                           \
-        if (rid >= 0 && rid < 32 && k >= 0 && k <= N) wp::prefetch(ws + ((long long)rid * S + k) * 32 + (l & 1) * 16); \
+        if (rid >= 0 && rid < 32 && k >= 0 && k <= N) wp::prefetch(ws + ((long long)rid * S + k) * LW + (l % LPR) * 16); \
     };                                                                                                 \
     auto prefetch_rows = [=](unsigned mask, int k) { prefetch_at(prefetch_lane(mask), k); };           \
     (void)prefetch_lane; (void)prefetch_at;                                                            \
@@ -59,6 +59,12 @@ template <int NR>
 struct WarpSolver {
     static constexpr int NS = 3 * NR, NC = 2 * NR, NZ = 5 * NR, M = NR * (NR - 1) / 2;
     static constexpr int LIN = NZ, NM = NZ + 1;
+    // lanes per instance ("team"): one warp up to 6 robots; two warps (one 64-thread CTA) for 7..11 robots
+    static constexpr int LW = (NZ + 1 <= 32) ? 32 : 64;
+    static constexpr int CFS = LW / 4;        // stride of the four coefficient groups inside a R_COEF row
+    static constexpr int LPR = LW / 16;       // 128-byte lines per scratch row
+    static constexpr int NRP = (NR <= 8) ? 8 : 16, MP = (M <= 16) ? 16 : 64;
+    static_assert(NZ + 1 <= 64 && M <= 64, "at most 11 robots on the lane-per-column path");
     enum Row {
         R_Z, R_ZL, R_ZU, R_DZ, R_DZ2, R_GX, R_YC, R_YTC, R_YTC2, R_RC, R_CSOC, R_COEF, R_LIN,
         R_S, R_VL, R_VU, R_YD, R_DS, R_DS2, R_YTD, R_YTD2, R_DSOC, R_GXQ, R_GYQ, R_RD, R_DQ, R_GS, R_DG,
@@ -67,14 +73,15 @@ struct WarpSolver {
     // shared-memory carve-up (doubles, per warp)
     enum {
         PLD = NS + 3,  // leading dimension of the P broadcast buffer: 3Nr columns of P, the pr column, 2 zero columns
-        SM_COL = 0, SM_PB = 64, SM_ZB = SM_PB + 18 * 21, SM_DZB = SM_ZB + 32, SM_RCB = SM_DZB + 32,
-        SM_PRB = SM_RCB + 32, SM_HB = SM_PRB + 32, SM_CS = SM_HB + 32, SM_SN = SM_CS + 8, SM_CA = SM_SN + 8, SM_CB = SM_CA + 8,
-        SM_TCS = SM_CB + 8, SM_TSN = SM_TCS + 8, SM_CRS = SM_TSN + 8, SM_THD = SM_CRS + 8,
-        SM_PXX = SM_THD + 8, SM_PYY = SM_PXX + 16, SM_PXY = SM_PYY + 16, SM_PHX = SM_PXY + 16,
-        SM_PHY = SM_PHX + 16, SM_FTH = SM_PHY + 16, SM_FPH = SM_FTH + 16, SM_MISC = SM_FPH + 16,
-        SM_DOUBLES = SM_MISC + 8
+        SM_COL = 0, SM_PB = 2 * LW, SM_ZB = SM_PB + ((NS * PLD + 1) & ~1), SM_DZB = SM_ZB + LW, SM_RCB = SM_DZB + LW,
+        SM_PRB = SM_RCB + LW, SM_HB = SM_PRB + LW, SM_CS = SM_HB + LW, SM_SN = SM_CS + NRP, SM_CA = SM_SN + NRP, SM_CB = SM_CA + NRP,
+        SM_TCS = SM_CB + NRP, SM_TSN = SM_TCS + NRP, SM_CRS = SM_TSN + NRP, SM_THD = SM_CRS + NRP,
+        SM_PXX = SM_THD + NRP, SM_PYY = SM_PXX + MP, SM_PXY = SM_PYY + MP, SM_PHX = SM_PXY + MP,
+        SM_PHY = SM_PHX + MP, SM_FTH = SM_PHY + MP, SM_FPH = SM_FTH + 16, SM_MISC = SM_FPH + 16,
+        SM_RED = SM_MISC + 8,            // cross-warp reduction scratch (two-warp teams)
+        SM_DOUBLES = SM_RED + 8
     };
-    static NMPC_HD long long ws_doubles(int N) { return ((long long)R_COUNT * (N + 1) + (long long)(N + 1) * NS) * 32; }
+    static NMPC_HD long long ws_doubles(int N) { return ((long long)R_COUNT * (N + 1) + (long long)(N + 1) * NS) * LW; }
 
     const NmpcSolveParams &P;
     double *sm, *ws;
@@ -86,8 +93,28 @@ struct WarpSolver {
 
     NMPC_DEV WarpSolver(const NmpcSolveParams &p, double *smem, double *wsp) : P(p), sm(smem), ws(wsp) {}
 
-    NMPC_DEV double *row(int r, int k) const { return ws + ((long long)r * S + k) * 32; }
-    NMPC_DEV double *frow(int k, int i) const { return ws + ((long long)R_COUNT * S + (long long)k * NS + i) * 32; }
+    // team-wide barrier and all-reduce (a team is one warp, or the two warps of a 64-thread CTA)
+    static NMPC_DEV void tsync() { if (LW == 32) wp::sync(); else wp::sync_cta(); }
+    NMPC_DEV double tred(double v, int op) const
+    {
+        double r = op == 0 ? wp::red_sum(v) : (op == 1 ? wp::red_max(v) : wp::red_min(v));
+        if (LW == 64) {
+            double *sc = wp::shared_ptr(this->sm) + SM_RED;
+            const int tl = wp::team_lane(LW);
+            tsync();
+            if ((tl & 31) == 0) sc[tl >> 5] = r;
+            tsync();
+            const double a = sc[0], b = sc[1];
+            r = op == 0 ? a + b : (op == 1 ? fmax(a, b) : fmin(a, b));
+        }
+        return r;
+    }
+    NMPC_DEV double tred_sum(double v) const { return tred(v, 0); }
+    NMPC_DEV double tred_max(double v) const { return tred(v, 1); }
+    NMPC_DEV double tred_min(double v) const { return tred(v, 2); }
+
+    NMPC_DEV double *row(int r, int k) const { return ws + ((long long)r * S + k) * LW; }
+    NMPC_DEV double *frow(int k, int i) const { return ws + ((long long)R_COUNT * S + (long long)k * NS + i) * LW; }
     NMPC_DEV bool zvalid(int k) const { return l < (k < N ? NZ : NS); }
     static NMPC_DEV int pairidx(int a, int b) { return a * (2 * NR - a - 1) / 2 + (b - a - 1); }
     static NMPC_DEV bool fin(double v) { return v > -NMPC_INF && v < NMPC_INF; }
@@ -95,7 +122,7 @@ struct WarpSolver {
     // ---------------------------------------------------------------------------------------
     NMPC_DEV void setup(int instance)
     {
-        inst = instance; N = P.N; S = N + 1; T = P.T; l = wp::lane();
+        inst = instance; N = P.N; S = N + 1; T = P.T; l = wp::team_lane(LW);
         isx = l < NS; isu = l >= NS && l < NZ; isz = l < NZ; isq = l < M;
         rob = isx ? l / 3 : (isu ? (l - NS) / 2 : 0);
         comp = isx ? l % 3 : (isu ? (l - NS) % 2 : 0);
@@ -106,17 +133,17 @@ struct WarpSolver {
                 for (int b = a + 1; b < NR; b++) { if (q == l) { pi = a; pj = b; } q++; }
         }
         const double *br = P.brows + (long long)inst * P.bstride;
-        BL = br + (long long)NMPC_BR_BL * S * 32; BU = br + (long long)NMPC_BR_BU * S * 32;
-        CE = br + (long long)NMPC_BR_CE * S * 32; DL = br + (long long)NMPC_BR_DL * S * 32;
-        DU = br + (long long)NMPC_BR_DU * S * 32;
+        BL = br + (long long)NMPC_BR_BL * S * LW; BU = br + (long long)NMPC_BR_BU * S * LW;
+        CE = br + (long long)NMPC_BR_CE * S * LW; DL = br + (long long)NMPC_BR_DL * S * LW;
+        DU = br + (long long)NMPC_BR_DU * S * LW;
         const double *pp = P.p + (long long)inst * 2 * NS;
         x0bar_l = isx ? pp[l] : 0.0;
         xs_l = isx ? pp[NS + l] : 0.0;
         qw = isx ? 2.0 * P.Q[comp] : (isu ? 2.0 * P.R[comp] : 0.0);
         df = 1.0; fn = 0;
         n_reg = n_resto = n_soc = n_fact = n_ls = 0;
-        for (int e = l; e < NS * PLD; e += 32) sm[SM_PB + e] = 0.0;
-        wp::sync();
+        for (int e = l; e < NS * PLD; e += LW) sm[SM_PB + e] = 0.0;
+        tsync();
     }
 
     NMPC_DEV double gradf(int k, double z) const { return (k < N && isz) ? qw * (z - xs_l) : 0.0; }
@@ -145,11 +172,11 @@ struct WarpSolver {
             gmax = fmax(gmax, fabs(gradf(k, z)));
             row(R_Z, k)[l] = z;
         }
-        gmax = wp::red_max(gmax);
+        gmax = tred_max(gmax);
         this->df = gmax > o.nlp_scaling_max_gradient ? fmax(o.nlp_scaling_max_gradient / gmax, 1e-8) : 1.0;
         double cnt_z = 0.0;
         for (int k = 0; k <= N; k++) {
-            double lo = BL[k * 32 + l], hi = BU[k * 32 + l];
+            double lo = BL[k * LW + l], hi = BU[k * LW + l];
             double z = push_in(row(R_Z, k)[l], lo, hi, o.bound_push, o.bound_frac);
             row(R_Z, k)[l] = z;
             bool hl = lo > -NMPC_INF, hu = hi < NMPC_INF;
@@ -159,12 +186,12 @@ struct WarpSolver {
             row(R_YC, k)[l] = 0.0; row(R_YD, k)[l] = 0.0;
             row(R_CSOC, k)[l] = 0.0; row(R_DSOC, k)[l] = 0.0;
         }
-        wp::sync();
+        tsync();
         double cnt_y = isx ? (double)S : 0.0;
         for (int b = 0; b <= N; b++) {
             double s = 0.0, vl = 0.0, vu = 0.0;
             if (isq) {
-                double lo = DL[b * 32 + l], hi = DU[b * 32 + l];
+                double lo = DL[b * LW + l], hi = DU[b * LW + l];
                 bool hl = lo > -NMPC_INF, hu = hi < NMPC_INF;
                 double dv = NMPC_DUMMY_ROW_VALUE;
                 if (b > 0) {
@@ -179,9 +206,9 @@ struct WarpSolver {
             }
             row(R_S, b)[l] = s; row(R_VL, b)[l] = vl; row(R_VU, b)[l] = vu;
         }
-        nzb_cnt = wp::red_sum(cnt_z);
-        ny_nzb = wp::red_sum(cnt_y) + nzb_cnt;
-        wp::sync();
+        nzb_cnt = tred_sum(cnt_z);
+        ny_nzb = tred_sum(cnt_y) + nzb_cnt;
+        tsync();
     }
 
     // ---------------------------------------------------------------------------------------
@@ -205,7 +232,7 @@ struct WarpSolver {
             ZRows r;
             k = k < N ? k : N;
             r.z = row(R_Z, k)[l]; r.dz = trial ? row(rdz, k)[l] : 0.0;
-            r.lo = BL[k * 32 + l]; r.hi = BU[k * 32 + l]; r.ce = CE[k * 32 + l];
+            r.lo = BL[k * LW + l]; r.hi = BU[k * LW + l]; r.ce = CE[k * LW + l];
             r.zl = FULL ? row(R_ZL, k)[l] : 0.0; r.zu = FULL ? row(R_ZU, k)[l] : 0.0; r.yc = FULL ? row(R_YC, k)[l] : 0.0;
             r.csoc = socacc ? row(R_CSOC, k)[l] : 0.0;
             return r;
@@ -214,7 +241,7 @@ struct WarpSolver {
             QRows r;
             b = b < N ? b : N;
             r.s = row(R_S, b)[l]; r.ds = trial ? row(rds, b)[l] : 0.0;
-            r.lo = DL[b * 32 + l]; r.hi = DU[b * 32 + l];
+            r.lo = DL[b * LW + l]; r.hi = DU[b * LW + l];
             r.yd = FULL ? row(R_YD, b)[l] : 0.0; r.vl = FULL ? row(R_VL, b)[l] : 0.0; r.vu = FULL ? row(R_VU, b)[l] : 0.0;
             r.dsoc = socacc ? row(R_DSOC, b)[l] : 0.0;
             return r;
@@ -250,9 +277,9 @@ struct WarpSolver {
             const bool zv = zvalid(k);
             const double zk = zv ? zc.z + alpha * zc.dz : 0.0;
             zb[l] = zk;
-            wp::sync();
+            tsync();
             if (k < N && l < NR) { double s_, c_; wp::sincos_(zb[3 * l + 2], &s_, &c_); cs[l] = c_; sn[l] = s_; }
-            wp::sync();
+            tsync();
             // ---- equality rows: block 0 (k == 0) and block k+1 ----
             if (isx) {
                 if (k == 0) {
@@ -319,13 +346,13 @@ struct WarpSolver {
                 }
             }
             zc = zn; zn = zf; qn = qf;
-            wp::sync();
+            tsync();
         }
-        E.pinf = wp::red_max(pinf); E.theta = wp::red_sum(th); E.f = wp::red_sum(fo);
-        E.slog = wp::red_sum(slog); E.sdamp = wp::red_sum(sdamp); E.viol = wp::red_max(viol);
+        E.pinf = tred_max(pinf); E.theta = tred_sum(th); E.f = tred_sum(fo);
+        E.slog = tred_sum(slog); E.sdamp = tred_sum(sdamp); E.viol = tred_max(viol);
         if (FULL) {
-            E.dinf = wp::red_max(dinf); E.c0 = wp::red_max(c0); E.cmu = wp::red_max(cmu);
-            E.ysum = wp::red_sum(ysum); E.zsum = wp::red_sum(zsum);
+            E.dinf = tred_max(dinf); E.c0 = tred_max(c0); E.cmu = tred_max(cmu);
+            E.ysum = tred_sum(ysum); E.zsum = tred_sum(zsum);
         }
     }
 
@@ -355,7 +382,7 @@ struct WarpSolver {
     {
         pxx = pyy = pxy = phx = phy = 0.0;
         double gxq = 0, gyq = 0, rd = 0, Dq = 0, gs = 0;
-        double lo = DL[b * 32 + l], hi = DU[b * 32 + l];
+        double lo = DL[b * LW + l], hi = DU[b * LW + l];
         if (lo > -NMPC_INF || hi < NMPC_INF) {
             double dv = NMPC_DUMMY_ROW_VALUE;
             if (b > 0) {
@@ -393,7 +420,7 @@ struct WarpSolver {
     {
         NMPC_LOCALS
         const double zeta = MODE == 2 ? sqrt(mu) : 0.0, kd = this->P.o.kappa_d;
-        const bool isL = (l == 31);
+        const bool isL = (l == LW - 1);
         double X[NS], U[NC];
         double plin = 0.0, dgx = 0.0;
         double *col = sm + SM_COL, *pb = sm + SM_PB, *zb = sm + SM_ZB, *rcb = sm + SM_RCB, *prb = sm + SM_PRB, *hb = sm + SM_HB;
@@ -403,13 +430,13 @@ struct WarpSolver {
         n_fact++;
         const int pf_a = prefetch_lane((1u << R_Z | 1u << R_ZL | 1u << R_ZU));
         const int pf_b = prefetch_lane((1u << R_YC | 1u << R_S | 1u << R_VL | 1u << R_VU | 1u << R_YD) | (soc ? (1u << R_CSOC | 1u << R_DSOC) : 0u));
-        wp::sync();
+        tsync();
         // terminal stage: X_N carries no cost and no distance rows, only its box
         {
             double sig = 0.0, gx = 0.0;
-            if (isx) sig_g<MODE>(kd, row(R_Z, N)[l], BL[N * 32 + l], BU[N * 32 + l], row(R_ZL, N)[l], row(R_ZU, N)[l], mu, 0.0, sig, gx);
+            if (isx) sig_g<MODE>(kd, row(R_Z, N)[l], BL[N * LW + l], BU[N * LW + l], row(R_ZL, N)[l], row(R_ZU, N)[l], mu, 0.0, sig, gx);
             hb[l] = isx ? gx : 0.0;
-            wp::sync();
+            tsync();
             NMPC_UNROLL
             for (int i = 0; i < NS; i++) X[i] = isL ? hb[i] : 0.0;
             dgx = isx ? sig + delta + zeta : 0.0;   // P_N = X + diag(dgx): the own-row diagonal is carried separately
@@ -423,7 +450,7 @@ struct WarpSolver {
         }
         NMPC_NOUNROLL
         for (int k = N - 1; k >= 0; k--) {
-            wp::sync();
+            tsync();
             prefetch_at(pf_a, k - 2);
             prefetch_at(pf_b, k - 1);
             const double zk = isz ? row(R_Z, k)[l] : 0.0;
@@ -436,7 +463,7 @@ struct WarpSolver {
                 double a_ = -T * v * s_, b_ = T * v * c_, tc = T * c_, ts = T * s_;
                 ca[l] = a_; cb[l] = b_; tcs[l] = tc; tsn[l] = ts;
                 double *cf = row(R_COEF, k);
-                cf[l] = a_; cf[8 + l] = b_; cf[16 + l] = tc; cf[24 + l] = ts;
+                cf[l] = a_; cf[CFS + l] = b_; cf[2 * CFS + l] = tc; cf[3 * CFS + l] = ts;
                 if (MODE == 0) {
                     const double *yc = row(R_YC, k + 1);
                     double lx = yc[3 * l], ly = yc[3 * l + 1];
@@ -448,7 +475,7 @@ struct WarpSolver {
                 for (int i = 0; i < NS; i++) pb[i * PLD + l] = X[i];
                 pb[l * PLD + l] += dgx;   // same lane wrote this element just above
             }
-            wp::sync();
+            tsync();
             // equality residual of block k+1 and the condensed inequality block k+1
             if (isx) {
                 double rc = 0.0;
@@ -457,7 +484,7 @@ struct WarpSolver {
                     else {
                         double v = zb[NS + 2 * rob];
                         double pred = comp == 0 ? zk + T * v * cs[rob] : (comp == 1 ? zk + T * v * sn[rob] : zk + T * zb[NS + 2 * rob + 1]);
-                        rc = row(R_Z, k + 1)[l] - pred - CE[(k + 1) * 32 + l];
+                        rc = row(R_Z, k + 1)[l] - pred - CE[(k + 1) * LW + l];
                     }
                 }
                 rcb[l] = rc; row(R_RC, k + 1)[l] = rc;
@@ -467,7 +494,7 @@ struct WarpSolver {
                 ineq_block<MODE>(row, DL, DU, l, pi, pj, kd, k + 1, mu, delta, soc, zb, a0, a1, a2, a3, a4);
                 pxx[l] = a0; pyy[l] = a1; pxy[l] = a2; phx[l] = a3; phy[l] = a4;
             }
-            wp::sync();
+            tsync();
             // pr = p_{k+1} + P_{k+1} r (r = -rc), published as one more column of pb for lane 31
             if (isx) {
                 double pr = plin;
@@ -481,7 +508,7 @@ struct WarpSolver {
             // stage gradient h_l (variable l) and diagonal curvature
             double sig = 0.0, gx = 0.0, dg = 0.0;
             if (isz) {
-                sig_g<MODE>(kd, zk, BL[k * 32 + l], BU[k * 32 + l], row(R_ZL, k)[l], row(R_ZU, k)[l], mu, df * gradf(k, zk), sig, gx);
+                sig_g<MODE>(kd, zk, BL[k * LW + l], BU[k * LW + l], row(R_ZL, k)[l], row(R_ZU, k)[l], mu, df * gradf(k, zk), sig, gx);
                 dg = sig + delta + zeta;
                 if (MODE == 0) { dg += df * qw; if (isx && comp == 2) dg += thd[rob]; }
             }
@@ -493,7 +520,7 @@ struct WarpSolver {
             if (isx) { if (comp == 0) al = 1.0; else if (comp == 1) be = 1.0; else { al = ca[rob]; be = cb[rob]; ga = 1.0; } }
             else if (isu) { if (comp == 0) { al = tcs[rob]; be = tsn[rob]; } else ga = T; }
             else if (isL) { al = 1.0; base = NS; }
-            wp::sync();
+            tsync();
             {
                 double W[NS];
                 NMPC_UNROLL
@@ -532,7 +559,7 @@ struct WarpSolver {
                 hl_ += glin;
             }
             hb[l] = isz ? hl_ : 0.0;
-            wp::sync();
+            tsync();
             // + diagonal (own row); lane 31 adds the gradient vector h; control lanes start their state rows at 0
             NMPC_UNROLL
             for (int u = 0; u < NC; u++) U[u] += (NS + u == l) ? dg : 0.0;
@@ -558,11 +585,11 @@ struct WarpSolver {
             const int ucol = l - NS;   // control column of this lane (if any)
             NMPC_NOUNROLL
             for (int j = 0; j < NC; j++) {
-                double *buf = col + 32 * (j & 1);
+                double *buf = col + LW * (j & 1);
                 int slot = l;
                 if (isu) { slot = ucol - j; slot += slot < 0 ? NC : 0; slot += NS; }
                 if (isz) buf[slot] = U[0];
-                wp::sync();
+                tsync();
                 const double d = buf[NS];
                 if (!(d > 0.0) || !(d < NMPC_INF)) return false;
                 const double inv = wp::rcp_pos(d);
@@ -598,14 +625,14 @@ struct WarpSolver {
                 U[NC - 1] = t;
             }
             // publish p_k / feed-forward (lane 31's column) and store the factors
-            wp::sync();
+            tsync();
             if (isL) {
                 NMPC_UNROLL
                 for (int i = 0; i < NS; i++) prb[i] = X[i];
                 NMPC_UNROLL
                 for (int u = 0; u < NC; u++) prb[NS + u] = U[u];
             }
-            wp::sync();
+            tsync();
             if (isz) {
                 const double v = prb[l];
                 plin = v;
@@ -614,10 +641,10 @@ struct WarpSolver {
                 for (int i = 0; i < NS; i++) frow(k, i)[l] = X[i];
             }
         }
-        wp::sync();
+        tsync();
         if (isx) row(R_RC, 0)[l] = MODE == 1 ? 0.0 : (soc ? row(R_CSOC, 0)[l] : row(R_Z, 0)[l] - x0bar_l - CE[l]);
         if (M > 0 && isq) { double a0, a1, a2, a3, a4; ineq_block<MODE>(row, DL, DU, l, pi, pj, kd, 0, mu, delta, soc, zb, a0, a1, a2, a3, a4); }
-        wp::sync();
+        tsync();
         return true;
     }
 
@@ -665,15 +692,15 @@ struct WarpSolver {
             }
         }
         for (int k = 0; k <= N; k++) {
-            wp::sync();
+            tsync();
             if (k + 2 <= N) {   // factor rows and vectors two stages ahead
-                wp::prefetch(frow(k + 2, l >> 1) + (l & 1) * 16);
-                if (NS > 16 && l < 2 * (NS - 16)) wp::prefetch(frow(k + 2, 16 + (l >> 1)) + (l & 1) * 16);
+                if (l / LPR < NS) wp::prefetch(frow(k + 2, l / LPR) + (l % LPR) * 16);
+                if (NS > 16 && l / LPR < NS - 16) wp::prefetch(frow(k + 2, 16 + l / LPR) + (l % LPR) * 16);
                 prefetch_at(pf_a, k + 2);
                 prefetch_at(pf_b, k + 3);
             }
             if (isx) dzb[l] = dx;
-            wp::sync();
+            tsync();
             double acc = 0.0;
             if (isz) {
                 double a0 = row(R_LIN, k)[l], a1 = isx ? row(R_DG, k)[l] * dzb[l] : 0.0, a2 = 0.0;
@@ -699,28 +726,28 @@ struct WarpSolver {
             row(rdz, k)[l] = dzl;
             if (zvalid(k)) {
                 double z = row(R_Z, k)[l];
-                slack_step_terms(z, dzl, BL[k * 32 + l], BU[k * 32 + l], row(R_ZL, k)[l], row(R_ZU, k)[l], mu, ap, az);
+                slack_step_terms(z, dzl, BL[k * LW + l], BU[k * LW + l], row(R_ZL, k)[l], row(R_ZU, k)[l], mu, ap, az);
                 gbd += row(R_GX, k)[l] * dzl; tiny = fmax(tiny, fabs(dzl) / (1.0 + fabs(z)));
             }
             if (k < N) {
-                wp::sync();
+                tsync();
                 double dn = 0.0;
                 if (isx) {
                     const double *cf = row(R_COEF, k);
-                    double cA = comp == 0 ? cf[rob] : (comp == 1 ? cf[8 + rob] : 0.0);
-                    double cB = comp == 0 ? cf[16 + rob] : (comp == 1 ? cf[24 + rob] : T);
+                    double cA = comp == 0 ? cf[rob] : (comp == 1 ? cf[CFS + rob] : 0.0);
+                    double cB = comp == 0 ? cf[2 * CFS + rob] : (comp == 1 ? cf[3 * CFS + rob] : T);
                     dn = dzb[l] + cA * dzb[3 * rob + 2] + cB * dzb[NS + 2 * rob + (comp == 2 ? 1 : 0)] - row(R_RC, k + 1)[l];
                 }
                 if (M > 0 && isq) {
                     const int b = k + 1;
-                    bool act = DL[b * 32 + l] > -NMPC_INF || DU[b * 32 + l] < NMPC_INF;
+                    bool act = DL[b * LW + l] > -NMPC_INF || DU[b * LW + l] < NMPC_INF;
                     double ds = 0.0, ytd = 0.0;
                     if (act) {
                         double gs = row(R_GS, b)[l];
                         ds = row(R_GXQ, b)[l] * (dzb[3 * pi] - dzb[3 * pj]) + row(R_GYQ, b)[l] * (dzb[3 * pi + 1] - dzb[3 * pj + 1]) + row(R_RD, b)[l];
                         ytd = row(R_DQ, b)[l] * ds + gs;
                         double s = row(R_S, b)[l];
-                        slack_step_terms(s, ds, DL[b * 32 + l], DU[b * 32 + l], row(R_VL, b)[l], row(R_VU, b)[l], mu, ap, az);
+                        slack_step_terms(s, ds, DL[b * LW + l], DU[b * LW + l], row(R_VL, b)[l], row(R_VU, b)[l], mu, ap, az);
                         gbd += gs * ds; tiny = fmax(tiny, fabs(ds) / (1.0 + fabs(s)));
                     }
                     row(rds, b)[l] = ds; row(rytd, b)[l] = ytd;
@@ -728,10 +755,10 @@ struct WarpSolver {
                 dx = dn;
             }
         }
-        ap = wp::red_max(ap); az = wp::red_max(az);
+        ap = tred_max(ap); az = tred_max(az);
         si.ap = ap > tau ? tau / ap : 1.0; si.az = az > tau ? tau / az : 1.0;
-        si.gbd = wp::red_sum(gbd); si.tiny = wp::red_max(tiny);
-        wp::sync();
+        si.gbd = tred_sum(gbd); si.tiny = tred_max(tiny);
+        tsync();
     }
 
     // ---------------------------------------------------------------------------------------
@@ -749,9 +776,9 @@ struct WarpSolver {
         auto load = [&](int k) {   // all rows of stage / block k, issued together one stage ahead of their use
             AR r;
             k = k < N ? k : N;
-            r.z = row(R_Z, k)[l]; r.dz = row(rdz, k)[l]; r.lo = BL[k * 32 + l]; r.hi = BU[k * 32 + l];
+            r.z = row(R_Z, k)[l]; r.dz = row(rdz, k)[l]; r.lo = BL[k * LW + l]; r.hi = BU[k * LW + l];
             r.zl = row(R_ZL, k)[l]; r.zu = row(R_ZU, k)[l]; r.yc = row(R_YC, k)[l]; r.ytc = row(rytc, k)[l];
-            r.s = row(R_S, k)[l]; r.ds = row(rds, k)[l]; r.dlo = DL[k * 32 + l]; r.dhi = DU[k * 32 + l];
+            r.s = row(R_S, k)[l]; r.ds = row(rds, k)[l]; r.dlo = DL[k * LW + l]; r.dhi = DU[k * LW + l];
             r.vl = row(R_VL, k)[l]; r.vu = row(R_VU, k)[l]; r.yd = row(R_YD, k)[l]; r.ytd = row(rytd, k)[l];
             return r;
         };
@@ -774,7 +801,7 @@ struct WarpSolver {
             }
             c = nx;
         }
-        wp::sync();
+        tsync();
     }
 
     NMPC_PASS void accept_primal(double alpha, int rdz, int rds)
@@ -782,9 +809,9 @@ struct WarpSolver {
         NMPC_LOCALS
         for (int k = 0; k <= N; k++) {
             if (zvalid(k)) row(R_Z, k)[l] += alpha * row(rdz, k)[l];
-            if (M > 0 && isq && (DL[k * 32 + l] > -NMPC_INF || DU[k * 32 + l] < NMPC_INF)) row(R_S, k)[l] += alpha * row(rds, k)[l];
+            if (M > 0 && isq && (DL[k * LW + l] > -NMPC_INF || DU[k * LW + l] < NMPC_INF)) row(R_S, k)[l] += alpha * row(rds, k)[l];
         }
-        wp::sync();
+        tsync();
     }
 
     // after the restoration fallback: equality multipliers reset, bound multipliers clipped
@@ -794,18 +821,18 @@ struct WarpSolver {
         const double ks = P.o.kappa_sigma;
         for (int k = 0; k <= N; k++) {
             if (zvalid(k)) {
-                double z = row(R_Z, k)[l], lo = BL[k * 32 + l], hi = BU[k * 32 + l];
+                double z = row(R_Z, k)[l], lo = BL[k * LW + l], hi = BU[k * LW + l];
                 if (lo > -NMPC_INF) { double s2 = z - lo; row(R_ZL, k)[l] = fmax(fmin(row(R_ZL, k)[l], ks * mu / s2), mu / (ks * s2)); }
                 if (hi < NMPC_INF) { double s2 = hi - z; row(R_ZU, k)[l] = fmax(fmin(row(R_ZU, k)[l], ks * mu / s2), mu / (ks * s2)); }
             }
             row(R_YC, k)[l] = 0.0; row(R_YD, k)[l] = 0.0;
             if (M > 0 && isq) {
-                double s = row(R_S, k)[l], lo = DL[k * 32 + l], hi = DU[k * 32 + l];
+                double s = row(R_S, k)[l], lo = DL[k * LW + l], hi = DU[k * LW + l];
                 if (lo > -NMPC_INF) { double s2 = s - lo; row(R_VL, k)[l] = fmax(fmin(row(R_VL, k)[l], ks * mu / s2), mu / (ks * s2)); }
                 if (hi < NMPC_INF) { double s2 = hi - s; row(R_VU, k)[l] = fmax(fmin(row(R_VU, k)[l], ks * mu / s2), mu / (ks * s2)); }
             }
         }
-        wp::sync();
+        tsync();
     }
 
     // restoration candidate: forward rollout of the current controls (every equality row becomes zero) and
@@ -820,29 +847,29 @@ struct WarpSolver {
             const bool zv = zvalid(k);
             row(R_DZ, k)[l] = zv ? zt - row(R_Z, k)[l] : 0.0;
             zb[l] = zv ? zt : 0.0;
-            wp::sync();
+            tsync();
             if (k < N && l < NR) { double s_, c_; wp::sincos_(zb[3 * l + 2], &s_, &c_); cs[l] = c_; sn[l] = s_; }
             if (M > 0 && isq) {
                 for (int pass = (k == 0 ? 0 : 1); pass < 2; pass++) {
                     if (pass == 1 && k == N) break;
                     const int b = pass == 0 ? 0 : k + 1;
-                    double lo = DL[b * 32 + l], hi = DU[b * 32 + l], dv = NMPC_DUMMY_ROW_VALUE;
+                    double lo = DL[b * LW + l], hi = DU[b * LW + l], dv = NMPC_DUMMY_ROW_VALUE;
                     if (pass == 1) { double dx = zb[3 * pi] - zb[3 * pj], dy = zb[3 * pi + 1] - zb[3 * pj + 1]; dv = dx * dx + dy * dy; }
                     bool act = lo > -NMPC_INF || hi < NMPC_INF;
                     row(R_DS, b)[l] = act ? push_in(dv, lo, hi, o.bound_push, o.bound_frac) - row(R_S, b)[l] : 0.0;
                 }
             }
-            wp::sync();
+            tsync();
             if (k < N) {
                 double zn = 0.0;
                 if (isx) {
                     double v = zb[NS + 2 * rob];
                     zn = comp == 0 ? zt + T * v * cs[rob] : (comp == 1 ? zt + T * v * sn[rob] : zt + T * zb[NS + 2 * rob + 1]);
-                    zn = push_in(zn + CE[(k + 1) * 32 + l], BL[(k + 1) * 32 + l], BU[(k + 1) * 32 + l], o.bound_push, o.bound_frac);
+                    zn = push_in(zn + CE[(k + 1) * LW + l], BL[(k + 1) * LW + l], BU[(k + 1) * LW + l], o.bound_push, o.bound_frac);
                 } else if (isu && k + 1 < N) zn = row(R_Z, k + 1)[l];
                 zt = zn;
             }
-            wp::sync();
+            tsync();
         }
     }
 
@@ -854,7 +881,7 @@ struct WarpSolver {
             row(R_CSOC, k)[l] = isx ? row(R_RC, k)[l] : 0.0;
             row(R_DSOC, k)[l] = (M > 0 && isq) ? row(R_RD, k)[l] : 0.0;
         }
-        wp::sync();
+        tsync();
     }
 
     // ---------------------------------------------------------------------------------------
@@ -871,7 +898,7 @@ struct WarpSolver {
     {
         NMPC_LOCALS
         double *fth = sm + SM_FTH, *fph = sm + SM_FPH, *misc = sm + SM_MISC;
-        wp::sync();
+        tsync();
         if (l == 0) {
             int m = 0;
             for (int i = 0; i < fn; i++)
@@ -883,7 +910,7 @@ struct WarpSolver {
             fth[m] = th; fph[m] = ph; m++;
             misc[0] = (double)m;
         }
-        wp::sync();
+        tsync();
         fn = (int)misc[0];
     }
     static NMPC_DEV bool cmp_le(double lhs, double rhs, double bas) { return lhs - rhs <= 10.0 * 2.220446049250313e-16 * fabs(bas); }
@@ -902,7 +929,7 @@ struct WarpSolver {
         double *zb = sm + SM_ZB, *cs = sm + SM_CS, *sn = sm + SM_SN;
         double fo = 0.0;
         for (int k = 0; k <= N; k++) {
-            wp::sync();
+            tsync();
             const bool zv = zvalid(k);
             double zk = zv ? row(R_Z, k)[l] : 0.0;
             zb[l] = zk;
@@ -912,9 +939,9 @@ struct WarpSolver {
                 if (lx) lx[idx] = (row(R_ZU, k)[l] - row(R_ZL, k)[l]) / df;
                 if (k < N) { double e = zk - xs_l; fo += 0.5 * qw * e * e; }
             }
-            wp::sync();
+            tsync();
             if (k < N && l < NR) { double s_, c_; wp::sincos_(zb[3 * l + 2], &s_, &c_); cs[l] = c_; sn[l] = s_; }
-            wp::sync();
+            tsync();
             if (isx) {
                 if (k == 0) {
                     if (g) g[l] = zk - x0bar_l;
@@ -939,7 +966,7 @@ struct WarpSolver {
                 }
             }
         }
-        fo = wp::red_sum(fo);
+        fo = tred_sum(fo);
         if (l == 0) {
             if (P.f) P.f[inst] = fo;
             if (P.status) P.status[inst] = st;
@@ -951,7 +978,7 @@ struct WarpSolver {
                 sp[NMPC_ST_N_FACTOR] = n_fact; sp[NMPC_ST_N_LS] = n_ls;
             }
         }
-        wp::sync();
+        tsync();
     }
 
     // trial-point acceptance test shared by the line search and the second-order correction
@@ -983,11 +1010,11 @@ struct WarpSolver {
             if (ok) forward(0.0, 0.99, R_DZ, R_DS, R_YC, R_YD, si);
             double ymax = 0.0;
             for (int k = 0; k <= N; k++) ymax = fmax(ymax, fmax(isx ? fabs(row(R_YC, k)[l]) : 0.0, (M > 0 && isq) ? fabs(row(R_YD, k)[l]) : 0.0));
-            ymax = wp::red_max(ymax);
+            ymax = tred_max(ymax);
             if (!ok || !(ymax <= o.constr_mult_init_max)) {
                 for (int k = 0; k <= N; k++) { row(R_YC, k)[l] = 0.0; row(R_YD, k)[l] = 0.0; }
             }
-            wp::sync();
+            tsync();
         }
         double mu = o.mu_init, tau = fmax(o.tau_min, 1.0 - mu);
         double theta_max = -1.0, theta_min = -1.0, delta_last = 0.0, f_prev = 0.0;

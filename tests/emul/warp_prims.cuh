@@ -15,19 +15,21 @@
 
 namespace wp {
 struct Emu {
-    ucontext_t main, ctx[32];
+    ucontext_t main, ctx[64];
     int cur;
-    bool done[32];
-    double xd[32];
-    int xi[32];
-    bool xb[32];
+    bool done[64];
+    double xd[64];
+    int xi[64];
+    bool xb[64];
 };
 extern thread_local Emu *emu;
-inline int lane() { return emu->cur; }
+inline int lane() { return emu->cur & 31; }
+inline int team_lane(int lw) { return emu->cur & (lw - 1); }
 inline void sync() { swapcontext(&emu->ctx[emu->cur], &emu->main); }
-inline double shfl(double v, int src) { emu->xd[emu->cur] = v; sync(); double r = emu->xd[src & 31]; sync(); return r; }
-inline double shfl_xor(double v, int m) { return shfl(v, emu->cur ^ m); }
-inline int shfl_i(int v, int src) { emu->xi[emu->cur] = v; sync(); int r = emu->xi[src & 31]; sync(); return r; }
+inline void sync_cta() { sync(); }
+inline double shfl(double v, int src) { emu->xd[emu->cur] = v; sync(); double r = emu->xd[(emu->cur & 32) | (src & 31)]; sync(); return r; }
+inline double shfl_xor(double v, int m) { return shfl(v, (emu->cur & 31) ^ m); }
+inline int shfl_i(int v, int src) { emu->xi[emu->cur] = v; sync(); int r = emu->xi[(emu->cur & 32) | (src & 31)]; sync(); return r; }
 inline bool any(bool p) { emu->xb[emu->cur] = p; sync(); bool r = false; for (int i = 0; i < 32; i++) r = r || emu->xb[i]; sync(); return r; }
 inline bool all(bool p) { emu->xb[emu->cur] = p; sync(); bool r = true; for (int i = 0; i < 32; i++) r = r && emu->xb[i]; sync(); return r; }
 inline int atomic_next(int *c) { return (*c)++; }

@@ -25,7 +25,7 @@ def _t(torch, a):
     return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device="cuda")
 
 
-@pytest.mark.parametrize("Nr,N,T", [(1, 25, 0.25), (2, 7, 0.1), (3, 5, 0.05), (6, 20, 0.3), (6, 35, 0.3)])
+@pytest.mark.parametrize("Nr,N,T", [(1, 25, 0.25), (2, 7, 0.1), (3, 5, 0.05), (6, 20, 0.3), (6, 35, 0.3), (8, 5, 0.02), (10, 20, 0.1)])
 def test_eval_kernel_matches_oracle(pkg, torch_cuda, Nr, N, T):
     torch = torch_cuda
     rng = np.random.default_rng(Nr + N)
@@ -177,7 +177,7 @@ def test_bound_errors_and_unsupported(pkg, torch_cuda):
     with pytest.raises(pkg.NmpcError):
         prob.solve_host(x0, P, lbx, ubx, lbg, bad)
     with pytest.raises(pkg.NmpcError):
-        pkg.Problem(7, 5, 0.1)
+        pkg.Problem(11, 5, 0.1)
 
 
 def test_infeasible_instance_reports_status_not_hang(pkg, torch_cuda):
@@ -191,3 +191,27 @@ def test_infeasible_instance_reports_status_not_hang(pkg, torch_cuda):
     ref = orc.solve(x0[0], P[0], lbx, ubx, lbg, ubg)
     assert out["status"][0] in (2, 3, 4) and out["status"][0] == ref["status"]
     assert np.all(np.isfinite(out["x"]))
+
+
+def _ring(Nr):
+    a = np.arange(Nr) * 2 * np.pi / Nr
+    st = np.stack([np.cos(a), np.sin(a), (a + 2 * np.pi) % (2 * np.pi) - np.pi], 1)
+    g = -st.copy(); g[:, 2] = st[:, 2]
+    return np.concatenate([st.ravel() + 0.01 * np.sin(np.arange(3 * Nr)), g.ravel()])
+
+
+@pytest.mark.parametrize("Nr,N,T,dmin", [(8, 5, 0.02, 0.25), (8, 12, 0.3, 0.25), (10, 20, 0.1, 0.3), (7, 10, 0.3, 0.3), (9, 8, 0.2, 0.3)])
+def test_two_warp_team_path_matches_oracle(pkg, torch_cuda, Nr, N, T, dmin):
+    """7..10 robots (mpc_online_casadi_tb3_eight_...py:148-156, ..._ten_...py:169-177): one instance per 64-thread CTA."""
+    torch = torch_cuda
+    prob, orc = pkg.Problem(Nr, N, T), Oracle(Nr, N, T)
+    lbx, ubx, lbg, ubg = prob.bounds(dmin, 0.22, 2.84)
+    rng = np.random.default_rng(Nr)
+    P = _ring(Nr)[None] + np.concatenate([0.03 * rng.normal(size=(12, 3 * Nr)), np.zeros((12, 3 * Nr))], axis=1)
+    x0 = prob.cold_start(P[:, :3 * Nr])
+    out = prob.solve(_t(torch, x0), _t(torch, P), _t(torch, lbx), _t(torch, ubx), _t(torch, lbg), _t(torch, ubg))
+    torch.cuda.synchronize()
+    ref = orc.solve_batch(x0, P, lbx, ubx, lbg, ubg)
+    same, du, df, it = _compare(out, ref, Nr, N, lbg, (Nr, N))
+    assert same.mean() >= 0.9, (du, df)
+    assert out["stats"][:, 0].max().item() <= 1e-8

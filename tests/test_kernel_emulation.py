@@ -58,3 +58,20 @@ def test_emulated_kernel_rejects_bad_bounds():
     bad = lbx.copy(); bad[0] = 20.0
     e = emu_solve(2, 3, 0.1, o.cold_start(p[:6]), p, bad, ubx, lbg, ubg)
     assert e["rc"] == -2 and e["status"][0] == -2
+
+
+def test_emulated_two_warp_team_eight_robots():
+    """Nr = 8 (mpc_online_casadi_tb3_eight_multi_centralized_collision_free.py:148-156: N = 5, T = 0.02): 64-lane team."""
+    Nr, N, T = 8, 5, 0.02
+    o = Oracle(Nr, N, T)
+    lbx, ubx, lbg, ubg = o.bounds(0.25, 0.22, 2.84)
+    a = np.arange(8) * np.pi / 4
+    st = np.stack([np.cos(a), np.sin(a), (a + 2 * np.pi) % (2 * np.pi) - np.pi], 1)
+    g = -st.copy(); g[:, 2] = st[:, 2]
+    p = np.concatenate([st.ravel() + 0.01 * np.sin(np.arange(24)), g.ravel()])
+    w0 = o.cold_start(p[:24])
+    r = o.solve(w0, p, lbx, ubx, lbg, ubg)
+    for rev in (0, 1):
+        e = emu_solve(Nr, N, T, w0, p, lbx, ubx, lbg, ubg, reverse=rev)
+        assert e["status"][0] == r["status"] == 0 and int(e["iters"][0]) == r["iters"]
+        assert np.abs(e["x"][0] - r["x"]).max() <= 1e-9
