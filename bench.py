@@ -214,17 +214,20 @@ def main():
     outw = {}
     prob.solve(d_x0w, d_p2, d_lbx, d_ubx, d_lbg, d_ubg, want=("stats",), out=outw)
     torch.cuda.synchronize()
-    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    flush.fill_(1)
-    w0.record()
-    prob.solve(d_x0w, d_p2, d_lbx, d_ubx, d_lbg, d_ubg, want=("stats",), out=outw)
-    w1.record()
+    wev = []
+    for _ in range(a.steps):
+        flush.fill_(1)
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record()
+        prob.solve(d_x0w, d_p2, d_lbx, d_ubx, d_lbg, d_ubg, want=("stats",), out=outw)
+        w1.record()
+        wev.append((w0, w1))
     torch.cuda.synchronize()
-    warm_ms = torch.tensor([w0.elapsed_time(w1)], dtype=torch.float64, device=dev)
+    warm_ms = torch.tensor([sum(e0.elapsed_time(e1) for e0, e1 in wev) / a.steps], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(warm_ms, op=dist.ReduceOp.MAX)
     warm = {"value": world * B / (warm_ms.item() * 1e-3), "unit": "solves/s", "mean_ip_iters": float(outw["iters"].double().mean().item()),
-            "solved_frac": float((outw["status"] == 0).double().mean().item()),
+            "solved_frac": float((outw["status"] == 0).double().mean().item()), "max_ip_iters": int(outw["iters"].max().item()),
             "note": "one MPC step later: Euler plant + reference shift as initial guess (the closed-loop regime)"}
 
     # ---- p50 single-solve latency: hexagon swap (C-6 constants, N=20), closed loop, batch = 1, host buffers ----
@@ -271,7 +274,8 @@ def main():
         "metric": "6-robot N=20 NMPC solves/sec", "value": value, "unit": "solves/s", "n_gpus": world, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": tot_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": config,
-        "solved_frac": solved, "mean_ip_iters": float(iters.mean()), "mean_factorisations": float(stats[:, 8].mean()),
+        "solved_frac": solved, "mean_ip_iters": float(iters.mean()), "max_ip_iters": int(iters.max()),
+        "mean_factorisations": float(stats[:, 8].mean()),
         "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                      "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                      "note": "solve_kernel is FP64-pipe/latency bound, not HBM bound (SURVEY.md 8d); see fp64"},

@@ -14,9 +14,11 @@
 #include "solver_body.cuh"
 #include "aux_kernels.cuh"
 
+#ifndef SOLVE_WARPS
 #define SOLVE_WARPS 4
+#endif
 #ifndef SOLVE_MIN_CTAS
-#define SOLVE_MIN_CTAS 4   // 16 resident warps per SM (<= 128 registers per thread)
+#define SOLVE_MIN_CTAS 3   // 12 resident instances per SM (15 KB of shared memory each, <= 168 registers per thread)
 #endif
 
 static thread_local char g_err[512] = "";

@@ -67,7 +67,7 @@ struct WarpSolver {
     static_assert(NZ + 1 <= 64 && M <= 64, "at most 11 robots on the lane-per-column path");
     enum Row {
         R_Z, R_ZL, R_ZU, R_DZ, R_DZ2, R_GX, R_YC, R_YTC, R_YTC2, R_RC, R_CSOC, R_COEF, R_LIN,
-        R_S, R_VL, R_VU, R_YD, R_DS, R_DS2, R_YTD, R_YTD2, R_DSOC, R_GXQ, R_GYQ, R_RD, R_DQ, R_GS, R_DG,
+        R_S, R_VL, R_VU, R_YD, R_DS, R_DS2, R_YTD, R_YTD2, R_DSOC, R_GXQ, R_GYQ, R_RD, R_DQ, R_GS, R_DG, R_TRIG, R_TRIG2,
         R_COUNT
     };
     // shared-memory carve-up (doubles, per warp)
@@ -79,7 +79,8 @@ struct WarpSolver {
         SM_PXX = SM_THD + NRP, SM_PYY = SM_PXX + MP, SM_PXY = SM_PYY + MP, SM_PHX = SM_PXY + MP,
         SM_PHY = SM_PHX + MP, SM_FTH = SM_PHY + MP, SM_FPH = SM_FTH + 16, SM_MISC = SM_FPH + 16,
         SM_RED = SM_MISC + 8,            // cross-warp reduction scratch (two-warp teams)
-        SM_DOUBLES = SM_RED + 8
+        SM_MC = SM_RED + 8,              // column buffer of the stage KKT matrix: mc[row][lane], NZ rows
+        SM_DOUBLES = SM_MC + NZ * LW
     };
     static NMPC_HD long long ws_doubles(int N) { return ((long long)R_COUNT * (N + 1) + (long long)(N + 1) * NS) * LW; }
 
@@ -209,6 +210,7 @@ struct WarpSolver {
         nzb_cnt = tred_sum(cnt_z);
         ny_nzb = tred_sum(cnt_y) + nzb_cnt;
         tsync();
+        trig_rows(row, l, N, 0.0, 0, false, R_TRIG);
     }
 
     // ---------------------------------------------------------------------------------------
@@ -216,9 +218,26 @@ struct WarpSolver {
     // ---------------------------------------------------------------------------------------
     struct EvalOut { double pinf, viol, dinf, c0, cmu, ysum, zsum, theta, f, slog, sdamp; };
 
+    // cos/sin of every heading of the evaluation point z + alpha dz, all stages at once (one robot-stage per lane per
+    // round): row(rt, k)[i] = cos(theta_{i,k}), row(rt, k)[NRP + i] = sin(theta_{i,k}).  Replaces one sincos call per
+    // stage in every pass by ceil(N Nr / lanes) calls per evaluation point.
+    template <class RowFn>
+    static NMPC_DEV void trig_rows(RowFn row, int l, int N, double alpha, int rdz, bool trial, int rt)
+    {
+        for (int idx = l; idx < N * NR; idx += LW) {
+            const int k = idx / NR, i = idx - k * NR;
+            double th = row(R_Z, k)[3 * i + 2];
+            if (trial) th += alpha * row(rdz, k)[3 * i + 2];
+            double s_, c_;
+            wp::sincos_(th, &s_, &c_);
+            row(rt, k)[i] = c_; row(rt, k)[NRP + i] = s_;
+        }
+        tsync();
+    }
+
     // Rows of one stage / inequality block, loaded one stage ahead of their use (register software pipeline:
     // the loads of stage k+1 are in flight while stage k is processed, so HBM latency is paid once per pass).
-    struct ZRows { double z, dz, lo, hi, zl, zu, yc, ce, csoc; };
+    struct ZRows { double z, dz, lo, hi, zl, zu, yc, ce, csoc, cs, sn; };
     struct QRows { double s, ds, lo, hi, yd, vl, vu, dsoc; };
 
     template <bool FULL>
@@ -226,11 +245,18 @@ struct WarpSolver {
     {
         NMPC_LOCALS
         const double kd = P.o.kappa_d;
-        double pinf = 0, viol = 0, dinf = 0, c0 = 0, cmu = 0, ysum = 0, zsum = 0, th = 0, fo = 0, slog = 0, sdamp = 0;
-        double *zb = sm + SM_ZB, *cs = sm + SM_CS, *sn = sm + SM_SN;
+        double pinf = 0, viol = 0, dinf = 0, c0 = 0, cmu = 0, ysum = 0, zsum = 0, th = 0, fo = 0, sdamp = 0;
+        double *zb = sm + SM_ZB;
+        // sum of log(slack) kept as (product of mantissas, sum of exponents): one log() per lane per pass
+        double lmant = 1.0;
+        int lexp = 0;
+        auto addlog = [&](double x) { int e; lmant = wp::frexp_(lmant * x, &e); lexp += e; };
+        const int rt = trial ? R_TRIG2 : R_TRIG;
+        trig_rows(row, l, N, alpha, rdz, trial, rt);
         auto load_z = [&](int k) {
             ZRows r;
             k = k < N ? k : N;
+            r.cs = row(rt, k < N ? k : N - 1)[rob]; r.sn = row(rt, k < N ? k : N - 1)[NRP + rob];
             r.z = row(R_Z, k)[l]; r.dz = trial ? row(rdz, k)[l] : 0.0;
             r.lo = BL[k * LW + l]; r.hi = BU[k * LW + l]; r.ce = CE[k * LW + l];
             r.zl = FULL ? row(R_ZL, k)[l] : 0.0; r.zu = FULL ? row(R_ZU, k)[l] : 0.0; r.yc = FULL ? row(R_YC, k)[l] : 0.0;
@@ -254,8 +280,8 @@ struct WarpSolver {
             pinf = fmax(pinf, fabs(dms)); th += fabs(dms);
             viol = fmax(viol, fmax(q.lo - dv, dv - q.hi));
             if (socacc) row(R_DSOC, b)[l] = asoc * q.dsoc + dms;
-            if (hl) slog += wp::log_(s - q.lo);
-            if (hu) slog += wp::log_(q.hi - s);
+            if (hl) addlog(s - q.lo);
+            if (hu) addlog(q.hi - s);
             if (hl && !hu) sdamp += s - q.lo;
             if (hu && !hl) sdamp += q.hi - s;
             if (FULL) {
@@ -278,8 +304,7 @@ struct WarpSolver {
             const double zk = zv ? zc.z + alpha * zc.dz : 0.0;
             zb[l] = zk;
             tsync();
-            if (k < N && l < NR) { double s_, c_; wp::sincos_(zb[3 * l + 2], &s_, &c_); cs[l] = c_; sn[l] = s_; }
-            tsync();
+            const double csr = zc.cs, snr = zc.sn;   // cos/sin of this lane's robot at stage k
             // ---- equality rows: block 0 (k == 0) and block k+1 ----
             if (isx) {
                 if (k == 0) {
@@ -290,7 +315,7 @@ struct WarpSolver {
                 if (k < N) {
                     double znx = zn.z + alpha * zn.dz;
                     double v = zb[NS + 2 * rob];
-                    double pred = comp == 0 ? zk + T * v * cs[rob] : (comp == 1 ? zk + T * v * sn[rob] : zk + T * zb[NS + 2 * rob + 1]);
+                    double pred = comp == 0 ? zk + T * v * csr : (comp == 1 ? zk + T * v * snr : zk + T * zb[NS + 2 * rob + 1]);
                     double c = znx - pred - zn.ce;
                     pinf = fmax(pinf, fabs(c)); th += fabs(c); viol = fmax(viol, fabs(c));
                     if (socacc) row(R_CSOC, k + 1)[l] = asoc * zn.csoc + c;
@@ -306,8 +331,8 @@ struct WarpSolver {
             if (zv) {
                 const double lo = zc.lo, hi = zc.hi;
                 bool hl = lo > -NMPC_INF, hu = hi < NMPC_INF;
-                if (hl) slog += wp::log_(zk - lo);
-                if (hu) slog += wp::log_(hi - zk);
+                if (hl) addlog(zk - lo);
+                if (hu) addlog(hi - zk);
                 if (hl && !hu) sdamp += zk - lo;
                 if (hu && !hl) sdamp += hi - zk;
                 if (k < N) { double e = zk - xs_l; fo += 0.5 * qw * e * e; }
@@ -322,7 +347,7 @@ struct WarpSolver {
                         if (isx) {
                             if (comp == 2) {
                                 double v = zb[NS + 2 * rob];
-                                r -= zn.yc + (-T * v * sn[rob]) * ycn[3 * rob] + (T * v * cs[rob]) * ycn[3 * rob + 1];
+                                r -= zn.yc + (-T * v * snr) * ycn[3 * rob] + (T * v * csr) * ycn[3 * rob + 1];
                             } else {
                                 r -= zn.yc;
                                 if (M > 0) {
@@ -336,7 +361,7 @@ struct WarpSolver {
                                 }
                             }
                         } else {
-                            if (comp == 0) r -= T * (cs[rob] * ycn[3 * rob] + sn[rob] * ycn[3 * rob + 1]);
+                            if (comp == 0) r -= T * (csr * ycn[3 * rob] + snr * ycn[3 * rob + 1]);
                             else r -= T * ycn[3 * rob + 2];
                         }
                     }
@@ -349,7 +374,7 @@ struct WarpSolver {
             tsync();
         }
         E.pinf = tred_max(pinf); E.theta = tred_sum(th); E.f = tred_sum(fo);
-        E.slog = tred_sum(slog); E.sdamp = tred_sum(sdamp); E.viol = tred_max(viol);
+        E.slog = tred_sum(wp::log_(lmant) + 0.6931471805599453 * (double)lexp); E.sdamp = tred_sum(sdamp); E.viol = tred_max(viol);
         if (FULL) {
             E.dinf = tred_max(dinf); E.c0 = tred_max(c0); E.cmu = tred_max(cmu);
             E.ysum = tred_sum(ysum); E.zsum = tred_sum(zsum);
@@ -423,7 +448,7 @@ struct WarpSolver {
         const bool isL = (l == LW - 1);
         double X[NS], U[NC];
         double plin = 0.0, dgx = 0.0;
-        double *col = sm + SM_COL, *pb = sm + SM_PB, *zb = sm + SM_ZB, *rcb = sm + SM_RCB, *prb = sm + SM_PRB, *hb = sm + SM_HB;
+        double *col = sm + SM_COL, *pb = sm + SM_PB, *zb = sm + SM_ZB, *rcb = sm + SM_RCB, *prb = sm + SM_PRB, *hb = sm + SM_HB, *mc = sm + SM_MC;
         double *cs = sm + SM_CS, *sn = sm + SM_SN, *ca = sm + SM_CA, *cb = sm + SM_CB, *tcs = sm + SM_TCS,
                *tsn = sm + SM_TSN, *crs = sm + SM_CRS, *thd = sm + SM_THD;
         double *pxx = sm + SM_PXX, *pyy = sm + SM_PYY, *pxy = sm + SM_PXY, *phx = sm + SM_PHX, *phy = sm + SM_PHY;
@@ -457,8 +482,7 @@ struct WarpSolver {
             zb[l] = zk;
             if (l < NR) {
                 const double *zr = row(R_Z, k);
-                double th = zr[3 * l + 2], v = zr[NS + 2 * l], s_, c_;
-                wp::sincos_(th, &s_, &c_);
+                const double v = zr[NS + 2 * l], c_ = row(R_TRIG, k)[l], s_ = row(R_TRIG, k)[NRP + l];
                 cs[l] = c_; sn[l] = s_;
                 double a_ = -T * v * s_, b_ = T * v * c_, tc = T * c_, ts = T * s_;
                 ca[l] = a_; cb[l] = b_; tcs[l] = tc; tsn[l] = ts;
@@ -514,71 +538,61 @@ struct WarpSolver {
             }
             row(R_GX, k)[l] = gx;
             double hl_ = gx;
-            // column l of [A B]:  al e_x + be e_y + ga e_theta of this lane's robot (lane 31: the pr column)
+            // column l of [A B]:  al e_x + be e_y + ga e_theta of this lane's robot (last lane: the pr column)
             double al = 0.0, be = 0.0, ga = 0.0;
             int base = 3 * rob;
             if (isx) { if (comp == 0) al = 1.0; else if (comp == 1) be = 1.0; else { al = ca[rob]; be = cb[rob]; ga = 1.0; } }
             else if (isu) { if (comp == 0) { al = tcs[rob]; be = tsn[rob]; } else ga = T; }
             else if (isL) { al = 1.0; base = NS; }
             tsync();
-            {
-                double W[NS];
-                NMPC_UNROLL
-                for (int r0 = 0; r0 < NS; r0 += 6) {   // loads of six rows are issued together, then the FMAs
-                    double t0[6], t1[6], t2[6];
-                    NMPC_UNROLL
-                    for (int r = 0; r < 6; r++)
-                        if (r0 + r < NS) { const double *q = pb + (r0 + r) * PLD + base; t0[r] = q[0]; t1[r] = q[1]; t2[r] = q[2]; }
-                    NMPC_UNROLL
-                    for (int r = 0; r < 6; r++)
-                        if (r0 + r < NS) W[r0 + r] = al * t0[r] + be * t1[r] + ga * t2[r];
-                }
-                NMPC_UNROLL
-                for (int i = 0; i < NR; i++) {
-                    double Wx = W[3 * i], Wy = W[3 * i + 1], Wt = W[3 * i + 2];
-                    X[3 * i] = Wx; X[3 * i + 1] = Wy; X[3 * i + 2] = Wt + ca[i] * Wx + cb[i] * Wy;
-                    U[2 * i] = tcs[i] * Wx + tsn[i] * Wy; U[2 * i + 1] = T * Wt;
-                }
+            // The column of M = [A B]' P+ [A B] + H is assembled in a shared-memory column buffer mc[row][lane] by
+            // ROLLED loops (robots, pairs) and loaded into registers once: the straight-line version of this code
+            // was ~1000 instructions per stage and missed the SM instruction cache on every stage
+            // (sm__icc hit rate 63 %, GPC instruction-cache bandwidth at 70-85 % of peak in ncu).
+            double *mcl = mc + l;
+            NMPC_NOUNROLL
+            for (int i = 0; i < NR; i++) {
+                const double *q0 = pb + (3 * i) * PLD + base;
+                const double Wx = al * q0[0] + be * q0[1] + ga * q0[2];
+                const double Wy = al * q0[PLD] + be * q0[PLD + 1] + ga * q0[PLD + 2];
+                const double Wt = al * q0[2 * PLD] + be * q0[2 * PLD + 1] + ga * q0[2 * PLD + 2];
+                // a control column's state rows stay 0 until its own pivot (see the sweep)
+                mcl[(3 * i) * LW] = isu ? 0.0 : Wx;
+                mcl[(3 * i + 1) * LW] = isu ? 0.0 : Wy;
+                mcl[(3 * i + 2) * LW] = isu ? 0.0 : Wt + ca[i] * Wx + cb[i] * Wy;
+                mcl[(NS + 2 * i) * LW] = tcs[i] * Wx + tsn[i] * Wy;
+                mcl[(NS + 2 * i + 1) * LW] = T * Wt;
             }
-            // collision curvature (state lanes, x/y rows) and gradient
-            if (M > 0 && isx && comp < 2) {
+            // own-column additions (each lane touches only its own column of mc: no barrier needed)
+            if (isu) mcl[l * LW] += dg;                                            // control diagonal
+            dgx = isx ? dg : 0.0;                                                   // state diagonal is carried lazily
+            if (MODE == 0 && isx && comp == 2) mcl[(NS + 2 * rob) * LW] += crs[rob];    // theta-v cross term
+            if (M > 0 && isx && comp < 2) {                                         // collision curvature and gradient
                 double ssame = 0.0, scross = 0.0, glin = 0.0;
-                NMPC_UNROLL
+                NMPC_NOUNROLL
                 for (int j = 0; j < NR; j++) {
                     if (j == rob) continue;
-                    int q = rob < j ? pairidx(rob, j) : pairidx(j, rob);
-                    double vs = comp == 0 ? pxx[q] : pyy[q], vc = pxy[q];
-                    double ph = comp == 0 ? phx[q] : phy[q];
-                    X[3 * j] -= comp == 0 ? vs : vc;
-                    X[3 * j + 1] -= comp == 0 ? vc : vs;
+                    const int q = rob < j ? pairidx(rob, j) : pairidx(j, rob);
+                    const double vs = comp == 0 ? pxx[q] : pyy[q], vc = pxy[q];
+                    const double ph = comp == 0 ? phx[q] : phy[q];
+                    mcl[(3 * j) * LW] -= comp == 0 ? vs : vc;
+                    mcl[(3 * j + 1) * LW] -= comp == 0 ? vc : vs;
                     ssame += vs; scross += vc; glin += rob < j ? ph : -ph;
                 }
-                NMPC_UNROLL
-                for (int j = 0; j < NR; j++)
-                    if (j == rob) { X[3 * j] += comp == 0 ? ssame : scross; X[3 * j + 1] += comp == 0 ? scross : ssame; }
+                mcl[(3 * rob) * LW] += comp == 0 ? ssame : scross;
+                mcl[(3 * rob + 1) * LW] += comp == 0 ? scross : ssame;
                 hl_ += glin;
             }
             hb[l] = isz ? hl_ : 0.0;
             tsync();
-            // + diagonal (own row); lane 31 adds the gradient vector h; control lanes start their state rows at 0
+            if (isL) {   // the linear-term column adds the stage gradient h
+                NMPC_NOUNROLL
+                for (int r = 0; r < NZ; r++) mcl[r * LW] += hb[r];
+            }
             NMPC_UNROLL
-            for (int u = 0; u < NC; u++) U[u] += (NS + u == l) ? dg : 0.0;
-            dgx = isx ? dg : 0.0;
-            if (isL) {
-                NMPC_UNROLL
-                for (int r = 0; r < NS; r++) X[r] += hb[r];
-                NMPC_UNROLL
-                for (int u = 0; u < NC; u++) U[u] += hb[NS + u];
-            }
-            if (isu) {
-                NMPC_UNROLL
-                for (int r = 0; r < NS; r++) X[r] = 0.0;
-            }
-            if (MODE == 0) {
-                NMPC_UNROLL
-                for (int i = 0; i < NR; i++)
-                    if (l == 3 * i + 2) U[2 * i] += crs[i];
-            }
+            for (int i = 0; i < NS; i++) X[i] = mcl[i * LW];
+            NMPC_UNROLL
+            for (int u = 0; u < NC; u++) U[u] = mcl[(NS + u) * LW];
             // symmetric sweep of the control pivots (rolled).  The pivot row is U[0] of every lane; it is
             // published in ROTATED order (slot NS + r holds control column (j + r) mod 2Nr), so the readers
             // use compile-time offsets and the rows rotate through the registers for free.

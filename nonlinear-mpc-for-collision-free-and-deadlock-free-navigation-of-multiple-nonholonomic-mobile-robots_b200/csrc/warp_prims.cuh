@@ -42,6 +42,7 @@ NMPC_DEV unsigned nth_set_bit(unsigned mask, int n) { return __fns(mask, 0, n + 
 // one shared copy of the long math routines: keeps the passes small enough for the instruction cache
 __device__ __noinline__ void sincos_(double x, double *s, double *c) { sincos(x, s, c); }
 __device__ __noinline__ double log_(double x) { return log(x); }
+NMPC_DEV double frexp_(double x, int *e) { return frexp(x, e); }
 
 __device__ __noinline__ double red_sum(double v)
 {

@@ -39,6 +39,7 @@ inline double rcp_pos(double d) { return 1.0 / d; }
 inline void prefetch(const void *) {}
 inline unsigned nth_set_bit(unsigned mask, int n) { for (unsigned b = 0; b < 32; b++) if (mask >> b & 1u) { if (n == 0) return b; n--; } return 0xffffffffu; }
 inline double log_(double x) { return ::log(x); }
+inline double frexp_(double x, int *e) { return ::frexp(x, e); }
 inline void sincos_(double x, double *s, double *c) { ::sincos(x, s, c); }
 inline double red_sum(double v) { for (int m = 16; m > 0; m >>= 1) v += shfl_xor(v, m); return v; }
 inline double red_max(double v) { for (int m = 16; m > 0; m >>= 1) v = fmax(v, shfl_xor(v, m)); return v; }
