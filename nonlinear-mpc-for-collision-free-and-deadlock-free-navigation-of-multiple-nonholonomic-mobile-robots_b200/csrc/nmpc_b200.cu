@@ -161,6 +161,10 @@ template <int NR> static cudaError_t config_solve(nmpc_handle *h)
     int nb = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, solve_kernel<NR>, SolveCfg<NR>::THREADS, h->solve_smem);
     h->ctas_per_sm = nb > 0 ? nb : 1;
+    if (const char *ov = getenv("NMPC_CTAS_PER_SM")) {   // tuning knob: fewer resident instances per SM
+        int v = atoi(ov);
+        if (v >= 1 && v < h->ctas_per_sm) h->ctas_per_sm = v;
+    }
     return e;
 }
 
