@@ -352,7 +352,7 @@ struct WarpSolver {
                                 r -= zn.yc;
                                 if (M > 0) {
                                     const double *ydn = row(R_YD, k + 1);
-                                    NMPC_UNROLL
+                                    NMPC_NOUNROLL
                                     for (int j = 0; j < NR; j++) {
                                         if (j == rob) continue;
                                         int q = rob < j ? pairidx(rob, j) : pairidx(j, rob);
