@@ -215,3 +215,28 @@ def test_two_warp_team_path_matches_oracle(pkg, torch_cuda, Nr, N, T, dmin):
     same, du, df, it = _compare(out, ref, Nr, N, lbg, (Nr, N))
     assert same.mean() >= 0.9, (du, df)
     assert out["stats"][:, 0].max().item() <= 1e-8
+
+
+def test_parity_statistics_2048_synthetic_instances(pkg, torch_cuda):
+    """Basin-agreement rate at scale: 2,048 cold six-robot instances, CUDA path vs oracle (hard part 1)."""
+    torch = torch_cuda
+    Nr, N, T = 6, 20, 0.3
+    prob, orc = pkg.Problem(Nr, N, T), Oracle(Nr, N, T)
+    lbx, ubx, lbg, ubg = prob.bounds(0.3, 0.22, 2.84)
+    P = synthetic_instances(2048, seed=7)
+    x0 = prob.cold_start(P[:, :18])
+    out = prob.solve(_t(torch, x0), _t(torch, P), _t(torch, lbx), _t(torch, ubx), _t(torch, lbg), _t(torch, ubg))
+    torch.cuda.synchronize()
+    ref = orc.solve_batch(x0, P, lbx, ubx, lbg, ubg)
+    x, f = out["x"].cpu().numpy(), out["f"].cpu().numpy()
+    st, it = out["status"].cpu().numpy(), out["iters"].cpu().numpy()
+    du = np.abs(x - ref["x"])[:, 18 * 21:].max(axis=1)
+    df = np.abs(f - ref["f"]) / np.maximum(1.0, np.abs(ref["f"]))
+    same = (du <= U_TOL) & (df <= F_RTOL) & (st == ref["status"])
+    print("agreement %.4f  solved gpu %.4f oracle %.4f  iters gpu %.2f oracle %.2f  max|it diff| %d" %
+          (same.mean(), (st == 0).mean(), (ref["status"] == 0).mean(), it.mean(), ref["iters"].mean(), np.abs(it - ref["iters"]).max()))
+    assert (st == 0).mean() >= 0.999 and (ref["status"] == 0).mean() >= 0.999
+    assert same.mean() >= 0.99, (same.mean(), du[~same][:10], df[~same][:10])
+    # where they part ways both are KKT points (different local minima of a multi-modal NLP), never a failure
+    assert out["stats"][:, 0].cpu().numpy().max() <= 1e-8
+    assert np.median(np.abs(it - ref["iters"])) == 0
