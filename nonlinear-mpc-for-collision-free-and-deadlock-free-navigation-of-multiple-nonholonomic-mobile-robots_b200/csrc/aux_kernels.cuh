@@ -21,6 +21,7 @@ struct NmpcEvalTables {
     const int *jac_init; // [ns]       slots of the identity block of the initial-condition rows
 };
 
+template <int PF>
 __global__ void __launch_bounds__(256) eval_kernel(int Nr, int N, double T, double Q0, double Q1, double Q2, double R0,
                                                    double R1, int B, const double *__restrict__ w, const double *__restrict__ p,
                                                    const double *__restrict__ lam, double *__restrict__ f, double *__restrict__ grad,
@@ -31,14 +32,39 @@ __global__ void __launch_bounds__(256) eval_kernel(int Nr, int N, double T, doub
     const int ns = 3 * Nr, nc = 2 * Nr, M = Nr * (Nr - 1) / 2, S = N + 1, blk = ns + M;
     const int n = ns * S + nc * N, mg = S * blk, nX = ns * S;
     const int nj = 3 * Nr + N * (11 * Nr + 4 * M), nh = N * (6 * Nr + 2 * M);
-    double *sw = sh, *sl = sw + n, *sp = sl + mg, *sgrad = sp + 2 * ns, *sg = sgrad + n, *sj = sg + mg, *shs = sj + nj,
-           *sred = shs + nh;
+    auto ev = [](int v) { return (v + 1) & ~1; };   // every segment starts 16-byte aligned (128-bit write-back)
+    double *sw = sh, *sl = sw + ev(n), *sp = sl + ev(mg), *sgrad = sp + ev(2 * ns), *sg = sgrad + ev(n), *sj = sg + ev(mg),
+           *shs = sj + ev(nj), *sred = shs + ev(nh);
     const double Qw[3] = {Q0, Q1, Q2}, Rw[2] = {R0, R1};
+    // The inputs of the next point are fetched into PF registers per array per thread right after the evaluation of
+    // the current point, so their HBM latency overlaps the write-back (PF = ceil(max(n, mg) / 256), 0 = no prefetch).
+    double rw[PF > 0 ? PF : 1], rl[PF > 0 ? PF : 1], rp = 0.0;
+    auto fetch = [&](int b) {
+        if (PF == 0 || b >= B) return;
+#pragma unroll
+        for (int j = 0; j < PF; j++) {
+            const int i = threadIdx.x + j * 256;
+            rw[j] = i < n ? w[(size_t)b * n + i] : 0.0;
+            rl[j] = (lam && i < mg) ? lam[(size_t)b * mg + i] : 0.0;
+        }
+        rp = (int)threadIdx.x < 2 * ns ? p[(size_t)b * 2 * ns + threadIdx.x] : 0.0;
+    };
+    fetch(blockIdx.x);
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
-        const double *wb = w + (size_t)b * n;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) sw[i] = wb[i];
-        for (int i = threadIdx.x; i < 2 * ns; i += blockDim.x) sp[i] = p[(size_t)b * 2 * ns + i];
-        if (lam) for (int i = threadIdx.x; i < mg; i += blockDim.x) sl[i] = lam[(size_t)b * mg + i];
+        if (PF > 0) {
+#pragma unroll
+            for (int j = 0; j < PF; j++) {
+                const int i = threadIdx.x + j * 256;
+                if (i < n) sw[i] = rw[j];
+                if (lam && i < mg) sl[i] = rl[j];
+            }
+            if ((int)threadIdx.x < 2 * ns) sp[threadIdx.x] = rp;
+        } else {
+            const double *wb = w + (size_t)b * n;
+            for (int i = threadIdx.x; i < n; i += blockDim.x) sw[i] = wb[i];
+            for (int i = threadIdx.x; i < 2 * ns; i += blockDim.x) sp[i] = p[(size_t)b * 2 * ns + i];
+            if (lam) for (int i = threadIdx.x; i < mg; i += blockDim.x) sl[i] = lam[(size_t)b * mg + i];
+        }
         __syncthreads();
         double facc = 0.0;
         // robot-stage work items, then pair-stage items, then the initial block
@@ -108,25 +134,47 @@ __global__ void __launch_bounds__(256) eval_kernel(int Nr, int N, double T, doub
             for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += sred[i];
             f[b] = t;
         }
-        if (grad) for (int i = threadIdx.x; i < n; i += blockDim.x) grad[(size_t)b * n + i] = sgrad[i];
-        if (g) for (int i = threadIdx.x; i < mg; i += blockDim.x) g[(size_t)b * mg + i] = sg[i];
-        if (jac) for (int i = threadIdx.x; i < nj; i += blockDim.x) jac[(size_t)b * nj + i] = sj[i];
-        if (hess && lam) for (int i = threadIdx.x; i < nh; i += blockDim.x) hess[(size_t)b * nh + i] = shs[i];
+        fetch(b + gridDim.x);   // next point's inputs: in flight during the write-back below
+        // coalesced write-back of the record; 128-bit stores where the segment is 16-byte aligned in global memory
+        auto copy_out = [&](double *dst, const double *src, int cnt) {
+            if (!dst) return;
+            if ((((size_t)dst | (size_t)src) & 15) == 0) {
+                const int c2 = cnt >> 1;
+                double2 *d2 = reinterpret_cast<double2 *>(dst);
+                const double2 *s2 = reinterpret_cast<const double2 *>(src);
+                for (int i = threadIdx.x; i < c2; i += blockDim.x) d2[i] = s2[i];
+                if ((cnt & 1) && threadIdx.x == 0) dst[cnt - 1] = src[cnt - 1];
+            } else {
+                for (int i = threadIdx.x; i < cnt; i += blockDim.x) dst[i] = src[i];
+            }
+        };
+        copy_out(grad ? grad + (size_t)b * n : nullptr, sgrad, n);
+        copy_out(g ? g + (size_t)b * mg : nullptr, sg, mg);
+        copy_out(jac ? jac + (size_t)b * nj : nullptr, sj, nj);
+        copy_out((hess && lam) ? hess + (size_t)b * nh : nullptr, shs, nh);
         __syncthreads();
     }
 }
 
 // u0 = [u[1:]; u[-1]]  and  X0 = [X[1:]; X[N-1]]   (row N-1, not N: the reference's quirk)
-__global__ void shift_kernel(int Nr, int N, long long total, const double *__restrict__ xp, double *__restrict__ xn)
+__global__ void __launch_bounds__(256) shift_kernel(int Nr, int N, long long total, const double *__restrict__ xp, double *__restrict__ xn)
 {
+    // one instance per CTA iteration; the source index is piecewise linear in the destination index:
+    //   states   j <  ns*N        -> j + ns          (X_{k+1})
+    //            j in last block  -> j - ns          (X_{N-1}: the reference appends row N-1, not N)
+    //   controls j <  nc*(N-1)    -> j + nc          (U_{k+1})
+    //            last block       -> j               (U_{N-1} repeated)
     const int ns = 3 * Nr, nc = 2 * Nr, nX = ns * (N + 1), n = nX + nc * N;
-    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const long long b = e / n;
-        const int j = (int)(e - b * n);
-        int src;
-        if (j < nX) { const int k = j / ns, c = j - k * ns; src = (k < N ? k + 1 : N - 1) * ns + c; }
-        else { const int k = (j - nX) / nc, c = (j - nX) - k * nc; src = nX + (k < N - 1 ? k + 1 : N - 1) * nc + c; }
-        xn[e] = xp[b * n + src];
+    const long long B = total / n;
+    for (long long b = blockIdx.x; b < B; b += gridDim.x) {
+        const double *src = xp + b * n;
+        double *dst = xn + b * n;
+        for (int j = threadIdx.x; j < n; j += blockDim.x) {
+            int s;
+            if (j < nX) s = j < ns * N ? j + ns : j - ns;
+            else s = (j - nX) < nc * (N - 1) ? j + nc : j;
+            dst[j] = src[s];
+        }
     }
 }
 

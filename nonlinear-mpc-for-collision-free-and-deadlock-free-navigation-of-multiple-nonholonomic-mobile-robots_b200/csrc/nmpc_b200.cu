@@ -217,8 +217,19 @@ extern "C" int nmpc_create(const nmpc_desc *d, const nmpc_opts *o, nmpc_handle *
     }
     if (e != cudaSuccess) { cudaFree(h->d_tables); delete h; return fail(NMPC_ECUDA, "nmpc_create: kernel configuration failed: %s", cudaGetErrorString(e)); }
     DBG("solve kernel configured");
-    h->eval_smem = (size_t)(2 * h->n + 2 * h->mg + 2 * h->ns + h->nnzj + h->nnzh + 32) * sizeof(double);
-    e = cudaFuncSetAttribute(eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->eval_smem);
+    h->eval_smem = (size_t)(2 * h->n + 2 * h->mg + 2 * h->ns + h->nnzj + h->nnzh + 32 + 8) * sizeof(double);
+    {
+        const int sz = (int)h->eval_smem;
+        e = cudaFuncSetAttribute(eval_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(eval_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(eval_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(eval_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(eval_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(eval_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(eval_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(eval_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(eval_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz);
+    }
     if (e != cudaSuccess) { cudaFree(h->d_tables); delete h; return fail(NMPC_ENOTSUP, "nmpc_create: eval record (%zu B) exceeds shared memory: %s", h->eval_smem, cudaGetErrorString(e)); }
     *out = h;
     return 0;
@@ -392,7 +403,7 @@ extern "C" int nmpc_shift(nmpc_handle *h, int B, const double *x_prev, double *x
     if (!h || !x_prev || !x0_next || B <= 0) return fail(NMPC_EINVAL, "nmpc_shift: bad argument");
     if (x_prev == x0_next) return fail(NMPC_EINVAL, "nmpc_shift: in-place shift is not supported");
     long long total = (long long)B * h->n;
-    int blocks = (int)std::min<long long>((total + 255) / 256, (long long)h->sm_count * 16);
+    int blocks = (int)std::min<long long>(B, (long long)h->sm_count * 8);
     shift_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(h->d.Nr, h->d.N, total, x_prev, x0_next);
     h->launches++;
     CUDA_OK(cudaGetLastError());
@@ -416,8 +427,16 @@ extern "C" int nmpc_eval(nmpc_handle *h, int B, const double *w, const double *p
     if (hess && !lam_g) return fail(NMPC_EINVAL, "nmpc_eval: hess needs lam_g");
     int per_sm = (int)std::max<size_t>(1, (size_t)(220 * 1024) / h->eval_smem);
     int blocks = std::min(B, h->sm_count * per_sm);
-    eval_kernel<<<blocks, 256, h->eval_smem, (cudaStream_t)stream>>>(h->d.Nr, h->d.N, h->d.T, h->d.Q[0], h->d.Q[1], h->d.Q[2],
-                                                                       h->d.R[0], h->d.R[1], B, w, p, lam_g, f, grad, g, jac, hess, h->tb);
+    const int pf = (std::max(h->n, h->mg) + 255) / 256;
+#define EVAL_LAUNCH(PFV)                                                                                                          \
+    eval_kernel<PFV><<<blocks, 256, h->eval_smem, (cudaStream_t)stream>>>(h->d.Nr, h->d.N, h->d.T, h->d.Q[0], h->d.Q[1], h->d.Q[2], \
+                                                                            h->d.R[0], h->d.R[1], B, w, p, lam_g, f, grad, g, jac, hess, h->tb)
+    switch (pf <= 8 ? pf : 0) {
+        case 1: EVAL_LAUNCH(1); break; case 2: EVAL_LAUNCH(2); break; case 3: EVAL_LAUNCH(3); break; case 4: EVAL_LAUNCH(4); break;
+        case 5: EVAL_LAUNCH(5); break; case 6: EVAL_LAUNCH(6); break; case 7: EVAL_LAUNCH(7); break; case 8: EVAL_LAUNCH(8); break;
+        default: EVAL_LAUNCH(0); break;
+    }
+#undef EVAL_LAUNCH
     h->launches++;
     CUDA_OK(cudaGetLastError());
     return 0;
