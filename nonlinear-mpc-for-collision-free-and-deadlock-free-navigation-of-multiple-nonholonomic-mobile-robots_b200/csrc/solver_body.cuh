@@ -593,49 +593,63 @@ struct WarpSolver {
             for (int i = 0; i < NS; i++) X[i] = mcl[i * LW];
             NMPC_UNROLL
             for (int u = 0; u < NC; u++) U[u] = mcl[(NS + u) * LW];
-            // symmetric sweep of the control pivots (rolled).  The pivot row is U[0] of every lane; it is
-            // published in ROTATED order (slot NS + r holds control column (j + r) mod 2Nr), so the readers
-            // use compile-time offsets and the rows rotate through the registers for free.
+            // symmetric sweep of the control pivots (rolled, with one-pivot LOOK-AHEAD).  The pivot row is U[0] of
+            // every lane; it is published in ROTATED order (slot NS + r holds control column (j + r) mod 2Nr), so the
+            // readers use compile-time offsets and the rows rotate through the registers for free.  Slot NZ carries
+            // 1/pivot, computed by the pivot's own lane (<= 0 or NaN: wrong inertia).  Inside step j the entry of
+            // the NEXT pivot row is updated and published first, so its shared-memory round trip and reciprocal
+            // overlap the remaining rank-1 update instead of sitting on the critical path of every pivot.
             const int ucol = l - NS;   // control column of this lane (if any)
+            {
+                if (isz) col[isu ? ucol + NS : l] = U[0];
+                if (ucol == 0) col[NZ] = (U[0] > 0.0 && U[0] < NMPC_INF) ? wp::rcp_pos(U[0]) : -1.0;
+            }
             NMPC_NOUNROLL
             for (int j = 0; j < NC; j++) {
-                double *buf = col + LW * (j & 1);
-                int slot = l;
-                if (isu) { slot = ucol - j; slot += slot < 0 ? NC : 0; slot += NS; }
-                if (isz) buf[slot] = U[0];
+                const double *buf = col + LW * (j & 1);
+                double *nbuf = col + LW * ((j + 1) & 1);
                 tsync();
-                const double d = buf[NS];
-                if (!(d > 0.0) || !(d < NMPC_INF)) return false;
-                const double inv = wp::rcp_pos(d);
-                const bool own = (ucol == j);
-                const double t = own ? -inv : U[0] * inv;
-                const double tx = (ucol > j && isu) ? 0.0 : t;
-                {   // state rows: the pivot row arrives in 128-bit loads, all issued before the FMAs
+                const double inv = buf[NZ];
+                if (!(inv > 0.0)) return false;
+                // the pivot row arrives in 128-bit loads, all issued before the FMAs
+                NmpcD2 bx[NS / 2];
+                double bu[NC];
+                {
                     const NmpcD2 *b2 = reinterpret_cast<const NmpcD2 *>(buf);
-                    NmpcD2 bx[NS / 2];
                     NMPC_UNROLL
                     for (int i = 0; i < NS / 2; i++) bx[i] = b2[i];
-                    NMPC_UNROLL
-                    for (int i = 0; i < NS / 2; i++) { X[2 * i] -= bx[i].x * tx; X[2 * i + 1] -= bx[i].y * tx; }
-                    if (NS & 1) X[NS - 1] -= buf[NS - 1] * tx;
-                }
-                if (own) {   // the pivot column becomes column / d: start its remaining rows from 0
-                    NMPC_UNROLL
-                    for (int r = 1; r < NC; r++) U[r] = 0.0;
-                }
-                {   // control rows (rotating): slots NS+1 .. NS+NC-1
-                    double bu[NC];
                     if ((NS & 1) == 0) {
-                        const NmpcD2 *b2 = reinterpret_cast<const NmpcD2 *>(buf + NS);
+                        const NmpcD2 *c2 = reinterpret_cast<const NmpcD2 *>(buf + NS);
                         NMPC_UNROLL
-                        for (int r = 0; r < NC / 2; r++) { NmpcD2 v = b2[r]; bu[2 * r] = v.x; bu[2 * r + 1] = v.y; }
+                        for (int r = 0; r < NC / 2; r++) { NmpcD2 v = c2[r]; bu[2 * r] = v.x; bu[2 * r + 1] = v.y; }
                     } else {
                         NMPC_UNROLL
                         for (int r = 0; r < NC; r++) bu[r] = buf[NS + r];
                     }
-                    NMPC_UNROLL
-                    for (int r = 1; r < NC; r++) U[r - 1] = U[r] - bu[r] * t;
                 }
+                const bool own = (ucol == j);
+                const double t = own ? -inv : U[0] * inv;
+                const double tx = (ucol > j && isu) ? 0.0 : t;
+                if (own) {   // the pivot column becomes column / d: start its remaining rows from 0
+                    NMPC_UNROLL
+                    for (int r = 1; r < NC; r++) U[r] = 0.0;
+                }
+                // look-ahead: this lane's entry of pivot row j+1
+                const double u1 = U[1] - bu[1] * t;
+                if (j + 1 < NC) {
+                    int slot = l;
+                    if (isu) { slot = ucol - (j + 1); slot += slot < 0 ? NC : 0; slot += NS; }
+                    if (isz) nbuf[slot] = u1;
+                    const double ri = wp::rcp_pos(u1);
+                    if (ucol == j + 1) nbuf[NZ] = (u1 > 0.0 && u1 < NMPC_INF) ? ri : -1.0;
+                }
+                NMPC_UNROLL
+                for (int i = 0; i < NS / 2; i++) { X[2 * i] -= bx[i].x * tx; X[2 * i + 1] -= bx[i].y * tx; }
+                if (NS & 1) X[NS - 1] -= buf[NS - 1] * tx;
+                // control rows (rotating): slots NS+2 .. NS+NC-1
+                U[0] = u1;
+                NMPC_UNROLL
+                for (int r = 2; r < NC; r++) U[r - 1] = U[r] - bu[r] * t;
                 U[NC - 1] = t;
             }
             // publish p_k / feed-forward (lane 31's column) and store the factors
