@@ -79,9 +79,32 @@ struct WarpSolver {
         SM_PXX = SM_THD + NRP, SM_PYY = SM_PXX + MP, SM_PXY = SM_PYY + MP, SM_PHX = SM_PXY + MP,
         SM_PHY = SM_PHX + MP, SM_FTH = SM_PHY + MP, SM_FPH = SM_FTH + 16, SM_MISC = SM_FPH + 16,
         SM_RED = SM_MISC + 8,            // cross-warp reduction scratch (two-warp teams)
-        SM_MC = SM_RED + 8,              // column buffer of the stage KKT matrix: mc[row][lane], NZ rows
-        SM_DOUBLES = SM_MC + NZ * LW
+        SM_TAB = SM_RED + 8,             // per-pass table of the staged rows' base pointers (64 entries)
+        SM_MC = SM_TAB + 64,             // column buffer of the stage KKT matrix: mc[row][lane], NZ rows
+        SM_STG = SM_MC + NZ * LW,        // rows of the NEXT stage, copied asynchronously (cp.async) while this one is processed
+        STG_ROWS = (20 - 2 * NR > 16) ? 20 - 2 * NR : 16,
+        SM_DOUBLES = SM_STG + STG_ROWS * LW
     };
+    // slots of the factorisation's staging buffer (sm + SM_STG): rows of stage k, then rows of block k+1
+    enum { FS_Z, FS_TRIG, FS_ZL, FS_ZU, FS_BL, FS_BU, FS_YC, FS_S, FS_VL, FS_VU, FS_YD, FS_CSOC, FS_DSOC, FS_CE, FS_DL, FS_DU, FS_COUNT };
+    // slots of the forward pass's staging buffer (sm + SM_MC, NZ + STG_ROWS rows): NS factor rows, vectors of stage k, then of block k+1
+    enum { WS_LIN = NS, WS_DG, WS_Z, WS_ZL, WS_ZU, WS_BL, WS_BU, WS_GX, WS_COEF, WS_RC, WS_DL, WS_DU, WS_GS, WS_GXQ, WS_GYQ, WS_RD, WS_DQ,
+           WS_S, WS_VL, WS_VU, WS_COUNT };
+    static_assert(FS_COUNT <= STG_ROWS && WS_COUNT <= NZ + STG_ROWS && WS_COUNT <= 64, "staging buffers");
+
+    // Issue the asynchronous copies of one stage's rows: slot s <- tab[s] + (k + (s >= kofs_from)) rows, stage clamped to N.
+    // Two rows per warp instruction (16 bytes per lane); completion: wp::cp_async_wait() + tsync().
+    static NMPC_DEV void stage_issue(double *sm, double *stg, int l, int N, int nslot, int kofs_from, int k)
+    {
+        const double *const *tab = reinterpret_cast<const double *const *>(sm + SM_TAB);
+        const int half = l / (LW / 2), c2 = (l % (LW / 2)) * 2;
+        NMPC_NOUNROLL
+        for (int s = half; s < nslot; s += 2) {
+            int kk = k + (s >= kofs_from ? 1 : 0);
+            kk = kk < N ? kk : N;
+            wp::cp_async16(stg + s * LW + c2, tab[s] + (long long)kk * LW + c2);
+        }
+    }
     static NMPC_HD long long ws_doubles(int N) { return ((long long)R_COUNT * (N + 1) + (long long)(N + 1) * NS) * LW; }
 
     const NmpcSolveParams &P;
@@ -399,26 +422,28 @@ struct WarpSolver {
         }
     }
 
-    // inequality block b: condensed weights; writes the per-pair rows the forward pass needs
+    // inequality block b: condensed weights; writes the per-pair rows the forward pass needs.  The caller supplies the
+    // block's inputs (from the staging buffer inside the sweep, from global memory for block 0).
+    struct QIn { double lo, hi, s, vl, vu, yd, dsoc; };
     template <int MODE, class RowFn>
-    static NMPC_DEV void ineq_block(RowFn row, const double *DL, const double *DU, int l, int pi, int pj, double kd, int b, double mu,
+    static NMPC_DEV void ineq_block(RowFn row, const QIn &in, int l, int pi, int pj, double kd, int b, double mu,
                                     double delta, bool soc, const double *zb, double &pxx, double &pyy, double &pxy, double &phx,
                                     double &phy)
     {
         pxx = pyy = pxy = phx = phy = 0.0;
         double gxq = 0, gyq = 0, rd = 0, Dq = 0, gs = 0;
-        double lo = DL[b * LW + l], hi = DU[b * LW + l];
+        const double lo = in.lo, hi = in.hi;
         if (lo > -NMPC_INF || hi < NMPC_INF) {
             double dv = NMPC_DUMMY_ROW_VALUE;
             if (b > 0) {
                 double dx = zb[3 * pi] - zb[3 * pj], dy = zb[3 * pi + 1] - zb[3 * pj + 1];
                 gxq = 2.0 * dx; gyq = 2.0 * dy; dv = dx * dx + dy * dy;
             }
-            double s = row(R_S, b)[l], sigs;
-            sig_g<MODE>(kd, s, lo, hi, row(R_VL, b)[l], row(R_VU, b)[l], mu, 0.0, sigs, gs);
-            rd = MODE == 1 ? 0.0 : (soc ? row(R_DSOC, b)[l] : dv - s);
+            double s = in.s, sigs;
+            sig_g<MODE>(kd, s, lo, hi, in.vl, in.vu, mu, 0.0, sigs, gs);
+            rd = MODE == 1 ? 0.0 : (soc ? in.dsoc : dv - s);
             Dq = sigs + delta;
-            double hq = Dq * rd + gs, mu2 = MODE == 0 ? 2.0 * row(R_YD, b)[l] : 0.0;
+            double hq = Dq * rd + gs, mu2 = MODE == 0 ? 2.0 * in.yd : 0.0;
             pxx = Dq * gxq * gxq + mu2; pyy = Dq * gyq * gyq + mu2; pxy = Dq * gxq * gyq;
             phx = gxq * hq; phy = gyq * hq;
         }
@@ -452,10 +477,25 @@ struct WarpSolver {
         double *cs = sm + SM_CS, *sn = sm + SM_SN, *ca = sm + SM_CA, *cb = sm + SM_CB, *tcs = sm + SM_TCS,
                *tsn = sm + SM_TSN, *crs = sm + SM_CRS, *thd = sm + SM_THD;
         double *pxx = sm + SM_PXX, *pyy = sm + SM_PYY, *pxy = sm + SM_PXY, *phx = sm + SM_PHX, *phy = sm + SM_PHY;
+        double *stg = sm + SM_STG;
         n_fact++;
-        const int pf_a = prefetch_lane((1u << R_Z | 1u << R_ZL | 1u << R_ZU));
-        const int pf_b = prefetch_lane((1u << R_YC | 1u << R_S | 1u << R_VL | 1u << R_VU | 1u << R_YD) | (soc ? (1u << R_CSOC | 1u << R_DSOC) : 0u));
         tsync();
+        if (l < FS_COUNT) {   // base pointers (stage 0) of the rows staged per stage; see FS_*
+            const double *p0 = nullptr;
+            switch (l) {
+                case FS_Z: p0 = row(R_Z, 0); break;      case FS_TRIG: p0 = row(R_TRIG, 0); break;
+                case FS_ZL: p0 = row(R_ZL, 0); break;    case FS_ZU: p0 = row(R_ZU, 0); break;
+                case FS_BL: p0 = BL; break;              case FS_BU: p0 = BU; break;
+                case FS_YC: p0 = row(R_YC, 0); break;    case FS_S: p0 = row(R_S, 0); break;
+                case FS_VL: p0 = row(R_VL, 0); break;    case FS_VU: p0 = row(R_VU, 0); break;
+                case FS_YD: p0 = row(R_YD, 0); break;    case FS_CSOC: p0 = row(R_CSOC, 0); break;
+                case FS_DSOC: p0 = row(R_DSOC, 0); break; case FS_CE: p0 = CE; break;
+                case FS_DL: p0 = DL; break;              default: p0 = DU; break;
+            }
+            reinterpret_cast<const double **>(sm + SM_TAB)[l] = p0;
+        }
+        tsync();
+        stage_issue(sm, stg, l, N, FS_COUNT, FS_YC, N - 1);   // in flight during the terminal stage
         // terminal stage: X_N carries no cost and no distance rows, only its box
         {
             double sig = 0.0, gx = 0.0;
@@ -472,24 +512,25 @@ struct WarpSolver {
             NMPC_UNROLL
             for (int i = 0; i < NS; i++) frow(N, i)[l] = isz ? X[i] : 0.0;
             row(R_LIN, N)[l] = plin; row(R_DG, N)[l] = dgx;
+            zb[l] = isx ? row(R_Z, N)[l] : 0.0;   // read back by the same lane as X_{k+1} of the first stage
         }
         NMPC_NOUNROLL
         for (int k = N - 1; k >= 0; k--) {
+            wp::cp_async_wait();
             tsync();
-            prefetch_at(pf_a, k - 2);
-            prefetch_at(pf_b, k - 1);
-            const double zk = isz ? row(R_Z, k)[l] : 0.0;
+            const double zk = isz ? stg[FS_Z * LW + l] : 0.0;
+            const double znx = zb[l];   // X_{k+1} (this lane's component): what the previous stage left here
             zb[l] = zk;
             if (l < NR) {
-                const double *zr = row(R_Z, k);
-                const double v = zr[NS + 2 * l], c_ = row(R_TRIG, k)[l], s_ = row(R_TRIG, k)[NRP + l];
+                const double *zr = stg + FS_Z * LW;
+                const double v = zr[NS + 2 * l], c_ = stg[FS_TRIG * LW + l], s_ = stg[FS_TRIG * LW + NRP + l];
                 cs[l] = c_; sn[l] = s_;
                 double a_ = -T * v * s_, b_ = T * v * c_, tc = T * c_, ts = T * s_;
                 ca[l] = a_; cb[l] = b_; tcs[l] = tc; tsn[l] = ts;
                 double *cf = row(R_COEF, k);
                 cf[l] = a_; cf[CFS + l] = b_; cf[2 * CFS + l] = tc; cf[3 * CFS + l] = ts;
                 if (MODE == 0) {
-                    const double *yc = row(R_YC, k + 1);
+                    const double *yc = stg + FS_YC * LW;
                     double lx = yc[3 * l], ly = yc[3 * l + 1];
                     crs[l] = T * (lx * s_ - ly * c_); thd[l] = T * v * (lx * c_ + ly * s_);
                 } else { crs[l] = 0.0; thd[l] = 0.0; }
@@ -504,18 +545,21 @@ struct WarpSolver {
             if (isx) {
                 double rc = 0.0;
                 if (MODE != 1) {
-                    if (soc) rc = row(R_CSOC, k + 1)[l];
+                    if (soc) rc = stg[FS_CSOC * LW + l];
                     else {
                         double v = zb[NS + 2 * rob];
                         double pred = comp == 0 ? zk + T * v * cs[rob] : (comp == 1 ? zk + T * v * sn[rob] : zk + T * zb[NS + 2 * rob + 1]);
-                        rc = row(R_Z, k + 1)[l] - pred - CE[(k + 1) * LW + l];
+                        rc = znx - pred - stg[FS_CE * LW + l];
                     }
                 }
                 rcb[l] = rc; row(R_RC, k + 1)[l] = rc;
             }
             if (M > 0 && isq) {
                 double a0, a1, a2, a3, a4;
-                ineq_block<MODE>(row, DL, DU, l, pi, pj, kd, k + 1, mu, delta, soc, zb, a0, a1, a2, a3, a4);
+                QIn in;
+                in.lo = stg[FS_DL * LW + l]; in.hi = stg[FS_DU * LW + l]; in.s = stg[FS_S * LW + l]; in.vl = stg[FS_VL * LW + l];
+                in.vu = stg[FS_VU * LW + l]; in.yd = stg[FS_YD * LW + l]; in.dsoc = stg[FS_DSOC * LW + l];
+                ineq_block<MODE>(row, in, l, pi, pj, kd, k + 1, mu, delta, soc, zb, a0, a1, a2, a3, a4);
                 pxx[l] = a0; pyy[l] = a1; pxy[l] = a2; phx[l] = a3; phy[l] = a4;
             }
             tsync();
@@ -532,7 +576,7 @@ struct WarpSolver {
             // stage gradient h_l (variable l) and diagonal curvature
             double sig = 0.0, gx = 0.0, dg = 0.0;
             if (isz) {
-                sig_g<MODE>(kd, zk, BL[k * LW + l], BU[k * LW + l], row(R_ZL, k)[l], row(R_ZU, k)[l], mu, df * gradf(k, zk), sig, gx);
+                sig_g<MODE>(kd, zk, stg[FS_BL * LW + l], stg[FS_BU * LW + l], stg[FS_ZL * LW + l], stg[FS_ZU * LW + l], mu, df * gradf(k, zk), sig, gx);
                 dg = sig + delta + zeta;
                 if (MODE == 0) { dg += df * qw; if (isx && comp == 2) dg += thd[rob]; }
             }
@@ -545,6 +589,7 @@ struct WarpSolver {
             else if (isu) { if (comp == 0) { al = tcs[rob]; be = tsn[rob]; } else ga = T; }
             else if (isL) { al = 1.0; base = NS; }
             tsync();
+            if (k > 0) stage_issue(sm, stg, l, N, FS_COUNT, FS_YC, k - 1);   // every lane has consumed the staged rows of stage k
             // The column of M = [A B]' P+ [A B] + H is assembled in a shared-memory column buffer mc[row][lane] by
             // ROLLED loops (robots, pairs) and loaded into registers once: the straight-line version of this code
             // was ~1000 instructions per stage and missed the SM instruction cache on every stage
@@ -610,7 +655,7 @@ struct WarpSolver {
                 double *nbuf = col + LW * ((j + 1) & 1);
                 tsync();
                 const double inv = buf[NZ];
-                if (!(inv > 0.0)) return false;
+                if (!(inv > 0.0)) { wp::cp_async_wait(); return false; }   // drain the staging copies before the retry
                 // the pivot row arrives in 128-bit loads, all issued before the FMAs
                 NmpcD2 bx[NS / 2];
                 double bu[NC];
@@ -671,7 +716,13 @@ struct WarpSolver {
         }
         tsync();
         if (isx) row(R_RC, 0)[l] = MODE == 1 ? 0.0 : (soc ? row(R_CSOC, 0)[l] : row(R_Z, 0)[l] - x0bar_l - CE[l]);
-        if (M > 0 && isq) { double a0, a1, a2, a3, a4; ineq_block<MODE>(row, DL, DU, l, pi, pj, kd, 0, mu, delta, soc, zb, a0, a1, a2, a3, a4); }
+        if (M > 0 && isq) {
+            double a0, a1, a2, a3, a4;
+            QIn in;
+            in.lo = DL[l]; in.hi = DU[l]; in.s = row(R_S, 0)[l]; in.vl = row(R_VL, 0)[l]; in.vu = row(R_VU, 0)[l];
+            in.yd = MODE == 0 ? row(R_YD, 0)[l] : 0.0; in.dsoc = soc ? row(R_DSOC, 0)[l] : 0.0;
+            ineq_block<MODE>(row, in, l, pi, pj, kd, 0, mu, delta, soc, zb, a0, a1, a2, a3, a4);
+        }
         tsync();
         return true;
     }
@@ -704,9 +755,40 @@ struct WarpSolver {
     {
         NMPC_LOCALS
         double ap = 0.0, az = 0.0, gbd = 0.0, tiny = 0.0;   // max ratios, see slack_step_terms
-        const int pf_a = prefetch_lane((1u << R_LIN | 1u << R_Z | 1u << R_ZL | 1u << R_ZU | 1u << R_GX | 1u << R_COEF | 1u << R_DG));
-        const int pf_b = prefetch_lane((1u << R_RC | 1u << R_GXQ | 1u << R_GYQ | 1u << R_RD | 1u << R_DQ | 1u << R_GS | 1u << R_S | 1u << R_VL | 1u << R_VU));
         double *dzb = sm + SM_DZB;
+        double *stg = sm + SM_MC;   // the factorisation's column buffer is free during this pass: NZ + STG_ROWS staging rows
+        tsync();
+        for (int s = NS + l; s < WS_COUNT; s += LW) {   // base pointers (stage 0) of the vector rows staged per stage; see WS_*
+            const double *p0 = nullptr;
+            switch (s) {
+                case WS_LIN: p0 = row(R_LIN, 0); break;  case WS_DG: p0 = row(R_DG, 0); break;
+                case WS_Z: p0 = row(R_Z, 0); break;      case WS_ZL: p0 = row(R_ZL, 0); break;
+                case WS_ZU: p0 = row(R_ZU, 0); break;    case WS_BL: p0 = BL; break;
+                case WS_BU: p0 = BU; break;              case WS_GX: p0 = row(R_GX, 0); break;
+                case WS_COEF: p0 = row(R_COEF, 0); break; case WS_RC: p0 = row(R_RC, 0); break;
+                case WS_DL: p0 = DL; break;              case WS_DU: p0 = DU; break;
+                case WS_GS: p0 = row(R_GS, 0); break;    case WS_GXQ: p0 = row(R_GXQ, 0); break;
+                case WS_GYQ: p0 = row(R_GYQ, 0); break;  case WS_RD: p0 = row(R_RD, 0); break;
+                case WS_DQ: p0 = row(R_DQ, 0); break;    case WS_S: p0 = row(R_S, 0); break;
+                case WS_VL: p0 = row(R_VL, 0); break;    default: p0 = row(R_VU, 0); break;
+            }
+            reinterpret_cast<const double **>(sm + SM_TAB)[s] = p0;
+        }
+        tsync();
+        // factor rows advance by NS rows per stage, vectors by one: the factor rows are issued separately
+        auto issue = [&](int k) {
+            const int half = l / (LW / 2), c2 = (l % (LW / 2)) * 2;
+            NMPC_NOUNROLL
+            for (int i = half; i < NS; i += 2) wp::cp_async16(stg + i * LW + c2, frow(k, i) + c2);
+            const double *const *tab = reinterpret_cast<const double *const *>(sm + SM_TAB);
+            NMPC_NOUNROLL
+            for (int s = NS + half; s < WS_COUNT; s += 2) {
+                int kk = k + (s >= WS_RC ? 1 : 0);
+                kk = kk < N ? kk : N;
+                wp::cp_async16(stg + s * LW + c2, tab[s] + (long long)kk * LW + c2);
+            }
+        };
+        issue(0);
         double dx = isx ? -row(R_RC, 0)[l] : 0.0;
         if (M > 0 && isq) {
             double rd = row(R_RD, 0)[l], Dq = row(R_DQ, 0)[l], gs = row(R_GS, 0)[l];
@@ -720,30 +802,33 @@ struct WarpSolver {
             }
         }
         for (int k = 0; k <= N; k++) {
-            tsync();
-            if (k + 2 <= N) {   // factor rows and vectors two stages ahead
-                if (l / LPR < NS) wp::prefetch(frow(k + 2, l / LPR) + (l % LPR) * 16);
-                if (NS > 16 && l / LPR < NS - 16) wp::prefetch(frow(k + 2, 16 + l / LPR) + (l % LPR) * 16);
-                prefetch_at(pf_a, k + 2);
-                prefetch_at(pf_b, k + 3);
-            }
+            wp::cp_async_wait();
             if (isx) dzb[l] = dx;
             tsync();
+            // everything this stage needs moves from the staging buffer to registers, then the buffer is refilled
+            // for stage k+1 while this stage computes
+            double fv[NS];
+            NMPC_UNROLL
+            for (int i = 0; i < NS; i++) fv[i] = stg[i * LW + l];
+            const double v_lin = stg[WS_LIN * LW + l], v_dg = stg[WS_DG * LW + l], v_z = stg[WS_Z * LW + l], v_zl = stg[WS_ZL * LW + l],
+                         v_zu = stg[WS_ZU * LW + l], v_bl = stg[WS_BL * LW + l], v_bu = stg[WS_BU * LW + l], v_gx = stg[WS_GX * LW + l];
+            const double *cf = stg + WS_COEF * LW;
+            const double cA = comp == 0 ? cf[rob] : (comp == 1 ? cf[CFS + rob] : 0.0);
+            const double cB = comp == 0 ? cf[2 * CFS + rob] : (comp == 1 ? cf[3 * CFS + rob] : T);
+            const double v_rc = stg[WS_RC * LW + l];
+            const double q_lo = stg[WS_DL * LW + l], q_hi = stg[WS_DU * LW + l], q_gs = stg[WS_GS * LW + l], q_gx = stg[WS_GXQ * LW + l],
+                         q_gy = stg[WS_GYQ * LW + l], q_rd = stg[WS_RD * LW + l], q_dq = stg[WS_DQ * LW + l], q_s = stg[WS_S * LW + l],
+                         q_vl = stg[WS_VL * LW + l], q_vu = stg[WS_VU * LW + l];
+            tsync();
+            if (k < N) issue(k + 1);
             double acc = 0.0;
             if (isz) {
-                double a0 = row(R_LIN, k)[l], a1 = isx ? row(R_DG, k)[l] * dzb[l] : 0.0, a2 = 0.0;
+                double a0 = v_lin, a1 = isx ? v_dg * dzb[l] : 0.0, a2 = 0.0;
                 NMPC_UNROLL
-                for (int i0 = 0; i0 < NS; i0 += 6) {   // six factor rows in flight, three accumulation chains
-                    double fv[6];
-                    NMPC_UNROLL
-                    for (int i = 0; i < 6; i++)
-                        if (i0 + i < NS) fv[i] = frow(k, i0 + i)[l];
-                    NMPC_UNROLL
-                    for (int i = 0; i < 6; i += 3) {
-                        if (i0 + i < NS) a0 += fv[i] * dzb[i0 + i];
-                        if (i0 + i + 1 < NS) a1 += fv[i + 1] * dzb[i0 + i + 1];
-                        if (i0 + i + 2 < NS) a2 += fv[i + 2] * dzb[i0 + i + 2];
-                    }
+                for (int i = 0; i < NS; i += 3) {   // three accumulation chains
+                    a0 += fv[i] * dzb[i];
+                    a1 += fv[i + 1] * dzb[i + 1];
+                    a2 += fv[i + 2] * dzb[i + 2];
                 }
                 acc = a0 + (a1 + a2);
             }
@@ -753,34 +838,27 @@ struct WarpSolver {
             const double dzl = isx ? dx : du;
             row(rdz, k)[l] = dzl;
             if (zvalid(k)) {
-                double z = row(R_Z, k)[l];
-                slack_step_terms(z, dzl, BL[k * LW + l], BU[k * LW + l], row(R_ZL, k)[l], row(R_ZU, k)[l], mu, ap, az);
-                gbd += row(R_GX, k)[l] * dzl; tiny = fmax(tiny, fabs(dzl) / (1.0 + fabs(z)));
+                slack_step_terms(v_z, dzl, v_bl, v_bu, v_zl, v_zu, mu, ap, az);
+                gbd += v_gx * dzl; tiny = fmax(tiny, fabs(dzl) / (1.0 + fabs(v_z)));
             }
             if (k < N) {
                 tsync();
                 double dn = 0.0;
-                if (isx) {
-                    const double *cf = row(R_COEF, k);
-                    double cA = comp == 0 ? cf[rob] : (comp == 1 ? cf[CFS + rob] : 0.0);
-                    double cB = comp == 0 ? cf[2 * CFS + rob] : (comp == 1 ? cf[3 * CFS + rob] : T);
-                    dn = dzb[l] + cA * dzb[3 * rob + 2] + cB * dzb[NS + 2 * rob + (comp == 2 ? 1 : 0)] - row(R_RC, k + 1)[l];
-                }
+                if (isx) dn = dzb[l] + cA * dzb[3 * rob + 2] + cB * dzb[NS + 2 * rob + (comp == 2 ? 1 : 0)] - v_rc;
                 if (M > 0 && isq) {
                     const int b = k + 1;
-                    bool act = DL[b * LW + l] > -NMPC_INF || DU[b * LW + l] < NMPC_INF;
+                    bool act = q_lo > -NMPC_INF || q_hi < NMPC_INF;
                     double ds = 0.0, ytd = 0.0;
                     if (act) {
-                        double gs = row(R_GS, b)[l];
-                        ds = row(R_GXQ, b)[l] * (dzb[3 * pi] - dzb[3 * pj]) + row(R_GYQ, b)[l] * (dzb[3 * pi + 1] - dzb[3 * pj + 1]) + row(R_RD, b)[l];
-                        ytd = row(R_DQ, b)[l] * ds + gs;
-                        double s = row(R_S, b)[l];
-                        slack_step_terms(s, ds, DL[b * LW + l], DU[b * LW + l], row(R_VL, b)[l], row(R_VU, b)[l], mu, ap, az);
-                        gbd += gs * ds; tiny = fmax(tiny, fabs(ds) / (1.0 + fabs(s)));
+                        ds = q_gx * (dzb[3 * pi] - dzb[3 * pj]) + q_gy * (dzb[3 * pi + 1] - dzb[3 * pj + 1]) + q_rd;
+                        ytd = q_dq * ds + q_gs;
+                        slack_step_terms(q_s, ds, q_lo, q_hi, q_vl, q_vu, mu, ap, az);
+                        gbd += q_gs * ds; tiny = fmax(tiny, fabs(ds) / (1.0 + fabs(q_s)));
                     }
                     row(rds, b)[l] = ds; row(rytd, b)[l] = ytd;
                 }
                 dx = dn;
+                tsync();   // dzb is rewritten at the top of the next stage
             }
         }
         ap = tred_max(ap); az = tred_max(az);

@@ -38,6 +38,14 @@ NMPC_DEV double rcp_pos(double d)
 }
 // L2 prefetch of a line that a later stage of the same pass will read (the per-warp scratch does not fit L1)
 NMPC_DEV void prefetch(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// asynchronous 16-byte global -> shared copy (LDGSTS, L2-only caching): stages the scratch rows of the NEXT Riccati
+// stage while the current one is being processed, without holding registers
+NMPC_DEV void cp_async16(double *smem_dst, const double *gsrc)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+NMPC_DEV void cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 NMPC_DEV unsigned nth_set_bit(unsigned mask, int n) { return __fns(mask, 0, n + 1); }
 // one shared copy of the long math routines: keeps the passes small enough for the instruction cache
 __device__ __noinline__ void sincos_(double x, double *s, double *c) { sincos(x, s, c); }

@@ -37,6 +37,8 @@ inline double *shared_ptr(double *p) { return p; }
 template <class Tp> inline Tp *global_ptr(Tp *p) { return p; }
 inline double rcp_pos(double d) { return 1.0 / d; }
 inline void prefetch(const void *) {}
+inline void cp_async16(double *dst, const double *src) { dst[0] = src[0]; dst[1] = src[1]; }
+inline void cp_async_wait() {}
 inline unsigned nth_set_bit(unsigned mask, int n) { for (unsigned b = 0; b < 32; b++) if (mask >> b & 1u) { if (n == 0) return b; n--; } return 0xffffffffu; }
 inline double log_(double x) { return ::log(x); }
 inline double frexp_(double x, int *e) { return ::frexp(x, e); }
