@@ -263,8 +263,14 @@ struct WarpSolver {
     struct ZRows { double z, dz, lo, hi, zl, zu, yc, ce, csoc, cs, sn; };
     struct QRows { double s, ds, lo, hi, yd, vl, vu, dsoc; };
 
+    // FULL (dual / complementarity terms as well) is a run-time flag: one copy of this pass serves the iterate and the
+    // trial points, which halves its instruction-cache footprint
     template <bool FULL>
-    NMPC_PASS void eval_pass(double mu, double alpha, int rdz, int rds, bool trial, bool socacc, double asoc, EvalOut &E)
+    NMPC_DEV void eval_pass(double mu, double alpha, int rdz, int rds, bool trial, bool socacc, double asoc, EvalOut &E)
+    {
+        eval_pass_rt(FULL, mu, alpha, rdz, rds, trial, socacc, asoc, E);
+    }
+    NMPC_PASS void eval_pass_rt(const bool FULL, double mu, double alpha, int rdz, int rds, bool trial, bool socacc, double asoc, EvalOut &E)
     {
         NMPC_LOCALS
         const double kd = P.o.kappa_d;
