@@ -18,6 +18,7 @@
 // step the same source through a CPU fibre emulation of a warp (tests/emul/).
 #pragma once
 #include "nmpc_internal.h"
+#include "ipm_driver.cuh"
 
 #ifndef NMPC_INF
 #define NMPC_INF ((double)INFINITY)
@@ -1105,178 +1106,35 @@ struct WarpSolver {
     }
 
     // ---------------------------------------------------------------------------------------
-    // K2: the interior-point iteration
+    // hooks used by the shared interior-point driver (ipm_driver.cuh)
     // ---------------------------------------------------------------------------------------
-    NMPC_DEV void run()
+    NMPC_DEV bool is_lead() const { return l == 0; }
+    NMPC_DEV bool factor_m(int mode, double mu, double delta, bool soc)
     {
-        const nmpc_opts &o = P.o;
+        return mode == 0 ? factor<0>(mu, delta, soc) : (mode == 1 ? factor<1>(mu, delta, soc) : factor<2>(mu, delta, soc));
+    }
+    NMPC_DEV void eval(bool full, double mu, double alpha, int rdz, int rds, bool trial, bool socacc, double asoc, EvalOut &E)
+    {
+        eval_pass_rt(full, mu, alpha, rdz, rds, trial, socacc, asoc, E);
+    }
+    // largest |y| over the equality and inequality multipliers (least-squares initialisation)
+    NMPC_DEV double mult_absmax()
+    {
+        double ymax = 0.0;
+        for (int k = 0; k <= N; k++) ymax = fmax(ymax, fmax(isx ? fabs(row(R_YC, k)[l]) : 0.0, (M > 0 && isq) ? fabs(row(R_YD, k)[l]) : 0.0));
+        return tred_max(ymax);
+    }
+    NMPC_DEV void mult_zero()
+    {
+        for (int k = 0; k <= N; k++) { row(R_YC, k)[l] = 0.0; row(R_YD, k)[l] = 0.0; }
+    }
+    NMPC_DEV bool bounds_rejected()
+    {
         if (P.bound_err && *P.bound_err) {  // bounds rejected by prep_bounds_kernel: report, do not solve
             if (l == 0) { if (P.status) P.status[inst] = *P.bound_err; if (P.iters) P.iters[inst] = 0; }
-            return;
+            return true;
         }
-        init_point();
-        // least-squares equality multipliers (W = 0, Sigma = I); discarded when too large
-        {
-            bool ok = factor<1>(0.0, 0.0, false);
-            StepInfo si;
-            if (ok) forward(0.0, 0.99, R_DZ, R_DS, R_YC, R_YD, si);
-            double ymax = 0.0;
-            for (int k = 0; k <= N; k++) ymax = fmax(ymax, fmax(isx ? fabs(row(R_YC, k)[l]) : 0.0, (M > 0 && isq) ? fabs(row(R_YD, k)[l]) : 0.0));
-            ymax = tred_max(ymax);
-            if (!ok || !(ymax <= o.constr_mult_init_max)) {
-                for (int k = 0; k <= N; k++) { row(R_YC, k)[l] = 0.0; row(R_YD, k)[l] = 0.0; }
-            }
-            tsync();
-        }
-        double mu = o.mu_init, tau = fmax(o.tau_min, 1.0 - mu);
-        double theta_max = -1.0, theta_min = -1.0, delta_last = 0.0, f_prev = 0.0;
-        int iter = 0, st = NMPC_MAX_ITER, n_acc = 0;
-        bool tiny_prev = false;
-        double E0 = 0.0;
-        const double mu_floor = fmin(o.tol, o.compl_inf_tol) / (o.barrier_tol_factor + 1.0);
-        EvalOut E;
-        E.dinf = E.c0 = E.cmu = E.ysum = E.zsum = 0.0;
-        for (;;) {
-            eval_pass<true>(mu, 0.0, 0, 0, false, false, 0.0, E);
-            const double smax = 100.0;
-            const double sd = fmax(smax, (E.ysum + E.zsum) / fmax(1.0, ny_nzb)) / smax;
-            const double sc = fmax(smax, E.zsum / fmax(1.0, nzb_cnt)) / smax;
-            for (int pass = 0;; pass++) {
-                E0 = fmax(fmax(E.dinf / sd, E.pinf), E.c0 / sc);
-                const double Emu = fmax(fmax(E.dinf / sd, E.pinf), E.cmu / sc);
-                if (pass == 0) {
-                    if (E0 <= o.tol && E.dinf / df <= o.dual_inf_tol && E.viol <= o.constr_viol_tol && E.c0 / df <= o.compl_inf_tol) { st = NMPC_SOLVED; goto finished; }
-                    bool acc = E0 <= o.acceptable_tol && E.dinf / df <= 1e10 && E.viol <= 1e-2 && E.c0 / df <= 1e-2 &&
-                               (iter == 0 || fabs(E.f - f_prev) / fmax(1.0, fabs(E.f)) <= o.acceptable_obj_change_tol);
-                    n_acc = acc ? n_acc + 1 : 0;
-                    if (n_acc >= o.acceptable_iter) { st = NMPC_ACCEPTABLE; goto finished; }
-                    if (iter >= o.max_iter) { st = NMPC_MAX_ITER; goto finished; }
-                }
-                if (!(Emu <= o.barrier_tol_factor * mu) && !(tiny_prev && pass == 0)) break;
-                const double nm = fmax(fmin(o.kappa_mu * mu, pow(mu, o.theta_mu)), mu_floor);
-                if (nm >= mu) break;
-                mu = nm; tau = fmax(o.tau_min, 1.0 - mu); fn = 0; tiny_prev = false;
-                eval_pass<true>(mu, 0.0, 0, 0, false, false, 0.0, E);
-            }
-            f_prev = E.f;
-            const double theta = E.theta;
-            const double phi = df * E.f - mu * E.slog + o.kappa_d * mu * E.sdamp;
-            if (theta_max < 0.0) { theta_max = 1e4 * fmax(1.0, theta); theta_min = 1e-4 * fmax(1.0, theta); }
-            double *tr = (P.trace && iter < P.max_trace) ? P.trace + ((long long)inst * P.max_trace + iter) * NMPC_NTRACE : nullptr;
-            if (tr && l == 0) { tr[0] = mu; tr[1] = E0; tr[2] = theta; tr[3] = E.f; tr[4] = tr[5] = tr[6] = tr[7] = 0.0; }
-            // ---- search direction with inertia correction ----
-            double delta = 0.0;
-            bool need_resto = false;
-            for (;;) {
-                if (factor<0>(mu, delta, false)) break;
-                if (delta == 0.0) delta = delta_last == 0.0 ? 1e-4 : fmax(1e-20, delta_last / 3.0);
-                else delta *= (delta_last == 0.0 || 1e5 * delta_last < delta) ? 100.0 : 8.0;
-                if (delta > 1e20) { need_resto = true; break; }
-            }
-            if (delta > 0.0 && !need_resto) { delta_last = delta; n_reg++; }
-            double alpha = 0.0, alpha_z = 0.0;
-            int ls_count = 0;
-            if (!need_resto) {
-                StepInfo si;
-                forward(mu, tau, R_DZ, R_DS, R_YTC, R_YTD, si);
-                const double gbd = si.gbd;
-                const bool tiny = si.tiny < 10.0 * 2.220446049250313e-16 && theta < 1e-4;
-                double amin = 1e-5;
-                if (gbd < 0.0) {
-                    amin = fmin(1e-5, 1e-8 * theta / (-gbd));
-                    if (theta <= theta_min) amin = fmin(amin, pow(theta, 1.1) / pow(-gbd, 2.3));
-                }
-                amin *= 0.05;
-                bool accepted = false, armijo_step = false, use_soc = false;
-                alpha = si.ap; alpha_z = si.az;
-                if (tiny) { accepted = true; tiny_prev = true; }
-                while (!accepted) {
-                    ls_count++;
-                    EvalOut Et;
-                    eval_pass<false>(mu, alpha, R_DZ, R_DS, true, false, 0.0, Et);
-                    const double th_t = Et.theta, ph_t = df * Et.f - mu * Et.slog + o.kappa_d * mu * Et.sdamp;
-                    const bool ftype = gbd < 0.0 && alpha * pow(-gbd, 2.3) > pow(theta, 1.1);
-                    if (trial_ok(th_t, ph_t, theta, phi, theta_max, theta_min, gbd, alpha, ftype)) {
-                        accepted = true; armijo_step = ftype && theta <= theta_min; break;
-                    }
-                    if (ls_count == 1 && th_t >= theta && o.max_soc > 0) {  // second-order correction
-                        double th_old = 0.0, th_tr = th_t, a_soc = alpha;
-                        int cnt = 0;
-                        soc_begin();
-                        int rz = R_DZ, rs = R_DS;  // direction whose trial point feeds the next correction
-                        while (cnt < o.max_soc && !accepted && (cnt == 0 || th_tr <= 0.99 * th_old)) {
-                            th_old = th_tr;
-                            EvalOut Ea;  // c_soc := a_soc c_soc + c(trial)
-                            eval_pass<false>(mu, a_soc, rz, rs, true, true, a_soc, Ea);
-                            n_soc++;
-                            if (!factor<0>(mu, delta, true)) break;
-                            StepInfo s2;
-                            forward(mu, tau, R_DZ2, R_DS2, R_YTC2, R_YTD2, s2);
-                            a_soc = s2.ap; rz = R_DZ2; rs = R_DS2;
-                            EvalOut E2;
-                            eval_pass<false>(mu, a_soc, R_DZ2, R_DS2, true, false, 0.0, E2);
-                            const double th2 = E2.theta, ph2 = df * E2.f - mu * E2.slog + o.kappa_d * mu * E2.sdamp;
-                            if (trial_ok(th2, ph2, theta, phi, theta_max, theta_min, gbd, alpha, ftype)) {
-                                accepted = true; armijo_step = ftype && theta <= theta_min; use_soc = true;
-                                alpha = a_soc; alpha_z = s2.az;
-                            } else { cnt++; th_tr = th2; }
-                        }
-                        if (accepted) break;
-                    }
-                    alpha *= 0.5;
-                    if (alpha < amin) break;
-                }
-                if (!accepted) need_resto = true;
-                else {
-                    if (!tiny && !armijo_step) filter_add((1.0 - 1e-5) * theta, phi - 1e-8 * theta);
-                    if (!tiny) tiny_prev = false;
-                    if (use_soc) accept(alpha, alpha_z, mu, R_DZ2, R_DS2, R_YTC2, R_YTD2);
-                    else accept(alpha, alpha_z, mu, R_DZ, R_DS, R_YTC, R_YTD);
-                }
-            }
-            if (need_resto) {
-                // bounded substitute for IPOPT's restoration phase (see oracle/nmpc_oracle.c)
-                n_resto++;
-                filter_add((1.0 - 1e-5) * theta, phi - 1e-8 * theta);
-                const double thR = theta;
-                bool ok = false;
-                {   // first candidate: rollout projection onto the dynamics (see oracle/nmpc_oracle.c)
-                    rollout_project();
-                    EvalOut Ep;
-                    eval_pass<false>(mu, 1.0, R_DZ, R_DS, true, false, 0.0, Ep);
-                    if (Ep.theta < thR) accept_primal(1.0, R_DZ, R_DS);
-                }
-                for (int r_it = 0; r_it < o.max_resto_iter; r_it++) {
-                    EvalOut Er;
-                    eval_pass<false>(mu, 0.0, 0, 0, false, false, 0.0, Er);
-                    const double th = Er.theta;
-                    if ((th <= 0.9 * thR || th <= 1e-9) &&
-                        filter_ok(th, df * Er.f - mu * Er.slog + o.kappa_d * mu * Er.sdamp)) { ok = true; break; }
-                    if (!factor<2>(mu, 0.0, false)) break;
-                    StepInfo sr;
-                    forward(mu, tau, R_DZ, R_DS, R_YTC, R_YTD, sr);
-                    double a = sr.ap, th_t = th;
-                    bool got = false;
-                    while (a > 1e-12) {
-                        EvalOut Et;
-                        eval_pass<false>(mu, a, R_DZ, R_DS, true, false, 0.0, Et);
-                        th_t = Et.theta;
-                        if (th_t <= (1.0 - 1e-4 * a) * th) { got = true; break; }
-                        a *= 0.5;
-                    }
-                    if (!got) break;
-                    accept_primal(a, R_DZ, R_DS);
-                    if (th - th_t < 1e-14 * fmax(1.0, th)) break;
-                }
-                if (!ok) { st = NMPC_INFEASIBLE; iter++; goto finished; }
-                resto_reset(mu);
-                alpha = 0.0; alpha_z = 0.0;
-            }
-            n_ls += ls_count;
-            if (tr && l == 0) { tr[4] = alpha; tr[5] = alpha_z; tr[6] = delta; tr[7] = ls_count; }
-            iter++;
-        }
-    finished:
-        write_outputs(st, iter, E0, E.pinf, E.dinf, E.c0, mu);
+        return false;
     }
+    NMPC_DEV void run() { ipm_run(*this); }
 };
