@@ -1,0 +1,894 @@
+// CTA-per-instance dense-block solver for large swarms (Nr > 10, e.g. the 64-robot configuration).
+//
+// Same NLP and the same interior-point iteration (ipm_driver.cuh) as the warp-per-instance solver, for the case where
+// a stage of the KKT system no longer fits the lanes of a warp: the stage blocks become dense matrices
+// (64 robots: P 192 x 192, control block 128 x 128, 2016 pair rows per stage).  Replaces, for one instance,
+//     sol = solver(x0=, p=, lbx=, ubx=, lbg=, ubg=)          centralized_six_robots_implementation.py:432
+// built by the many-robot scripts (mpc_online_casadi_tb3_ten_robots...py:169-380 is the largest in the reference).
+//
+// Mapping: one CTA (BLOCK_THREADS threads) per instance, instances pulled from an atomic queue.  Vectors live in a
+// per-CTA scratch area in global memory (L2 resident) as [row][stage][W] with W >= max(5 Nr, M); the vector passes are
+// flat thread-strided loops over (stage, variable / pair).  The Riccati factorisation keeps the control block of the
+// stage matrix in shared memory:
+//     M = H~ + [A B]' P+ [A B]     assembled per robot pair from the 3x3 blocks of P+ (A, B are unicycle-sparse)
+//     M_uu = L L'                  Cholesky in shared memory; a pivot <= 0 is IPOPT's wrong-inertia signal
+//     Y = L^-1 [M_ux | m_u]        P = M_xx - Y'Y,  p = m_x - Y' y_m      (the dense contractions of this path)
+// and the forward pass applies  du = -L^-T (Y dx + y_m).
+#pragma once
+#include "nmpc_internal.h"
+#include "ipm_driver.cuh"
+#include "solver_body.cuh"
+
+#define NMPC_BLOCK_THREADS 512
+#define NMPC_BPASS __device__ __noinline__
+
+struct BlockSolver {
+    enum Row {
+        R_Z, R_ZL, R_ZU, R_DZ, R_DZ2, R_GX, R_YC, R_YTC, R_YTC2, R_RC, R_CSOC, R_COEF, R_COEF2, R_LIN, R_DGV,
+        R_S, R_VL, R_VU, R_YD, R_DS, R_DS2, R_YTD, R_YTD2, R_DSOC, R_GXQ, R_GYQ, R_RD, R_DQ, R_GS,
+        R_PXX, R_PYY, R_PXY, R_PHX, R_PHY, R_TRIG, R_TRIG2, R_ZT, R_ST,
+        R_COUNT
+    };
+    struct EvalOut { double pinf, viol, dinf, c0, cmu, ysum, zsum, theta, f, slog, sdamp; };
+    struct StepInfo { double ap, az, gbd, tiny; };
+    typedef WarpSolver<1> WS;   // scalar helpers (push_in, slack_step_terms, cmp_le, fin) are shared with the warp solver
+
+    const NmpcSolveParams &P;
+    double *sm, *ws;
+    int Nr, N, S, ns, nc, nz, M, W, tid, nt, inst, fn;
+    const double *BL, *BU, *CE, *DL, *DU, *pp;
+    const int *pairs;
+    double *Pall, *Yall, *Lall;
+    double T, df, ny_nzb, nzb_cnt;
+    int n_reg, n_resto, n_soc, n_fact, n_ls;
+    // shared-memory carve-up (doubles)
+    int SM_RED, SM_FTH, SM_FPH, SM_MISC, SM_DZB, SM_DXN, SM_TB, SM_XB, SM_PR, SM_CS, SM_MUU;
+
+    static NMPC_HD int row_width(int Nr) { int nz = 5 * Nr, M = Nr * (Nr - 1) / 2, w = nz > M ? nz : M; return (w + 31) & ~31; }
+    static NMPC_HD long long ws_doubles(int Nr, int N)
+    {
+        const long long S = N + 1, ns = 3 * Nr, nc = 2 * Nr, W = row_width(Nr);
+        return (long long)R_COUNT * S * W + S * ns * ns + (long long)N * nc * (ns + 1) + (long long)N * nc * nc;
+    }
+    static NMPC_HD long long sm_doubles(int Nr)
+    {
+        const long long ns = 3 * Nr, nc = 2 * Nr, nz = 5 * Nr;
+        return 32 * 12 + 16 + 16 + 8 + nz + ns + nc + nc + ns + 2 * Nr + nc * nc + 8;
+    }
+
+    __device__ BlockSolver(const NmpcSolveParams &p, double *smem, double *wsp) : P(p), sm(smem), ws(wsp) {}
+
+    static __device__ __forceinline__ void tsync() { __syncthreads(); }
+    __device__ __forceinline__ double *row(int r, int k) const { return ws + ((long long)r * S + k) * W; }
+    __device__ __forceinline__ bool is_lead() const { return tid == 0; }
+    __device__ __forceinline__ int pairidx(int a, int b) const { return a * (2 * Nr - a - 1) / 2 + (b - a - 1); }
+    __device__ __forceinline__ double qw(int l) const { return l < ns ? 2.0 * P.Q[l % 3] : 2.0 * P.R[(l - ns) & 1]; }
+    __device__ __forceinline__ double xs(int l) const { return l < ns ? pp[ns + l] : 0.0; }
+    __device__ __forceinline__ double gradf(int k, int l, double z) const { return k < N ? qw(l) * (z - xs(l)) : 0.0; }
+    __device__ __forceinline__ int nvalid(int k) const { return k < N ? nz : ns; }
+
+    // block-wide reduction of K values at once; bit i of maxmask: max (else sum); bit i of minmask: min
+    template <int K>
+    __device__ void breduce(double (&v)[K], unsigned maxmask)
+    {
+        double *red = sm + SM_RED;
+        const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+#pragma unroll
+        for (int i = 0; i < K; i++) {
+            double x = v[i];
+#pragma unroll
+            for (int m = 16; m > 0; m >>= 1) {
+                double y = __shfl_xor_sync(0xffffffffu, x, m);
+                x = (maxmask >> i & 1u) ? fmax(x, y) : x + y;
+            }
+            v[i] = x;
+        }
+        __syncthreads();
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < K; i++) red[wid * 12 + i] = v[i];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < K; i++) {
+            double x = red[i];
+            for (int w = 1; w < nw; w++) { double y = red[w * 12 + i]; x = (maxmask >> i & 1u) ? fmax(x, y) : x + y; }
+            v[i] = x;
+        }
+        __syncthreads();
+    }
+    __device__ double bsum(double x) { double v[1] = {x}; breduce<1>(v, 0u); return v[0]; }
+    __device__ double bmax(double x) { double v[1] = {x}; breduce<1>(v, 1u); return v[0]; }
+
+    // ---------------------------------------------------------------------------------------
+    __device__ void setup(int instance)
+    {
+        inst = instance; Nr = P.Nr; N = P.N; S = N + 1; ns = 3 * Nr; nc = 2 * Nr; nz = 5 * Nr; M = Nr * (Nr - 1) / 2;
+        W = row_width(Nr); T = P.T; tid = threadIdx.x; nt = blockDim.x;
+        const double *br = P.brows + (long long)inst * P.bstride;
+        BL = br + (long long)NMPC_BR_BL * S * W; BU = br + (long long)NMPC_BR_BU * S * W;
+        CE = br + (long long)NMPC_BR_CE * S * W; DL = br + (long long)NMPC_BR_DL * S * W;
+        DU = br + (long long)NMPC_BR_DU * S * W;
+        pp = P.p + (long long)inst * 2 * ns;
+        pairs = P.pairs;
+        Pall = ws + (long long)R_COUNT * S * W;
+        Yall = Pall + (long long)S * ns * ns;
+        Lall = Yall + (long long)N * nc * (ns + 1);
+        SM_RED = 0; SM_FTH = 32 * 12; SM_FPH = SM_FTH + 16; SM_MISC = SM_FPH + 16; SM_DZB = SM_MISC + 8; SM_DXN = SM_DZB + nz;
+        SM_TB = SM_DXN + ns; SM_XB = SM_TB + nc; SM_PR = SM_XB + nc; SM_CS = SM_PR + ns; SM_MUU = (SM_CS + 2 * Nr + 1) & ~1;
+        df = 1.0; fn = 0;
+        n_reg = n_resto = n_soc = n_fact = n_ls = 0;
+        __syncthreads();
+    }
+    __device__ bool bounds_rejected()
+    {
+        if (P.bound_err && *P.bound_err) {
+            if (tid == 0) { if (P.status) P.status[inst] = *P.bound_err; if (P.iters) P.iters[inst] = 0; }
+            return true;
+        }
+        return false;
+    }
+
+    // cos / sin of every heading of the evaluation point: row(rt,k)[i] = cos, row(rt,k)[Nr+i] = sin
+    __device__ void trig_rows(double alpha, int rdz, bool trial, int rt)
+    {
+        for (int idx = tid; idx < N * Nr; idx += nt) {
+            const int k = idx / Nr, i = idx - k * Nr;
+            double th = row(R_Z, k)[3 * i + 2];
+            if (trial) th += alpha * row(rdz, k)[3 * i + 2];
+            double s_, c_;
+            sincos(th, &s_, &c_);
+            row(rt, k)[i] = c_; row(rt, k)[Nr + i] = s_;
+        }
+        __syncthreads();
+    }
+
+    // starting point: objective scaling, push into bounds, slacks, bound multipliers (IPOPT defaults)
+    NMPC_BPASS void init_point()
+    {
+        const long long n = (long long)ns * S + (long long)nc * N;
+        const double *x0 = P.x0 + inst * n;
+        const nmpc_opts &o = P.o;
+        double gmax = 0.0;
+        for (int idx = tid; idx < S * nz; idx += nt) {
+            const int k = idx / nz, l = idx - k * nz;
+            const double z = l < ns ? x0[k * ns + l] : (k < N ? x0[ns * S + k * nc + (l - ns)] : 0.0);
+            gmax = fmax(gmax, fabs(gradf(k, l, z)));
+            row(R_Z, k)[l] = z;
+        }
+        gmax = bmax(gmax);
+        df = gmax > o.nlp_scaling_max_gradient ? fmax(o.nlp_scaling_max_gradient / gmax, 1e-8) : 1.0;
+        double cnt_z = 0.0, cnt_y = tid == 0 ? (double)(ns * S) : 0.0;
+        for (int idx = tid; idx < S * W; idx += nt) {
+            const int k = idx / W, l = idx - k * W;
+            if (l < nz) {
+                const double lo = BL[k * W + l], hi = BU[k * W + l];
+                row(R_Z, k)[l] = WS::push_in(row(R_Z, k)[l], lo, hi, o.bound_push, o.bound_frac);
+                const bool hl = lo > -NMPC_INF, hu = hi < NMPC_INF;
+                row(R_ZL, k)[l] = hl ? o.bound_mult_init_val : 0.0;
+                row(R_ZU, k)[l] = hu ? o.bound_mult_init_val : 0.0;
+                cnt_z += (hl ? 1.0 : 0.0) + (hu ? 1.0 : 0.0);
+            }
+            row(R_YC, k)[l] = 0.0; row(R_YD, k)[l] = 0.0; row(R_CSOC, k)[l] = 0.0; row(R_DSOC, k)[l] = 0.0;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < S * M; idx += nt) {
+            const int b = idx / M, q = idx - b * M;
+            const double lo = DL[b * W + q], hi = DU[b * W + q];
+            const bool hl = lo > -NMPC_INF, hu = hi < NMPC_INF;
+            double dv = NMPC_DUMMY_ROW_VALUE;
+            if (b > 0) {
+                const double *zr = row(R_Z, b - 1);
+                const int pi = pairs[2 * q], pj = pairs[2 * q + 1];
+                const double dx = zr[3 * pi] - zr[3 * pj], dy = zr[3 * pi + 1] - zr[3 * pj + 1];
+                dv = dx * dx + dy * dy;
+            }
+            row(R_S, b)[q] = (hl || hu) ? WS::push_in(dv, lo, hi, o.bound_push, o.bound_frac) : dv;
+            row(R_VL, b)[q] = hl ? o.bound_mult_init_val : 0.0;
+            row(R_VU, b)[q] = hu ? o.bound_mult_init_val : 0.0;
+            cnt_z += (hl ? 1.0 : 0.0) + (hu ? 1.0 : 0.0);
+            cnt_y += (hl || hu) ? 1.0 : 0.0;
+        }
+        double v[2] = {cnt_z, cnt_y};
+        breduce<2>(v, 0u);
+        nzb_cnt = v[0]; ny_nzb = v[1] + v[0];
+        trig_rows(0.0, 0, false, R_TRIG);
+    }
+
+    // one predicted state component: X_k + T f(X_k, U_k), component l of the state vector
+    __device__ __forceinline__ double predict(const double *zr, const double *tr, int l) const
+    {
+        const int rob = l / 3, comp = l - 3 * rob;
+        const double v = zr[ns + 2 * rob];
+        return comp == 0 ? zr[l] + T * v * tr[rob] : (comp == 1 ? zr[l] + T * v * tr[Nr + rob] : zr[l] + T * zr[ns + 2 * rob + 1]);
+    }
+
+    // ---------------------------------------------------------------------------------------
+    // residuals / merit quantities at the iterate (full) or at a trial point z + alpha dz
+    // ---------------------------------------------------------------------------------------
+    NMPC_BPASS void eval(bool full, double mu, double alpha, int rdz, int rds, bool trial, bool socacc, double asoc, EvalOut &E)
+    {
+        const double kd = P.o.kappa_d;
+        const int rt = trial ? R_TRIG2 : R_TRIG, rz = trial ? R_ZT : R_Z, rs = trial ? R_ST : R_S;
+        if (trial) {   // materialise the trial point once
+            for (int idx = tid; idx < S * W; idx += nt) {
+                const int k = idx / W, l = idx - k * W;
+                if (l < nz) row(R_ZT, k)[l] = l < nvalid(k) ? row(R_Z, k)[l] + alpha * row(rdz, k)[l] : 0.0;
+                if (l < M) row(R_ST, k)[l] = row(R_S, k)[l] + alpha * row(rds, k)[l];
+            }
+        }
+        trig_rows(alpha, rdz, trial, rt);   // ends with a barrier
+        double pinf = 0, viol = 0, dinf = 0, c0 = 0, cmu = 0, ysum = 0, zsum = 0, th = 0, fo = 0, sdamp = 0, slog = 0;
+        // ---- equality rows ----
+        for (int idx = tid; idx < S * ns; idx += nt) {
+            const int k = idx / ns, l = idx - k * ns;
+            double c;
+            if (k == 0) c = row(rz, 0)[l] - pp[l] - CE[l];
+            else c = row(rz, k)[l] - predict(row(rz, k - 1), row(rt, k - 1), l) - CE[k * W + l];
+            pinf = fmax(pinf, fabs(c)); th += fabs(c); viol = fmax(viol, fabs(c));
+            if (socacc) row(R_CSOC, k)[l] = asoc * row(R_CSOC, k)[l] + c;
+            if (full) ysum += fabs(row(R_YC, k)[l]);
+        }
+        // ---- inequality rows ----
+        for (int idx = tid; idx < S * M; idx += nt) {
+            const int b = idx / M, q = idx - b * M;
+            const double lo = DL[b * W + q], hi = DU[b * W + q];
+            const bool hl = lo > -NMPC_INF, hu = hi < NMPC_INF;
+            if (!(hl || hu)) continue;
+            double dv = NMPC_DUMMY_ROW_VALUE;
+            if (b > 0) {
+                const double *zr = row(rz, b - 1);
+                const int pi = pairs[2 * q], pj = pairs[2 * q + 1];
+                const double dx = zr[3 * pi] - zr[3 * pj], dy = zr[3 * pi + 1] - zr[3 * pj + 1];
+                dv = dx * dx + dy * dy;
+            }
+            const double s = row(rs, b)[q], dms = dv - s;
+            pinf = fmax(pinf, fabs(dms)); th += fabs(dms);
+            viol = fmax(viol, fmax(lo - dv, dv - hi));
+            if (socacc) row(R_DSOC, b)[q] = asoc * row(R_DSOC, b)[q] + dms;
+            if (hl) slog += log(s - lo);
+            if (hu) slog += log(hi - s);
+            if (hl && !hu) sdamp += s - lo;
+            if (hu && !hl) sdamp += hi - s;
+            if (full) {
+                const double yd = row(R_YD, b)[q], vl = row(R_VL, b)[q], vu = row(R_VU, b)[q];
+                ysum += fabs(yd);
+                double t = -yd - vl + vu;
+                if (hl && !hu) t += kd * mu;
+                if (hu && !hl) t -= kd * mu;
+                dinf = fmax(dinf, fabs(t));
+                if (hl) { double u = (s - lo) * vl; c0 = fmax(c0, fabs(u)); cmu = fmax(cmu, fabs(u - mu)); zsum += fabs(vl); }
+                if (hu) { double u = (hi - s) * vu; c0 = fmax(c0, fabs(u)); cmu = fmax(cmu, fabs(u - mu)); zsum += fabs(vu); }
+            }
+        }
+        // ---- variable bounds, objective, stationarity ----
+        for (int idx = tid; idx < S * nz; idx += nt) {
+            const int k = idx / nz, l = idx - k * nz;
+            if (l >= nvalid(k)) continue;
+            const double *zr = row(rz, k);
+            const double zk = zr[l], lo = BL[k * W + l], hi = BU[k * W + l];
+            const bool hl = lo > -NMPC_INF, hu = hi < NMPC_INF;
+            if (hl) slog += log(zk - lo);
+            if (hu) slog += log(hi - zk);
+            if (hl && !hu) sdamp += zk - lo;
+            if (hu && !hl) sdamp += hi - zk;
+            if (k < N) { const double e = zk - xs(l); fo += 0.5 * qw(l) * e * e; }
+            if (full) {
+                const double zl = row(R_ZL, k)[l], zu = row(R_ZU, k)[l];
+                double r = df * gradf(k, l, zk) - zl + zu;
+                if (hl && !hu) r += kd * mu;
+                if (hu && !hl) r -= kd * mu;
+                const bool isx = l < ns;
+                const int rob = isx ? l / 3 : (l - ns) / 2, comp = isx ? l - 3 * rob : (l - ns) & 1;
+                if (isx) r += row(R_YC, k)[l];
+                if (k < N) {
+                    const double *ycn = row(R_YC, k + 1), *tr = row(rt, k);
+                    const double csr = tr[rob], snr = tr[Nr + rob];
+                    if (isx) {
+                        if (comp == 2) {
+                            const double v = zr[ns + 2 * rob];
+                            r -= ycn[l] + (-T * v * snr) * ycn[3 * rob] + (T * v * csr) * ycn[3 * rob + 1];
+                        } else {
+                            r -= ycn[l];
+                            const double *ydn = row(R_YD, k + 1);
+                            for (int j = 0; j < Nr; j++) {
+                                if (j == rob) continue;
+                                const int q = rob < j ? pairidx(rob, j) : pairidx(j, rob);
+                                r += 2.0 * (zk - zr[3 * j + comp]) * ydn[q];
+                            }
+                        }
+                    } else {
+                        if (comp == 0) r -= T * (csr * ycn[3 * rob] + snr * ycn[3 * rob + 1]);
+                        else r -= T * ycn[3 * rob + 2];
+                    }
+                }
+                dinf = fmax(dinf, fabs(r));
+                if (hl) { double u = (zk - lo) * zl; c0 = fmax(c0, fabs(u)); cmu = fmax(cmu, fabs(u - mu)); zsum += fabs(zl); }
+                if (hu) { double u = (hi - zk) * zu; c0 = fmax(c0, fabs(u)); cmu = fmax(cmu, fabs(u - mu)); zsum += fabs(zu); }
+            }
+        }
+        double v[11] = {pinf, viol, dinf, c0, cmu, ysum, zsum, th, fo, slog, sdamp};
+        breduce<11>(v, 0x1Fu);   // first five are maxima
+        E.pinf = v[0]; E.viol = v[1]; E.theta = v[7]; E.f = v[8]; E.slog = v[9]; E.sdamp = v[10];
+        if (full) { E.dinf = v[2]; E.c0 = v[3]; E.cmu = v[4]; E.ysum = v[5]; E.zsum = v[6]; }
+    }
+
+    // barrier Hessian / gradient pieces of one variable or slack (mode 0: primal-dual, 1: least squares, 2: restoration)
+    static __device__ __forceinline__ void sig_g(int mode, double kd, double v, double lo, double hi, double ml, double mu_, double mu,
+                                                 double g0, double &sig, double &g)
+    {
+        const bool hl = lo > -NMPC_INF, hu = hi < NMPC_INF;
+        if (mode == 1) { sig = 1.0; g = g0 - ml + mu_; return; }
+        sig = 0.0; g = mode == 0 ? g0 : 0.0;
+        if (hl) { const double r = 1.0 / (v - lo); sig += mode == 0 ? ml * r : mu * r * r; g -= mu * r; }
+        if (hu) { const double r = 1.0 / (hi - v); sig += mode == 0 ? mu_ * r : mu * r * r; g += mu * r; }
+        if (mode == 0) {
+            if (hl && !hu) g += kd * mu;
+            if (hu && !hl) g -= kd * mu;
+        }
+    }
+
+    // ---------------------------------------------------------------------------------------
+    // K3: backward Riccati sweep with dense stage blocks.  false = wrong inertia (a control pivot <= 0).
+    // ---------------------------------------------------------------------------------------
+    __device__ bool factor_m(int mode, double mu, double delta, bool soc)
+    {
+        return factor(mode, mu, delta, soc);
+    }
+    NMPC_BPASS bool factor(int mode, double mu, double delta, bool soc)
+    {
+        const double zeta = mode == 2 ? sqrt(mu) : 0.0, kd = P.o.kappa_d;
+        double *Muu = sm + SM_MUU, *prv = sm + SM_PR, *misc = sm + SM_MISC;
+        const int ldy = ns + 1;
+        n_fact++;
+        __syncthreads();
+        // ---- stage-parallel part: barrier terms, coefficients, residuals, condensed inequality blocks ----
+        for (int idx = tid; idx < S * nz; idx += nt) {
+            const int k = idx / nz, l = idx - k * nz;
+            double sig = 0.0, gx = 0.0, dg = 0.0;
+            if (l < nvalid(k)) {
+                const double zk = row(R_Z, k)[l];
+                sig_g(mode, kd, zk, BL[k * W + l], BU[k * W + l], row(R_ZL, k)[l], row(R_ZU, k)[l], mu, df * gradf(k, l, zk), sig, gx);
+                dg = sig + delta + zeta;
+                if (mode == 0 && k < N) dg += df * qw(l);
+            }
+            row(R_GX, k)[l] = gx; row(R_DGV, k)[l] = dg;
+        }
+        for (int idx = tid; idx < N * Nr; idx += nt) {
+            const int k = idx / Nr, i = idx - k * Nr;
+            const double v = row(R_Z, k)[ns + 2 * i], c_ = row(R_TRIG, k)[i], s_ = row(R_TRIG, k)[Nr + i];
+            double *cf = row(R_COEF, k), *cf2 = row(R_COEF2, k);
+            cf[i] = -T * v * s_; cf[Nr + i] = T * v * c_; cf[2 * Nr + i] = T * c_; cf[3 * Nr + i] = T * s_;
+            if (mode == 0) {
+                const double lx = row(R_YC, k + 1)[3 * i], ly = row(R_YC, k + 1)[3 * i + 1];
+                cf2[i] = T * (lx * s_ - ly * c_); cf2[Nr + i] = T * v * (lx * c_ + ly * s_);
+            } else { cf2[i] = 0.0; cf2[Nr + i] = 0.0; }
+        }
+        for (int idx = tid; idx < S * ns; idx += nt) {
+            const int k = idx / ns, l = idx - k * ns;
+            double rc = 0.0;
+            if (mode != 1) {
+                if (soc) rc = row(R_CSOC, k)[l];
+                else if (k == 0) rc = row(R_Z, 0)[l] - pp[l] - CE[l];
+                else rc = row(R_Z, k)[l] - predict(row(R_Z, k - 1), row(R_TRIG, k - 1), l) - CE[k * W + l];
+            }
+            row(R_RC, k)[l] = rc;
+        }
+        for (int idx = tid; idx < S * M; idx += nt) {
+            const int b = idx / M, q = idx - b * M;
+            double pxx = 0, pyy = 0, pxy = 0, phx = 0, phy = 0, gxq = 0, gyq = 0, rd = 0, Dq = 0, gs = 0;
+            const double lo = DL[b * W + q], hi = DU[b * W + q];
+            if (lo > -NMPC_INF || hi < NMPC_INF) {
+                double dv = NMPC_DUMMY_ROW_VALUE;
+                if (b > 0) {
+                    const double *zr = row(R_Z, b - 1);
+                    const int pi = pairs[2 * q], pj = pairs[2 * q + 1];
+                    const double dx = zr[3 * pi] - zr[3 * pj], dy = zr[3 * pi + 1] - zr[3 * pj + 1];
+                    gxq = 2.0 * dx; gyq = 2.0 * dy; dv = dx * dx + dy * dy;
+                }
+                const double s = row(R_S, b)[q];
+                double sigs;
+                sig_g(mode, kd, s, lo, hi, row(R_VL, b)[q], row(R_VU, b)[q], mu, 0.0, sigs, gs);
+                rd = mode == 1 ? 0.0 : (soc ? row(R_DSOC, b)[q] : dv - s);
+                Dq = sigs + delta;
+                const double hq = Dq * rd + gs, mu2 = mode == 0 ? 2.0 * row(R_YD, b)[q] : 0.0;
+                pxx = Dq * gxq * gxq + mu2; pyy = Dq * gyq * gyq + mu2; pxy = Dq * gxq * gyq;
+                phx = gxq * hq; phy = gyq * hq;
+            }
+            row(R_GXQ, b)[q] = gxq; row(R_GYQ, b)[q] = gyq; row(R_RD, b)[q] = rd; row(R_DQ, b)[q] = Dq; row(R_GS, b)[q] = gs;
+            row(R_PXX, b)[q] = pxx; row(R_PYY, b)[q] = pyy; row(R_PXY, b)[q] = pxy; row(R_PHX, b)[q] = phx; row(R_PHY, b)[q] = phy;
+        }
+        // ---- terminal stage: X_N carries no cost and no distance rows, only its box ----
+        {
+            double *PN = Pall + (long long)N * ns * ns;
+            for (int idx = tid; idx < ns * ns; idx += nt) PN[idx] = 0.0;
+            __syncthreads();
+            for (int l = tid; l < ns; l += nt) { PN[l * ns + l] = row(R_DGV, N)[l]; row(R_LIN, N)[l] = row(R_GX, N)[l]; }
+        }
+        __syncthreads();
+        const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+        for (int k = N - 1; k >= 0; k--) {
+            const double *Pn = Pall + (long long)(k + 1) * ns * ns;
+            double *Pk = Pall + (long long)k * ns * ns, *Yk = Yall + (long long)k * nc * ldy, *Lk = Lall + (long long)k * nc * nc;
+            const double *cf = row(R_COEF, k), *cf2 = row(R_COEF2, k);
+            // A. pr = p_{k+1} - P_{k+1} rc_{k+1}   (one warp per row)
+            {
+                const double *rcn = row(R_RC, k + 1), *pn = row(R_LIN, k + 1);
+                for (int r = wid; r < ns; r += nw) {
+                    double acc = 0.0;
+                    for (int j = lane; j < ns; j += 32) acc += Pn[r * ns + j] * rcn[j];
+#pragma unroll
+                    for (int m = 16; m > 0; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+                    if (lane == 0) prv[r] = pn[r] - acc;
+                }
+            }
+            __syncthreads();
+            // B. stage matrix M = H~ + [A B]' P+ [A B], one robot pair (i, j) per thread: the 5x5 block C_i' Pb C_j
+            for (int idx = tid; idx < Nr * Nr; idx += nt) {
+                const int i = idx / Nr, j = idx - i * Nr;
+                const double ai = cf[i], bi = cf[Nr + i], tci = cf[2 * Nr + i], tsi = cf[3 * Nr + i];
+                const double aj = cf[j], bj = cf[Nr + j], tcj = cf[2 * Nr + j], tsj = cf[3 * Nr + j];
+                double t[3][5];
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    const double *pr3 = Pn + (long long)(3 * i + a) * ns + 3 * j;
+                    const double p0 = pr3[0], p1 = pr3[1], p2 = pr3[2];
+                    t[a][0] = p0; t[a][1] = p1; t[a][2] = p2 + aj * p0 + bj * p1; t[a][3] = tcj * p0 + tsj * p1; t[a][4] = T * p2;
+                }
+                double G[5][5];
+#pragma unroll
+                for (int c = 0; c < 5; c++) {
+                    G[0][c] = t[0][c]; G[1][c] = t[1][c]; G[2][c] = t[2][c] + ai * t[0][c] + bi * t[1][c];
+                    G[3][c] = tci * t[0][c] + tsi * t[1][c]; G[4][c] = T * t[2][c];
+                }
+                if (i == j) {
+                    const double *dgv = row(R_DGV, k), *gxr = row(R_GX, k);
+                    G[0][0] += dgv[3 * i]; G[1][1] += dgv[3 * i + 1]; G[2][2] += dgv[3 * i + 2] + cf2[Nr + i];
+                    G[3][3] += dgv[ns + 2 * i]; G[4][4] += dgv[ns + 2 * i + 1];
+                    G[2][3] += cf2[i]; G[3][2] += cf2[i];
+                    double sxx = 0, syy = 0, sxy = 0, glx = 0, gly = 0;
+                    const double *pxx = row(R_PXX, k + 1), *pyy = row(R_PYY, k + 1), *pxy = row(R_PXY, k + 1),
+                                 *phx = row(R_PHX, k + 1), *phy = row(R_PHY, k + 1);
+                    for (int jj = 0; jj < Nr; jj++) {
+                        if (jj == i) continue;
+                        const int q = i < jj ? pairidx(i, jj) : pairidx(jj, i);
+                        sxx += pxx[q]; syy += pyy[q]; sxy += pxy[q];
+                        glx += i < jj ? phx[q] : -phx[q]; gly += i < jj ? phy[q] : -phy[q];
+                    }
+                    G[0][0] += sxx; G[1][1] += syy; G[0][1] += sxy; G[1][0] += sxy;
+                    // m = [A B]' pr + h
+                    const double p0 = prv[3 * i], p1 = prv[3 * i + 1], p2 = prv[3 * i + 2];
+                    row(R_LIN, k)[3 * i] = p0 + gxr[3 * i] + glx;
+                    row(R_LIN, k)[3 * i + 1] = p1 + gxr[3 * i + 1] + gly;
+                    row(R_LIN, k)[3 * i + 2] = p2 + ai * p0 + bi * p1 + gxr[3 * i + 2];
+                    Yk[(long long)(2 * i) * ldy + ns] = tci * p0 + tsi * p1 + gxr[ns + 2 * i];
+                    Yk[(long long)(2 * i + 1) * ldy + ns] = T * p2 + gxr[ns + 2 * i + 1];
+                } else {
+                    const int q = i < j ? pairidx(i, j) : pairidx(j, i);
+                    const double vxx = row(R_PXX, k + 1)[q], vyy = row(R_PYY, k + 1)[q], vxy = row(R_PXY, k + 1)[q];
+                    G[0][0] -= vxx; G[1][1] -= vyy; G[0][1] -= vxy; G[1][0] -= vxy;
+                }
+#pragma unroll
+                for (int a = 0; a < 3; a++)
+#pragma unroll
+                    for (int c = 0; c < 3; c++) Pk[(long long)(3 * i + a) * ns + 3 * j + c] = G[a][c];
+#pragma unroll
+                for (int a = 0; a < 2; a++) {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) Yk[(long long)(2 * i + a) * ldy + 3 * j + c] = G[3 + a][c];
+#pragma unroll
+                    for (int c = 0; c < 2; c++) Muu[(2 * i + a) * nc + 2 * j + c] = G[3 + a][3 + c];
+                }
+            }
+            __syncthreads();
+            // C. Cholesky of the control block in shared memory (right-looking); pivot <= 0: wrong inertia
+            for (int j = 0; j < nc; j++) {
+                const double d = Muu[j * nc + j];
+                if (!(d > 0.0) || !(d < NMPC_INF)) return false;   // uniform: every thread reads the same value
+                const double rs = rsqrt(d);
+                __syncthreads();
+                for (int i = j + tid; i < nc; i += nt) Muu[i * nc + j] = i == j ? d * rs : Muu[i * nc + j] * rs;
+                __syncthreads();
+                const int rem = nc - j - 1;
+                for (int e = tid; e < rem * rem; e += nt) {
+                    const int a = j + 1 + e / rem, c = j + 1 + e % rem;
+                    if (c <= a) Muu[a * nc + c] -= Muu[a * nc + j] * Muu[c * nc + j];
+                }
+                __syncthreads();
+            }
+            // D. Y = L^-1 [M_ux | m_u], one column per thread (forward substitution, rows of Y in global memory)
+            for (int c = tid; c < ldy; c += nt) {
+                for (int i = 0; i < nc; i++) {
+                    double acc = Yk[(long long)i * ldy + c];
+                    const double *Li = Muu + i * nc;
+                    for (int j = 0; j < i; j++) acc -= Li[j] * Yk[(long long)j * ldy + c];
+                    Yk[(long long)i * ldy + c] = acc / Li[i];
+                }
+            }
+            // E. keep L for the forward pass
+            for (int e = tid; e < nc * nc; e += nt) Lk[e] = Muu[e];
+            __syncthreads();
+            // F. P_k = M_xx - Y'Y (upper 4x4 tiles, mirrored), p_k = m_x - Y' y_m
+            {
+                const int nt4 = (ns + 3) / 4;
+                for (int e = tid; e < nt4 * nt4; e += nt) {
+                    const int tr = e / nt4, tc = e - tr * nt4;
+                    if (tc < tr) continue;
+                    const int r0 = 4 * tr, c0 = 4 * tc;
+                    double acc[4][4];
+#pragma unroll
+                    for (int a = 0; a < 4; a++)
+#pragma unroll
+                        for (int c = 0; c < 4; c++) acc[a][c] = 0.0;
+                    for (int u = 0; u < nc; u++) {
+                        const double *yr = Yk + (long long)u * ldy;
+                        double ya[4], yc[4];
+#pragma unroll
+                        for (int a = 0; a < 4; a++) { ya[a] = r0 + a < ns ? yr[r0 + a] : 0.0; yc[a] = c0 + a < ns ? yr[c0 + a] : 0.0; }
+#pragma unroll
+                        for (int a = 0; a < 4; a++)
+#pragma unroll
+                            for (int c = 0; c < 4; c++) acc[a][c] += ya[a] * yc[c];
+                    }
+#pragma unroll
+                    for (int a = 0; a < 4; a++)
+#pragma unroll
+                        for (int c = 0; c < 4; c++) {
+                            const int r = r0 + a, cc = c0 + c;
+                            if (r < ns && cc < ns && r <= cc) {
+                                const double v = Pk[(long long)r * ns + cc] - acc[a][c];
+                                Pk[(long long)r * ns + cc] = v; Pk[(long long)cc * ns + r] = v;
+                            }
+                        }
+                }
+                for (int r = tid; r < ns; r += nt) {
+                    double acc = 0.0;
+                    for (int u = 0; u < nc; u++) acc += Yk[(long long)u * ldy + r] * Yk[(long long)u * ldy + ns];
+                    row(R_LIN, k)[r] -= acc;
+                }
+            }
+            __syncthreads();
+        }
+        (void)misc;
+        return true;
+    }
+
+    // ---------------------------------------------------------------------------------------
+    // forward pass: steps, new multipliers, fraction-to-boundary step sizes, grad(phi)'d
+    // ---------------------------------------------------------------------------------------
+    NMPC_BPASS void forward(double mu, double tau, int rdz, int rds, int rytc, int rytd, StepInfo &si)
+    {
+        double ap = 0.0, az = 0.0, gbd = 0.0, tiny = 0.0;
+        double *dzb = sm + SM_DZB, *dxn = sm + SM_DXN, *tb = sm + SM_TB, *xb = sm + SM_XB, *Ls = sm + SM_MUU;
+        const int ldy = ns + 1, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+        __syncthreads();
+        for (int q = tid; q < M; q += nt) {
+            const double rd = row(R_RD, 0)[q], Dq = row(R_DQ, 0)[q], gs = row(R_GS, 0)[q];
+            const bool act = DL[q] > -NMPC_INF || DU[q] < NMPC_INF;
+            const double ds = act ? rd : 0.0, ytd = act ? Dq * ds + gs : 0.0;
+            row(rds, 0)[q] = ds; row(rytd, 0)[q] = ytd;
+            if (act) {
+                const double s = row(R_S, 0)[q];
+                WS::slack_step_terms(s, ds, DL[q], DU[q], row(R_VL, 0)[q], row(R_VU, 0)[q], mu, ap, az);
+                gbd += gs * ds; tiny = fmax(tiny, fabs(ds) / (1.0 + fabs(s)));
+            }
+        }
+        for (int l = tid; l < nz; l += nt) dzb[l] = l < ns ? -row(R_RC, 0)[l] : 0.0;
+        __syncthreads();
+        for (int k = 0; k <= N; k++) {
+            const double *Pk = Pall + (long long)k * ns * ns;
+            const double *Yk = Yall + (long long)(k < N ? k : 0) * nc * ldy, *Lk = Lall + (long long)(k < N ? k : 0) * nc * nc;
+            if (k < N) for (int e = tid; e < nc * nc; e += nt) Ls[e] = Lk[e];
+            // y~c_k = -(P_k dx + p_k);  t = Y_k dx + y_m      (one warp per row)
+            for (int r = wid; r < ns + (k < N ? nc : 0); r += nw) {
+                const double *mr = r < ns ? Pk + (long long)r * ns : Yk + (long long)(r - ns) * ldy;
+                double acc = 0.0;
+                for (int j = lane; j < ns; j += 32) acc += mr[j] * dzb[j];
+#pragma unroll
+                for (int m = 16; m > 0; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+                if (lane == 0) {
+                    if (r < ns) row(rytc, k)[r] = -(acc + row(R_LIN, k)[r]);
+                    else tb[r - ns] = acc + mr[ns];
+                }
+            }
+            __syncthreads();
+            if (k < N) {   // L' x = t (column-oriented back substitution), du = -x
+                for (int i = nc - 1; i >= 0; i--) {
+                    const double xi = tb[i] / Ls[i * nc + i];   // tb[i] is final: rows > i were eliminated before the last barrier
+                    if (tid == 0) xb[i] = xi;
+                    for (int j = tid; j < i; j += nt) tb[j] -= Ls[i * nc + j] * xi;
+                    __syncthreads();
+                }
+                for (int u = tid; u < nc; u += nt) dzb[ns + u] = -xb[u];
+            } else {
+                for (int u = tid; u < nc; u += nt) dzb[ns + u] = 0.0;
+            }
+            __syncthreads();
+            for (int l = tid; l < nz; l += nt) {
+                const double dzl = dzb[l];
+                row(rdz, k)[l] = dzl;
+                if (l < nvalid(k)) {
+                    const double z = row(R_Z, k)[l];
+                    WS::slack_step_terms(z, dzl, BL[k * W + l], BU[k * W + l], row(R_ZL, k)[l], row(R_ZU, k)[l], mu, ap, az);
+                    gbd += row(R_GX, k)[l] * dzl; tiny = fmax(tiny, fabs(dzl) / (1.0 + fabs(z)));
+                }
+            }
+            if (k < N) {
+                const double *cf = row(R_COEF, k);
+                for (int l = tid; l < ns; l += nt) {
+                    const int rob = l / 3, comp = l - 3 * rob;
+                    const double cA = comp == 0 ? cf[rob] : (comp == 1 ? cf[Nr + rob] : 0.0);
+                    const double cB = comp == 0 ? cf[2 * Nr + rob] : (comp == 1 ? cf[3 * Nr + rob] : T);
+                    dxn[l] = dzb[l] + cA * dzb[3 * rob + 2] + cB * dzb[ns + 2 * rob + (comp == 2 ? 1 : 0)] - row(R_RC, k + 1)[l];
+                }
+                const int b = k + 1;
+                for (int q = tid; q < M; q += nt) {
+                    const double lo = DL[b * W + q], hi = DU[b * W + q];
+                    const bool act = lo > -NMPC_INF || hi < NMPC_INF;
+                    double ds = 0.0, ytd = 0.0;
+                    if (act) {
+                        const int pi = pairs[2 * q], pj = pairs[2 * q + 1];
+                        const double gs = row(R_GS, b)[q];
+                        ds = row(R_GXQ, b)[q] * (dzb[3 * pi] - dzb[3 * pj]) + row(R_GYQ, b)[q] * (dzb[3 * pi + 1] - dzb[3 * pj + 1]) + row(R_RD, b)[q];
+                        ytd = row(R_DQ, b)[q] * ds + gs;
+                        const double s = row(R_S, b)[q];
+                        WS::slack_step_terms(s, ds, lo, hi, row(R_VL, b)[q], row(R_VU, b)[q], mu, ap, az);
+                        gbd += gs * ds; tiny = fmax(tiny, fabs(ds) / (1.0 + fabs(s)));
+                    }
+                    row(rds, b)[q] = ds; row(rytd, b)[q] = ytd;
+                }
+                __syncthreads();
+                for (int l = tid; l < nz; l += nt) dzb[l] = l < ns ? dxn[l] : 0.0;
+            }
+            __syncthreads();
+        }
+        double v[4] = {ap, az, gbd, tiny};
+        breduce<4>(v, 0xBu);   // ap, az, tiny are maxima; gbd a sum
+        si.ap = v[0] > tau ? tau / v[0] : 1.0; si.az = v[1] > tau ? tau / v[1] : 1.0;
+        si.gbd = v[2]; si.tiny = v[3];
+    }
+
+    // ---------------------------------------------------------------------------------------
+    NMPC_BPASS void accept(double alpha, double az, double mu, int rdz, int rds, int rytc, int rytd)
+    {
+        const double ks = P.o.kappa_sigma, iks = 1.0 / ks;
+        auto mult = [=](double m, double sl_old, double sl_new, double dv_signed) {
+            const double r = 1.0 / sl_old, c = mu / sl_new;
+            const double m2 = m + az * (mu * r - m + m * r * dv_signed);
+            return fmax(fmin(m2, ks * c), iks * c);
+        };
+        for (int idx = tid; idx < S * W; idx += nt) {
+            const int k = idx / W, l = idx - k * W;
+            if (l < nvalid(k)) {
+                const double z = row(R_Z, k)[l], dz = row(rdz, k)[l], lo = BL[k * W + l], hi = BU[k * W + l];
+                const double zn = z + alpha * dz;
+                if (lo > -NMPC_INF) row(R_ZL, k)[l] = mult(row(R_ZL, k)[l], z - lo, zn - lo, -dz);
+                if (hi < NMPC_INF) row(R_ZU, k)[l] = mult(row(R_ZU, k)[l], hi - z, hi - zn, dz);
+                row(R_Z, k)[l] = zn;
+            }
+            if (l < ns) { const double yc = row(R_YC, k)[l]; row(R_YC, k)[l] = yc + alpha * (row(rytc, k)[l] - yc); }
+            if (l < M) {
+                const double lo = DL[k * W + l], hi = DU[k * W + l];
+                if (lo > -NMPC_INF || hi < NMPC_INF) {
+                    const double s = row(R_S, k)[l], ds = row(rds, k)[l], sn_ = s + alpha * ds;
+                    if (lo > -NMPC_INF) row(R_VL, k)[l] = mult(row(R_VL, k)[l], s - lo, sn_ - lo, -ds);
+                    if (hi < NMPC_INF) row(R_VU, k)[l] = mult(row(R_VU, k)[l], hi - s, hi - sn_, ds);
+                    row(R_S, k)[l] = sn_;
+                    const double yd = row(R_YD, k)[l];
+                    row(R_YD, k)[l] = yd + alpha * (row(rytd, k)[l] - yd);
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    NMPC_BPASS void accept_primal(double alpha, int rdz, int rds)
+    {
+        for (int idx = tid; idx < S * W; idx += nt) {
+            const int k = idx / W, l = idx - k * W;
+            if (l < nvalid(k)) row(R_Z, k)[l] += alpha * row(rdz, k)[l];
+            if (l < M && (DL[k * W + l] > -NMPC_INF || DU[k * W + l] < NMPC_INF)) row(R_S, k)[l] += alpha * row(rds, k)[l];
+        }
+        __syncthreads();
+    }
+
+    // after the restoration fallback: equality multipliers reset, bound multipliers clipped
+    NMPC_BPASS void resto_reset(double mu)
+    {
+        const double ks = P.o.kappa_sigma;
+        for (int idx = tid; idx < S * W; idx += nt) {
+            const int k = idx / W, l = idx - k * W;
+            if (l < nvalid(k)) {
+                const double z = row(R_Z, k)[l], lo = BL[k * W + l], hi = BU[k * W + l];
+                if (lo > -NMPC_INF) { const double s2 = z - lo; row(R_ZL, k)[l] = fmax(fmin(row(R_ZL, k)[l], ks * mu / s2), mu / (ks * s2)); }
+                if (hi < NMPC_INF) { const double s2 = hi - z; row(R_ZU, k)[l] = fmax(fmin(row(R_ZU, k)[l], ks * mu / s2), mu / (ks * s2)); }
+            }
+            row(R_YC, k)[l] = 0.0; row(R_YD, k)[l] = 0.0;
+            if (l < M) {
+                const double s = row(R_S, k)[l], lo = DL[k * W + l], hi = DU[k * W + l];
+                if (lo > -NMPC_INF) { const double s2 = s - lo; row(R_VL, k)[l] = fmax(fmin(row(R_VL, k)[l], ks * mu / s2), mu / (ks * s2)); }
+                if (hi < NMPC_INF) { const double s2 = hi - s; row(R_VU, k)[l] = fmax(fmin(row(R_VU, k)[l], ks * mu / s2), mu / (ks * s2)); }
+            }
+        }
+        __syncthreads();
+    }
+
+    // restoration candidate: forward rollout of the current controls, slacks reset from the distances;
+    // written as a direction (R_DZ, R_DS) = candidate - iterate
+    NMPC_BPASS void rollout_project()
+    {
+        const nmpc_opts &o = P.o;
+        double *zt = sm + SM_DZB, *zn = sm + SM_TB /* ns <= nc + nc + ... : see below */, *cs = sm + SM_CS;
+        // zn needs ns doubles: SM_TB (nc) and SM_XB (nc) are contiguous, 2 nc = 4 Nr >= 3 Nr
+        __syncthreads();
+        for (int l = tid; l < nz; l += nt)
+            zt[l] = l < ns ? WS::push_in(pp[l] + CE[l], BL[l], BU[l], o.bound_push, o.bound_frac) : row(R_Z, 0)[l];
+        __syncthreads();
+        for (int k = 0; k <= N; k++) {
+            for (int l = tid; l < nz; l += nt) row(R_DZ, k)[l] = l < nvalid(k) ? zt[l] - row(R_Z, k)[l] : 0.0;
+            if (k < N) for (int i = tid; i < Nr; i += nt) { double s_, c_; sincos(zt[3 * i + 2], &s_, &c_); cs[i] = c_; cs[Nr + i] = s_; }
+            for (int q = tid; q < M; q += nt) {
+                for (int pass = (k == 0 ? 0 : 1); pass < 2; pass++) {
+                    if (pass == 1 && k == N) break;
+                    const int b = pass == 0 ? 0 : k + 1;
+                    const double lo = DL[b * W + q], hi = DU[b * W + q];
+                    double dv = NMPC_DUMMY_ROW_VALUE;
+                    if (pass == 1) {
+                        const int pi = pairs[2 * q], pj = pairs[2 * q + 1];
+                        const double dx = zt[3 * pi] - zt[3 * pj], dy = zt[3 * pi + 1] - zt[3 * pj + 1];
+                        dv = dx * dx + dy * dy;
+                    }
+                    const bool act = lo > -NMPC_INF || hi < NMPC_INF;
+                    row(R_DS, b)[q] = act ? WS::push_in(dv, lo, hi, o.bound_push, o.bound_frac) - row(R_S, b)[q] : 0.0;
+                }
+            }
+            __syncthreads();
+            if (k < N) {
+                for (int l = tid; l < ns; l += nt) {
+                    const int rob = l / 3, comp = l - 3 * rob;
+                    const double v = zt[ns + 2 * rob];
+                    double x = comp == 0 ? zt[l] + T * v * cs[rob] : (comp == 1 ? zt[l] + T * v * cs[Nr + rob] : zt[l] + T * zt[ns + 2 * rob + 1]);
+                    zn[l] = WS::push_in(x + CE[(k + 1) * W + l], BL[(k + 1) * W + l], BU[(k + 1) * W + l], o.bound_push, o.bound_frac);
+                }
+                __syncthreads();
+                for (int l = tid; l < nz; l += nt) zt[l] = l < ns ? zn[l] : (k + 1 < N ? row(R_Z, k + 1)[l] : 0.0);
+            }
+            __syncthreads();
+        }
+    }
+
+    NMPC_BPASS void soc_begin()
+    {
+        for (int idx = tid; idx < S * W; idx += nt) {
+            const int k = idx / W, l = idx - k * W;
+            row(R_CSOC, k)[l] = l < ns ? row(R_RC, k)[l] : 0.0;
+            row(R_DSOC, k)[l] = l < M ? row(R_RD, k)[l] : 0.0;
+        }
+        __syncthreads();
+    }
+
+    __device__ double mult_absmax()
+    {
+        double ymax = 0.0;
+        for (int idx = tid; idx < S * W; idx += nt) {
+            const int k = idx / W, l = idx - k * W;
+            if (l < ns) ymax = fmax(ymax, fabs(row(R_YC, k)[l]));
+            if (l < M) ymax = fmax(ymax, fabs(row(R_YD, k)[l]));
+        }
+        return bmax(ymax);
+    }
+    __device__ void mult_zero()
+    {
+        for (int idx = tid; idx < S * W; idx += nt) { const int k = idx / W, l = idx - k * W; row(R_YC, k)[l] = 0.0; row(R_YD, k)[l] = 0.0; }
+    }
+
+    // ---------------------------------------------------------------------------------------
+    // filter (shared memory; thread 0 edits)
+    // ---------------------------------------------------------------------------------------
+    __device__ bool filter_ok(double th, double ph) const
+    {
+        const double *fth = sm + SM_FTH, *fph = sm + SM_FPH;
+        for (int i = 0; i < fn; i++)
+            if (!(th < fth[i] || ph < fph[i])) return false;
+        return true;
+    }
+    NMPC_BPASS void filter_add(double th, double ph)
+    {
+        double *fth = sm + SM_FTH, *fph = sm + SM_FPH, *misc = sm + SM_MISC;
+        __syncthreads();
+        if (tid == 0) {
+            int m = 0;
+            for (int i = 0; i < fn; i++)
+                if (!(fth[i] >= th && fph[i] >= ph)) { fth[m] = fth[i]; fph[m] = fph[i]; m++; }
+            if (m == NMPC_FILTER_CAP) {
+                for (int i = 1; i < m; i++) { fth[i - 1] = fth[i]; fph[i - 1] = fph[i]; }
+                m--;
+            }
+            fth[m] = th; fph[m] = ph; m++;
+            misc[0] = (double)m;
+        }
+        __syncthreads();
+        fn = (int)misc[0];
+        __syncthreads();
+    }
+    __device__ bool trial_ok(double th_t, double ph_t, double theta, double phi, double theta_max, double theta_min, double gbd,
+                             double alpha_test, bool ftype) const
+    {
+        if (!(WS::fin(th_t) && WS::fin(ph_t)) || !WS::cmp_le(th_t, theta_max, theta)) return false;
+        bool ok;
+        if (ftype && theta <= theta_min) ok = WS::cmp_le(ph_t - phi, 1e-8 * alpha_test * gbd, phi);
+        else ok = WS::cmp_le(th_t, (1.0 - 1e-5) * theta, theta) || WS::cmp_le(ph_t - phi, -1e-8 * theta, phi);
+        return ok && filter_ok(th_t, ph_t);
+    }
+
+    // outputs in the reference layout, multipliers in CasADi's sign convention
+    NMPC_BPASS void write_outputs(int st, int iter, double E0, double pinf, double dinf, double c0, double mu)
+    {
+        const long long n = (long long)ns * S + (long long)nc * N, mg = (long long)S * (ns + M);
+        double *x = P.x + inst * n;
+        double *lx = P.lam_x ? P.lam_x + inst * n : nullptr;
+        double *g = P.g ? P.g + inst * mg : nullptr;
+        double *lg = P.lam_g ? P.lam_g + inst * mg : nullptr;
+        double fo = 0.0;
+        trig_rows(0.0, 0, false, R_TRIG);
+        for (int idx = tid; idx < S * nz; idx += nt) {
+            const int k = idx / nz, l = idx - k * nz;
+            if (l >= nvalid(k)) continue;
+            const double zk = row(R_Z, k)[l];
+            const long long xi = l < ns ? (long long)k * ns + l : (long long)ns * S + (long long)k * nc + (l - ns);
+            x[xi] = zk;
+            if (lx) lx[xi] = (row(R_ZU, k)[l] - row(R_ZL, k)[l]) / df;
+            if (k < N) { const double e = zk - xs(l); fo += 0.5 * qw(l) * e * e; }
+        }
+        for (int idx = tid; idx < S * ns; idx += nt) {
+            const int k = idx / ns, l = idx - k * ns;
+            if (g) g[(long long)k * (ns + M) + l] = k == 0 ? row(R_Z, 0)[l] - pp[l] : row(R_Z, k)[l] - predict(row(R_Z, k - 1), row(R_TRIG, k - 1), l);
+            if (lg) lg[(long long)k * (ns + M) + l] = row(R_YC, k)[l] / df;
+        }
+        for (int idx = tid; idx < S * M; idx += nt) {
+            const int b = idx / M, q = idx - b * M;
+            double dv = NMPC_DUMMY_ROW_VALUE;
+            if (b > 0) {
+                const double *zr = row(R_Z, b - 1);
+                const int pi = pairs[2 * q], pj = pairs[2 * q + 1];
+                const double dx = zr[3 * pi] - zr[3 * pj], dy = zr[3 * pi + 1] - zr[3 * pj + 1];
+                dv = dx * dx + dy * dy;
+            }
+            if (g) g[(long long)b * (ns + M) + ns + q] = dv;
+            if (lg) lg[(long long)b * (ns + M) + ns + q] = row(R_YD, b)[q] / df;
+        }
+        fo = bsum(fo);
+        if (tid == 0) {
+            if (P.f) P.f[inst] = fo;
+            if (P.status) P.status[inst] = st;
+            if (P.iters) P.iters[inst] = iter;
+            if (P.stats) {
+                double *sp = P.stats + (long long)inst * NMPC_NSTATS;
+                sp[NMPC_ST_KKT_ERR] = E0; sp[NMPC_ST_PRIMAL_INF] = pinf; sp[NMPC_ST_DUAL_INF] = dinf; sp[NMPC_ST_COMPL] = c0;
+                sp[NMPC_ST_MU] = mu; sp[NMPC_ST_N_REG] = n_reg; sp[NMPC_ST_N_RESTO] = n_resto; sp[NMPC_ST_N_SOC] = n_soc;
+                sp[NMPC_ST_N_FACTOR] = n_fact; sp[NMPC_ST_N_LS] = n_ls;
+            }
+        }
+        __syncthreads();
+    }
+
+    __device__ void run() { ipm_run(*this); }
+};
+
+// persistent kernel: one CTA per instance, instances pulled from the same atomic queue as the warp kernel
+__global__ void __launch_bounds__(NMPC_BLOCK_THREADS, 1) solve_kernel_block(const NmpcSolveParams P)
+{
+    extern __shared__ double smem[];
+    double *ws = P.ws + (long long)blockIdx.x * P.ws_stride;
+    BlockSolver s(P, smem, ws);
+    __shared__ int next_inst;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) next_inst = atomicAdd(P.counter, 1);
+        __syncthreads();
+        const int inst = next_inst;
+        if (inst >= P.B) break;
+        s.setup(inst);
+        s.run();
+    }
+}

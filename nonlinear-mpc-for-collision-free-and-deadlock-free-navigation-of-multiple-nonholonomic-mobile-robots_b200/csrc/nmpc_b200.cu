@@ -12,6 +12,7 @@
 #include "nmpc_b200.h"
 #include "warp_prims.cuh"
 #include "solver_body.cuh"
+#include "block_solver.cuh"
 #include "aux_kernels.cuh"
 
 #ifndef SOLVE_WARPS
@@ -90,6 +91,8 @@ struct nmpc_handle {
     long long launches;
     size_t ws_doubles_per_slot, solve_smem, eval_smem;
     int ctas_per_sm, lw, teams_per_cta, threads;
+    bool block_path, eval_ok;                 // Nr > 10: CTA-per-instance dense-block solver; eval record fits shared memory
+    int *d_pairs;                             // pair table (i, j) of the inequality rows, block path
     // host-pointer API staging
     char *d_buf;
     size_t d_bytes;
@@ -172,7 +175,8 @@ extern "C" int nmpc_create(const nmpc_desc *d, const nmpc_opts *o, nmpc_handle *
 {
     if (!d || !out) return fail(NMPC_EINVAL, "nmpc_create: NULL argument");
     if (d->N < 1 || !(d->T > 0)) return fail(NMPC_EINVAL, "nmpc_create: need N >= 1 and T > 0");
-    if (d->Nr < 1 || d->Nr > 10) return fail(NMPC_ENOTSUP, "nmpc_create: Nr = %d; the lane-per-column Riccati path covers 1..10 robots", d->Nr);
+    if (d->Nr < 1 || d->Nr > NMPC_MAX_ROBOTS)
+        return fail(NMPC_ENOTSUP, "nmpc_create: Nr = %d; supported: 1..10 robots (warp-per-instance) and 11..%d (CTA-per-instance dense blocks)", d->Nr, NMPC_MAX_ROBOTS);
     const bool dbg = getenv("NMPC_DEBUG") != nullptr;
 #define DBG(msg) do { if (dbg) { fprintf(stderr, "[nmpc_create] %s\n", msg); fflush(stderr); } } while (0)
     DBG("enter");
@@ -186,6 +190,7 @@ extern "C" int nmpc_create(const nmpc_desc *d, const nmpc_opts *o, nmpc_handle *
     h->n = h->ns * h->S + h->nc * d->N; h->mg = h->S * (h->ns + h->M); h->np = 2 * h->ns;
     h->nnzj = 3 * d->Nr + d->N * (11 * d->Nr + 4 * h->M); h->nnzh = d->N * (6 * d->Nr + 2 * h->M);
     h->launches = 0; h->d_buf = nullptr; h->d_bytes = 0; h->stream = nullptr; h->d_tables = nullptr;
+    h->block_path = d->Nr > 10; h->eval_ok = true; h->d_pairs = nullptr;
     DBG("device count ok");
     cudaGetDevice(&h->dev);
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->dev);
@@ -213,12 +218,25 @@ extern "C" int nmpc_create(const nmpc_desc *d, const nmpc_opts *o, nmpc_handle *
         case 7: h->ws_doubles_per_slot = slot_doubles<7>(N); e = config_solve<7>(h); break;
         case 8: h->ws_doubles_per_slot = slot_doubles<8>(N); e = config_solve<8>(h); break;
         case 9: h->ws_doubles_per_slot = slot_doubles<9>(N); e = config_solve<9>(h); break;
-        default: h->ws_doubles_per_slot = slot_doubles<10>(N); e = config_solve<10>(h); break;
+        case 10: h->ws_doubles_per_slot = slot_doubles<10>(N); e = config_solve<10>(h); break;
+        default: {   // dense-block path: one 512-thread CTA per instance, the control block of the stage matrix in shared memory
+            h->ws_doubles_per_slot = (size_t)BlockSolver::ws_doubles(Nr, N);
+            h->lw = BlockSolver::row_width(Nr); h->teams_per_cta = 1; h->threads = NMPC_BLOCK_THREADS; h->ctas_per_sm = 1;
+            h->solve_smem = (size_t)BlockSolver::sm_doubles(Nr) * sizeof(double);
+            e = cudaFuncSetAttribute(solve_kernel_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->solve_smem);
+            std::vector<int> pr;
+            for (int a = 0; a < Nr; a++)
+                for (int b = a + 1; b < Nr; b++) { pr.push_back(a); pr.push_back(b); }
+            if (e == cudaSuccess) e = cudaMalloc(&h->d_pairs, pr.size() * sizeof(int));
+            if (e == cudaSuccess) e = cudaMemcpy(h->d_pairs, pr.data(), pr.size() * sizeof(int), cudaMemcpyHostToDevice);
+            break;
+        }
     }
     if (e != cudaSuccess) { cudaFree(h->d_tables); delete h; return fail(NMPC_ECUDA, "nmpc_create: kernel configuration failed: %s", cudaGetErrorString(e)); }
     DBG("solve kernel configured");
     h->eval_smem = (size_t)(2 * h->n + 2 * h->mg + 2 * h->ns + h->nnzj + h->nnzh + 32 + 8) * sizeof(double);
-    {
+    if (h->eval_smem > (size_t)220 * 1024) h->eval_ok = false;   // large swarms: the stand-alone evaluation record exceeds shared memory
+    else {
         const int sz = (int)h->eval_smem;
         e = cudaFuncSetAttribute(eval_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(eval_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz);
@@ -239,6 +257,7 @@ extern "C" void nmpc_destroy(nmpc_handle *h)
 {
     if (!h) return;
     if (h->d_tables) cudaFree(h->d_tables);
+    if (h->d_pairs) cudaFree(h->d_pairs);
     if (h->d_buf) cudaFree(h->d_buf);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -306,9 +325,10 @@ static int solve_impl(nmpc_handle *h, int B, const double *x0, const double *p, 
     P.bstride = bounds_batched ? (long long)NMPC_BR_COUNT * h->S * h->lw : 0;
     P.bound_err = berr; P.x = x; P.f = f; P.g = g; P.lam_x = lam_x; P.lam_g = lam_g; P.status = status; P.iters = iters;
     P.stats = stats; P.trace = trace; P.max_trace = max_trace; P.ws = slots; P.ws_stride = (long long)h->ws_doubles_per_slot;
-    P.counter = counter;
+    P.counter = counter; P.pairs = h->d_pairs;
     const int grid = solve_grid(h, B);
-    switch (h->d.Nr) {
+    if (h->block_path) solve_kernel_block<<<grid, h->threads, h->solve_smem, st>>>(P);
+    else switch (h->d.Nr) {
         case 1: solve_kernel<1><<<grid, h->threads, h->solve_smem, st>>>(P); break;
         case 2: solve_kernel<2><<<grid, h->threads, h->solve_smem, st>>>(P); break;
         case 3: solve_kernel<3><<<grid, h->threads, h->solve_smem, st>>>(P); break;
@@ -425,6 +445,7 @@ extern "C" int nmpc_eval(nmpc_handle *h, int B, const double *w, const double *p
 {
     if (!h || !w || !p || B <= 0) return fail(NMPC_EINVAL, "nmpc_eval: bad argument");
     if (hess && !lam_g) return fail(NMPC_EINVAL, "nmpc_eval: hess needs lam_g");
+    if (!h->eval_ok) return fail(NMPC_ENOTSUP, "nmpc_eval: the evaluation record of a %d-robot problem (%zu B) exceeds shared memory", h->d.Nr, h->eval_smem);
     int per_sm = (int)std::max<size_t>(1, (size_t)(220 * 1024) / h->eval_smem);
     int blocks = std::min(B, h->sm_count * per_sm);
     const int pf = (std::max(h->n, h->mg) + 255) / 256;

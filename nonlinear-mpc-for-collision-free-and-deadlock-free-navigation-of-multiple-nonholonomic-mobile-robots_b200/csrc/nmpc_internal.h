@@ -7,6 +7,7 @@
 #define NMPC_FILTER_CAP 16
 #define NMPC_DUMMY_ROW_VALUE 3.5 /* centralized_six_robots_implementation.py:278 */
 #define NMPC_NTRACE 8
+#define NMPC_MAX_ROBOTS 64
 
 /* Stage-layout bound rows prepared by prep_bounds_kernel, each [S][32] doubles per bound set:
  *   BL, BU : relaxed variable bounds of stage k (lanes 0..3Nr-1 states, 3Nr..5Nr-1 controls)
@@ -30,6 +31,7 @@ typedef struct NmpcSolveParams {
     double *ws;                      /* per-warp-slot scratch                            */
     long long ws_stride;             /* doubles per warp slot                            */
     int *counter;                    /* work queue                                       */
+    const int *pairs;                /* [M][2] pair table (dense-block path only)        */
 } NmpcSolveParams;
 
 #endif

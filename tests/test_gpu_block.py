@@ -1,0 +1,79 @@
+"""GPU parity tests of the CTA-per-instance dense-block solver (more than 10 robots; BASELINE.json configs[4] is the
+64-robot swarm).  Same oracle, same tolerances as the warp-per-instance path (north_star):
+max|u - u_ref| <= 1e-4, relative objective <= 1e-6, constraint violation <= 1e-6."""
+import numpy as np
+import pytest
+
+from oracle.nlp_numpy import UnicycleNLP, synthetic_instances
+from oracle.oracle_lib import Oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def _t(torch, a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device="cuda:0")
+
+
+def _solve_both(pkg, torch, Nr, N, T, P, dmin=0.3):
+    prob, orc = pkg.Problem(Nr, N, T), Oracle(Nr, N, T)
+    lbx, ubx, lbg, ubg = prob.bounds(dmin, 0.22, 2.84)
+    x0 = prob.cold_start(P[:, :3 * Nr])
+    out = prob.solve(_t(torch, x0), _t(torch, P), _t(torch, lbx), _t(torch, ubx), _t(torch, lbg), _t(torch, ubg))
+    torch.cuda.synchronize()
+    ref = orc.solve_batch(x0, P, lbx, ubx, lbg, ubg)
+    return prob, out, ref, (lbx, ubx, lbg, ubg)
+
+
+def _check(out, ref, Nr, N, lbg, P, dmin):
+    nX = 3 * Nr * (N + 1)
+    x = out["x"].cpu().numpy()
+    st = out["status"].cpu().numpy()
+    f = out["f"].cpu().numpy()
+    g = out["g"].cpu().numpy()
+    assert (st == 0).all(), (st, out["iters"].cpu().numpy())
+    assert (ref["status"] == 0).all(), ref["status"]
+    # solver-independent acceptance: constraints, collisions, scaled KKT error
+    viol = np.maximum(lbg[None] - g, 0.0).max()
+    assert viol <= 1e-6, viol
+    assert out["stats"][:, 0].max().item() <= 1e-8
+    du = np.abs(x - ref["x"])[:, nX:].max(axis=1)
+    df = np.abs(f - ref["f"]) / np.maximum(1.0, np.abs(ref["f"]))
+    return du, df
+
+
+@pytest.mark.parametrize("Nr,N,T,box", [(11, 6, 0.3, 3.0), (12, 10, 0.3, 3.0), (16, 10, 0.3, 3.5), (24, 8, 0.3, 4.5)])
+def test_block_path_matches_oracle(pkg, torch_cuda, Nr, N, T, box):
+    P = synthetic_instances(4, Nr=Nr, seed=100 + Nr, box=box)
+    prob, out, ref, (lbx, ubx, lbg, ubg) = _solve_both(pkg, torch_cuda, Nr, N, T, P)
+    du, df = _check(out, ref, Nr, N, lbg, P, 0.3)
+    same = (du <= 1e-4) & (df <= 1e-6)
+    assert same.all(), (du, df, out["iters"].cpu().numpy(), ref["iters"])
+    assert np.abs(out["iters"].cpu().numpy() - ref["iters"]).max() <= 5
+
+
+def test_block_path_64_robot_swarm(pkg, torch_cuda):
+    """BASELINE.json configs[4]: 64-robot centralized swarm, 2016 pairwise constraints per stage, N = 20
+    (SURVEY.md 8d recipe: starts / goals uniform in [-8, 8]^2, separation >= 0.5)."""
+    torch = torch_cuda
+    Nr, N, T = 64, 20, 0.3
+    P = synthetic_instances(2, Nr=Nr, seed=20261018, box=8.0)
+    prob, out, ref, (lbx, ubx, lbg, ubg) = _solve_both(pkg, torch, Nr, N, T, P)
+    du, df = _check(out, ref, Nr, N, lbg, P, 0.3)
+    assert (du <= 1e-4).all() and (df <= 1e-6).all(), (du, df, out["iters"].cpu().numpy(), ref["iters"])
+    # pairwise distances of the predicted trajectory respect dmin at every stage the NLP constrains
+    x = out["x"].cpu().numpy()[:, :3 * Nr * (N + 1)].reshape(2, N + 1, Nr, 3)[:, :N, :, :2]
+    d = np.linalg.norm(x[:, :, :, None] - x[:, :, None], axis=-1) + np.eye(Nr)[None, None] * 1e9
+    assert d.min() >= 0.3 - 1e-6, d.min()
+    # the product's own KKT report agrees with an independent NumPy evaluation of the NLP at the returned point
+    nlp = UnicycleNLP(Nr, N, T)
+    w = out["x"].cpu().numpy()[0]
+    g_np = nlp.g(w, P[0])
+    np.testing.assert_allclose(out["g"].cpu().numpy()[0], g_np, rtol=0, atol=1e-10)
+    assert abs(nlp.f(w, P[0]) - out["f"].cpu().numpy()[0]) <= 1e-9 * max(1.0, abs(out["f"].cpu().numpy()[0]))

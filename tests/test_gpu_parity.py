@@ -177,7 +177,7 @@ def test_bound_errors_and_unsupported(pkg, torch_cuda):
     with pytest.raises(pkg.NmpcError):
         prob.solve_host(x0, P, lbx, ubx, lbg, bad)
     with pytest.raises(pkg.NmpcError):
-        pkg.Problem(11, 5, 0.1)
+        pkg.Problem(65, 5, 0.1)   # 11..64 robots run on the dense-block path (tests/test_gpu_block.py)
 
 
 def test_infeasible_instance_reports_status_not_hang(pkg, torch_cuda):
