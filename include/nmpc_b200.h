@@ -144,6 +144,11 @@ int nmpc_hess_pattern(const nmpc_handle *h, int32_t *colptr, int32_t *rowidx);
  * kernel -- the roofline denominator for the factorisation (MEASURED_PEAKS.json has no FP64 figure). */
 int nmpc_probe_fp64(double *tflops_out);
 
+/* Debug aid: cycle counters of the phases of the dense-block factorisation (Nr > 10), CTA 0 only:
+ * [0] stage-parallel pre-pass, [1] p + P r mat-vec, [2] stage-matrix assembly, [3] control-block elimination,
+ * [4] first contraction, [5] second contraction.  reset != 0 clears the counters after the read. */
+int nmpc_debug_block_profile(long long *out16, int reset);
+
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
 long long nmpc_launch_count(const nmpc_handle *h);
 

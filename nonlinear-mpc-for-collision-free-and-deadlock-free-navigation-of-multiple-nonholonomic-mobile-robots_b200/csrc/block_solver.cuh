@@ -11,15 +11,24 @@
 // flat thread-strided loops over (stage, variable / pair).  The Riccati factorisation keeps the control block of the
 // stage matrix in shared memory:
 //     M = H~ + [A B]' P+ [A B]     assembled per robot pair from the 3x3 blocks of P+ (A, B are unicycle-sparse)
-//     M_uu = L L'                  Cholesky in shared memory; a pivot <= 0 is IPOPT's wrong-inertia signal
-//     Y = L^-1 [M_ux | m_u]        P = M_xx - Y'Y,  p = m_x - Y' y_m      (the dense contractions of this path)
-// and the forward pass applies  du = -L^-T (Y dx + y_m).
+//     M_uu = L L'                  right-looking Cholesky, the matrix distributed over the registers of the CTA (8 x 4 entries
+//                                  per thread), pivot column broadcast through shared memory; a pivot <= 0 is IPOPT's
+//                                  wrong-inertia signal
+//     Y = L^-1 [M_ux | m_u]        blocked forward substitution on shared-memory column panels (32 x 32 diagonal blocks of
+//                                  L inverted once per stage, everything else is a contraction)
+//     P = M_xx - Y'Y, p = m_x - Y' y_m     4x4 register tiles over Y resident in shared memory
+// and the forward pass applies  du = -L^-T (Y dx + y_m).  FP64 has no tcgen05 kind, and the legacy DMMA (mma.sync m8n8k4)
+// has the same peak as the DFMA pipe on B200, so the contractions run as register tiles on the FP64 pipe.
 #pragma once
 #include "nmpc_internal.h"
 #include "ipm_driver.cuh"
 #include "solver_body.cuh"
 
 #define NMPC_BLOCK_THREADS 512
+// cycle counters of CTA 0 (thread 0) per phase of the dense-block solver; read with nmpc_debug_block_profile()
+__device__ long long g_block_prof[16];
+#define NMPC_PROF_BEGIN long long prof_t0_ = clock64();
+#define NMPC_PROF(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0) { long long t_ = clock64(); g_block_prof[slot] += t_ - prof_t0_; prof_t0_ = t_; } } while (0)
 #define NMPC_BPASS __device__ __noinline__
 
 struct BlockSolver {
@@ -29,6 +38,7 @@ struct BlockSolver {
         R_PXX, R_PYY, R_PXY, R_PHX, R_PHY, R_TRIG, R_TRIG2, R_ZT, R_ST,
         R_COUNT
     };
+    enum { PANEL_W = 52 };   // columns of [M_ux | m_u] per shared-memory panel of the triangular solve (multiple of 4)
     struct EvalOut { double pinf, viol, dinf, c0, cmu, ysum, zsum, theta, f, slog, sdamp; };
     struct StepInfo { double ap, az, gbd, tiny; };
     typedef WarpSolver<1> WS;   // scalar helpers (push_in, slack_step_terms, cmp_le, fin) are shared with the warp solver
@@ -38,22 +48,27 @@ struct BlockSolver {
     int Nr, N, S, ns, nc, nz, M, W, tid, nt, inst, fn;
     const double *BL, *BU, *CE, *DL, *DU, *pp;
     const int *pairs;
-    double *Pall, *Yall, *Lall;
+    double *Pall, *Yall, *Lall, *Bm;
+    int ncp;   // nc rounded up to a multiple of 32 (blocked triangular solves)
+    int ldy;   // leading dimension of Z_k and of [M_ux | m_u]: ns + 1 rounded up to a multiple of 4
     double T, df, ny_nzb, nzb_cnt;
     int n_reg, n_resto, n_soc, n_fact, n_ls;
     // shared-memory carve-up (doubles)
-    int SM_RED, SM_FTH, SM_FPH, SM_MISC, SM_DZB, SM_DXN, SM_TB, SM_XB, SM_PR, SM_CS, SM_MUU;
+    int SM_RED, SM_FTH, SM_FPH, SM_MISC, SM_DZB, SM_DXN, SM_TB, SM_XB, SM_DINV, SM_PR, SM_CS, SM_MUU;
 
     static NMPC_HD int row_width(int Nr) { int nz = 5 * Nr, M = Nr * (Nr - 1) / 2, w = nz > M ? nz : M; return (w + 31) & ~31; }
     static NMPC_HD long long ws_doubles(int Nr, int N)
     {
         const long long S = N + 1, ns = 3 * Nr, nc = 2 * Nr, W = row_width(Nr);
-        return (long long)R_COUNT * S * W + S * ns * ns + (long long)N * nc * (ns + 1) + (long long)N * nc * nc;
+        const long long ldy = (ns + 1 + 3) & ~3LL;
+        const long long ncp = (nc + 31) & ~31LL;
+        return (long long)R_COUNT * S * W + ((S * ns * ns + 1) & ~1LL) + (long long)(N + 1) * nc * ldy + (long long)N * ncp * ncp;   // every block 16-byte aligned
     }
     static NMPC_HD long long sm_doubles(int Nr)
     {
-        const long long ns = 3 * Nr, nc = 2 * Nr, nz = 5 * Nr;
-        return 32 * 12 + 16 + 16 + 8 + nz + ns + nc + nc + ns + 2 * Nr + nc * nc + 8;
+        const long long ns = 3 * Nr, nc = 2 * Nr, nz = 5 * Nr, ncp = (nc + 31) & ~31LL, ns4 = (ns + 3) & ~3LL;
+        const long long a = ncp * ncp + ncp * PANEL_W, b = nc * ns4;   // Cholesky factor + panel, or Y resident for the rank-k update
+        return 32 * 12 + 16 + 16 + 8 + nz + ns + 3 * ncp + ns + 2 * Nr + (a > b ? a : b) + 16;
     }
 
     __device__ BlockSolver(const NmpcSolveParams &p, double *smem, double *wsp) : P(p), sm(smem), ws(wsp) {}
@@ -112,10 +127,12 @@ struct BlockSolver {
         pp = P.p + (long long)inst * 2 * ns;
         pairs = P.pairs;
         Pall = ws + (long long)R_COUNT * S * W;
-        Yall = Pall + (long long)S * ns * ns;
-        Lall = Yall + (long long)N * nc * (ns + 1);
+        ldy = (ns + 1 + 3) & ~3; ncp = (nc + 31) & ~31;
+        Yall = Pall + (((long long)S * ns * ns + 1) & ~1LL);
+        Bm = Yall + (long long)N * nc * ldy;
+        Lall = Bm + (long long)nc * ldy;
         SM_RED = 0; SM_FTH = 32 * 12; SM_FPH = SM_FTH + 16; SM_MISC = SM_FPH + 16; SM_DZB = SM_MISC + 8; SM_DXN = SM_DZB + nz;
-        SM_TB = SM_DXN + ns; SM_XB = SM_TB + nc; SM_PR = SM_XB + nc; SM_CS = SM_PR + ns; SM_MUU = (SM_CS + 2 * Nr + 1) & ~1;
+        SM_TB = SM_DXN + ns; SM_XB = SM_TB + ncp; SM_DINV = SM_XB + ncp; SM_PR = SM_DINV + ncp; SM_CS = SM_PR + ns; SM_MUU = (SM_CS + 2 * Nr + 1) & ~1;
         df = 1.0; fn = 0;
         n_reg = n_resto = n_soc = n_fact = n_ls = 0;
         __syncthreads();
@@ -338,10 +355,10 @@ struct BlockSolver {
     NMPC_BPASS bool factor(int mode, double mu, double delta, bool soc)
     {
         const double zeta = mode == 2 ? sqrt(mu) : 0.0, kd = P.o.kappa_d;
-        double *Muu = sm + SM_MUU, *prv = sm + SM_PR, *misc = sm + SM_MISC;
-        const int ldy = ns + 1;
+        double *Muu = sm + SM_MUU, *prv = sm + SM_PR, *colb = sm + SM_TB, *dinv = sm + SM_DINV;   // colb: 2 ncp doubles (SM_TB, SM_XB contiguous)
         n_fact++;
         __syncthreads();
+        NMPC_PROF_BEGIN
         // ---- stage-parallel part: barrier terms, coefficients, residuals, condensed inequality blocks ----
         for (int idx = tid; idx < S * nz; idx += nt) {
             const int k = idx / nz, l = idx - k * nz;
@@ -406,10 +423,11 @@ struct BlockSolver {
             for (int l = tid; l < ns; l += nt) { PN[l * ns + l] = row(R_DGV, N)[l]; row(R_LIN, N)[l] = row(R_GX, N)[l]; }
         }
         __syncthreads();
+        NMPC_PROF(0);
         const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
         for (int k = N - 1; k >= 0; k--) {
             const double *Pn = Pall + (long long)(k + 1) * ns * ns;
-            double *Pk = Pall + (long long)k * ns * ns, *Yk = Yall + (long long)k * nc * ldy, *Lk = Lall + (long long)k * nc * nc;
+            double *Pk = Pall + (long long)k * ns * ns, *Yk = Yall + (long long)k * nc * ldy, *Lk = Lall + (long long)k * ncp * ncp;
             const double *cf = row(R_COEF, k), *cf2 = row(R_COEF2, k);
             // A. pr = p_{k+1} - P_{k+1} rc_{k+1}   (one warp per row)
             {
@@ -423,6 +441,7 @@ struct BlockSolver {
                 }
             }
             __syncthreads();
+            NMPC_PROF(1);
             // B. stage matrix M = H~ + [A B]' P+ [A B], one robot pair (i, j) per thread: the 5x5 block C_i' Pb C_j
             for (int idx = tid; idx < Nr * Nr; idx += nt) {
                 const int i = idx / Nr, j = idx - i * Nr;
@@ -461,8 +480,8 @@ struct BlockSolver {
                     row(R_LIN, k)[3 * i] = p0 + gxr[3 * i] + glx;
                     row(R_LIN, k)[3 * i + 1] = p1 + gxr[3 * i + 1] + gly;
                     row(R_LIN, k)[3 * i + 2] = p2 + ai * p0 + bi * p1 + gxr[3 * i + 2];
-                    Yk[(long long)(2 * i) * ldy + ns] = tci * p0 + tsi * p1 + gxr[ns + 2 * i];
-                    Yk[(long long)(2 * i + 1) * ldy + ns] = T * p2 + gxr[ns + 2 * i + 1];
+                    Bm[(long long)(2 * i) * ldy + ns] = tci * p0 + tsi * p1 + gxr[ns + 2 * i];
+                    Bm[(long long)(2 * i + 1) * ldy + ns] = T * p2 + gxr[ns + 2 * i + 1];
                 } else {
                     const int q = i < j ? pairidx(i, j) : pairidx(j, i);
                     const double vxx = row(R_PXX, k + 1)[q], vyy = row(R_PYY, k + 1)[q], vxy = row(R_PXY, k + 1)[q];
@@ -475,42 +494,154 @@ struct BlockSolver {
 #pragma unroll
                 for (int a = 0; a < 2; a++) {
 #pragma unroll
-                    for (int c = 0; c < 3; c++) Yk[(long long)(2 * i + a) * ldy + 3 * j + c] = G[3 + a][c];
+                    for (int c = 0; c < 3; c++) Bm[(long long)(2 * i + a) * ldy + 3 * j + c] = G[3 + a][c];
 #pragma unroll
                     for (int c = 0; c < 2; c++) Muu[(2 * i + a) * nc + 2 * j + c] = G[3 + a][3 + c];
                 }
             }
             __syncthreads();
-            // C. Cholesky of the control block in shared memory (right-looking); pivot <= 0: wrong inertia
-            for (int j = 0; j < nc; j++) {
-                const double d = Muu[j * nc + j];
-                if (!(d > 0.0) || !(d < NMPC_INF)) return false;   // uniform: every thread reads the same value
-                const double rs = rsqrt(d);
-                __syncthreads();
-                for (int i = j + tid; i < nc; i += nt) Muu[i * nc + j] = i == j ? d * rs : Muu[i * nc + j] * rs;
-                __syncthreads();
-                const int rem = nc - j - 1;
-                for (int e = tid; e < rem * rem; e += nt) {
-                    const int a = j + 1 + e / rem, c = j + 1 + e % rem;
-                    if (c <= a) Muu[a * nc + c] -= Muu[a * nc + j] * Muu[c * nc + j];
-                }
-                __syncthreads();
-            }
-            // D. Y = L^-1 [M_ux | m_u], one column per thread (forward substitution, rows of Y in global memory)
-            for (int c = tid; c < ldy; c += nt) {
-                for (int i = 0; i < nc; i++) {
-                    double acc = Yk[(long long)i * ldy + c];
-                    const double *Li = Muu + i * nc;
-                    for (int j = 0; j < i; j++) acc -= Li[j] * Yk[(long long)j * ldy + c];
-                    Yk[(long long)i * ldy + c] = acc / Li[i];
-                }
-            }
-            // E. keep L for the forward pass
-            for (int e = tid; e < nc * nc; e += nt) Lk[e] = Muu[e];
-            __syncthreads();
-            // F. P_k = M_xx - Y'Y (upper 4x4 tiles, mirrored), p_k = m_x - Y' y_m
+            NMPC_PROF(2);
+            // C. right-looking Cholesky M_uu = L L'.  Thread (ti, tj) keeps rows 8 ti .. 8 ti + 7 and columns tj + 32 q of the
+            //    trailing matrix in registers; the pivot column is broadcast through a double-buffered shared vector; L goes to
+            //    shared memory (leading dimension ncp, identity padding).  Pivot <= 0: wrong inertia.
+            double *Ls = Muu;
             {
-                const int nt4 = (ns + 3) / 4;
+                const int ti = tid >> 5, tj = tid & 31;
+                double tile[8][4];
+#pragma unroll
+                for (int a = 0; a < 8; a++)
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int r = 8 * ti + a, c = tj + 32 * q;
+                        tile[a][q] = (r < nc && c < nc) ? Muu[r * nc + c] : 0.0;
+                    }
+                __syncthreads();
+                for (int e = tid; e < ncp * ncp; e += nt) { const int r = e / ncp, c = e - r * ncp; Ls[e] = (r == c && r >= nc) ? 1.0 : 0.0; }
+                if (tj == 0 && 8 * ti < ncp) {
+#pragma unroll
+                    for (int a = 0; a < 8; a++) colb[8 * ti + a] = tile[a][0];
+                }
+                __syncthreads();
+                for (int j = 0; j < nc; j++) {
+                    const double *cb = colb + (j & 1) * ncp;
+                    double *cbn = colb + ((j + 1) & 1) * ncp;
+                    const double d = cb[j];
+                    if (!(d > 0.0) || !(d < NMPC_INF)) return false;   // uniform: every thread reads the same value
+                    const double inv = 1.0 / d, rinv = rsqrt(d);
+                    if (8 * ti + 7 > j) {   // warp-uniform: this warp still owns rows of the trailing matrix
+                        double ca[8], cc[4];
+#pragma unroll
+                        for (int a = 0; a < 8; a++) { const int r = 8 * ti + a; ca[a] = r > j ? cb[r] : 0.0; }
+#pragma unroll
+                        for (int q = 0; q < 4; q++) { const int c = tj + 32 * q; cc[q] = c > j ? cb[c] * inv : 0.0; }
+#pragma unroll
+                        for (int a = 0; a < 8; a++)
+#pragma unroll
+                            for (int q = 0; q < 4; q++) tile[a][q] -= ca[a] * cc[q];
+                    }
+                    for (int t = tid; t < nc; t += nt) Ls[t * ncp + j] = t >= j ? cb[t] * rinv : 0.0;
+                    if (j + 1 < nc && tj == ((j + 1) & 31) && 8 * ti < ncp) {   // owners of the next pivot column publish it
+                        const int jq = (j + 1) >> 5;
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+                            if (q == jq) {
+#pragma unroll
+                                for (int a = 0; a < 8; a++) cbn[8 * ti + a] = tile[a][q];
+                            }
+                    }
+                    __syncthreads();
+                }
+            }
+            // inverses of the 32 x 32 diagonal blocks of L (one warp per block, one column per lane), stored transposed in
+            // the unused upper triangle of the block; reciprocal diagonal in dinv
+            {
+                const int nblk = ncp >> 5;
+                if (wid < nblk) {
+                    const int o = wid * 32;
+                    double x[32];
+#pragma unroll
+                    for (int i = 0; i < 32; i++) {
+                        double acc = i == lane ? 1.0 : 0.0;
+#pragma unroll
+                        for (int jj = 0; jj < i; jj++) acc -= Ls[(o + i) * ncp + o + jj] * x[jj];   // x[jj] = 0 for jj < lane
+                        x[i] = i >= lane ? acc / Ls[(o + i) * ncp + o + i] : 0.0;
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 32; i++) {
+                        if (i > lane) Ls[(o + lane) * ncp + o + i] = x[i];   // Linv[i][lane], transposed into the upper triangle
+                        if (i == lane) dinv[o + lane] = x[i];
+                    }
+                }
+            }
+            __syncthreads();
+            for (int e = tid; e < ncp * ncp; e += nt) Lk[e] = Ls[e];   // kept for the forward pass (lower triangle)
+            NMPC_PROF(3);
+            // D. Y = L^-1 [M_ux | m_u]: column panels in shared memory, blocked forward substitution; each thread owns a
+            //    1 x 4 strip of the current 32-row block
+            {
+                double *Yp = Ls + ncp * ncp;
+                const int spr = PANEL_W / 4, nblk = ncp >> 5;
+                const int r_l = tid / spr, cq = tid - r_l * spr;
+                for (int p0 = 0; p0 < ldy; p0 += PANEL_W) {
+                    const int pw = ldy - p0 < PANEL_W ? ldy - p0 : PANEL_W;
+                    for (int e = tid; e < ncp * PANEL_W; e += nt) {
+                        const int u = e / PANEL_W, c = e - u * PANEL_W;
+                        Yp[e] = (u < nc && c < pw) ? Bm[(long long)u * ldy + p0 + c] : 0.0;
+                    }
+                    __syncthreads();
+                    const bool act = r_l < 32 && 4 * cq < pw;
+                    for (int I = 0; I < nblk; I++) {
+                        const int r = 32 * I + r_l;
+                        double acc[4] = {0, 0, 0, 0};
+                        if (act) {
+                            const double *yo = Yp + r * PANEL_W + 4 * cq;
+                            acc[0] = yo[0]; acc[1] = yo[1]; acc[2] = yo[2]; acc[3] = yo[3];
+                            const double *lr = Ls + r * ncp;
+#pragma unroll 4
+                            for (int u = 0; u < 32 * I; u++) {
+                                const double lv = lr[u];
+                                const double *yu = Yp + u * PANEL_W + 4 * cq;
+                                acc[0] -= lv * yu[0]; acc[1] -= lv * yu[1]; acc[2] -= lv * yu[2]; acc[3] -= lv * yu[3];
+                            }
+                            double *yw = Yp + r * PANEL_W + 4 * cq;
+                            yw[0] = acc[0]; yw[1] = acc[1]; yw[2] = acc[2]; yw[3] = acc[3];
+                        }
+                        __syncthreads();
+                        if (act) {   // y = Linv_II t  (Linv_II[r_l][u] sits transposed at Ls[32 I + u][32 I + r_l], u < r_l)
+                            const double di = dinv[r];
+                            acc[0] *= di; acc[1] *= di; acc[2] *= di; acc[3] *= di;
+                            for (int u = 0; u < r_l; u++) {
+                                const double lv = Ls[(32 * I + u) * ncp + r];
+                                const double *yu = Yp + (32 * I + u) * PANEL_W + 4 * cq;
+                                acc[0] += lv * yu[0]; acc[1] += lv * yu[1]; acc[2] += lv * yu[2]; acc[3] += lv * yu[3];
+                            }
+                        }
+                        __syncthreads();
+                        if (act) {
+                            double *yw = Yp + r * PANEL_W + 4 * cq;
+                            yw[0] = acc[0]; yw[1] = acc[1]; yw[2] = acc[2]; yw[3] = acc[3];
+                        }
+                        __syncthreads();
+                    }
+                    for (int e = tid; e < nc * PANEL_W; e += nt) {
+                        const int u = e / PANEL_W, c = e - u * PANEL_W;
+                        if (c < pw) Yk[(long long)u * ldy + p0 + c] = Yp[e];
+                    }
+                    __syncthreads();
+                }
+            }
+            NMPC_PROF(4);
+            // F. P_k = M_xx - Y'Y (upper 4x4 tiles over Y resident in shared memory, mirrored), p_k = m_x - Y' y_m
+            {
+                const int ns4 = (ns + 3) & ~3, nt4 = ns4 / 4;
+                double *Ys = Muu;
+                for (int e = tid; e < nc * (ns4 / 2); e += nt) {
+                    const int u = e / (ns4 / 2), c2 = e - u * (ns4 / 2);
+                    reinterpret_cast<double2 *>(Ys + u * ns4)[c2] = reinterpret_cast<const double2 *>(Yk + (long long)u * ldy)[c2];
+                }
+                for (int u = tid; u < nc; u += nt) colb[u] = Yk[(long long)u * ldy + ns];
+                __syncthreads();
                 for (int e = tid; e < nt4 * nt4; e += nt) {
                     const int tr = e / nt4, tc = e - tr * nt4;
                     if (tc < tr) continue;
@@ -520,15 +651,16 @@ struct BlockSolver {
                     for (int a = 0; a < 4; a++)
 #pragma unroll
                         for (int c = 0; c < 4; c++) acc[a][c] = 0.0;
+#pragma unroll 4
                     for (int u = 0; u < nc; u++) {
-                        const double *yr = Yk + (long long)u * ldy;
-                        double ya[4], yc[4];
-#pragma unroll
-                        for (int a = 0; a < 4; a++) { ya[a] = r0 + a < ns ? yr[r0 + a] : 0.0; yc[a] = c0 + a < ns ? yr[c0 + a] : 0.0; }
+                        const double2 *yr = reinterpret_cast<const double2 *>(Ys + u * ns4 + r0);
+                        const double2 *yc = reinterpret_cast<const double2 *>(Ys + u * ns4 + c0);
+                        const double2 y01 = yr[0], y23 = yr[1], z01 = yc[0], z23 = yc[1];
+                        const double ya[4] = {y01.x, y01.y, y23.x, y23.y}, zc[4] = {z01.x, z01.y, z23.x, z23.y};
 #pragma unroll
                         for (int a = 0; a < 4; a++)
 #pragma unroll
-                            for (int c = 0; c < 4; c++) acc[a][c] += ya[a] * yc[c];
+                            for (int c = 0; c < 4; c++) acc[a][c] += ya[a] * zc[c];
                     }
 #pragma unroll
                     for (int a = 0; a < 4; a++)
@@ -543,13 +675,13 @@ struct BlockSolver {
                 }
                 for (int r = tid; r < ns; r += nt) {
                     double acc = 0.0;
-                    for (int u = 0; u < nc; u++) acc += Yk[(long long)u * ldy + r] * Yk[(long long)u * ldy + ns];
+                    for (int u = 0; u < nc; u++) acc += Ys[u * ns4 + r] * colb[u];
                     row(R_LIN, k)[r] -= acc;
                 }
             }
             __syncthreads();
+            NMPC_PROF(5);
         }
-        (void)misc;
         return true;
     }
 
@@ -560,7 +692,7 @@ struct BlockSolver {
     {
         double ap = 0.0, az = 0.0, gbd = 0.0, tiny = 0.0;
         double *dzb = sm + SM_DZB, *dxn = sm + SM_DXN, *tb = sm + SM_TB, *xb = sm + SM_XB, *Ls = sm + SM_MUU;
-        const int ldy = ns + 1, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+        const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
         __syncthreads();
         for (int q = tid; q < M; q += nt) {
             const double rd = row(R_RD, 0)[q], Dq = row(R_DQ, 0)[q], gs = row(R_GS, 0)[q];
@@ -577,8 +709,8 @@ struct BlockSolver {
         __syncthreads();
         for (int k = 0; k <= N; k++) {
             const double *Pk = Pall + (long long)k * ns * ns;
-            const double *Yk = Yall + (long long)(k < N ? k : 0) * nc * ldy, *Lk = Lall + (long long)(k < N ? k : 0) * nc * nc;
-            if (k < N) for (int e = tid; e < nc * nc; e += nt) Ls[e] = Lk[e];
+            const double *Yk = Yall + (long long)(k < N ? k : 0) * nc * ldy, *Lk = Lall + (long long)(k < N ? k : 0) * ncp * ncp;
+            if (k < N) for (int e = tid; e < ncp * ncp; e += nt) Ls[e] = Lk[e];
             // y~c_k = -(P_k dx + p_k);  t = Y_k dx + y_m      (one warp per row)
             for (int r = wid; r < ns + (k < N ? nc : 0); r += nw) {
                 const double *mr = r < ns ? Pk + (long long)r * ns : Yk + (long long)(r - ns) * ldy;
@@ -592,11 +724,11 @@ struct BlockSolver {
                 }
             }
             __syncthreads();
-            if (k < N) {   // L' x = t (column-oriented back substitution), du = -x
+            if (k < N) {   // L' x = t (column-oriented back substitution, one barrier per pivot), du = -x
                 for (int i = nc - 1; i >= 0; i--) {
-                    const double xi = tb[i] / Ls[i * nc + i];   // tb[i] is final: rows > i were eliminated before the last barrier
+                    const double xi = tb[i] / Ls[i * ncp + i];   // tb[i] is final: rows > i were eliminated before the last barrier
                     if (tid == 0) xb[i] = xi;
-                    for (int j = tid; j < i; j += nt) tb[j] -= Ls[i * nc + j] * xi;
+                    for (int j = tid; j < i; j += nt) tb[j] -= Ls[i * ncp + j] * xi;
                     __syncthreads();
                 }
                 for (int u = tid; u < nc; u += nt) dzb[ns + u] = -xb[u];

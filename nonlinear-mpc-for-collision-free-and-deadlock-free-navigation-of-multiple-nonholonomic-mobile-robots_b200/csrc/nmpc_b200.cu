@@ -479,6 +479,15 @@ __global__ void __launch_bounds__(256) dfma_probe_kernel(int iters, double *out)
     if (r == 123.456) out[0] = r;
 }
 
+// debug aid: cycle counters per phase of the dense-block factorisation (CTA 0); reset = 1 clears them after the read
+extern "C" int nmpc_debug_block_profile(long long *out16, int reset)
+{
+    if (!out16) return fail(NMPC_EINVAL, "nmpc_debug_block_profile: NULL argument");
+    CUDA_OK(cudaMemcpyFromSymbol(out16, g_block_prof, sizeof(long long) * 16));
+    if (reset) { long long z[16] = {0}; CUDA_OK(cudaMemcpyToSymbol(g_block_prof, z, sizeof z)); }
+    return 0;
+}
+
 extern "C" int nmpc_probe_fp64(double *tflops_out)
 {
     if (!tflops_out) return fail(NMPC_EINVAL, "nmpc_probe_fp64: NULL argument");

@@ -193,3 +193,21 @@ def test_api_errors():
     bad = ubg.copy(); bad[0] = 1.0
     with pytest.raises(ValueError):
         o.solve(o.cold_start(p[:6]), p, lbx, ubx, lbg, bad)
+
+
+def test_swarm64_golden_fixture_is_a_kkt_point():
+    """tests/golden/swarm64_oracle.npz (64 robots, N = 20; made by tests/golden/make_swarm64_golden.py): the stored oracle
+    solution is feasible, collision free and reproduces its objective under the NumPy restatement of the NLP."""
+    import os
+    from oracle.nlp_numpy import UnicycleNLP, synthetic_instances
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "swarm64_oracle.npz"))
+    Nr, N, T = 64, 20, 0.3
+    np.testing.assert_array_equal(gold["P"], synthetic_instances(2, Nr=Nr, seed=20261018, box=8.0))
+    nlp = UnicycleNLP(Nr, N, T)
+    assert (gold["status"] == 0).all()
+    for b in range(2):
+        w, p = gold["x"][b], gold["P"][b]
+        g = nlp.g(w, p).reshape(N + 1, -1)
+        assert np.abs(g[:, :3 * Nr]).max() <= 1e-8            # dynamics defects and initial condition
+        assert g[1:, 3 * Nr:].min() >= 0.3 ** 2 - 1e-8        # squared pair distances
+        assert abs(nlp.f(w, p) - gold["f"][b]) <= 1e-9 * abs(gold["f"][b])
