@@ -31,6 +31,24 @@ __device__ long long g_block_prof[16];
 #define NMPC_PROF(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0) { long long t_ = clock64(); g_block_prof[slot] += t_ - prof_t0_; prof_t0_ = t_; } } while (0)
 #define NMPC_BPASS __device__ __noinline__
 
+// Inside a pass the solver object lives in local memory and its pointers are generic: shadow them with locals that carry
+// their address space (shared / global), so that the compiler emits LDS / LDG instead of generic loads.
+#define NMPC_BLK_LOCALS                                                                                                \
+    double *const sm = wp::shared_ptr(this->sm);                                                                       \
+    double *const ws = wp::global_ptr(this->ws);                                                                       \
+    const double *const BL = wp::global_ptr(this->BL), *const BU = wp::global_ptr(this->BU),                            \
+                 *const CE = wp::global_ptr(this->CE), *const DL = wp::global_ptr(this->DL),                            \
+                 *const DU = wp::global_ptr(this->DU), *const pp = wp::global_ptr(this->pp);                            \
+    const int *const pairs = wp::global_ptr(this->pairs);                                                              \
+    double *const Pall = wp::global_ptr(this->Pall), *const Yall = wp::global_ptr(this->Yall),                          \
+                 *const Lall = wp::global_ptr(this->Lall), *const Bm = wp::global_ptr(this->Bm);                        \
+    const int S = this->S, W = this->W, N = this->N, Nr = this->Nr, ns = this->ns, nc = this->nc, nz = this->nz,        \
+              M = this->M, tid = this->tid, nt = this->nt;                                                             \
+    auto row = [=](int r, int k) -> double * { return ws + ((long long)r * S + k) * W; };                              \
+    (void)sm; (void)ws; (void)BL; (void)BU; (void)CE; (void)DL; (void)DU; (void)pp; (void)pairs; (void)Pall;            \
+    (void)Yall; (void)Lall; (void)Bm; (void)S; (void)W; (void)N; (void)Nr; (void)ns; (void)nc; (void)nz; (void)M;       \
+    (void)tid; (void)nt; (void)row;
+
 struct BlockSolver {
     enum Row {
         R_Z, R_ZL, R_ZU, R_DZ, R_DZ2, R_GX, R_YC, R_YTC, R_YTC2, R_RC, R_CSOC, R_COEF, R_COEF2, R_LIN, R_DGV,
@@ -54,7 +72,7 @@ struct BlockSolver {
     double T, df, ny_nzb, nzb_cnt;
     int n_reg, n_resto, n_soc, n_fact, n_ls;
     // shared-memory carve-up (doubles)
-    int SM_RED, SM_FTH, SM_FPH, SM_MISC, SM_DZB, SM_DXN, SM_TB, SM_XB, SM_DINV, SM_PR, SM_CS, SM_MUU;
+    int SM_RED, SM_FTH, SM_FPH, SM_MISC, SM_DZB, SM_DXN, SM_TB, SM_XB, SM_DINV, SM_PR, SM_CS, SM_DS, SM_MUU;
 
     static NMPC_HD int row_width(int Nr) { int nz = 5 * Nr, M = Nr * (Nr - 1) / 2, w = nz > M ? nz : M; return (w + 31) & ~31; }
     static NMPC_HD long long ws_doubles(int Nr, int N)
@@ -68,7 +86,7 @@ struct BlockSolver {
     {
         const long long ns = 3 * Nr, nc = 2 * Nr, nz = 5 * Nr, ncp = (nc + 31) & ~31LL, ns4 = (ns + 3) & ~3LL;
         const long long a = ncp * ncp + ncp * PANEL_W, b = nc * ns4;   // Cholesky factor + panel, or Y resident for the rank-k update
-        return 32 * 12 + 16 + 16 + 8 + nz + ns + 3 * ncp + ns + 2 * Nr + (a > b ? a : b) + 16;
+        return 32 * 12 + 16 + 16 + 8 + nz + ns + 3 * ncp + ns + 7 * Nr + (a > b ? a : b) + 16;
     }
 
     __device__ BlockSolver(const NmpcSolveParams &p, double *smem, double *wsp) : P(p), sm(smem), ws(wsp) {}
@@ -86,6 +104,7 @@ struct BlockSolver {
     template <int K>
     __device__ void breduce(double (&v)[K], unsigned maxmask)
     {
+        NMPC_BLK_LOCALS
         double *red = sm + SM_RED;
         const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
 #pragma unroll
@@ -132,7 +151,7 @@ struct BlockSolver {
         Bm = Yall + (long long)N * nc * ldy;
         Lall = Bm + (long long)nc * ldy;
         SM_RED = 0; SM_FTH = 32 * 12; SM_FPH = SM_FTH + 16; SM_MISC = SM_FPH + 16; SM_DZB = SM_MISC + 8; SM_DXN = SM_DZB + nz;
-        SM_TB = SM_DXN + ns; SM_XB = SM_TB + ncp; SM_DINV = SM_XB + ncp; SM_PR = SM_DINV + ncp; SM_CS = SM_PR + ns; SM_MUU = (SM_CS + 2 * Nr + 1) & ~1;
+        SM_TB = SM_DXN + ns; SM_XB = SM_TB + ncp; SM_DINV = SM_XB + ncp; SM_PR = SM_DINV + ncp; SM_CS = SM_PR + ns; SM_DS = SM_CS + 2 * Nr; SM_MUU = (SM_DS + 5 * Nr + 1) & ~1;
         df = 1.0; fn = 0;
         n_reg = n_resto = n_soc = n_fact = n_ls = 0;
         __syncthreads();
@@ -149,6 +168,7 @@ struct BlockSolver {
     // cos / sin of every heading of the evaluation point: row(rt,k)[i] = cos, row(rt,k)[Nr+i] = sin
     __device__ void trig_rows(double alpha, int rdz, bool trial, int rt)
     {
+        NMPC_BLK_LOCALS
         for (int idx = tid; idx < N * Nr; idx += nt) {
             const int k = idx / Nr, i = idx - k * Nr;
             double th = row(R_Z, k)[3 * i + 2];
@@ -163,6 +183,7 @@ struct BlockSolver {
     // starting point: objective scaling, push into bounds, slacks, bound multipliers (IPOPT defaults)
     NMPC_BPASS void init_point()
     {
+        NMPC_BLK_LOCALS
         const long long n = (long long)ns * S + (long long)nc * N;
         const double *x0 = P.x0 + inst * n;
         const nmpc_opts &o = P.o;
@@ -225,6 +246,7 @@ struct BlockSolver {
     // ---------------------------------------------------------------------------------------
     NMPC_BPASS void eval(bool full, double mu, double alpha, int rdz, int rds, bool trial, bool socacc, double asoc, EvalOut &E)
     {
+        NMPC_BLK_LOCALS
         const double kd = P.o.kappa_d;
         const int rt = trial ? R_TRIG2 : R_TRIG, rz = trial ? R_ZT : R_Z, rs = trial ? R_ST : R_S;
         if (trial) {   // materialise the trial point once
@@ -354,6 +376,7 @@ struct BlockSolver {
     }
     NMPC_BPASS bool factor(int mode, double mu, double delta, bool soc)
     {
+        NMPC_BLK_LOCALS
         const double zeta = mode == 2 ? sqrt(mu) : 0.0, kd = P.o.kappa_d;
         double *Muu = sm + SM_MUU, *prv = sm + SM_PR, *colb = sm + SM_TB, *dinv = sm + SM_DINV;   // colb: 2 ncp doubles (SM_TB, SM_XB contiguous)
         n_fact++;
@@ -440,6 +463,18 @@ struct BlockSolver {
                     if (lane == 0) prv[r] = pn[r] - acc;
                 }
             }
+            // per-robot sums of the condensed collision blocks (curvature and gradient), one (array, robot) per thread
+            {
+                double *dsum = sm + SM_DS;
+                for (int idx = tid; idx < 5 * Nr; idx += nt) {
+                    const int c = idx / Nr, i = idx - c * Nr;
+                    const double *arr = row(R_PXX + c, k + 1);   // R_PXX, R_PYY, R_PXY, R_PHX, R_PHY are consecutive rows
+                    double acc = 0.0;
+                    for (int jj = 0; jj < i; jj++) { const double v = arr[pairidx(jj, i)]; acc += c >= 3 ? -v : v; }
+                    for (int jj = i + 1; jj < Nr; jj++) acc += arr[pairidx(i, jj)];
+                    dsum[idx] = acc;
+                }
+            }
             __syncthreads();
             NMPC_PROF(1);
             // B. stage matrix M = H~ + [A B]' P+ [A B], one robot pair (i, j) per thread: the 5x5 block C_i' Pb C_j
@@ -465,15 +500,8 @@ struct BlockSolver {
                     G[0][0] += dgv[3 * i]; G[1][1] += dgv[3 * i + 1]; G[2][2] += dgv[3 * i + 2] + cf2[Nr + i];
                     G[3][3] += dgv[ns + 2 * i]; G[4][4] += dgv[ns + 2 * i + 1];
                     G[2][3] += cf2[i]; G[3][2] += cf2[i];
-                    double sxx = 0, syy = 0, sxy = 0, glx = 0, gly = 0;
-                    const double *pxx = row(R_PXX, k + 1), *pyy = row(R_PYY, k + 1), *pxy = row(R_PXY, k + 1),
-                                 *phx = row(R_PHX, k + 1), *phy = row(R_PHY, k + 1);
-                    for (int jj = 0; jj < Nr; jj++) {
-                        if (jj == i) continue;
-                        const int q = i < jj ? pairidx(i, jj) : pairidx(jj, i);
-                        sxx += pxx[q]; syy += pyy[q]; sxy += pxy[q];
-                        glx += i < jj ? phx[q] : -phx[q]; gly += i < jj ? phy[q] : -phy[q];
-                    }
+                    const double *dsum = sm + SM_DS;
+                    const double sxx = dsum[i], syy = dsum[Nr + i], sxy = dsum[2 * Nr + i], glx = dsum[3 * Nr + i], gly = dsum[4 * Nr + i];
                     G[0][0] += sxx; G[1][1] += syy; G[0][1] += sxy; G[1][0] += sxy;
                     // m = [A B]' pr + h
                     const double p0 = prv[3 * i], p1 = prv[3 * i + 1], p2 = prv[3 * i + 2];
@@ -581,8 +609,8 @@ struct BlockSolver {
             //    1 x 4 strip of the current 32-row block
             {
                 double *Yp = Ls + ncp * ncp;
-                const int spr = PANEL_W / 4, nblk = ncp >> 5;
-                const int r_l = tid / spr, cq = tid - r_l * spr;
+                const int nblk = ncp >> 5;
+                const int r_l = tid >> 4, cq = tid & 15;   // 16 lanes per row of the block (PANEL_W / 4 = 13 of them active): 32 rows x 16 = 512 threads
                 for (int p0 = 0; p0 < ldy; p0 += PANEL_W) {
                     const int pw = ldy - p0 < PANEL_W ? ldy - p0 : PANEL_W;
                     for (int e = tid; e < ncp * PANEL_W; e += nt) {
@@ -590,19 +618,21 @@ struct BlockSolver {
                         Yp[e] = (u < nc && c < pw) ? Bm[(long long)u * ldy + p0 + c] : 0.0;
                     }
                     __syncthreads();
-                    const bool act = r_l < 32 && 4 * cq < pw;
+                    const bool act = 4 * cq < pw && cq < PANEL_W / 4;
                     for (int I = 0; I < nblk; I++) {
                         const int r = 32 * I + r_l;
                         double acc[4] = {0, 0, 0, 0};
                         if (act) {
-                            const double *yo = Yp + r * PANEL_W + 4 * cq;
-                            acc[0] = yo[0]; acc[1] = yo[1]; acc[2] = yo[2]; acc[3] = yo[3];
+                            const double2 *yo = reinterpret_cast<const double2 *>(Yp + r * PANEL_W + 4 * cq);
+                            const double2 o01 = yo[0], o23 = yo[1];
+                            acc[0] = o01.x; acc[1] = o01.y; acc[2] = o23.x; acc[3] = o23.y;
                             const double *lr = Ls + r * ncp;
-#pragma unroll 4
+#pragma unroll 8
                             for (int u = 0; u < 32 * I; u++) {
                                 const double lv = lr[u];
-                                const double *yu = Yp + u * PANEL_W + 4 * cq;
-                                acc[0] -= lv * yu[0]; acc[1] -= lv * yu[1]; acc[2] -= lv * yu[2]; acc[3] -= lv * yu[3];
+                                const double2 *yu = reinterpret_cast<const double2 *>(Yp + u * PANEL_W + 4 * cq);
+                                const double2 y01 = yu[0], y23 = yu[1];
+                                acc[0] -= lv * y01.x; acc[1] -= lv * y01.y; acc[2] -= lv * y23.x; acc[3] -= lv * y23.y;
                             }
                             double *yw = Yp + r * PANEL_W + 4 * cq;
                             yw[0] = acc[0]; yw[1] = acc[1]; yw[2] = acc[2]; yw[3] = acc[3];
@@ -611,10 +641,12 @@ struct BlockSolver {
                         if (act) {   // y = Linv_II t  (Linv_II[r_l][u] sits transposed at Ls[32 I + u][32 I + r_l], u < r_l)
                             const double di = dinv[r];
                             acc[0] *= di; acc[1] *= di; acc[2] *= di; acc[3] *= di;
+#pragma unroll 4
                             for (int u = 0; u < r_l; u++) {
                                 const double lv = Ls[(32 * I + u) * ncp + r];
-                                const double *yu = Yp + (32 * I + u) * PANEL_W + 4 * cq;
-                                acc[0] += lv * yu[0]; acc[1] += lv * yu[1]; acc[2] += lv * yu[2]; acc[3] += lv * yu[3];
+                                const double2 *yu = reinterpret_cast<const double2 *>(Yp + (32 * I + u) * PANEL_W + 4 * cq);
+                                const double2 y01 = yu[0], y23 = yu[1];
+                                acc[0] += lv * y01.x; acc[1] += lv * y01.y; acc[2] += lv * y23.x; acc[3] += lv * y23.y;
                             }
                         }
                         __syncthreads();
@@ -690,6 +722,7 @@ struct BlockSolver {
     // ---------------------------------------------------------------------------------------
     NMPC_BPASS void forward(double mu, double tau, int rdz, int rds, int rytc, int rytd, StepInfo &si)
     {
+        NMPC_BLK_LOCALS
         double ap = 0.0, az = 0.0, gbd = 0.0, tiny = 0.0;
         double *dzb = sm + SM_DZB, *dxn = sm + SM_DXN, *tb = sm + SM_TB, *xb = sm + SM_XB, *Ls = sm + SM_MUU;
         const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
@@ -783,6 +816,7 @@ struct BlockSolver {
     // ---------------------------------------------------------------------------------------
     NMPC_BPASS void accept(double alpha, double az, double mu, int rdz, int rds, int rytc, int rytd)
     {
+        NMPC_BLK_LOCALS
         const double ks = P.o.kappa_sigma, iks = 1.0 / ks;
         auto mult = [=](double m, double sl_old, double sl_new, double dv_signed) {
             const double r = 1.0 / sl_old, c = mu / sl_new;
@@ -816,6 +850,7 @@ struct BlockSolver {
 
     NMPC_BPASS void accept_primal(double alpha, int rdz, int rds)
     {
+        NMPC_BLK_LOCALS
         for (int idx = tid; idx < S * W; idx += nt) {
             const int k = idx / W, l = idx - k * W;
             if (l < nvalid(k)) row(R_Z, k)[l] += alpha * row(rdz, k)[l];
@@ -827,6 +862,7 @@ struct BlockSolver {
     // after the restoration fallback: equality multipliers reset, bound multipliers clipped
     NMPC_BPASS void resto_reset(double mu)
     {
+        NMPC_BLK_LOCALS
         const double ks = P.o.kappa_sigma;
         for (int idx = tid; idx < S * W; idx += nt) {
             const int k = idx / W, l = idx - k * W;
@@ -849,6 +885,7 @@ struct BlockSolver {
     // written as a direction (R_DZ, R_DS) = candidate - iterate
     NMPC_BPASS void rollout_project()
     {
+        NMPC_BLK_LOCALS
         const nmpc_opts &o = P.o;
         double *zt = sm + SM_DZB, *zn = sm + SM_TB /* ns <= nc + nc + ... : see below */, *cs = sm + SM_CS;
         // zn needs ns doubles: SM_TB (nc) and SM_XB (nc) are contiguous, 2 nc = 4 Nr >= 3 Nr
@@ -891,6 +928,7 @@ struct BlockSolver {
 
     NMPC_BPASS void soc_begin()
     {
+        NMPC_BLK_LOCALS
         for (int idx = tid; idx < S * W; idx += nt) {
             const int k = idx / W, l = idx - k * W;
             row(R_CSOC, k)[l] = l < ns ? row(R_RC, k)[l] : 0.0;
@@ -901,6 +939,7 @@ struct BlockSolver {
 
     __device__ double mult_absmax()
     {
+        NMPC_BLK_LOCALS
         double ymax = 0.0;
         for (int idx = tid; idx < S * W; idx += nt) {
             const int k = idx / W, l = idx - k * W;
@@ -911,6 +950,7 @@ struct BlockSolver {
     }
     __device__ void mult_zero()
     {
+        NMPC_BLK_LOCALS
         for (int idx = tid; idx < S * W; idx += nt) { const int k = idx / W, l = idx - k * W; row(R_YC, k)[l] = 0.0; row(R_YD, k)[l] = 0.0; }
     }
 
@@ -919,6 +959,7 @@ struct BlockSolver {
     // ---------------------------------------------------------------------------------------
     __device__ bool filter_ok(double th, double ph) const
     {
+        NMPC_BLK_LOCALS
         const double *fth = sm + SM_FTH, *fph = sm + SM_FPH;
         for (int i = 0; i < fn; i++)
             if (!(th < fth[i] || ph < fph[i])) return false;
@@ -926,6 +967,7 @@ struct BlockSolver {
     }
     NMPC_BPASS void filter_add(double th, double ph)
     {
+        NMPC_BLK_LOCALS
         double *fth = sm + SM_FTH, *fph = sm + SM_FPH, *misc = sm + SM_MISC;
         __syncthreads();
         if (tid == 0) {
@@ -956,6 +998,7 @@ struct BlockSolver {
     // outputs in the reference layout, multipliers in CasADi's sign convention
     NMPC_BPASS void write_outputs(int st, int iter, double E0, double pinf, double dinf, double c0, double mu)
     {
+        NMPC_BLK_LOCALS
         const long long n = (long long)ns * S + (long long)nc * N, mg = (long long)S * (ns + M);
         double *x = P.x + inst * n;
         double *lx = P.lam_x ? P.lam_x + inst * n : nullptr;
