@@ -248,6 +248,7 @@ struct BlockSolver {
     {
         NMPC_BLK_LOCALS
         const double kd = P.o.kappa_d;
+        NMPC_PROF_BEGIN
         const int rt = trial ? R_TRIG2 : R_TRIG, rz = trial ? R_ZT : R_Z, rs = trial ? R_ST : R_S;
         if (trial) {   // materialise the trial point once
             for (int idx = tid; idx < S * W; idx += nt) {
@@ -346,6 +347,7 @@ struct BlockSolver {
                 if (hu) { double u = (hi - zk) * zu; c0 = fmax(c0, fabs(u)); cmu = fmax(cmu, fabs(u - mu)); zsum += fabs(zu); }
             }
         }
+        NMPC_PROF(7);
         double v[11] = {pinf, viol, dinf, c0, cmu, ysum, zsum, th, fo, slog, sdamp};
         breduce<11>(v, 0x1Fu);   // first five are maxima
         E.pinf = v[0]; E.viol = v[1]; E.theta = v[7]; E.f = v[8]; E.slog = v[9]; E.sdamp = v[10];
@@ -724,6 +726,7 @@ struct BlockSolver {
     {
         NMPC_BLK_LOCALS
         double ap = 0.0, az = 0.0, gbd = 0.0, tiny = 0.0;
+        NMPC_PROF_BEGIN
         double *dzb = sm + SM_DZB, *dxn = sm + SM_DXN, *tb = sm + SM_TB, *xb = sm + SM_XB, *Ls = sm + SM_MUU;
         const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
         __syncthreads();
@@ -808,6 +811,7 @@ struct BlockSolver {
             __syncthreads();
         }
         double v[4] = {ap, az, gbd, tiny};
+        NMPC_PROF(6);
         breduce<4>(v, 0xBu);   // ap, az, tiny are maxima; gbd a sum
         si.ap = v[0] > tau ? tau / v[0] : 1.0; si.az = v[1] > tau ? tau / v[1] : 1.0;
         si.gbd = v[2]; si.tiny = v[3];
