@@ -56,7 +56,6 @@ struct BlockSolver {
         R_PXX, R_PYY, R_PXY, R_PHX, R_PHY, R_TRIG, R_TRIG2, R_ZT, R_ST,
         R_COUNT
     };
-    enum { PANEL_W = 52 };   // columns of [M_ux | m_u] per shared-memory panel of the triangular solve (multiple of 4)
     struct EvalOut { double pinf, viol, dinf, c0, cmu, ysum, zsum, theta, f, slog, sdamp; };
     struct StepInfo { double ap, az, gbd, tiny; };
     typedef WarpSolver<1> WS;   // scalar helpers (push_in, slack_step_terms, cmp_le, fin) are shared with the warp solver
@@ -85,7 +84,8 @@ struct BlockSolver {
     static NMPC_HD long long sm_doubles(int Nr)
     {
         const long long ns = 3 * Nr, nc = 2 * Nr, nz = 5 * Nr, ncp = (nc + 31) & ~31LL, ns4 = (ns + 3) & ~3LL;
-        const long long a = ncp * ncp + ncp * PANEL_W, b = nc * ns4;   // Cholesky factor + panel, or Y resident for the rank-k update
+        const long long a = ncp * ncp, b = nc * ((ns + 1 + 3) & ~3LL);   // Cholesky factor, then Y resident for the triangular solve and the rank-k update
+        (void)ns4;
         return 32 * 12 + 16 + 16 + 8 + nz + ns + 3 * ncp + ns + 7 * Nr + (a > b ? a : b) + 16;
     }
 
@@ -607,75 +607,90 @@ struct BlockSolver {
             __syncthreads();
             for (int e = tid; e < ncp * ncp; e += nt) Lk[e] = Ls[e];   // kept for the forward pass (lower triangle)
             NMPC_PROF(3);
-            // D. Y = L^-1 [M_ux | m_u]: column panels in shared memory, blocked forward substitution; each thread owns a
-            //    1 x 4 strip of the current 32-row block
+            // D. Y = L^-1 [M_ux | m_u] with Y resident in shared memory (it stays there for the rank-k update): blocked forward
+            //    substitution over 32-row blocks, 4x4 register tiles; L (and the inverses of its diagonal blocks, stored
+            //    transposed in the upper triangles) is read back from global memory through L1
+            __syncthreads();   // Ls has been copied to Lk by every thread: its shared memory now becomes Y
+            double *Ys = Muu;
             {
-                double *Yp = Ls + ncp * ncp;
-                const int nblk = ncp >> 5;
-                const int r_l = tid >> 4, cq = tid & 15;   // 16 lanes per row of the block (PANEL_W / 4 = 13 of them active): 32 rows x 16 = 512 threads
-                for (int p0 = 0; p0 < ldy; p0 += PANEL_W) {
-                    const int pw = ldy - p0 < PANEL_W ? ldy - p0 : PANEL_W;
-                    for (int e = tid; e < ncp * PANEL_W; e += nt) {
-                        const int u = e / PANEL_W, c = e - u * PANEL_W;
-                        Yp[e] = (u < nc && c < pw) ? Bm[(long long)u * ldy + p0 + c] : 0.0;
+                const double *Lg = Lk;
+                for (int e = tid; e < nc * (ldy / 2); e += nt)
+                    reinterpret_cast<double2 *>(Ys)[e] = reinterpret_cast<const double2 *>(Bm)[e];
+                __syncthreads();
+                const int tcn = ldy / 4, nblk = ncp >> 5;
+                const int tr = tid / tcn, tc = tid - tr * tcn;   // 8 tile rows x (ldy / 4) tile columns per 32-row block
+                const bool act = tr < 8;
+                const int c0 = 4 * tc;
+                for (int I = 0; I < nblk; I++) {
+                    const int r0 = 32 * I + 4 * tr;
+                    double acc[4][4];
+                    if (act && r0 < nc) {
+#pragma unroll
+                        for (int a = 0; a < 4; a++) {
+                            const double2 *yo = reinterpret_cast<const double2 *>(Ys + (r0 + a) * ldy + c0);
+                            const double2 o01 = r0 + a < nc ? yo[0] : make_double2(0.0, 0.0), o23 = r0 + a < nc ? yo[1] : make_double2(0.0, 0.0);
+                            acc[a][0] = o01.x; acc[a][1] = o01.y; acc[a][2] = o23.x; acc[a][3] = o23.y;
+                        }
+#pragma unroll 4
+                        for (int u = 0; u < 32 * I; u++) {
+                            const double2 *yu = reinterpret_cast<const double2 *>(Ys + u * ldy + c0);
+                            const double2 y01 = yu[0], y23 = yu[1];
+                            const double yv[4] = {y01.x, y01.y, y23.x, y23.y};
+#pragma unroll
+                            for (int a = 0; a < 4; a++) {
+                                const double lv = __ldg(Lg + (long long)(r0 + a) * ncp + u);
+#pragma unroll
+                                for (int c = 0; c < 4; c++) acc[a][c] -= lv * yv[c];
+                            }
+                        }
+#pragma unroll
+                        for (int a = 0; a < 4; a++)
+                            if (r0 + a < nc) {
+                                double2 *yw = reinterpret_cast<double2 *>(Ys + (r0 + a) * ldy + c0);
+                                yw[0] = make_double2(acc[a][0], acc[a][1]); yw[1] = make_double2(acc[a][2], acc[a][3]);
+                            }
                     }
                     __syncthreads();
-                    const bool act = 4 * cq < pw && cq < PANEL_W / 4;
-                    for (int I = 0; I < nblk; I++) {
-                        const int r = 32 * I + r_l;
-                        double acc[4] = {0, 0, 0, 0};
-                        if (act) {
-                            const double2 *yo = reinterpret_cast<const double2 *>(Yp + r * PANEL_W + 4 * cq);
-                            const double2 o01 = yo[0], o23 = yo[1];
-                            acc[0] = o01.x; acc[1] = o01.y; acc[2] = o23.x; acc[3] = o23.y;
-                            const double *lr = Ls + r * ncp;
-#pragma unroll 8
-                            for (int u = 0; u < 32 * I; u++) {
-                                const double lv = lr[u];
-                                const double2 *yu = reinterpret_cast<const double2 *>(Yp + u * PANEL_W + 4 * cq);
-                                const double2 y01 = yu[0], y23 = yu[1];
-                                acc[0] -= lv * y01.x; acc[1] -= lv * y01.y; acc[2] -= lv * y23.x; acc[3] -= lv * y23.y;
-                            }
-                            double *yw = Yp + r * PANEL_W + 4 * cq;
-                            yw[0] = acc[0]; yw[1] = acc[1]; yw[2] = acc[2]; yw[3] = acc[3];
+                    double out[4][4];
+                    if (act && r0 < nc) {   // y = Linv_II t;  Linv_II[i][u] (u < i) sits at L[32 I + u][32 I + i], its diagonal in dinv
+#pragma unroll
+                        for (int a = 0; a < 4; a++) {
+                            const double di = dinv[r0 + a];
+#pragma unroll
+                            for (int c = 0; c < 4; c++) out[a][c] = acc[a][c] * di;
                         }
-                        __syncthreads();
-                        if (act) {   // y = Linv_II t  (Linv_II[r_l][u] sits transposed at Ls[32 I + u][32 I + r_l], u < r_l)
-                            const double di = dinv[r];
-                            acc[0] *= di; acc[1] *= di; acc[2] *= di; acc[3] *= di;
-#pragma unroll 4
-                            for (int u = 0; u < r_l; u++) {
-                                const double lv = Ls[(32 * I + u) * ncp + r];
-                                const double2 *yu = reinterpret_cast<const double2 *>(Yp + (32 * I + u) * PANEL_W + 4 * cq);
-                                const double2 y01 = yu[0], y23 = yu[1];
-                                acc[0] += lv * y01.x; acc[1] += lv * y01.y; acc[2] += lv * y23.x; acc[3] += lv * y23.y;
+                        const int rl = 4 * tr;   // local row of the tile inside the block
+                        const int ub = rl + 3 < nc - 32 * I ? rl + 3 : nc - 32 * I;   // rows of Y beyond nc do not exist
+                        for (int u = 0; u < ub; u++) {
+                            const double2 *yu = reinterpret_cast<const double2 *>(Ys + (32 * I + u) * ldy + c0);
+                            const double2 y01 = yu[0], y23 = yu[1];
+                            const double yv[4] = {y01.x, y01.y, y23.x, y23.y};
+#pragma unroll
+                            for (int a = 0; a < 4; a++) {
+                                const double lv = u < rl + a ? __ldg(Lg + (long long)(32 * I + u) * ncp + r0 + a) : 0.0;
+#pragma unroll
+                                for (int c = 0; c < 4; c++) out[a][c] += lv * yv[c];
                             }
                         }
-                        __syncthreads();
-                        if (act) {
-                            double *yw = Yp + r * PANEL_W + 4 * cq;
-                            yw[0] = acc[0]; yw[1] = acc[1]; yw[2] = acc[2]; yw[3] = acc[3];
-                        }
-                        __syncthreads();
                     }
-                    for (int e = tid; e < nc * PANEL_W; e += nt) {
-                        const int u = e / PANEL_W, c = e - u * PANEL_W;
-                        if (c < pw) Yk[(long long)u * ldy + p0 + c] = Yp[e];
+                    __syncthreads();
+                    if (act && r0 < nc) {
+#pragma unroll
+                        for (int a = 0; a < 4; a++)
+                            if (r0 + a < nc) {
+                                double2 *yw = reinterpret_cast<double2 *>(Ys + (r0 + a) * ldy + c0);
+                                yw[0] = make_double2(out[a][0], out[a][1]); yw[1] = make_double2(out[a][2], out[a][3]);
+                            }
                     }
                     __syncthreads();
                 }
+                for (int e = tid; e < nc * (ldy / 2); e += nt)   // kept for the forward pass
+                    reinterpret_cast<double2 *>(Yk)[e] = reinterpret_cast<const double2 *>(Ys)[e];
             }
             NMPC_PROF(4);
             // F. P_k = M_xx - Y'Y (upper 4x4 tiles over Y resident in shared memory, mirrored), p_k = m_x - Y' y_m
             {
                 const int ns4 = (ns + 3) & ~3, nt4 = ns4 / 4;
-                double *Ys = Muu;
-                for (int e = tid; e < nc * (ns4 / 2); e += nt) {
-                    const int u = e / (ns4 / 2), c2 = e - u * (ns4 / 2);
-                    reinterpret_cast<double2 *>(Ys + u * ns4)[c2] = reinterpret_cast<const double2 *>(Yk + (long long)u * ldy)[c2];
-                }
-                for (int u = tid; u < nc; u += nt) colb[u] = Yk[(long long)u * ldy + ns];
-                __syncthreads();
                 for (int e = tid; e < nt4 * nt4; e += nt) {
                     const int tr = e / nt4, tc = e - tr * nt4;
                     if (tc < tr) continue;
@@ -687,8 +702,8 @@ struct BlockSolver {
                         for (int c = 0; c < 4; c++) acc[a][c] = 0.0;
 #pragma unroll 4
                     for (int u = 0; u < nc; u++) {
-                        const double2 *yr = reinterpret_cast<const double2 *>(Ys + u * ns4 + r0);
-                        const double2 *yc = reinterpret_cast<const double2 *>(Ys + u * ns4 + c0);
+                        const double2 *yr = reinterpret_cast<const double2 *>(Ys + u * ldy + r0);
+                        const double2 *yc = reinterpret_cast<const double2 *>(Ys + u * ldy + c0);
                         const double2 y01 = yr[0], y23 = yr[1], z01 = yc[0], z23 = yc[1];
                         const double ya[4] = {y01.x, y01.y, y23.x, y23.y}, zc[4] = {z01.x, z01.y, z23.x, z23.y};
 #pragma unroll
@@ -709,7 +724,7 @@ struct BlockSolver {
                 }
                 for (int r = tid; r < ns; r += nt) {
                     double acc = 0.0;
-                    for (int u = 0; u < nc; u++) acc += Ys[u * ns4 + r] * colb[u];
+                    for (int u = 0; u < nc; u++) acc += Ys[u * ldy + r] * Ys[u * ldy + ns];
                     row(R_LIN, k)[r] -= acc;
                 }
             }
