@@ -23,6 +23,9 @@ sys.path.insert(0, ROOT)
 NR, NH, T, DMIN, VMAX, WMAX = 6, 20, 0.3, 0.3, 0.22, 2.84      # sixth_scenario.py:127-135, N overridden to 20
 PER_GPU = 8192
 ALG_BYTES_PER_SOLVE = 15728       # p + w0 in, x + f + g out
+# dram__bytes_read.sum + dram__bytes_write.sum of solve_kernel<6> per solve, from the ncu --set full capture of v14
+# (profiles/ncu_solve_kernel_r1_v14.txt: 93.64 + 63.40 GB for 3552 cold-start instances): scratch rows stream through HBM
+TRAFFIC_BYTES_PER_SOLVE = int((93.639603e9 + 63.399507e9) / 3552)
 F_FACT, F_SOLVE, F_EVAL = 1100160, 92160, 14700   # SURVEY.md 8d dense-stage FP64 flop counts @ Nr=6, N=20
 
 
@@ -98,6 +101,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--per-gpu", type=int, default=PER_GPU)
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--swarm", type=int, default=148, help="N=1 only: also time this many 64-robot swarm instances (BASELINE.json configs[4]) on the dense-block path; 0 = skip")
     ap.add_argument("--clone", type=int, default=-1, help="diagnostic: replicate one instance B times (all warps run in lockstep)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -253,6 +257,34 @@ def main():
         lat = {"p50_ms": 1e3 * float(np.median(times[1:])), "p95_ms": 1e3 * float(np.percentile(times[1:], 95)), "first_cold_ms": 1e3 * times[0],
                "steps": 60, "note": "batch=1 closed loop through nmpc_solve_host (H2D of p and guess, solve, D2H of x), wall clock"}
 
+    # ---- BASELINE.json configs[4]: 64-robot swarm on the CTA-per-instance dense-block path (one timed launch) ----
+    swarm = None
+    if rank == 0 and world == 1 and a.swarm > 0:
+        from oracle.nlp_numpy import synthetic_instances
+        Bs, Ns = a.swarm, 64
+        Ps = synthetic_instances(min(Bs, 8), Nr=Ns, seed=20261018, box=8.0)
+        Ps = np.tile(Ps, ((Bs + len(Ps) - 1) // len(Ps), 1))[:Bs]      # 8 distinct instances, repeated (rejection sampling 64 robots is slow)
+        sp = pkg.Problem(Ns, NH, T)
+        sb = sp.bounds(DMIN, VMAX, WMAX)
+        sargs = [t(sp.cold_start(Ps[:, :3 * Ns])), t(Ps)] + [t(v) for v in sb]
+        so = {}
+        sp.solve(sargs[0][:1], sargs[1][:1], *sargs[2:], want=("stats",), out={})      # warm-up launch: one instance
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(); sp.solve(*sargs, want=("stats",), out=so); s1.record()
+        torch.cuda.synchronize()
+        s_ms = s0.elapsed_time(s1)
+        nf = so["stats"][:, 8].double().mean().item()
+        nx, nu = 3 * Ns, 2 * Ns
+        dense = NH * (4 * nx ** 3 + 6 * nx * nx * nu + 3 * nx * nu * nu + nu ** 3 / 3.0)       # SURVEY.md 8d dense-stage count
+        executed = NH * (nu ** 3 / 3.0 + nu * nu * (nx + 1) + nx * nx * nu)                    # Cholesky + triangular solve + symmetric rank-k update
+        swarm = {"workload": "64-robot N=20 cold-start swarm (2016 pair rows per stage), %d instances, one CTA per instance" % Bs,
+                 "value": Bs / (s_ms * 1e-3), "unit": "solves/s", "ms": s_ms, "solved_frac": float((so["status"] == 0).double().mean().item()),
+                 "mean_ip_iters": float(so["iters"].double().mean().item()), "mean_factorisations": nf,
+                 "fp64_tflops_dense_stage_count": Bs / (s_ms * 1e-3) * nf * dense / 1e12,
+                 "fp64_tflops_executed_upper_bound": Bs / (s_ms * 1e-3) * nf * executed / 1e12}
+        del sp, sargs, so
+
     if rank != 0:
         return
     value = world * B * a.steps / (tot_ms * 1e-3)
@@ -277,7 +309,7 @@ def main():
         "solved_frac": solved, "mean_ip_iters": float(iters.mean()), "max_ip_iters": int(iters.max()),
         "mean_factorisations": float(stats[:, 8].mean()),
         "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                     "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                     "traffic": TRAFFIC_BYTES_PER_SOLVE * B, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                      "note": "solve_kernel is FP64-pipe/latency bound, not HBM bound (SURVEY.md 8d); see fp64"},
         "fp64": {"achieved_tflops": ach_tf, "peak_tflops": tf.value, "frac": ach_tf / tf.value if tf.value else None,
                  "flops_per_solve": flops_per_solve, "peak_source": "nmpc_probe_fp64 (DFMA microbenchmark, this run)"},
@@ -285,7 +317,7 @@ def main():
                          "sample": "%d cold-start instances of the same workload in %.1f s, restated IPOPT (oracle/), OpenMP" % (cpu_n, cpu_dt),
                          "mean_iters": cpu_it},
         "e2e": {"value": e2e_val, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "warm_start": warm, "latency": lat,
+        "warm_start": warm, "latency": lat, "swarm64": swarm,
         "gpu_launches": launches, "clocks": sampler.summary(),
     }
     print(json.dumps(line))

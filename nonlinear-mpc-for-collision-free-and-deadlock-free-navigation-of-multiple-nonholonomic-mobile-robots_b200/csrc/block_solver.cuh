@@ -695,11 +695,14 @@ struct BlockSolver {
                     const int tr = e / nt4, tc = e - tr * nt4;
                     if (tc < tr) continue;
                     const int r0 = 4 * tr, c0 = 4 * tc;
-                    double acc[4][4];
+                    double acc[4][4], pv[4][4];
 #pragma unroll
                     for (int a = 0; a < 4; a++)
 #pragma unroll
-                        for (int c = 0; c < 4; c++) acc[a][c] = 0.0;
+                        for (int c = 0; c < 4; c++) {   // M_xx tile: issued before the contraction so that its latency overlaps
+                            acc[a][c] = 0.0;
+                            pv[a][c] = (r0 + a < ns && c0 + c < ns) ? Pk[(long long)(r0 + a) * ns + c0 + c] : 0.0;
+                        }
 #pragma unroll 4
                     for (int u = 0; u < nc; u++) {
                         const double2 *yr = reinterpret_cast<const double2 *>(Ys + u * ldy + r0);
@@ -717,7 +720,7 @@ struct BlockSolver {
                         for (int c = 0; c < 4; c++) {
                             const int r = r0 + a, cc = c0 + c;
                             if (r < ns && cc < ns && r <= cc) {
-                                const double v = Pk[(long long)r * ns + cc] - acc[a][c];
+                                const double v = pv[a][c] - acc[a][c];
                                 Pk[(long long)r * ns + cc] = v; Pk[(long long)cc * ns + r] = v;
                             }
                         }
@@ -761,7 +764,6 @@ struct BlockSolver {
         for (int k = 0; k <= N; k++) {
             const double *Pk = Pall + (long long)k * ns * ns;
             const double *Yk = Yall + (long long)(k < N ? k : 0) * nc * ldy, *Lk = Lall + (long long)(k < N ? k : 0) * ncp * ncp;
-            if (k < N) for (int e = tid; e < ncp * ncp; e += nt) Ls[e] = Lk[e];
             // y~c_k = -(P_k dx + p_k);  t = Y_k dx + y_m      (one warp per row)
             for (int r = wid; r < ns + (k < N ? nc : 0); r += nw) {
                 const double *mr = r < ns ? Pk + (long long)r * ns : Yk + (long long)(r - ns) * ldy;
@@ -775,11 +777,26 @@ struct BlockSolver {
                 }
             }
             __syncthreads();
-            if (k < N) {   // L' x = t (column-oriented back substitution, one barrier per pivot), du = -x
-                for (int i = nc - 1; i >= 0; i--) {
-                    const double xi = tb[i] / Ls[i * ncp + i];   // tb[i] is final: rows > i were eliminated before the last barrier
-                    if (tid == 0) xb[i] = xi;
-                    for (int j = tid; j < i; j += nt) tb[j] -= Ls[i * ncp + j] * xi;
+            if (k < N) {   // L' x = t by 32-row blocks: x_I = Linv_II' (t_I - sum_{J > I} L_JI' x_J), du = -x.  L comes straight
+                           // from global memory (coalesced along its rows); Linv_II sits transposed in the upper triangle of block (I, I)
+                double *red = Ls;   // nw x 32 partial sums
+                for (int I = (ncp >> 5) - 1; I >= 0; I--) {
+                    const int i = lane, gi = 32 * I + lane;
+                    double part = 0.0;
+                    for (int u = 32 * (I + 1) + wid; u < nc; u += nw) part += __ldg(Lk + (long long)u * ncp + gi) * xb[u];
+                    red[wid * 32 + i] = part;
+                    __syncthreads();
+                    if (wid == 0) {
+                        double ti = gi < nc ? tb[gi] : 0.0;
+                        for (int w = 0; w < nw; w++) ti -= red[w * 32 + i];
+                        double acc = ti / __ldg(Lk + (long long)gi * ncp + gi);
+                        for (int u = 1; u < 32; u++) {
+                            const double tu = __shfl_sync(0xffffffffu, ti, u);
+                            const double lv = u > i ? __ldg(Lk + (long long)gi * ncp + 32 * I + u) : 0.0;
+                            acc += lv * tu;
+                        }
+                        if (gi < nc) xb[gi] = acc;
+                    }
                     __syncthreads();
                 }
                 for (int u = tid; u < nc; u += nt) dzb[ns + u] = -xb[u];
