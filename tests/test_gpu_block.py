@@ -89,3 +89,39 @@ def test_block_path_64_robot_swarm(pkg, torch_cuda):
     np.testing.assert_allclose(out["g"].cpu().numpy()[0], nlp.g(w, P[0]), rtol=0, atol=1e-10)
     f0 = out["f"].cpu().numpy()[0]
     assert abs(nlp.f(w, P[0]) - f0) <= 1e-9 * max(1.0, abs(f0))
+
+
+def _ring(Nr, radius):
+    a = np.arange(Nr) * 2 * np.pi / Nr
+    st = np.stack([radius * np.cos(a), radius * np.sin(a), a + np.pi], axis=1)
+    g = np.stack([-radius * np.cos(a), -radius * np.sin(a), a + np.pi], axis=1)
+    return np.concatenate([st.ravel() + 0.01 * np.sin(np.arange(3 * Nr)), g.ravel()])
+
+
+def test_block_path_closed_loop_and_host_api(pkg, torch_cuda):
+    """12 robots on the dense-block path: (a) the host-buffer entry point equals the device one bit for bit; (b) the batched
+    device-resident closed loop (solve -> plant -> shift, warm starts) keeps every pair >= dmin and moves every robot towards
+    its antipodal goal (ten-robot script pattern, mpc_online_casadi_tb3_ten_...py:169-380, with two more robots)."""
+    torch = torch_cuda
+    Nr, N, T, dmin = 12, 10, 0.3, 0.3
+    prob = pkg.Problem(Nr, N, T)
+    lbx, ubx, lbg, ubg = prob.bounds(dmin, 0.22, 2.84)
+    rng = np.random.default_rng(12)
+    P = _ring(Nr, 1.6)[None] + np.concatenate([0.03 * rng.normal(size=(3, 3 * Nr)), np.zeros((3, 3 * Nr))], axis=1)
+    x0 = prob.cold_start(P[:, :3 * Nr])
+    dev = prob.solve(_t(torch, x0), _t(torch, P), _t(torch, lbx), _t(torch, ubx), _t(torch, lbg), _t(torch, ubg))
+    torch.cuda.synchronize()
+    host = prob.solve_host(x0, P, lbx, ubx, lbg, ubg)
+    np.testing.assert_array_equal(host["x"], dev["x"].cpu().numpy())
+    np.testing.assert_array_equal(host["status"], dev["status"].cpu().numpy())
+    res = pkg.closed_loop(prob, _t(torch, P), _t(torch, lbx), _t(torch, ubx), _t(torch, lbg), _t(torch, ubg), steps=25, tol=1e-1)
+    torch.cuda.synchronize()
+    assert (res["status"].cpu().numpy() <= 1).all(), res["status"].cpu().numpy()
+    assert res["min_dist"].min().item() >= dmin - 1e-6, res["min_dist"]
+    traj = res["traj"].cpu().numpy()
+    goal = P[:, 3 * Nr:].reshape(3, Nr, 3)[..., :2]
+    d0 = np.linalg.norm(traj[0].reshape(3, Nr, 3)[..., :2] - goal, axis=-1)
+    d1 = np.linalg.norm(traj[-1].reshape(3, Nr, 3)[..., :2] - goal, axis=-1)
+    assert (d1 < d0 - 0.5).all(), (d0, d1)      # 25 steps at <= 0.066 m per step: every robot has made > 0.5 m of progress
+    warm = res["iters"].cpu().numpy()[1:].mean()
+    assert warm < res["iters"].cpu().numpy()[0].mean(), "warm starts should need fewer iterations than the cold first step"
