@@ -221,9 +221,17 @@ extern "C" int nmpc_create(const nmpc_desc *d, const nmpc_opts *o, nmpc_handle *
         case 10: h->ws_doubles_per_slot = slot_doubles<10>(N); e = config_solve<10>(h); break;
         default: {   // dense-block path: one 512-thread CTA per instance, the control block of the stage matrix in shared memory
             h->ws_doubles_per_slot = (size_t)BlockSolver::ws_doubles(Nr, N);
-            h->lw = BlockSolver::row_width(Nr); h->teams_per_cta = 1; h->threads = NMPC_BLOCK_THREADS; h->ctas_per_sm = 1;
+            // CTA size: the register-resident Cholesky needs 8 rows per warp over ncp = roundup(2 Nr, 32) rows, i.e. 4 ncp threads
+            // (128 for 11..16 robots, 512 for 49..64); smaller swarms then fit several CTAs per SM
+            h->lw = BlockSolver::row_width(Nr); h->teams_per_cta = 1;
+            h->threads = 4 * ((2 * Nr + 31) & ~31);
+            if (h->threads > NMPC_BLOCK_THREADS) h->threads = NMPC_BLOCK_THREADS;
             h->solve_smem = (size_t)BlockSolver::sm_doubles(Nr) * sizeof(double);
             e = cudaFuncSetAttribute(solve_kernel_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->solve_smem);
+            int nb = 0;
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, solve_kernel_block, h->threads, h->solve_smem);
+            h->ctas_per_sm = nb > 0 ? nb : 1;
+            if (const char *ov = getenv("NMPC_CTAS_PER_SM")) { int v = atoi(ov); if (v >= 1 && v < h->ctas_per_sm) h->ctas_per_sm = v; }
             std::vector<int> pr;
             for (int a = 0; a < Nr; a++)
                 for (int b = a + 1; b < Nr; b++) { pr.push_back(a); pr.push_back(b); }
