@@ -218,6 +218,8 @@ def main():
     outw = {}
     prob.solve(d_x0w, d_p2, d_lbx, d_ubx, d_lbg, d_ubg, want=("stats",), out=outw)
     torch.cuda.synchronize()
+    # longest-first scheduling from the PREVIOUS solve's iteration counts (what a closed loop has at hand: nmpc_set_order)
+    prob.set_order(prob.order_from_iters(out["iters"]))
     wev = []
     for _ in range(a.steps):
         flush.fill_(1)
@@ -227,12 +229,14 @@ def main():
         w1.record()
         wev.append((w0, w1))
     torch.cuda.synchronize()
+    prob.set_order(None)
     warm_ms = torch.tensor([sum(e0.elapsed_time(e1) for e0, e1 in wev) / a.steps], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(warm_ms, op=dist.ReduceOp.MAX)
     warm = {"value": world * B / (warm_ms.item() * 1e-3), "unit": "solves/s", "mean_ip_iters": float(outw["iters"].double().mean().item()),
             "solved_frac": float((outw["status"] == 0).double().mean().item()), "max_ip_iters": int(outw["iters"].max().item()),
-            "note": "one MPC step later: Euler plant + reference shift as initial guess (the closed-loop regime)"}
+            "note": "one MPC step later: Euler plant + reference shift as initial guess (the closed-loop regime); instances "
+                    "scheduled longest-first by the previous step's iteration counts (nmpc_set_order)"}
 
     # ---- p50 single-solve latency: hexagon swap (C-6 constants, N=20), closed loop, batch = 1, host buffers ----
     lat = None

@@ -106,6 +106,13 @@ int nmpc_solve(nmpc_handle *h, int B, const double *x0, const double *p,
                int32_t *status, int32_t *iters, double *stats,
                void *workspace, size_t workspace_bytes, void *stream);
 
+/* Scheduling hint for the following nmpc_solve* calls on this handle: order [B] (DEVICE int32, caller owned, a permutation
+ * of 0..B-1) is the sequence in which the persistent teams pull instances from the work queue; NULL restores index order.
+ * Instances differ in iteration count (17 on average, up to 70, one MPC step after a solve), so a closed loop that passes
+ * the previous step's iteration counts sorted in descending order (longest first) shortens the tail of the launch.
+ * Results do not depend on the order. */
+int nmpc_set_order(nmpc_handle *h, const int32_t *order);
+
 /* nmpc_solve plus a per-iteration trace [B][max_trace][8] = (mu, scaled KKT error, theta, f, alpha_primal,
  * alpha_dual, delta_w, line-search trials) -- the parity tests compare it with the oracle's trace. */
 int nmpc_solve_trace(nmpc_handle *h, int B, const double *x0, const double *p,

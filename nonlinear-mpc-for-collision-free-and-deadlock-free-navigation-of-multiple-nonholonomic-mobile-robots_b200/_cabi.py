@@ -14,7 +14,7 @@ SYMBOLS = ["nmpc_default_opts", "nmpc_last_error", "nmpc_create", "nmpc_destroy"
            "nmpc_nnz_jac", "nmpc_nnz_hess", "nmpc_workspace_bytes", "nmpc_workspace_bytes_batched_bounds", "nmpc_solve",
            "nmpc_solve_trace", "nmpc_solve_host", "nmpc_shift",
            "nmpc_plant", "nmpc_eval", "nmpc_jac_pattern", "nmpc_hess_pattern", "nmpc_launch_count", "nmpc_probe_fp64",
-           "nmpc_debug_block_profile"]
+           "nmpc_debug_block_profile", "nmpc_set_order"]
 
 
 class Desc(C.Structure):
@@ -72,6 +72,7 @@ def lib():
     L.nmpc_launch_count.argtypes = [H]
     L.nmpc_probe_fp64.argtypes = [C.POINTER(C.c_double)]
     L.nmpc_debug_block_profile.argtypes = [C.POINTER(C.c_longlong), C.c_int]
+    L.nmpc_set_order.argtypes = [H, vp]
     L.nmpc_launch_count.restype = C.c_longlong
     _LIB = L
     return L

@@ -1097,9 +1097,9 @@ __global__ void __launch_bounds__(NMPC_BLOCK_THREADS, 1) solve_kernel_block(cons
         __syncthreads();
         if (threadIdx.x == 0) next_inst = atomicAdd(P.counter, 1);
         __syncthreads();
-        const int inst = next_inst;
-        if (inst >= P.B) break;
-        s.setup(inst);
+        const int slot = next_inst;
+        if (slot >= P.B) break;
+        s.setup(P.order ? P.order[slot] : slot);
         s.run();
     }
 }

@@ -74,8 +74,9 @@ __global__ void __launch_bounds__(SolveCfg<NR>::THREADS, SolveCfg<NR>::MIN_CTAS)
         WarpSolver<NR>::tsync();
         if (tl == 0) sm[WarpSolver<NR>::SM_MISC + 1] = (double)atomicAdd(P.counter, 1);
         WarpSolver<NR>::tsync();
-        const int inst = (int)sm[WarpSolver<NR>::SM_MISC + 1];
-        if (inst >= P.B) break;
+        const int slot = (int)sm[WarpSolver<NR>::SM_MISC + 1];
+        if (slot >= P.B) break;
+        const int inst = P.order ? P.order[slot] : slot;   // longest-first scheduling when the caller has a predictor
         s.setup(inst);
         s.run();
     }
@@ -91,6 +92,7 @@ struct nmpc_handle {
     long long launches;
     size_t ws_doubles_per_slot, solve_smem, eval_smem;
     int ctas_per_sm, lw, teams_per_cta, threads;
+    const int *d_order;                       // optional processing order (device, caller owned), see nmpc_set_order
     bool block_path, eval_ok;                 // Nr > 10: CTA-per-instance dense-block solver; eval record fits shared memory
     int *d_pairs;                             // pair table (i, j) of the inequality rows, block path
     // host-pointer API staging
@@ -190,7 +192,7 @@ extern "C" int nmpc_create(const nmpc_desc *d, const nmpc_opts *o, nmpc_handle *
     h->n = h->ns * h->S + h->nc * d->N; h->mg = h->S * (h->ns + h->M); h->np = 2 * h->ns;
     h->nnzj = 3 * d->Nr + d->N * (11 * d->Nr + 4 * h->M); h->nnzh = d->N * (6 * d->Nr + 2 * h->M);
     h->launches = 0; h->d_buf = nullptr; h->d_bytes = 0; h->stream = nullptr; h->d_tables = nullptr;
-    h->block_path = d->Nr > 10; h->eval_ok = true; h->d_pairs = nullptr;
+    h->block_path = d->Nr > 10; h->eval_ok = true; h->d_pairs = nullptr; h->d_order = nullptr;
     DBG("device count ok");
     cudaGetDevice(&h->dev);
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->dev);
@@ -333,7 +335,7 @@ static int solve_impl(nmpc_handle *h, int B, const double *x0, const double *p, 
     P.bstride = bounds_batched ? (long long)NMPC_BR_COUNT * h->S * h->lw : 0;
     P.bound_err = berr; P.x = x; P.f = f; P.g = g; P.lam_x = lam_x; P.lam_g = lam_g; P.status = status; P.iters = iters;
     P.stats = stats; P.trace = trace; P.max_trace = max_trace; P.ws = slots; P.ws_stride = (long long)h->ws_doubles_per_slot;
-    P.counter = counter; P.pairs = h->d_pairs;
+    P.counter = counter; P.pairs = h->d_pairs; P.order = h->d_order;
     const int grid = solve_grid(h, B);
     if (h->block_path) solve_kernel_block<<<grid, h->threads, h->solve_smem, st>>>(P);
     else switch (h->d.Nr) {
@@ -350,6 +352,13 @@ static int solve_impl(nmpc_handle *h, int B, const double *x0, const double *p, 
     }
     h->launches++;
     CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int nmpc_set_order(nmpc_handle *h, const int32_t *order)
+{
+    if (!h) return fail(NMPC_EINVAL, "nmpc_set_order: NULL handle");
+    h->d_order = order;
     return 0;
 }
 

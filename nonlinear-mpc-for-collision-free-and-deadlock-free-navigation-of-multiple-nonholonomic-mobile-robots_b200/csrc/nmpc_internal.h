@@ -32,6 +32,7 @@ typedef struct NmpcSolveParams {
     long long ws_stride;             /* doubles per warp slot                            */
     int *counter;                    /* work queue                                       */
     const int *pairs;                /* [M][2] pair table (dense-block path only)        */
+    const int *order;                /* optional [B] processing order of the instances   */
 } NmpcSolveParams;
 
 #endif

@@ -216,6 +216,21 @@ class Problem:
             check(self.L.nmpc_solve(*args, ws.data_ptr(), ws.numel(), stream))
         return o
 
+    def set_order(self, order=None):
+        """Scheduling hint (nmpc_set_order): int32 CUDA tensor [B], a permutation of the instances, longest expected solve
+        first; None restores index order.  The tensor is kept alive by the handle."""
+        if order is not None:
+            torch = self._torch()
+            if not (order.is_cuda and order.dtype == torch.int32 and order.is_contiguous()):
+                raise ValueError("order must be a contiguous int32 CUDA tensor")
+        self._order = order
+        check(self.L.nmpc_set_order(self.h, None if order is None else order.data_ptr()))
+
+    def order_from_iters(self, iters):
+        """Longest-first order from the iteration counts of the previous MPC step (the closed-loop predictor)."""
+        torch = self._torch()
+        return torch.argsort(iters, descending=True, stable=True).to(torch.int32).contiguous()
+
     def shift(self, x_prev, out=None):
         torch = self._torch()
         out = torch.empty_like(x_prev) if out is None else out
@@ -270,8 +285,10 @@ def closed_loop(prob, P, lbx, ubx, lbg, ubg, steps, tol=1e-1, dmin=None):
         p[:, :ns] = torch.where(active[:, None], nxt, p[:, :ns])
         us[t] = torch.where(active[:, None], u0, torch.zeros_like(u0))
         st[t], its[t] = out["status"], out["iters"]
+        prob.set_order(prob.order_from_iters(out["iters"]))      # longest solves first in the next step
         x0 = prob.shift(out["x"])
         traj[t + 1] = p[:, :ns]
+    prob.set_order(None)
     res = dict(traj=traj, u=us, status=st, iters=its, active=act)
     if prob.Nr > 1:
         pos = traj.reshape(steps + 1, B, prob.Nr, 3)[..., :2]

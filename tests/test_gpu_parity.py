@@ -240,3 +240,22 @@ def test_parity_statistics_2048_synthetic_instances(pkg, torch_cuda):
     # where they part ways both are KKT points (different local minima of a multi-modal NLP), never a failure
     assert out["stats"][:, 0].cpu().numpy().max() <= 1e-8
     assert np.median(np.abs(it - ref["iters"])) == 0
+
+
+def test_scheduling_order_does_not_change_results(pkg, torch_cuda):
+    """nmpc_set_order only changes which resident team picks which instance: outputs are bit-identical."""
+    torch = torch_cuda
+    Nr, N, T = 6, 20, 0.3
+    prob = pkg.Problem(Nr, N, T)
+    lbx, ubx, lbg, ubg = prob.bounds(0.3, 0.22, 2.84)
+    P = synthetic_instances(300, Nr=Nr, seed=77)
+    x0 = prob.cold_start(P[:, :3 * Nr])
+    args = [_t(torch, a) for a in (x0, P, lbx, ubx, lbg, ubg)]
+    a = prob.solve(*args)
+    torch.cuda.synchronize()
+    prob.set_order(prob.order_from_iters(a["iters"]))
+    b = prob.solve(*args)
+    torch.cuda.synchronize()
+    prob.set_order(None)
+    for k in ("x", "f", "g", "lam_g", "status", "iters"):
+        assert torch.equal(a[k], b[k]), k
