@@ -74,14 +74,15 @@ struct WarpSolver {
     // shared-memory carve-up (doubles, per warp)
     enum {
         PLD = NS + 3,  // leading dimension of the P broadcast buffer: 3Nr columns of P, the pr column, 2 zero columns
-        SM_COL = 0, SM_PB = 2 * LW, SM_ZB = SM_PB + ((NS * PLD + 1) & ~1), SM_DZB = SM_ZB + LW, SM_RCB = SM_DZB + LW,
+        SM_COL = 0,                      // two pivot-row buffers, each LW values + LW reciprocals
+        SM_PB = 4 * LW, SM_ZB = SM_PB + ((NS * PLD + 1) & ~1), SM_DZB = SM_ZB + LW, SM_RCB = SM_DZB + LW,
         SM_PRB = SM_RCB + LW, SM_HB = SM_PRB + LW, SM_CS = SM_HB + LW, SM_SN = SM_CS + NRP, SM_CA = SM_SN + NRP, SM_CB = SM_CA + NRP,
         SM_TCS = SM_CB + NRP, SM_TSN = SM_TCS + NRP, SM_CRS = SM_TSN + NRP, SM_THD = SM_CRS + NRP,
         SM_PXX = SM_THD + NRP, SM_PYY = SM_PXX + MP, SM_PXY = SM_PYY + MP, SM_PHX = SM_PXY + MP,
         SM_PHY = SM_PHX + MP, SM_FTH = SM_PHY + MP, SM_FPH = SM_FTH + 16, SM_MISC = SM_FPH + 16,
         SM_RED = SM_MISC + 8,            // cross-warp reduction scratch (two-warp teams)
         SM_TAB = SM_RED + 8,             // per-pass table of the staged rows' base pointers (64 entries)
-        SM_MC = SM_TAB + 64,             // column buffer of the stage KKT matrix: mc[row][lane], NZ rows
+        SM_MC = SM_TAB + ((NS + 20 + 1) & ~1),   // column buffer of the stage KKT matrix: mc[row][lane], NZ rows
         SM_STG = SM_MC + NZ * LW,        // rows of the NEXT stage, copied asynchronously (cp.async) while this one is processed
         STG_ROWS = (20 - 2 * NR > 16) ? 20 - 2 * NR : 16,
         SM_DOUBLES = SM_STG + STG_ROWS * LW
@@ -276,11 +277,13 @@ struct WarpSolver {
         NMPC_LOCALS
         const double kd = P.o.kappa_d;
         double pinf = 0, viol = 0, dinf = 0, c0 = 0, cmu = 0, ysum = 0, zsum = 0, th = 0, fo = 0, sdamp = 0;
-        double *zb = sm + SM_ZB;
+        double *zb = sm + SM_ZB, *ycb = sm + SM_RCB, *ydb = sm + SM_HB;   // (the factorisation's buffers are free during this pass)
         // sum of log(slack) kept as (product of mantissas, sum of exponents): one log() per lane per pass
         double lmant = 1.0;
         int lexp = 0;
-        auto addlog = [&](double x) { int e; lmant = wp::frexp_(lmant * x, &e); lexp += e; };
+        double sprod = 1.0;   // product of this stage's (<= 4) slacks; folded into (mantissa, exponent) once per stage
+        auto addlog = [&](double x) { sprod *= x; };
+        auto foldlog = [&]() { int e; lmant = wp::frexp_(lmant * sprod, &e); lexp += e; sprod = 1.0; };
         const int rt = trial ? R_TRIG2 : R_TRIG;
         trig_rows(row, l, N, alpha, rdz, trial, rt);
         auto load_z = [&](int k) {
@@ -333,6 +336,7 @@ struct WarpSolver {
             const bool zv = zvalid(k);
             const double zk = zv ? zc.z + alpha * zc.dz : 0.0;
             zb[l] = zk;
+            if (FULL) { ycb[l] = zn.yc; ydb[l] = qn.yd; }   // multipliers of block k+1, read by the other lanes' stationarity rows
             tsync();
             const double csr = zc.cs, snr = zc.sn;   // cos/sin of this lane's robot at stage k
             // ---- equality rows: block 0 (k == 0) and block k+1 ----
@@ -373,7 +377,7 @@ struct WarpSolver {
                     if (hu && !hl) r -= kd * mu;
                     if (isx) r += zc.yc;
                     if (k < N) {
-                        const double *ycn = row(R_YC, k + 1);
+                        const double *ycn = ycb;
                         if (isx) {
                             if (comp == 2) {
                                 double v = zb[NS + 2 * rob];
@@ -381,7 +385,7 @@ struct WarpSolver {
                             } else {
                                 r -= zn.yc;
                                 if (M > 0) {
-                                    const double *ydn = row(R_YD, k + 1);
+                                    const double *ydn = ydb;
                                     NMPC_NOUNROLL
                                     for (int j = 0; j < NR; j++) {
                                         if (j == rob) continue;
@@ -400,6 +404,7 @@ struct WarpSolver {
                     if (hu) { double u = (hi - zk) * zu; c0 = fmax(c0, fabs(u)); cmu = fmax(cmu, fabs(u - mu)); zsum += fabs(zu); }
                 }
             }
+            foldlog();
             zc = zn; zn = zf; qn = qf;
             tsync();
         }
@@ -635,34 +640,30 @@ struct WarpSolver {
                 mcl[(3 * rob + 1) * LW] += comp == 0 ? scross : ssame;
                 hl_ += glin;
             }
-            hb[l] = isz ? hl_ : 0.0;
             tsync();
-            if (isL) {   // the linear-term column adds the stage gradient h
-                NMPC_NOUNROLL
-                for (int r = 0; r < NZ; r++) mcl[r * LW] += hb[r];
-            }
+            if (isz) mc[l * LW + (LW - 1)] += hl_;   // the linear-term column (last lane's) adds the stage gradient h, one row per lane
+            tsync();
             NMPC_UNROLL
             for (int i = 0; i < NS; i++) X[i] = mcl[i * LW];
             NMPC_UNROLL
             for (int u = 0; u < NC; u++) U[u] = mcl[(NS + u) * LW];
             // symmetric sweep of the control pivots (rolled, with one-pivot LOOK-AHEAD).  The pivot row is U[0] of
             // every lane; it is published in ROTATED order (slot NS + r holds control column (j + r) mod 2Nr), so the
-            // readers use compile-time offsets and the rows rotate through the registers for free.  Slot NZ carries
-            // 1/pivot, computed by the pivot's own lane (<= 0 or NaN: wrong inertia).  Inside step j the entry of
+            // readers use compile-time offsets and the rows rotate through the registers for free.  A second row of
+            // the buffer carries 1/entry, so 1/pivot comes from the pivot's own lane (<= 0, inf or NaN: wrong inertia).  Inside step j the entry of
             // the NEXT pivot row is updated and published first, so its shared-memory round trip and reciprocal
             // overlap the remaining rank-1 update instead of sitting on the critical path of every pivot.
             const int ucol = l - NS;   // control column of this lane (if any)
             {
-                if (isz) col[isu ? ucol + NS : l] = U[0];
-                if (ucol == 0) col[NZ] = (U[0] > 0.0 && U[0] < NMPC_INF) ? wp::rcp_pos(U[0]) : -1.0;
+                if (isz) { const int s0 = isu ? ucol + NS : l; col[s0] = U[0]; col[LW + s0] = wp::rcp_pos(U[0]); }
             }
             NMPC_NOUNROLL
             for (int j = 0; j < NC; j++) {
-                const double *buf = col + LW * (j & 1);
-                double *nbuf = col + LW * ((j + 1) & 1);
+                const double *buf = col + 2 * LW * (j & 1);
+                double *nbuf = col + 2 * LW * ((j + 1) & 1);
                 tsync();
-                const double inv = buf[NZ];
-                if (!(inv > 0.0)) { wp::cp_async_wait(); return false; }   // drain the staging copies before the retry
+                const double inv = buf[LW + NS];   // 1 / pivot, from the pivot's own lane (rotated slot NS)
+                if (!(inv > 0.0) || !(inv < NMPC_INF)) { wp::cp_async_wait(); return false; }   // drain the staging copies before the retry
                 // the pivot row arrives in 128-bit loads, all issued before the FMAs
                 NmpcD2 bx[NS / 2];
                 double bu[NC];
@@ -691,9 +692,7 @@ struct WarpSolver {
                 if (j + 1 < NC) {
                     int slot = l;
                     if (isu) { slot = ucol - (j + 1); slot += slot < 0 ? NC : 0; slot += NS; }
-                    if (isz) nbuf[slot] = u1;
-                    const double ri = wp::rcp_pos(u1);
-                    if (ucol == j + 1) nbuf[NZ] = (u1 > 0.0 && u1 < NMPC_INF) ? ri : -1.0;
+                    if (isz) { nbuf[slot] = u1; nbuf[LW + slot] = wp::rcp_pos(u1); }   // every lane: no divergent reciprocal
                 }
                 NMPC_UNROLL
                 for (int i = 0; i < NS / 2; i++) { X[2 * i] -= bx[i].x * tx; X[2 * i + 1] -= bx[i].y * tx; }
