@@ -23,9 +23,9 @@ sys.path.insert(0, ROOT)
 NR, NH, T, DMIN, VMAX, WMAX = 6, 20, 0.3, 0.3, 0.22, 2.84      # sixth_scenario.py:127-135, N overridden to 20
 PER_GPU = 8192
 ALG_BYTES_PER_SOLVE = 15728       # p + w0 in, x + f + g out
-# dram__bytes_read.sum + dram__bytes_write.sum of solve_kernel<6> per solve, from the ncu --set full capture of v14
-# (profiles/ncu_solve_kernel_r1_v14.txt: 93.64 + 63.40 GB for 3552 cold-start instances): scratch rows stream through HBM
-TRAFFIC_BYTES_PER_SOLVE = int((93.639603e9 + 63.399507e9) / 3552)
+# dram__bytes_read.sum + dram__bytes_write.sum of solve_kernel<6> per solve, from the ncu --set full capture of v17
+# (profiles/ncu_solve_kernel_r1_v17.txt: 92.05 + 63.46 GB for 3552 cold-start instances): scratch rows stream through HBM
+TRAFFIC_BYTES_PER_SOLVE = int((92.046642e9 + 63.455251e9) / 3552)
 F_FACT, F_SOLVE, F_EVAL = 1100160, 92160, 14700   # SURVEY.md 8d dense-stage FP64 flop counts @ Nr=6, N=20
 
 
@@ -220,6 +220,8 @@ def main():
     torch.cuda.synchronize()
     # longest-first scheduling from the PREVIOUS solve's iteration counts (what a closed loop has at hand: nmpc_set_order)
     prob.set_order(prob.order_from_iters(out["iters"]))
+    prob.solve(d_x0w, d_p2, d_lbx, d_ubx, d_lbg, d_ubg, want=("stats",), out=outw)      # untimed warm-up in the new order
+    torch.cuda.synchronize()
     wev = []
     for _ in range(a.steps):
         flush.fill_(1)
@@ -233,7 +235,7 @@ def main():
     warm_ms = torch.tensor([sum(e0.elapsed_time(e1) for e0, e1 in wev) / a.steps], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(warm_ms, op=dist.ReduceOp.MAX)
-    warm = {"value": world * B / (warm_ms.item() * 1e-3), "unit": "solves/s", "mean_ip_iters": float(outw["iters"].double().mean().item()),
+    warm = {"value": world * B / (warm_ms.item() * 1e-3), "unit": "solves/s", "ms_steps": [round(e0.elapsed_time(e1), 2) for e0, e1 in wev], "mean_ip_iters": float(outw["iters"].double().mean().item()),
             "solved_frac": float((outw["status"] == 0).double().mean().item()), "max_ip_iters": int(outw["iters"].max().item()),
             "note": "one MPC step later: Euler plant + reference shift as initial guess (the closed-loop regime); instances "
                     "scheduled longest-first by the previous step's iteration counts (nmpc_set_order)"}
