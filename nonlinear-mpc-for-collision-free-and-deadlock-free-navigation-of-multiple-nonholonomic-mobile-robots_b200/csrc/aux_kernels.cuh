@@ -21,6 +21,16 @@ struct NmpcEvalTables {
     const int *jac_init; // [ns]       slots of the identity block of the initial-condition rows
 };
 
+// TMA bulk store shared -> global (cp.async.bulk, one elected thread issues it; completion tracked per bulk group)
+__device__ __forceinline__ void bulk_store_s2g(void *gdst, const void *ssrc, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 template <int PF>
 __global__ void __launch_bounds__(256) eval_kernel(int Nr, int N, double T, double Q0, double Q1, double Q2, double R0,
                                                    double R1, int B, const double *__restrict__ w, const double *__restrict__ p,
@@ -33,7 +43,7 @@ __global__ void __launch_bounds__(256) eval_kernel(int Nr, int N, double T, doub
     const int n = ns * S + nc * N, mg = S * blk, nX = ns * S;
     const int nj = 3 * Nr + N * (11 * Nr + 4 * M), nh = N * (6 * Nr + 2 * M);
     auto ev = [](int v) { return (v + 1) & ~1; };   // every segment starts 16-byte aligned (128-bit write-back)
-    double *sw = sh, *sl = sw + ev(n), *sp = sl + ev(mg), *sgrad = sp + ev(2 * ns), *sg = sgrad + ev(n), *sj = sg + ev(mg),
+    double *sw = sh, *sl = sw + ev(n), *sp = sl + ev(mg), *sgrad = sp + ev(2 * ns), *sg0 = sgrad + ev(n), *sj = sg0 + ev(mg + 1),
            *shs = sj + ev(nj), *sred = shs + ev(nh);
     const double Qw[3] = {Q0, Q1, Q2}, Rw[2] = {R0, R1};
     // The inputs of the next point are fetched into PF registers per array per thread right after the evaluation of
@@ -51,6 +61,9 @@ __global__ void __launch_bounds__(256) eval_kernel(int Nr, int N, double T, doub
     };
     fetch(blockIdx.x);
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        // g has an odd length at Nr = 6 (mg = 693): its shared copy starts 8 bytes in whenever the global segment does,
+        // so that all but its first / last element can leave through an aligned bulk store as well
+        double *sg = sg0 + ((g && (((size_t)(g + (size_t)b * mg)) & 15)) ? 1 : 0);
         if (PF > 0) {
 #pragma unroll
             for (int j = 0; j < PF; j++) {
@@ -59,7 +72,9 @@ __global__ void __launch_bounds__(256) eval_kernel(int Nr, int N, double T, doub
                 if (lam && i < mg) sl[i] = rl[j];
             }
             if ((int)threadIdx.x < 2 * ns) sp[threadIdx.x] = rp;
+            if (threadIdx.x == 0) bulk_wait_read_all();   // the previous point's bulk stores have finished reading the record
         } else {
+            if (threadIdx.x == 0) bulk_wait_read_all();
             const double *wb = w + (size_t)b * n;
             for (int i = threadIdx.x; i < n; i += blockDim.x) sw[i] = wb[i];
             for (int i = threadIdx.x; i < 2 * ns; i += blockDim.x) sp[i] = p[(size_t)b * 2 * ns + i];
@@ -128,6 +143,7 @@ __global__ void __launch_bounds__(256) eval_kernel(int Nr, int N, double T, doub
         // block reduction of f
         for (int m = 16; m > 0; m >>= 1) facc += __shfl_xor_sync(0xffffffffu, facc, m);
         if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = facc;
+        fence_proxy_async_smem();   // the record written above becomes visible to the bulk-copy engine
         __syncthreads();
         if (threadIdx.x == 0 && f) {
             double t = 0.0;
@@ -135,10 +151,21 @@ __global__ void __launch_bounds__(256) eval_kernel(int Nr, int N, double T, doub
             f[b] = t;
         }
         fetch(b + gridDim.x);   // next point's inputs: in flight during the write-back below
-        // coalesced write-back of the record; 128-bit stores where the segment is 16-byte aligned in global memory
+        // write-back of the record: segments that are 16-byte aligned with an even length leave through ONE TMA bulk
+        // store each (cp.async.bulk shared -> global, issued by thread 0, asynchronous: the CTA goes on to the next point
+        // and only waits, above, until the engine has read the record); the others (g: mg is odd at Nr = 6) through
+        // coalesced stores, 128-bit where possible
         auto copy_out = [&](double *dst, const double *src, int cnt) {
             if (!dst) return;
-            if ((((size_t)dst | (size_t)src) & 15) == 0) {
+            if ((((size_t)dst ^ (size_t)src) & 15) == 0 && (((size_t)dst) & 7) == 0) {
+                // same 16-byte phase on both sides: scalar head / tail, aligned bulk body
+                const int head = (((size_t)dst) & 15) ? 1 : 0, body = (cnt - head) & ~1, tail = cnt - head - body;
+                if (threadIdx.x == 0) {
+                    if (head) dst[0] = src[0];
+                    if (body) bulk_store_s2g(dst + head, src + head, (unsigned)body * 8u);
+                    if (tail) dst[cnt - 1] = src[cnt - 1];
+                }
+            } else if ((((size_t)dst | (size_t)src) & 15) == 0) {
                 const int c2 = cnt >> 1;
                 double2 *d2 = reinterpret_cast<double2 *>(dst);
                 const double2 *s2 = reinterpret_cast<const double2 *>(src);
@@ -152,8 +179,10 @@ __global__ void __launch_bounds__(256) eval_kernel(int Nr, int N, double T, doub
         copy_out(g ? g + (size_t)b * mg : nullptr, sg, mg);
         copy_out(jac ? jac + (size_t)b * nj : nullptr, sj, nj);
         copy_out((hess && lam) ? hess + (size_t)b * nh : nullptr, shs, nh);
+        if (threadIdx.x == 0) bulk_commit();
         __syncthreads();
     }
+    if (threadIdx.x == 0) bulk_wait_read_all();   // shared memory must outlive the last bulk stores
 }
 
 // u0 = [u[1:]; u[-1]]  and  X0 = [X[1:]; X[N-1]]   (row N-1, not N: the reference's quirk)
@@ -166,6 +195,23 @@ __global__ void __launch_bounds__(256) shift_kernel(int Nr, int N, long long tot
     //            last block       -> j               (U_{N-1} repeated)
     const int ns = 3 * Nr, nc = 2 * Nr, nX = ns * (N + 1), n = nX + nc * N;
     const long long B = total / n;
+    // every segment boundary (ns, nc, nX, n) is even when Nr is even: the copy then runs on 128-bit loads and stores
+    const bool vec = ((ns | nc | n) & 1) == 0 && ((((size_t)xp) | ((size_t)xn)) & 15) == 0;
+    if (vec) {   // flat grid-stride loop over all 128-bit elements of the batch: full warps whatever n is
+        const int n2 = n / 2;
+        const long long total2 = B * n2;
+        const double2 *s2 = reinterpret_cast<const double2 *>(xp);
+        double2 *d2 = reinterpret_cast<double2 *>(xn);
+        for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total2; e += (long long)gridDim.x * blockDim.x) {
+            const long long b = e / n2;
+            const int j = 2 * (int)(e - b * n2);
+            int s;
+            if (j < nX) s = j < ns * N ? j + ns : j - ns;
+            else s = (j - nX) < nc * (N - 1) ? j + nc : j;
+            d2[e] = s2[b * n2 + (s >> 1)];
+        }
+        return;
+    }
     for (long long b = blockIdx.x; b < B; b += gridDim.x) {
         const double *src = xp + b * n;
         double *dst = xn + b * n;
