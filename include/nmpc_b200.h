@@ -106,6 +106,16 @@ int nmpc_solve(nmpc_handle *h, int B, const double *x0, const double *p,
                int32_t *status, int32_t *iters, double *stats,
                void *workspace, size_t workspace_bytes, void *stream);
 
+/* Static circular obstacles (the reference's obstacle-avoidance scripts, first_/third_scenario_mpc_obstacle_avoidance.py:96-152):
+ * same variables, cost and dynamics, plus n_obs rows per robot and stage
+ *     sqrt((x_i - ox)^2 + (y_i - oy)^2) - clearance          on X_k, k = 0..N-1
+ * with clearance = rob_dim + r_obs (:125), bounded below by the margin the scripts put in lbg (0.05 / 0.1) and above by +inf.
+ * obs: HOST array [n_obs][3] = (ox, oy, clearance).  Row layout of g / lbg / ubg / lam_g (as the scripts build it, :109-125):
+ * [X_0 - x0bar (3 Nr)], then for k = 0..N-1: [defect rows (3 Nr); pair rows (M, none for one robot); obstacle rows, robot-major
+ * (Nr n_obs)]; mg = 3 Nr + N (3 Nr + M + Nr n_obs).  Runs on the CTA-per-instance dense-block path for every Nr; nmpc_eval and
+ * the CCS patterns are not available for this family. */
+int nmpc_create_obstacles(const nmpc_desc *d, const nmpc_opts *o, int n_obs, const double *obs, nmpc_handle **out);
+
 /* Scheduling hint for the following nmpc_solve* calls on this handle: order [B] (DEVICE int32, caller owned, a permutation
  * of 0..B-1) is the sequence in which the persistent teams pull instances from the work queue; NULL restores index order.
  * Instances differ in iteration count (17 on average, up to 70, one MPC step after a solve), so a closed loop that passes

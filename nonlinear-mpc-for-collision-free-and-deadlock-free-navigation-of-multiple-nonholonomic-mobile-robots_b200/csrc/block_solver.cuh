@@ -40,6 +40,8 @@ __device__ long long g_block_prof[16];
                  *const CE = wp::global_ptr(this->CE), *const DL = wp::global_ptr(this->DL),                            \
                  *const DU = wp::global_ptr(this->DU), *const pp = wp::global_ptr(this->pp);                            \
     const int *const pairs = wp::global_ptr(this->pairs);                                                              \
+    const double *const obs = wp::global_ptr(this->obs);                                                               \
+    const int Mp = this->Mp, nobs = this->nobs;                                                                        \
     double *const Pall = wp::global_ptr(this->Pall), *const Yall = wp::global_ptr(this->Yall),                          \
                  *const Lall = wp::global_ptr(this->Lall), *const Bm = wp::global_ptr(this->Bm);                        \
     const int S = this->S, W = this->W, N = this->N, Nr = this->Nr, ns = this->ns, nc = this->nc, nz = this->nz,        \
@@ -47,7 +49,7 @@ __device__ long long g_block_prof[16];
     auto row = [=](int r, int k) -> double * { return ws + ((long long)r * S + k) * W; };                              \
     (void)sm; (void)ws; (void)BL; (void)BU; (void)CE; (void)DL; (void)DU; (void)pp; (void)pairs; (void)Pall;            \
     (void)Yall; (void)Lall; (void)Bm; (void)S; (void)W; (void)N; (void)Nr; (void)ns; (void)nc; (void)nz; (void)M;       \
-    (void)tid; (void)nt; (void)row;
+    (void)tid; (void)nt; (void)row; (void)obs; (void)Mp; (void)nobs;
 
 struct BlockSolver {
     enum Row {
@@ -62,7 +64,9 @@ struct BlockSolver {
 
     const NmpcSolveParams &P;
     double *sm, *ws;
-    int Nr, N, S, ns, nc, nz, M, W, tid, nt, inst, fn;
+    int Nr, N, S, ns, nc, nz, M, W, tid, nt, inst, fn;   // M: inequality rows per block = pair rows + obstacle rows
+    int Mp, nobs, family;                                 // pair rows, static obstacles per robot, row layout (0 centralized, 1 obstacles)
+    const double *obs;                                    // [nobs][3]: centre x, y, clearance radius
     const double *BL, *BU, *CE, *DL, *DU, *pp;
     const int *pairs;
     double *Pall, *Yall, *Lall, *Bm;
@@ -73,10 +77,10 @@ struct BlockSolver {
     // shared-memory carve-up (doubles)
     int SM_RED, SM_FTH, SM_FPH, SM_MISC, SM_DZB, SM_DXN, SM_TB, SM_XB, SM_DINV, SM_PR, SM_CS, SM_DS, SM_MUU;
 
-    static NMPC_HD int row_width(int Nr) { int nz = 5 * Nr, M = Nr * (Nr - 1) / 2, w = nz > M ? nz : M; return (w + 31) & ~31; }
-    static NMPC_HD long long ws_doubles(int Nr, int N)
+    static NMPC_HD int row_width(int Nr, int nobs = 0) { int nz = 5 * Nr, M = Nr * (Nr - 1) / 2 + Nr * nobs, w = nz > M ? nz : M; return (w + 31) & ~31; }
+    static NMPC_HD long long ws_doubles(int Nr, int N, int nobs = 0)
     {
-        const long long S = N + 1, ns = 3 * Nr, nc = 2 * Nr, W = row_width(Nr);
+        const long long S = N + 1, ns = 3 * Nr, nc = 2 * Nr, W = row_width(Nr, nobs);
         const long long ldy = (ns + 1 + 3) & ~3LL;
         const long long ncp = (nc + 31) & ~31LL;
         return (long long)R_COUNT * S * W + ((S * ns * ns + 1) & ~1LL) + (long long)(N + 1) * nc * ldy + (long long)N * ncp * ncp;   // every block 16-byte aligned
@@ -137,8 +141,9 @@ struct BlockSolver {
     // ---------------------------------------------------------------------------------------
     __device__ void setup(int instance)
     {
-        inst = instance; Nr = P.Nr; N = P.N; S = N + 1; ns = 3 * Nr; nc = 2 * Nr; nz = 5 * Nr; M = Nr * (Nr - 1) / 2;
-        W = row_width(Nr); T = P.T; tid = threadIdx.x; nt = blockDim.x;
+        inst = instance; Nr = P.Nr; N = P.N; S = N + 1; ns = 3 * Nr; nc = 2 * Nr; nz = 5 * Nr;
+        Mp = Nr * (Nr - 1) / 2; nobs = P.nobs; family = P.family; obs = P.obs; M = Mp + Nr * nobs;
+        W = row_width(Nr, nobs); T = P.T; tid = threadIdx.x; nt = blockDim.x;
         const double *br = P.brows + (long long)inst * P.bstride;
         BL = br + (long long)NMPC_BR_BL * S * W; BU = br + (long long)NMPC_BR_BU * S * W;
         CE = br + (long long)NMPC_BR_CE * S * W; DL = br + (long long)NMPC_BR_DL * S * W;
@@ -215,12 +220,7 @@ struct BlockSolver {
             const double lo = DL[b * W + q], hi = DU[b * W + q];
             const bool hl = lo > -NMPC_INF, hu = hi < NMPC_INF;
             double dv = NMPC_DUMMY_ROW_VALUE;
-            if (b > 0) {
-                const double *zr = row(R_Z, b - 1);
-                const int pi = pairs[2 * q], pj = pairs[2 * q + 1];
-                const double dx = zr[3 * pi] - zr[3 * pj], dy = zr[3 * pi + 1] - zr[3 * pj + 1];
-                dv = dx * dx + dy * dy;
-            }
+            if (b > 0) dv = rowgeom(row(R_Z, b - 1), q, Mp, nobs, pairs, obs).dv;
             row(R_S, b)[q] = (hl || hu) ? WS::push_in(dv, lo, hi, o.bound_push, o.bound_frac) : dv;
             row(R_VL, b)[q] = hl ? o.bound_mult_init_val : 0.0;
             row(R_VU, b)[q] = hu ? o.bound_mult_init_val : 0.0;
@@ -240,6 +240,32 @@ struct BlockSolver {
         const double v = zr[ns + 2 * rob];
         return comp == 0 ? zr[l] + T * v * tr[rob] : (comp == 1 ? zr[l] + T * v * tr[Nr + rob] : zr[l] + T * zr[ns + 2 * rob + 1]);
     }
+
+    // Inequality row q of a block evaluated on the stage vector zr.  Rows q < Mp are the pairwise squared distances
+    // (centralized_six_robots_implementation.py:288-306); rows q >= Mp are the static circular obstacles of family F,
+    // sqrt((x - ox)^2 + (y - oy)^2) - r_rob - r_obs (first_scenario_mpc_obstacle_avoidance.py:125), nobs per robot.
+    // i, j: robots (j = -1 for an obstacle row); (gx, gy): gradient w.r.t. (x_i, y_i) (negated for robot j);
+    // (hxx, hyy, hxy): second derivatives w.r.t. (x_i, y_i).
+    struct RowG { double dv, gx, gy, hxx, hyy, hxy; int i, j; };
+    static __device__ __forceinline__ RowG rowgeom(const double *zr, int q, int Mp, int nobs, const int *pairs, const double *obs)
+    {
+        RowG r;
+        if (q < Mp) {
+            r.i = pairs[2 * q]; r.j = pairs[2 * q + 1];
+            const double dx = zr[3 * r.i] - zr[3 * r.j], dy = zr[3 * r.i + 1] - zr[3 * r.j + 1];
+            r.dv = dx * dx + dy * dy; r.gx = 2.0 * dx; r.gy = 2.0 * dy; r.hxx = 2.0; r.hyy = 2.0; r.hxy = 0.0;
+        } else {
+            const int e = q - Mp, o = e % nobs;
+            r.i = e / nobs; r.j = -1;
+            const double dx = zr[3 * r.i] - obs[3 * o], dy = zr[3 * r.i + 1] - obs[3 * o + 1];
+            const double rho = sqrt(dx * dx + dy * dy), ir = 1.0 / rho;
+            r.gx = dx * ir; r.gy = dy * ir; r.dv = rho - obs[3 * o + 2];
+            r.hxx = (1.0 - r.gx * r.gx) * ir; r.hyy = (1.0 - r.gy * r.gy) * ir; r.hxy = -r.gx * r.gy * ir;
+        }
+        return r;
+    }
+    // offset of block k in the flat g / lam_g vectors: family 1 has no inequality rows in block 0
+    __device__ __forceinline__ long long goff(int k) const { return family ? (k == 0 ? 0 : ns + (long long)(k - 1) * (ns + M)) : (long long)k * (ns + M); }
 
     // ---------------------------------------------------------------------------------------
     // residuals / merit quantities at the iterate (full) or at a trial point z + alpha dz
@@ -276,12 +302,7 @@ struct BlockSolver {
             const bool hl = lo > -NMPC_INF, hu = hi < NMPC_INF;
             if (!(hl || hu)) continue;
             double dv = NMPC_DUMMY_ROW_VALUE;
-            if (b > 0) {
-                const double *zr = row(rz, b - 1);
-                const int pi = pairs[2 * q], pj = pairs[2 * q + 1];
-                const double dx = zr[3 * pi] - zr[3 * pj], dy = zr[3 * pi + 1] - zr[3 * pj + 1];
-                dv = dx * dx + dy * dy;
-            }
+            if (b > 0) dv = rowgeom(row(rz, b - 1), q, Mp, nobs, pairs, obs).dv;
             const double s = row(rs, b)[q], dms = dv - s;
             pinf = fmax(pinf, fabs(dms)); th += fabs(dms);
             viol = fmax(viol, fmax(lo - dv, dv - hi));
@@ -335,6 +356,11 @@ struct BlockSolver {
                                 if (j == rob) continue;
                                 const int q = rob < j ? pairidx(rob, j) : pairidx(j, rob);
                                 r += 2.0 * (zk - zr[3 * j + comp]) * ydn[q];
+                            }
+                            for (int o = 0; o < nobs; o++) {   // static obstacles of this robot
+                                const int q = Mp + rob * nobs + o;
+                                const RowG rg = rowgeom(zr, q, Mp, nobs, pairs, obs);
+                                r += (comp == 0 ? rg.gx : rg.gy) * ydn[q];
                             }
                         }
                     } else {
@@ -421,20 +447,18 @@ struct BlockSolver {
             double pxx = 0, pyy = 0, pxy = 0, phx = 0, phy = 0, gxq = 0, gyq = 0, rd = 0, Dq = 0, gs = 0;
             const double lo = DL[b * W + q], hi = DU[b * W + q];
             if (lo > -NMPC_INF || hi < NMPC_INF) {
-                double dv = NMPC_DUMMY_ROW_VALUE;
+                double dv = NMPC_DUMMY_ROW_VALUE, hxx = 0.0, hyy = 0.0, hxy = 0.0;
                 if (b > 0) {
-                    const double *zr = row(R_Z, b - 1);
-                    const int pi = pairs[2 * q], pj = pairs[2 * q + 1];
-                    const double dx = zr[3 * pi] - zr[3 * pj], dy = zr[3 * pi + 1] - zr[3 * pj + 1];
-                    gxq = 2.0 * dx; gyq = 2.0 * dy; dv = dx * dx + dy * dy;
+                    const RowG rg = rowgeom(row(R_Z, b - 1), q, Mp, nobs, pairs, obs);
+                    gxq = rg.gx; gyq = rg.gy; dv = rg.dv; hxx = rg.hxx; hyy = rg.hyy; hxy = rg.hxy;
                 }
                 const double s = row(R_S, b)[q];
                 double sigs;
                 sig_g(mode, kd, s, lo, hi, row(R_VL, b)[q], row(R_VU, b)[q], mu, 0.0, sigs, gs);
                 rd = mode == 1 ? 0.0 : (soc ? row(R_DSOC, b)[q] : dv - s);
                 Dq = sigs + delta;
-                const double hq = Dq * rd + gs, mu2 = mode == 0 ? 2.0 * row(R_YD, b)[q] : 0.0;
-                pxx = Dq * gxq * gxq + mu2; pyy = Dq * gyq * gyq + mu2; pxy = Dq * gxq * gyq;
+                const double hq = Dq * rd + gs, yq = mode == 0 ? row(R_YD, b)[q] : 0.0;   // multiplier times the row's own curvature
+                pxx = Dq * gxq * gxq + yq * hxx; pyy = Dq * gyq * gyq + yq * hyy; pxy = Dq * gxq * gyq + yq * hxy;
                 phx = gxq * hq; phy = gyq * hq;
             }
             row(R_GXQ, b)[q] = gxq; row(R_GYQ, b)[q] = gyq; row(R_RD, b)[q] = rd; row(R_DQ, b)[q] = Dq; row(R_GS, b)[q] = gs;
@@ -474,6 +498,7 @@ struct BlockSolver {
                     double acc = 0.0;
                     for (int jj = 0; jj < i; jj++) { const double v = arr[pairidx(jj, i)]; acc += c >= 3 ? -v : v; }
                     for (int jj = i + 1; jj < Nr; jj++) acc += arr[pairidx(i, jj)];
+                    for (int o = 0; o < nobs; o++) acc += arr[Mp + i * nobs + o];   // this robot's static obstacles
                     dsum[idx] = acc;
                 }
             }
@@ -827,9 +852,11 @@ struct BlockSolver {
                     const bool act = lo > -NMPC_INF || hi < NMPC_INF;
                     double ds = 0.0, ytd = 0.0;
                     if (act) {
-                        const int pi = pairs[2 * q], pj = pairs[2 * q + 1];
                         const double gs = row(R_GS, b)[q];
-                        ds = row(R_GXQ, b)[q] * (dzb[3 * pi] - dzb[3 * pj]) + row(R_GYQ, b)[q] * (dzb[3 * pi + 1] - dzb[3 * pj + 1]) + row(R_RD, b)[q];
+                        double ddx, ddy;
+                        if (q < Mp) { const int pi = pairs[2 * q], pj = pairs[2 * q + 1]; ddx = dzb[3 * pi] - dzb[3 * pj]; ddy = dzb[3 * pi + 1] - dzb[3 * pj + 1]; }
+                        else { const int pi = (q - Mp) / nobs; ddx = dzb[3 * pi]; ddy = dzb[3 * pi + 1]; }
+                        ds = row(R_GXQ, b)[q] * ddx + row(R_GYQ, b)[q] * ddy + row(R_RD, b)[q];
                         ytd = row(R_DQ, b)[q] * ds + gs;
                         const double s = row(R_S, b)[q];
                         WS::slack_step_terms(s, ds, lo, hi, row(R_VL, b)[q], row(R_VU, b)[q], mu, ap, az);
@@ -938,11 +965,7 @@ struct BlockSolver {
                     const int b = pass == 0 ? 0 : k + 1;
                     const double lo = DL[b * W + q], hi = DU[b * W + q];
                     double dv = NMPC_DUMMY_ROW_VALUE;
-                    if (pass == 1) {
-                        const int pi = pairs[2 * q], pj = pairs[2 * q + 1];
-                        const double dx = zt[3 * pi] - zt[3 * pj], dy = zt[3 * pi + 1] - zt[3 * pj + 1];
-                        dv = dx * dx + dy * dy;
-                    }
+                    if (pass == 1) dv = rowgeom(zt, q, Mp, nobs, pairs, obs).dv;
                     const bool act = lo > -NMPC_INF || hi < NMPC_INF;
                     row(R_DS, b)[q] = act ? WS::push_in(dv, lo, hi, o.bound_push, o.bound_frac) - row(R_S, b)[q] : 0.0;
                 }
@@ -1035,7 +1058,7 @@ struct BlockSolver {
     NMPC_BPASS void write_outputs(int st, int iter, double E0, double pinf, double dinf, double c0, double mu)
     {
         NMPC_BLK_LOCALS
-        const long long n = (long long)ns * S + (long long)nc * N, mg = (long long)S * (ns + M);
+        const long long n = (long long)ns * S + (long long)nc * N, mg = goff(N) + ns + M;
         double *x = P.x + inst * n;
         double *lx = P.lam_x ? P.lam_x + inst * n : nullptr;
         double *g = P.g ? P.g + inst * mg : nullptr;
@@ -1053,20 +1076,16 @@ struct BlockSolver {
         }
         for (int idx = tid; idx < S * ns; idx += nt) {
             const int k = idx / ns, l = idx - k * ns;
-            if (g) g[(long long)k * (ns + M) + l] = k == 0 ? row(R_Z, 0)[l] - pp[l] : row(R_Z, k)[l] - predict(row(R_Z, k - 1), row(R_TRIG, k - 1), l);
-            if (lg) lg[(long long)k * (ns + M) + l] = row(R_YC, k)[l] / df;
+            if (g) g[goff(k) + l] = k == 0 ? row(R_Z, 0)[l] - pp[l] : row(R_Z, k)[l] - predict(row(R_Z, k - 1), row(R_TRIG, k - 1), l);
+            if (lg) lg[goff(k) + l] = row(R_YC, k)[l] / df;
         }
         for (int idx = tid; idx < S * M; idx += nt) {
             const int b = idx / M, q = idx - b * M;
+            if (family && b == 0) continue;   // family 1: block 0 holds the initial condition only
             double dv = NMPC_DUMMY_ROW_VALUE;
-            if (b > 0) {
-                const double *zr = row(R_Z, b - 1);
-                const int pi = pairs[2 * q], pj = pairs[2 * q + 1];
-                const double dx = zr[3 * pi] - zr[3 * pj], dy = zr[3 * pi + 1] - zr[3 * pj + 1];
-                dv = dx * dx + dy * dy;
-            }
-            if (g) g[(long long)b * (ns + M) + ns + q] = dv;
-            if (lg) lg[(long long)b * (ns + M) + ns + q] = row(R_YD, b)[q] / df;
+            if (b > 0) dv = rowgeom(row(R_Z, b - 1), q, Mp, nobs, pairs, obs).dv;
+            if (g) g[goff(b) + ns + q] = dv;
+            if (lg) lg[goff(b) + ns + q] = row(R_YD, b)[q] / df;
         }
         fo = bsum(fo);
         if (tid == 0) {

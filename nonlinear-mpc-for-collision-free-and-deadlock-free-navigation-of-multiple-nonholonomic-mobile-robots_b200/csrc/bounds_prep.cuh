@@ -19,10 +19,14 @@ NMPC_HD inline double nmpc_relax_lo(double v, double f) { return v > -NMPC_INF ?
 NMPC_HD inline double nmpc_relax_hi(double v, double f) { return v < NMPC_INF ? v + f * fmax(1.0, fabs(v)) : NMPC_INF; }
 
 // rows: [NMPC_BR_COUNT][S][lw] of this bound set (lw = 32 or 64 lanes per instance).  Returns 0 or a negative NMPC_E* code.
+// nobs / family: rows per block = pair rows + Nr * nobs obstacle rows; family 1 (static obstacles,
+// first_scenario_mpc_obstacle_avoidance.py:150) has no inequality rows in block 0, so block k starts at ns + (k-1)(ns+M).
 NMPC_HD inline int nmpc_prep_bounds_elem(int Nr, int N, double relax, const double *lbx, const double *ubx,
-                                         const double *lbg, const double *ubg, int k, int lane, int lw, double *rows)
+                                         const double *lbg, const double *ubg, int k, int lane, int lw, double *rows,
+                                         int nobs = 0, int family = 0)
 {
-    const int ns = 3 * Nr, nc = 2 * Nr, nz = 5 * Nr, M = Nr * (Nr - 1) / 2, S = N + 1, blk = ns + M;
+    const int ns = 3 * Nr, nc = 2 * Nr, nz = 5 * Nr, M = Nr * (Nr - 1) / 2 + Nr * nobs, S = N + 1;
+    const long long goff = family ? (k == 0 ? 0 : ns + (long long)(k - 1) * (ns + M)) : (long long)k * (ns + M);
     const long long rs = (long long)S * lw;
     const int e = k * lw + lane;
     int err = 0;
@@ -35,14 +39,14 @@ NMPC_HD inline int nmpc_prep_bounds_elem(int Nr, int N, double relax, const doub
     rows[NMPC_BR_BU * rs + e] = nmpc_relax_hi(hi, relax);
     double ce = 0.0;
     if (lane < ns) {
-        double l = lbg[k * blk + lane], u = ubg[k * blk + lane];
+        double l = lbg[goff + lane], u = ubg[goff + lane];
         if (!(l == u) || !(l > -NMPC_INF && l < NMPC_INF)) err = err ? err : NMPC_ENOTSUP;  // dynamics rows are equalities
         ce = l;
     }
     rows[NMPC_BR_CE * rs + e] = ce;
     double dl = -NMPC_INF, du = NMPC_INF;
-    if (lane < M) {
-        dl = lbg[k * blk + ns + lane]; du = ubg[k * blk + ns + lane];
+    if (lane < M && !(family && k == 0)) {
+        dl = lbg[goff + ns + lane]; du = ubg[goff + ns + lane];
         if (!(dl <= du)) err = err ? err : NMPC_EBOUNDS;
         else if (dl == du) err = err ? err : NMPC_ENOTSUP;  // equality on a distance row
     }

@@ -93,6 +93,8 @@ struct nmpc_handle {
     size_t ws_doubles_per_slot, solve_smem, eval_smem;
     int ctas_per_sm, lw, teams_per_cta, threads;
     const int *d_order;                       // optional processing order (device, caller owned), see nmpc_set_order
+    int nobs, family;                         // static obstacles per robot; row layout of g (0 centralized, 1 obstacles)
+    double *d_obs;                            // [nobs][3] on the device
     bool block_path, eval_ok;                 // Nr > 10: CTA-per-instance dense-block solver; eval record fits shared memory
     int *d_pairs;                             // pair table (i, j) of the inequality rows, block path
     // host-pointer API staging
@@ -173,7 +175,20 @@ template <int NR> static cudaError_t config_solve(nmpc_handle *h)
     return e;
 }
 
-extern "C" int nmpc_create(const nmpc_desc *d, const nmpc_opts *o, nmpc_handle **out)
+static int create_impl(const nmpc_desc *d, const nmpc_opts *o, int nobs, const double *obs, nmpc_handle **out);
+
+extern "C" int nmpc_create(const nmpc_desc *d, const nmpc_opts *o, nmpc_handle **out) { return create_impl(d, o, 0, nullptr, out); }
+
+extern "C" int nmpc_create_obstacles(const nmpc_desc *d, const nmpc_opts *o, int n_obs, const double *obs, nmpc_handle **out)
+{
+    if (n_obs < 1 || n_obs > NMPC_MAX_OBSTACLES || !obs)
+        return fail(NMPC_EINVAL, "nmpc_create_obstacles: need 1..%d obstacles (x, y, clearance radius each)", NMPC_MAX_OBSTACLES);
+    for (int i = 0; i < n_obs; i++)
+        if (!(obs[3 * i + 2] >= 0.0)) return fail(NMPC_EINVAL, "nmpc_create_obstacles: obstacle %d has a negative clearance radius", i);
+    return create_impl(d, o, n_obs, obs, out);
+}
+
+static int create_impl(const nmpc_desc *d, const nmpc_opts *o, int nobs, const double *obs, nmpc_handle **out)
 {
     if (!d || !out) return fail(NMPC_EINVAL, "nmpc_create: NULL argument");
     if (d->N < 1 || !(d->T > 0)) return fail(NMPC_EINVAL, "nmpc_create: need N >= 1 and T > 0");
@@ -189,10 +204,16 @@ extern "C" int nmpc_create(const nmpc_desc *d, const nmpc_opts *o, nmpc_handle *
     h->d = *d;
     if (o) h->o = *o; else nmpc_default_opts(&h->o);
     h->ns = 3 * d->Nr; h->nc = 2 * d->Nr; h->M = d->Nr * (d->Nr - 1) / 2; h->S = d->N + 1;
-    h->n = h->ns * h->S + h->nc * d->N; h->mg = h->S * (h->ns + h->M); h->np = 2 * h->ns;
+    h->nobs = nobs; h->family = nobs > 0 ? 1 : 0; h->d_obs = nullptr;
+    h->n = h->ns * h->S + h->nc * d->N; h->np = 2 * h->ns;
+    // row layout: family 0 = (N+1) blocks of [ns equality rows ; M pair rows]; family 1 (static obstacles) = ns rows, then N
+    // blocks of [ns ; M + Nr n_obs]   (first_scenario_mpc_obstacle_avoidance.py:109-125)
+    h->mg = h->family ? h->ns + d->N * (h->ns + h->M + d->Nr * nobs) : h->S * (h->ns + h->M);
     h->nnzj = 3 * d->Nr + d->N * (11 * d->Nr + 4 * h->M); h->nnzh = d->N * (6 * d->Nr + 2 * h->M);
     h->launches = 0; h->d_buf = nullptr; h->d_bytes = 0; h->stream = nullptr; h->d_tables = nullptr;
-    h->block_path = d->Nr > 10; h->eval_ok = true; h->d_pairs = nullptr; h->d_order = nullptr;
+    h->d_pairs = nullptr; h->d_order = nullptr;
+    // the obstacle family runs on the dense-block path for every Nr; NMPC_FORCE_BLOCK: test hook, any Nr on that path
+    h->block_path = d->Nr > 10 || h->family != 0 || getenv("NMPC_FORCE_BLOCK") != nullptr; h->eval_ok = h->family == 0;
     DBG("device count ok");
     cudaGetDevice(&h->dev);
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->dev);
@@ -210,7 +231,7 @@ extern "C" int nmpc_create(const nmpc_desc *d, const nmpc_opts *o, nmpc_handle *
     h->tb.jac_init = h->tb.jac_ps + (size_t)N * M * 4;
     h->tb.hes_rs = h->d_tables + h->nnzj;
     h->tb.hes_ps = h->tb.hes_rs + (size_t)N * Nr * 6;
-    switch (Nr) {
+    switch (h->block_path ? 0 : Nr) {
         case 1: h->ws_doubles_per_slot = slot_doubles<1>(N); e = config_solve<1>(h); break;
         case 2: h->ws_doubles_per_slot = slot_doubles<2>(N); e = config_solve<2>(h); break;
         case 3: h->ws_doubles_per_slot = slot_doubles<3>(N); e = config_solve<3>(h); break;
@@ -222,10 +243,10 @@ extern "C" int nmpc_create(const nmpc_desc *d, const nmpc_opts *o, nmpc_handle *
         case 9: h->ws_doubles_per_slot = slot_doubles<9>(N); e = config_solve<9>(h); break;
         case 10: h->ws_doubles_per_slot = slot_doubles<10>(N); e = config_solve<10>(h); break;
         default: {   // dense-block path: one 512-thread CTA per instance, the control block of the stage matrix in shared memory
-            h->ws_doubles_per_slot = (size_t)BlockSolver::ws_doubles(Nr, N);
+            h->ws_doubles_per_slot = (size_t)BlockSolver::ws_doubles(Nr, N, h->nobs);
             // CTA size: the register-resident Cholesky needs 8 rows per warp over ncp = roundup(2 Nr, 32) rows, i.e. 4 ncp threads
             // (128 for 11..16 robots, 512 for 49..64); smaller swarms then fit several CTAs per SM
-            h->lw = BlockSolver::row_width(Nr); h->teams_per_cta = 1;
+            h->lw = BlockSolver::row_width(Nr, h->nobs); h->teams_per_cta = 1;
             h->threads = 4 * ((2 * Nr + 31) & ~31);
             if (h->threads > NMPC_BLOCK_THREADS) h->threads = NMPC_BLOCK_THREADS;
             h->solve_smem = (size_t)BlockSolver::sm_doubles(Nr) * sizeof(double);
@@ -237,15 +258,19 @@ extern "C" int nmpc_create(const nmpc_desc *d, const nmpc_opts *o, nmpc_handle *
             std::vector<int> pr;
             for (int a = 0; a < Nr; a++)
                 for (int b = a + 1; b < Nr; b++) { pr.push_back(a); pr.push_back(b); }
-            if (e == cudaSuccess) e = cudaMalloc(&h->d_pairs, pr.size() * sizeof(int));
-            if (e == cudaSuccess) e = cudaMemcpy(h->d_pairs, pr.data(), pr.size() * sizeof(int), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMalloc(&h->d_pairs, (pr.size() + 2) * sizeof(int));
+            if (e == cudaSuccess && !pr.empty()) e = cudaMemcpy(h->d_pairs, pr.data(), pr.size() * sizeof(int), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess && h->nobs > 0) {
+                e = cudaMalloc(&h->d_obs, (size_t)3 * h->nobs * sizeof(double));
+                if (e == cudaSuccess) e = cudaMemcpy(h->d_obs, obs, (size_t)3 * h->nobs * sizeof(double), cudaMemcpyHostToDevice);
+            }
             break;
         }
     }
     if (e != cudaSuccess) { cudaFree(h->d_tables); delete h; return fail(NMPC_ECUDA, "nmpc_create: kernel configuration failed: %s", cudaGetErrorString(e)); }
     DBG("solve kernel configured");
     h->eval_smem = (size_t)(2 * h->n + 2 * h->mg + 2 * h->ns + h->nnzj + h->nnzh + 32 + 8) * sizeof(double);
-    if (h->eval_smem > (size_t)220 * 1024) h->eval_ok = false;   // large swarms: the stand-alone evaluation record exceeds shared memory
+    if (h->eval_smem > (size_t)220 * 1024 || h->family != 0) h->eval_ok = false;   // large swarms: the stand-alone evaluation record exceeds shared memory
     else {
         const int sz = (int)h->eval_smem;
         e = cudaFuncSetAttribute(eval_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz);
@@ -268,6 +293,7 @@ extern "C" void nmpc_destroy(nmpc_handle *h)
     if (!h) return;
     if (h->d_tables) cudaFree(h->d_tables);
     if (h->d_pairs) cudaFree(h->d_pairs);
+    if (h->d_obs) cudaFree(h->d_obs);
     if (h->d_buf) cudaFree(h->d_buf);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -283,12 +309,14 @@ extern "C" long long nmpc_launch_count(const nmpc_handle *h) { return h ? h->lau
 extern "C" int nmpc_jac_pattern(const nmpc_handle *h, int32_t *colptr, int32_t *rowidx)
 {
     if (!h || !colptr || !rowidx) return fail(NMPC_EINVAL, "nmpc_jac_pattern: NULL argument");
+    if (h->family) return fail(NMPC_ENOTSUP, "nmpc_jac_pattern: not available for the static-obstacle family");
     memcpy(colptr, h->jcol.data(), sizeof(int) * (h->n + 1)); memcpy(rowidx, h->jrow.data(), sizeof(int) * h->nnzj);
     return 0;
 }
 extern "C" int nmpc_hess_pattern(const nmpc_handle *h, int32_t *colptr, int32_t *rowidx)
 {
     if (!h || !colptr || !rowidx) return fail(NMPC_EINVAL, "nmpc_hess_pattern: NULL argument");
+    if (h->family) return fail(NMPC_ENOTSUP, "nmpc_hess_pattern: not available for the static-obstacle family");
     memcpy(colptr, h->hcol.data(), sizeof(int) * (h->n + 1)); memcpy(rowidx, h->hrow.data(), sizeof(int) * h->nnzh);
     return 0;
 }
@@ -324,7 +352,7 @@ static int solve_impl(nmpc_handle *h, int B, const double *x0, const double *p, 
     {
         long long total = (long long)nb * h->S * h->lw;
         int blocks = (int)std::min<long long>((total + 255) / 256, 4096);
-        prep_bounds_kernel<<<blocks, 256, 0, st>>>(h->d.Nr, h->d.N, h->o.bound_relax_factor, nb, h->lw, lbx, ubx, lbg, ubg, brows, berr);
+        prep_bounds_kernel<<<blocks, 256, 0, st>>>(h->d.Nr, h->d.N, h->o.bound_relax_factor, nb, h->lw, lbx, ubx, lbg, ubg, brows, berr, h->nobs, h->family);
         h->launches++;
     }
     NmpcSolveParams P;
@@ -335,7 +363,7 @@ static int solve_impl(nmpc_handle *h, int B, const double *x0, const double *p, 
     P.bstride = bounds_batched ? (long long)NMPC_BR_COUNT * h->S * h->lw : 0;
     P.bound_err = berr; P.x = x; P.f = f; P.g = g; P.lam_x = lam_x; P.lam_g = lam_g; P.status = status; P.iters = iters;
     P.stats = stats; P.trace = trace; P.max_trace = max_trace; P.ws = slots; P.ws_stride = (long long)h->ws_doubles_per_slot;
-    P.counter = counter; P.pairs = h->d_pairs; P.order = h->d_order;
+    P.counter = counter; P.pairs = h->d_pairs; P.order = h->d_order; P.nobs = h->nobs; P.family = h->family; P.obs = h->d_obs;
     const int grid = solve_grid(h, B);
     if (h->block_path) solve_kernel_block<<<grid, h->threads, h->solve_smem, st>>>(P);
     else switch (h->d.Nr) {
@@ -462,7 +490,8 @@ extern "C" int nmpc_eval(nmpc_handle *h, int B, const double *w, const double *p
 {
     if (!h || !w || !p || B <= 0) return fail(NMPC_EINVAL, "nmpc_eval: bad argument");
     if (hess && !lam_g) return fail(NMPC_EINVAL, "nmpc_eval: hess needs lam_g");
-    if (!h->eval_ok) return fail(NMPC_ENOTSUP, "nmpc_eval: the evaluation record of a %d-robot problem (%zu B) exceeds shared memory", h->d.Nr, h->eval_smem);
+    if (!h->eval_ok) return fail(NMPC_ENOTSUP, h->family ? "nmpc_eval: not available for the static-obstacle family"
+                                                        : "nmpc_eval: the evaluation record of a %d-robot problem (%zu B) exceeds shared memory", h->d.Nr, h->eval_smem);
     int per_sm = (int)std::max<size_t>(1, (size_t)(220 * 1024) / h->eval_smem);
     int blocks = std::min(B, h->sm_count * per_sm);
     const int pf = (std::max(h->n, h->mg) + 255) / 256;

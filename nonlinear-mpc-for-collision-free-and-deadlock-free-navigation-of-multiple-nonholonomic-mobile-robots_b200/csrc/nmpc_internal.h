@@ -8,6 +8,7 @@
 #define NMPC_DUMMY_ROW_VALUE 3.5 /* centralized_six_robots_implementation.py:278 */
 #define NMPC_NTRACE 8
 #define NMPC_MAX_ROBOTS 64
+#define NMPC_MAX_OBSTACLES 32
 
 /* Stage-layout bound rows prepared by prep_bounds_kernel, each [S][32] doubles per bound set:
  *   BL, BU : relaxed variable bounds of stage k (lanes 0..3Nr-1 states, 3Nr..5Nr-1 controls)
@@ -33,6 +34,8 @@ typedef struct NmpcSolveParams {
     int *counter;                    /* work queue                                       */
     const int *pairs;                /* [M][2] pair table (dense-block path only)        */
     const int *order;                /* optional [B] processing order of the instances   */
+    int nobs, family;                /* static obstacles per robot; row layout (0 / 1)   */
+    const double *obs;               /* [nobs][3] centre x, y, clearance radius (device) */
 } NmpcSolveParams;
 
 #endif

@@ -97,13 +97,21 @@ def _flat(a, size, name):
 class Problem:
     """Handle on the CUDA library for one (Nr, N, T, Q, R) problem family."""
 
-    def __init__(self, Nr, N, T, Q=(1.0, 5.0, 0.1), R=(0.5, 0.05), **opts):
+    def __init__(self, Nr, N, T, Q=(1.0, 5.0, 0.1), R=(0.5, 0.05), obstacles=None, **opts):
+        """obstacles: optional [n_obs, 3] array of static circular obstacles (centre x, y, clearance = rob_dim + r_obs): the
+        reference's obstacle-avoidance family (first_scenario_mpc_obstacle_avoidance.py:96-152), see nmpc_create_obstacles."""
         self.L = lib()
         self.desc = Desc(int(Nr), int(N), float(T), (C.c_double * 3)(*[float(q) for q in Q]),
                          (C.c_double * 2)(*[float(r) for r in R]))
         self.opts = default_opts(**opts)
         self.h = C.c_void_p()
-        check(self.L.nmpc_create(C.byref(self.desc), C.byref(self.opts), C.byref(self.h)))
+        self.obstacles = None if obstacles is None else np.ascontiguousarray(np.asarray(obstacles, dtype=np.float64).reshape(-1, 3))
+        if self.obstacles is None:
+            check(self.L.nmpc_create(C.byref(self.desc), C.byref(self.opts), C.byref(self.h)))
+        else:
+            check(self.L.nmpc_create_obstacles(C.byref(self.desc), C.byref(self.opts), int(self.obstacles.shape[0]),
+                                               self.obstacles.ctypes.data, C.byref(self.h)))
+        self.nobs = 0 if self.obstacles is None else int(self.obstacles.shape[0])
         self.Nr, self.N, self.T = int(Nr), int(N), float(T)
         self.ns, self.nc = 3 * self.Nr, 2 * self.Nr
         self.M = self.Nr * (self.Nr - 1) // 2
@@ -127,6 +135,19 @@ class Problem:
         ubx = -lbx
         lbg = np.tile(np.concatenate([np.zeros(self.ns), np.full(self.M, dmin * dmin)]), self.N + 1)
         ubg = np.tile(np.concatenate([np.zeros(self.ns), np.full(self.M, inf)]), self.N + 1)
+        return lbx, ubx, lbg, ubg
+
+    def bounds_obstacles(self, margin, v_max, w_max, dmin=0.0, xy_box=10.0, th_box=2.0 * np.pi):
+        """Bounds of the obstacle-avoidance scripts (first_scenario_mpc_obstacle_avoidance.py:150-152): theta boxed to +-2 pi,
+        equality rows 0, obstacle rows >= margin (0.05 there, 0.1 in the third scenario), pair rows (Nr > 1) >= dmin^2."""
+        inf = np.inf
+        lbx = np.concatenate([np.tile([-xy_box, -xy_box, -th_box], self.Nr * (self.N + 1)),
+                              np.tile([-v_max, -w_max], self.Nr * self.N)])
+        ubx = -lbx
+        blk_lo = np.concatenate([np.zeros(self.ns), np.full(self.M, dmin * dmin), np.full(self.Nr * self.nobs, margin)])
+        blk_hi = np.concatenate([np.zeros(self.ns), np.full(self.M + self.Nr * self.nobs, inf)])
+        lbg = np.concatenate([np.zeros(self.ns), np.tile(blk_lo, self.N)])
+        ubg = np.concatenate([np.zeros(self.ns), np.tile(blk_hi, self.N)])
         return lbx, ubx, lbg, ubg
 
     def cold_start(self, x0):
@@ -335,10 +356,13 @@ def nlpsol(name, plugin, nlp, opts=None):
     """
     if plugin not in ("ipopt", "b200ipm"):
         raise ValueError("plugin %r: this library implements the interior-point path only" % (plugin,))
-    if not isinstance(nlp, dict) or nlp.get("family", "unicycle_centralized") != "unicycle_centralized":
-        raise ValueError("nlp must be a descriptor {'family':'unicycle_centralized','Nr','N','T',...}")
+    if not isinstance(nlp, dict) or nlp.get("family", "unicycle_centralized") not in ("unicycle_centralized", "unicycle_obstacles"):
+        raise ValueError("nlp must be a descriptor {'family':'unicycle_centralized'|'unicycle_obstacles','Nr','N','T',...}")
+    if nlp.get("family") == "unicycle_obstacles" and nlp.get("obstacles") is None:
+        raise ValueError("family 'unicycle_obstacles' needs 'obstacles': [[x, y, clearance], ...]")
     ip = dict((opts or {}).get("ipopt", {}))
     ip.update({k: v for k, v in (opts or {}).items() if k in _IPOPT_KEYS})
     kw = {k: v for k, v in ip.items() if k in _IPOPT_KEYS}          # print_level etc. are accepted and ignored
-    prob = Problem(nlp["Nr"], nlp["N"], nlp["T"], nlp.get("Q", (1.0, 5.0, 0.1)), nlp.get("R", (0.5, 0.05)), **kw)
+    prob = Problem(nlp["Nr"], nlp["N"], nlp["T"], nlp.get("Q", (1.0, 5.0, 0.1)), nlp.get("R", (0.5, 0.05)),
+                   obstacles=nlp.get("obstacles") if nlp.get("family") == "unicycle_obstacles" else None, **kw)
     return NlpSolver(name, prob)

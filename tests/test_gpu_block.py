@@ -125,3 +125,15 @@ def test_block_path_closed_loop_and_host_api(pkg, torch_cuda):
     assert (d1 < d0 - 0.5).all(), (d0, d1)      # 25 steps at <= 0.066 m per step: every robot has made > 0.5 m of progress
     warm = res["iters"].cpu().numpy()[1:].mean()
     assert warm < res["iters"].cpu().numpy()[0].mean(), "warm starts should need fewer iterations than the cold first step"
+
+
+@pytest.mark.parametrize("Nr,N,T", [(1, 25, 0.25), (2, 7, 0.1), (3, 10, 0.3), (6, 20, 0.3)])
+def test_block_path_equals_oracle_on_small_robot_counts(pkg, torch_cuda, Nr, N, T, monkeypatch):
+    """The dense-block solver is generic in Nr: forced onto 1..6 robots (NMPC_FORCE_BLOCK) it must reproduce the oracle
+    exactly like the warp-per-instance path does."""
+    monkeypatch.setenv("NMPC_FORCE_BLOCK", "1")
+    P = synthetic_instances(6, Nr=Nr, seed=300 + Nr, box=2.0)
+    prob, out, ref, (lbx, ubx, lbg, ubg) = _solve_both(pkg, torch_cuda, Nr, N, T, P, dmin=0.3)
+    du, df = _check(out, ref, Nr, N, lbg, P, 0.3)
+    assert ((du <= 1e-4) & (df <= 1e-6)).all(), (du, df, out["iters"].cpu().numpy(), ref["iters"])
+    assert np.abs(out["iters"].cpu().numpy() - ref["iters"]).max() <= 3
