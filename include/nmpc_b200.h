@@ -116,6 +116,15 @@ int nmpc_solve(nmpc_handle *h, int B, const double *x0, const double *p,
  * the CCS patterns are not available for this family. */
 int nmpc_create_obstacles(const nmpc_desc *d, const nmpc_opts *o, int n_obs, const double *obs, nmpc_handle **out);
 
+/* Small generic optimal-control problems, one GPU thread per instance.  model NMPC_OCP_VAN_DER_POL is the direct-multiple-shooting
+ * demo of mpc_pose_control_casadi.py:22-114: 2 states, 1 control, N intervals over the horizon T, each integrated by rk_steps RK4
+ * steps together with the cost quadrature; decision vector INTERLEAVED [X_0, U_0, X_1, ..., U_{N-1}, X_N] (n = 3N + 2, :77-106),
+ * g = F(X_k, U_k) - X_{k+1} (mg = 2N, :104), no parameter vector (pass p = NULL).  The initial state must be fixed through
+ * lbx == ubx on X_0 (:79-80; IPOPT's make_parameter treatment); other variables must have lb < ub.  o == NULL: IPOPT defaults
+ * (max_iter 3000).  nmpc_solve / nmpc_solve_host / nmpc_n / nmpc_mg work on the handle; shift, plant and eval do not apply. */
+enum { NMPC_OCP_VAN_DER_POL = 1 };
+int nmpc_create_ocp(int model, int N, double T, int rk_steps, const nmpc_opts *o, nmpc_handle **out);
+
 /* Scheduling hint for the following nmpc_solve* calls on this handle: order [B] (DEVICE int32, caller owned, a permutation
  * of 0..B-1) is the sequence in which the persistent teams pull instances from the work queue; NULL restores index order.
  * Instances differ in iteration count (17 on average, up to 70, one MPC step after a solve), so a closed loop that passes

@@ -14,7 +14,7 @@ SYMBOLS = ["nmpc_default_opts", "nmpc_last_error", "nmpc_create", "nmpc_destroy"
            "nmpc_nnz_jac", "nmpc_nnz_hess", "nmpc_workspace_bytes", "nmpc_workspace_bytes_batched_bounds", "nmpc_solve",
            "nmpc_solve_trace", "nmpc_solve_host", "nmpc_shift",
            "nmpc_plant", "nmpc_eval", "nmpc_jac_pattern", "nmpc_hess_pattern", "nmpc_launch_count", "nmpc_probe_fp64",
-           "nmpc_debug_block_profile", "nmpc_set_order", "nmpc_create_obstacles"]
+           "nmpc_debug_block_profile", "nmpc_set_order", "nmpc_create_obstacles", "nmpc_create_ocp"]
 
 
 class Desc(C.Structure):
@@ -54,6 +54,7 @@ def lib():
     L.nmpc_last_error.restype = C.c_char_p
     L.nmpc_create.argtypes = [C.POINTER(Desc), C.POINTER(Opts), C.POINTER(H)]
     L.nmpc_create_obstacles.argtypes = [C.POINTER(Desc), C.POINTER(Opts), C.c_int, vp, C.POINTER(H)]
+    L.nmpc_create_ocp.argtypes = [C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(Opts), C.POINTER(H)]
     L.nmpc_destroy.argtypes = [H]
     L.nmpc_destroy.restype = None
     for fn in ("nmpc_n", "nmpc_mg", "nmpc_np", "nmpc_nnz_jac", "nmpc_nnz_hess"):

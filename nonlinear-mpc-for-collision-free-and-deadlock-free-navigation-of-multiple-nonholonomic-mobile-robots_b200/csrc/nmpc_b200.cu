@@ -13,6 +13,7 @@
 #include "warp_prims.cuh"
 #include "solver_body.cuh"
 #include "block_solver.cuh"
+#include "small_ocp.cuh"
 #include "aux_kernels.cuh"
 
 #ifndef SOLVE_WARPS
@@ -93,7 +94,7 @@ struct nmpc_handle {
     size_t ws_doubles_per_slot, solve_smem, eval_smem;
     int ctas_per_sm, lw, teams_per_cta, threads;
     const int *d_order;                       // optional processing order (device, caller owned), see nmpc_set_order
-    int nobs, family;                         // static obstacles per robot; row layout of g (0 centralized, 1 obstacles)
+    int nobs, family, rk_steps;               // static obstacles per robot; family: 0 centralized, 1 obstacles, 2 small OCP (thread per instance)
     double *d_obs;                            // [nobs][3] on the device
     bool block_path, eval_ok;                 // Nr > 10: CTA-per-instance dense-block solver; eval record fits shared memory
     int *d_pairs;                             // pair table (i, j) of the inequality rows, block path
@@ -186,6 +187,32 @@ extern "C" int nmpc_create_obstacles(const nmpc_desc *d, const nmpc_opts *o, int
     for (int i = 0; i < n_obs; i++)
         if (!(obs[3 * i + 2] >= 0.0)) return fail(NMPC_EINVAL, "nmpc_create_obstacles: obstacle %d has a negative clearance radius", i);
     return create_impl(d, o, n_obs, obs, out);
+}
+
+// Small generic OCP family (thread per instance): currently the Van der Pol demo of mpc_pose_control_casadi.py
+extern "C" int nmpc_create_ocp(int model, int N, double T, int rk_steps, const nmpc_opts *o, nmpc_handle **out)
+{
+    if (!out) return fail(NMPC_EINVAL, "nmpc_create_ocp: NULL argument");
+    if (model != NMPC_OCP_VAN_DER_POL) return fail(NMPC_ENOTSUP, "nmpc_create_ocp: unknown model %d", model);
+    if (N < 1 || !(T > 0) || rk_steps < 1) return fail(NMPC_EINVAL, "nmpc_create_ocp: need N >= 1, T > 0, rk_steps >= 1");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(NMPC_ECUDA, "nmpc_create_ocp: no CUDA device -- this library has no CPU fallback");
+    nmpc_handle *h = new nmpc_handle();
+    memset(&h->d, 0, sizeof h->d);
+    h->d.Nr = 0; h->d.N = N; h->d.T = T;
+    if (o) h->o = *o; else { nmpc_default_opts(&h->o); h->o.max_iter = 3000; }   // IPOPT's default max_iter: the demo sets no options
+    typedef ThreadSolver<VanDerPol> TS;
+    h->ns = TS::NX; h->nc = TS::NU; h->M = 0; h->S = N + 1; h->nobs = 0; h->family = 2; h->rk_steps = rk_steps;
+    h->n = TS::NZ * N + TS::NX; h->mg = TS::NX * N; h->np = 0; h->nnzj = 0; h->nnzh = 0;
+    h->launches = 0; h->d_buf = nullptr; h->d_bytes = 0; h->stream = nullptr; h->d_tables = nullptr; h->d_pairs = nullptr;
+    h->d_order = nullptr; h->d_obs = nullptr; h->block_path = false; h->eval_ok = false;
+    cudaGetDevice(&h->dev);
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->dev);
+    h->ws_doubles_per_slot = (size_t)TS::ws_doubles(N);
+    h->lw = 0; h->teams_per_cta = 64; h->threads = 64; h->ctas_per_sm = 1 << 16; h->solve_smem = 0; h->eval_smem = 0;
+    *out = h;
+    return 0;
 }
 
 static int create_impl(const nmpc_desc *d, const nmpc_opts *o, int nobs, const double *obs, nmpc_handle **out)
@@ -339,7 +366,7 @@ static int solve_impl(nmpc_handle *h, int B, const double *x0, const double *p, 
                       double *lam_x, double *lam_g, int32_t *status, int32_t *iters, double *stats, double *trace,
                       int max_trace, void *workspace, size_t workspace_bytes, cudaStream_t st)
 {
-    if (!h || !x0 || !p || !lbx || !ubx || !lbg || !ubg || !x || !workspace) return fail(NMPC_EINVAL, "nmpc_solve: NULL argument");
+    if (!h || !x0 || (!p && h->np > 0) || !lbx || !ubx || !lbg || !ubg || !x || !workspace) return fail(NMPC_EINVAL, "nmpc_solve: NULL argument");
     if (B <= 0) return fail(NMPC_EINVAL, "nmpc_solve: B must be positive");
     const int nb = bounds_batched ? B : 1;
     const size_t need = ws_bytes_for(h, B, nb);
@@ -349,7 +376,7 @@ static int solve_impl(nmpc_handle *h, int B, const double *x0, const double *p, 
     double *brows = (double *)(base + 256);
     double *slots = (double *)(base + 256 + bound_rows_bytes(h, nb));
     CUDA_OK(cudaMemsetAsync(base, 0, 256, st));
-    {
+    if (h->family != 2) {
         long long total = (long long)nb * h->S * h->lw;
         int blocks = (int)std::min<long long>((total + 255) / 256, 4096);
         prep_bounds_kernel<<<blocks, 256, 0, st>>>(h->d.Nr, h->d.N, h->o.bound_relax_factor, nb, h->lw, lbx, ubx, lbg, ubg, brows, berr, h->nobs, h->family);
@@ -364,8 +391,10 @@ static int solve_impl(nmpc_handle *h, int B, const double *x0, const double *p, 
     P.bound_err = berr; P.x = x; P.f = f; P.g = g; P.lam_x = lam_x; P.lam_g = lam_g; P.status = status; P.iters = iters;
     P.stats = stats; P.trace = trace; P.max_trace = max_trace; P.ws = slots; P.ws_stride = (long long)h->ws_doubles_per_slot;
     P.counter = counter; P.pairs = h->d_pairs; P.order = h->d_order; P.nobs = h->nobs; P.family = h->family; P.obs = h->d_obs;
+    P.lbx = lbx; P.ubx = ubx; P.lbg = lbg; P.ubg = ubg; P.bounds_batched = bounds_batched; P.rk_steps = h->rk_steps;
     const int grid = solve_grid(h, B);
-    if (h->block_path) solve_kernel_block<<<grid, h->threads, h->solve_smem, st>>>(P);
+    if (h->family == 2) solve_kernel_small_ocp<VanDerPol><<<grid, h->threads, 0, st>>>(P);
+    else if (h->block_path) solve_kernel_block<<<grid, h->threads, h->solve_smem, st>>>(P);
     else switch (h->d.Nr) {
         case 1: solve_kernel<1><<<grid, h->threads, h->solve_smem, st>>>(P); break;
         case 2: solve_kernel<2><<<grid, h->threads, h->solve_smem, st>>>(P); break;
@@ -415,7 +444,7 @@ extern "C" int nmpc_solve_host(nmpc_handle *h, int B, const double *x0, const do
                                const double *lbg, const double *ubg, int bounds_batched, double *x, double *f, double *g,
                                double *lam_x, double *lam_g, int32_t *status, int32_t *iters, double *stats)
 {
-    if (!h || !x0 || !p || !lbx || !ubx || !lbg || !ubg || !x) return fail(NMPC_EINVAL, "nmpc_solve_host: NULL argument");
+    if (!h || !x0 || (!p && h->np > 0) || !lbx || !ubx || !lbg || !ubg || !x) return fail(NMPC_EINVAL, "nmpc_solve_host: NULL argument");
     if (B <= 0) return fail(NMPC_EINVAL, "nmpc_solve_host: B must be positive");
     const int nb = bounds_batched ? B : 1;
     const size_t n = h->n, mg = h->mg, np = h->np, D = sizeof(double);
@@ -435,7 +464,7 @@ extern "C" int nmpc_solve_host(nmpc_handle *h, int B, const double *x0, const do
     char *b = h->d_buf;
     cudaStream_t st = h->stream;
     CUDA_OK(cudaMemcpyAsync(b + o_x0, x0, B * n * D, cudaMemcpyHostToDevice, st));
-    CUDA_OK(cudaMemcpyAsync(b + o_p, p, B * np * D, cudaMemcpyHostToDevice, st));
+    if (np > 0) CUDA_OK(cudaMemcpyAsync(b + o_p, p, B * np * D, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaMemcpyAsync(b + o_lbx, lbx, nb * n * D, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaMemcpyAsync(b + o_ubx, ubx, nb * n * D, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaMemcpyAsync(b + o_lbg, lbg, nb * mg * D, cudaMemcpyHostToDevice, st));
@@ -466,6 +495,7 @@ extern "C" int nmpc_solve_host(nmpc_handle *h, int B, const double *x0, const do
 extern "C" int nmpc_shift(nmpc_handle *h, int B, const double *x_prev, double *x0_next, void *stream)
 {
     if (!h || !x_prev || !x0_next || B <= 0) return fail(NMPC_EINVAL, "nmpc_shift: bad argument");
+    if (h->family == 2) return fail(NMPC_ENOTSUP, "nmpc_shift: the small-OCP family is a single solve, it has no MPC shift");
     if (x_prev == x0_next) return fail(NMPC_EINVAL, "nmpc_shift: in-place shift is not supported");
     long long total = (long long)B * h->n;
     int blocks = (int)std::min<long long>(B, (long long)h->sm_count * 8);
@@ -478,6 +508,7 @@ extern "C" int nmpc_shift(nmpc_handle *h, int B, const double *x_prev, double *x
 extern "C" int nmpc_plant(nmpc_handle *h, int B, const double *state, const double *x_opt, double *state_next, void *stream)
 {
     if (!h || !state || !x_opt || !state_next || B <= 0) return fail(NMPC_EINVAL, "nmpc_plant: bad argument");
+    if (h->family == 2) return fail(NMPC_ENOTSUP, "nmpc_plant: not available for the small-OCP family");
     int blocks = std::min((B * h->d.Nr + 255) / 256, h->sm_count * 16);
     plant_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(h->d.Nr, h->d.N, h->d.T, B, state, x_opt, state_next);
     h->launches++;

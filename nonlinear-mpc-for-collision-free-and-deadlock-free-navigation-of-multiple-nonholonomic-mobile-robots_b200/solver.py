@@ -319,6 +319,36 @@ def closed_loop(prob, P, lbx, ubx, lbg, ubg, steps, tol=1e-1, dmin=None):
     return res
 
 
+class SmallOcp(Problem):
+    """Small generic OCP, one GPU thread per instance (nmpc_create_ocp).  model 'van_der_pol' is the direct-multiple-shooting
+    demo of mpc_pose_control_casadi.py:22-114: interleaved decision vector [X_0, U_0, ..., X_N] (n = 3N + 2), g = F(X_k, U_k) -
+    X_{k+1} (mg = 2N), initial state fixed through its bounds, no parameter vector."""
+    MODELS = {"van_der_pol": 1}
+
+    def __init__(self, model="van_der_pol", N=20, T=10.0, rk_steps=4, **opts):
+        self.L = lib()
+        self.opts = default_opts(**({"max_iter": 3000} | opts))      # the demo sets no options: IPOPT's default max_iter
+        self.h = C.c_void_p()
+        check(self.L.nmpc_create_ocp(self.MODELS[model], int(N), float(T), int(rk_steps), C.byref(self.opts), C.byref(self.h)))
+        self.model, self.Nr, self.N, self.T, self.rk_steps = model, 0, int(N), float(T), int(rk_steps)
+        self.ns, self.nc, self.M, self.nobs, self.obstacles = 2, 1, 0, 0, None
+        self.n, self.mg, self.np_ = self.L.nmpc_n(self.h), self.L.nmpc_mg(self.h), 0
+        self.nnz_jac = self.nnz_hess = 0
+        self._ws = None
+
+    def demo_arrays(self):
+        """w0, lbw, ubw, lbg, ubg exactly as the demo assembles them (mpc_pose_control_casadi.py:77-106)."""
+        inf = np.inf
+        w0, lbw, ubw = [0.0, 1.0], [0.0, 1.0], [0.0, 1.0]
+        for _ in range(self.N):
+            w0 += [0.0, 0.0, 0.0]; lbw += [-1.0, -0.25, -inf]; ubw += [1.0, inf, inf]
+        return np.array(w0), np.array(lbw), np.array(ubw), np.zeros(self.mg), np.zeros(self.mg)
+
+    def solve_host(self, x0, lbx, ubx, lbg, ubg, want=("f", "g", "lam_x", "lam_g", "stats"), out=None):
+        x0 = np.atleast_2d(np.ascontiguousarray(x0, dtype=np.float64))
+        return Problem.solve_host(self, x0, np.zeros((x0.shape[0], 0)), lbx, ubx, lbg, ubg, want=want, out=out)
+
+
 class NlpSolver:
     """What nlpsol(...) returns: callable with the reference's keyword arguments (:432)."""
 
@@ -328,15 +358,20 @@ class NlpSolver:
 
     def __call__(self, x0=0.0, p=None, lbx=-np.inf, ubx=np.inf, lbg=-np.inf, ubg=np.inf, lam_x0=None, lam_g0=None):
         P = self.problem
-        if p is None:
-            raise ValueError("p = [x0; xs] is required")
-        o = P.solve_host(_flat(x0, P.n, "x0")[None], _flat(p, P.np_, "p")[None], _flat(lbx, P.n, "lbx"),
-                         _flat(ubx, P.n, "ubx"), _flat(lbg, P.mg, "lbg"), _flat(ubg, P.mg, "ubg"))
+        if P.np_ == 0:      # parameter-free problem (the Van der Pol demo calls solver(x0=, lbx=, ubx=, lbg=, ubg=), :113)
+            o = P.solve_host(_flat(x0, P.n, "x0")[None], _flat(lbx, P.n, "lbx"), _flat(ubx, P.n, "ubx"), _flat(lbg, P.mg, "lbg"),
+                             _flat(ubg, P.mg, "ubg"))
+        else:
+            if p is None:
+                raise ValueError("p = [x0; xs] is required")
+            o = P.solve_host(_flat(x0, P.n, "x0")[None], _flat(p, P.np_, "p")[None], _flat(lbx, P.n, "lbx"),
+                             _flat(ubx, P.n, "ubx"), _flat(lbg, P.mg, "lbg"), _flat(ubg, P.mg, "ubg"))
         st = int(o["status"][0])
         self._stats = dict(return_status=_cabi.STATUS.get(st, str(st)), success=st in (0, 1),
                            iter_count=int(o["iters"][0]), kkt_error=float(o["stats"][0, 0]))
         lam_p = np.zeros(P.np_)
-        lam_p[:P.ns] = -o["lam_g"][0, :P.ns]        # d f*/d x0bar: only the initial-condition rows depend on p[0:ns]
+        if P.np_:
+            lam_p[:P.ns] = -o["lam_g"][0, :P.ns]    # d f*/d x0bar: only the initial-condition rows depend on p[0:ns]
         return {"x": DM(o["x"][0]), "f": DM(o["f"][:1]), "g": DM(o["g"][0]), "lam_x": DM(o["lam_x"][0]),
                 "lam_g": DM(o["lam_g"][0]), "lam_p": DM(lam_p)}
 
@@ -356,6 +391,10 @@ def nlpsol(name, plugin, nlp, opts=None):
     """
     if plugin not in ("ipopt", "b200ipm"):
         raise ValueError("plugin %r: this library implements the interior-point path only" % (plugin,))
+    if isinstance(nlp, dict) and nlp.get("family") == "van_der_pol":
+        ip = dict((opts or {}).get("ipopt", {}))
+        kw = {k: v for k, v in ip.items() if k in _IPOPT_KEYS}
+        return NlpSolver(name, SmallOcp("van_der_pol", nlp.get("N", 20), nlp.get("T", 10.0), nlp.get("rk_steps", 4), **kw))
     if not isinstance(nlp, dict) or nlp.get("family", "unicycle_centralized") not in ("unicycle_centralized", "unicycle_obstacles"):
         raise ValueError("nlp must be a descriptor {'family':'unicycle_centralized'|'unicycle_obstacles','Nr','N','T',...}")
     if nlp.get("family") == "unicycle_obstacles" and nlp.get("obstacles") is None:
