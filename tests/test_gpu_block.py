@@ -137,3 +137,30 @@ def test_block_path_equals_oracle_on_small_robot_counts(pkg, torch_cuda, Nr, N, 
     du, df = _check(out, ref, Nr, N, lbg, P, 0.3)
     assert ((du <= 1e-4) & (df <= 1e-6)).all(), (du, df, out["iters"].cpu().numpy(), ref["iters"])
     assert np.abs(out["iters"].cpu().numpy() - ref["iters"]).max() <= 3
+
+
+def test_solves_are_bitwise_reproducible(pkg, torch_cuda):
+    """Shared-memory hazards show up as run-to-run differences: the same batch solved three times must give identical bits
+    on the warp path (6 robots), the two-warp team path (8), the dense-block path (12, 24) and the obstacle family."""
+    torch = torch_cuda
+    cases = [(6, 20, 2.0, 64, None), (8, 8, 2.5, 24, None), (12, 10, 3.0, 8, None), (24, 6, 4.5, 4, None), (1, 15, 2.0, 6, [[0.45, 0.5, 0.3]])]
+    for Nr, N, box, B, obs in cases:
+        prob = pkg.Problem(Nr, N, 0.3, obstacles=obs)
+        if obs is None:
+            P = synthetic_instances(B, Nr=Nr, seed=900 + Nr, box=box)
+            bnd = prob.bounds(0.3, 0.22, 2.84)
+        else:
+            rng = np.random.default_rng(5)
+            P = np.array([[0.0, 0.0, 0.6, 1.2, 1.3, 0.0]]) + 0.05 * rng.normal(size=(B, 6))
+            bnd = prob.bounds_obstacles(0.05, 0.2, np.pi / 4)
+        args = [_t(torch, prob.cold_start(P[:, :3 * Nr])), _t(torch, P)] + [_t(torch, a) for a in bnd]
+        ref = None
+        for rep in range(3):
+            out = prob.solve(*args)
+            torch.cuda.synchronize()
+            cur = {k: out[k].clone() for k in ("x", "f", "g", "lam_g", "iters", "status")}
+            if ref is None:
+                ref = cur
+            else:
+                for k in ref:
+                    assert torch.equal(ref[k], cur[k]), (Nr, N, k, rep)
