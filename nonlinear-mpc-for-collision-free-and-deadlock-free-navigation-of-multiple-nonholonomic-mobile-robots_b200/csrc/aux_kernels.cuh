@@ -21,6 +21,83 @@ struct NmpcEvalTables {
     const int *jac_init; // [ns]       slots of the identity block of the initial-condition rows
 };
 
+// All work items of one evaluation point (robot-stage, pair-stage, initial block): fills grad, g and the CCS value arrays of
+// the Jacobian and the Hessian of the Lagrangian through the position tables; returns this thread's share of f.  The arrays
+// may live in shared memory (eval_kernel: the record is assembled on chip and leaves through bulk stores) or directly in global
+// memory (eval_kernel_big: records too large for shared memory, e.g. 2.5 MB at 64 robots); NULL outputs are skipped.
+__device__ __forceinline__ double eval_point_items(int Nr, int N, double T, const double *Qw, const double *Rw, const double *sw,
+                                                   const double *sl, const double *sp, double *sgrad, double *sg, double *sj,
+                                                   double *shs, const NmpcEvalTables &tb, bool lam, bool hess)
+{
+    const int ns = 3 * Nr, nc = 2 * Nr, M = Nr * (Nr - 1) / 2, S = N + 1, blk = ns + M, nX = ns * S;
+    double facc = 0.0;
+        // robot-stage work items, then pair-stage items, then the initial block
+        const int nRS = N * Nr, nPS = N * M;
+        for (int it = threadIdx.x; it < nRS + nPS + ns + M + ns; it += blockDim.x) {
+            if (it < nRS) {
+                const int k = it / Nr, i = it % Nr, r0 = (k + 1) * blk + 3 * i;
+                const int ix = k * ns + 3 * i, iu = nX + k * nc + 2 * i;
+                const double x = sw[ix], y = sw[ix + 1], th = sw[ix + 2], v = sw[iu], om = sw[iu + 1];
+                double s_, c_;
+                sincos(th, &s_, &c_);
+                const double ex = x - sp[ns + 3 * i], ey = y - sp[ns + 3 * i + 1], et = th - sp[ns + 3 * i + 2];
+                facc += Qw[0] * ex * ex + Qw[1] * ey * ey + Qw[2] * et * et + Rw[0] * v * v + Rw[1] * om * om;
+                if (sgrad) {
+                    sgrad[ix] = 2 * Qw[0] * ex; sgrad[ix + 1] = 2 * Qw[1] * ey; sgrad[ix + 2] = 2 * Qw[2] * et;
+                    sgrad[iu] = 2 * Rw[0] * v; sgrad[iu + 1] = 2 * Rw[1] * om;
+                }
+                if (sg) {
+                    sg[r0] = sw[ix + ns] - (x + T * v * c_);
+                    sg[r0 + 1] = sw[ix + ns + 1] - (y + T * v * s_);
+                    sg[r0 + 2] = sw[ix + ns + 2] - (th + T * om);
+                }
+                const int *js = tb.jac_rs + (size_t)it * 11;
+                if (sj) {
+                sj[js[0]] = 1.0; sj[js[1]] = -1.0; sj[js[2]] = T * v * s_; sj[js[3]] = -T * c_;
+                sj[js[4]] = 1.0; sj[js[5]] = -1.0; sj[js[6]] = -T * v * c_; sj[js[7]] = -T * s_;
+                sj[js[8]] = 1.0; sj[js[9]] = -1.0; sj[js[10]] = -T;
+                }
+                if (lam && hess && shs) {
+                    const double lx = sl[r0], ly = sl[r0 + 1];
+                    double sm2 = 0.0;
+                    for (int j = 0; j < Nr; j++) {
+                        if (j == i) continue;
+                        const int a = i < j ? i : j, c2 = i < j ? j : i;
+                        sm2 += 2.0 * sl[(k + 1) * blk + ns + a * (2 * Nr - a - 1) / 2 + (c2 - a - 1)];
+                    }
+                    const int *hs = tb.hes_rs + (size_t)it * 6;
+                    shs[hs[0]] = 2 * Qw[0] + sm2; shs[hs[1]] = 2 * Qw[1] + sm2;
+                    shs[hs[2]] = 2 * Qw[2] + T * v * (lx * c_ + ly * s_);
+                    shs[hs[3]] = T * (lx * s_ - ly * c_);
+                    shs[hs[4]] = 2 * Rw[0]; shs[hs[5]] = 2 * Rw[1];
+                }
+            } else if (it < nRS + nPS) {
+                const int e = it - nRS, k = e / M, q = e % M;
+                int a = 0, rem = q;
+                while (rem >= Nr - 1 - a) { rem -= Nr - 1 - a; a++; }
+                const int c2 = a + 1 + rem;
+                const double dx = sw[k * ns + 3 * a] - sw[k * ns + 3 * c2], dy = sw[k * ns + 3 * a + 1] - sw[k * ns + 3 * c2 + 1];
+                if (sg) sg[(k + 1) * blk + ns + q] = dx * dx + dy * dy;
+                const int *js = tb.jac_ps + (size_t)e * 4;
+                if (sj) { sj[js[0]] = 2 * dx; sj[js[1]] = -2 * dx; sj[js[2]] = 2 * dy; sj[js[3]] = -2 * dy; }
+                if (lam && hess && shs) {
+                    const double mu = sl[(k + 1) * blk + ns + q];
+                    const int *hs = tb.hes_ps + (size_t)e * 2;
+                    shs[hs[0]] = -2 * mu; shs[hs[1]] = -2 * mu;
+                }
+            } else if (it < nRS + nPS + ns) {
+                const int r = it - nRS - nPS;
+                if (sg) sg[r] = sw[r] - sp[r];
+                if (sj) sj[tb.jac_init[r]] = 1.0;
+            } else if (it < nRS + nPS + ns + M) {
+                if (sg) sg[ns + (it - nRS - nPS - ns)] = NMPC_DUMMY_ROW_VALUE;
+            } else {
+                if (sgrad) sgrad[N * ns + (it - nRS - nPS - ns - M)] = 0.0;  // X_N is not in the cost
+            }
+        }
+    return facc;
+}
+
 // TMA bulk store shared -> global (cp.async.bulk, one elected thread issues it; completion tracked per bulk group)
 __device__ __forceinline__ void bulk_store_s2g(void *gdst, const void *ssrc, unsigned bytes)
 {
@@ -81,65 +158,7 @@ __global__ void __launch_bounds__(256) eval_kernel(int Nr, int N, double T, doub
             if (lam) for (int i = threadIdx.x; i < mg; i += blockDim.x) sl[i] = lam[(size_t)b * mg + i];
         }
         __syncthreads();
-        double facc = 0.0;
-        // robot-stage work items, then pair-stage items, then the initial block
-        const int nRS = N * Nr, nPS = N * M;
-        for (int it = threadIdx.x; it < nRS + nPS + ns + M + ns; it += blockDim.x) {
-            if (it < nRS) {
-                const int k = it / Nr, i = it % Nr, r0 = (k + 1) * blk + 3 * i;
-                const int ix = k * ns + 3 * i, iu = nX + k * nc + 2 * i;
-                const double x = sw[ix], y = sw[ix + 1], th = sw[ix + 2], v = sw[iu], om = sw[iu + 1];
-                double s_, c_;
-                sincos(th, &s_, &c_);
-                const double ex = x - sp[ns + 3 * i], ey = y - sp[ns + 3 * i + 1], et = th - sp[ns + 3 * i + 2];
-                facc += Qw[0] * ex * ex + Qw[1] * ey * ey + Qw[2] * et * et + Rw[0] * v * v + Rw[1] * om * om;
-                sgrad[ix] = 2 * Qw[0] * ex; sgrad[ix + 1] = 2 * Qw[1] * ey; sgrad[ix + 2] = 2 * Qw[2] * et;
-                sgrad[iu] = 2 * Rw[0] * v; sgrad[iu + 1] = 2 * Rw[1] * om;
-                sg[r0] = sw[ix + ns] - (x + T * v * c_);
-                sg[r0 + 1] = sw[ix + ns + 1] - (y + T * v * s_);
-                sg[r0 + 2] = sw[ix + ns + 2] - (th + T * om);
-                const int *js = tb.jac_rs + (size_t)it * 11;
-                sj[js[0]] = 1.0; sj[js[1]] = -1.0; sj[js[2]] = T * v * s_; sj[js[3]] = -T * c_;
-                sj[js[4]] = 1.0; sj[js[5]] = -1.0; sj[js[6]] = -T * v * c_; sj[js[7]] = -T * s_;
-                sj[js[8]] = 1.0; sj[js[9]] = -1.0; sj[js[10]] = -T;
-                if (lam && hess) {
-                    const double lx = sl[r0], ly = sl[r0 + 1];
-                    double sm2 = 0.0;
-                    for (int j = 0; j < Nr; j++) {
-                        if (j == i) continue;
-                        const int a = i < j ? i : j, c2 = i < j ? j : i;
-                        sm2 += 2.0 * sl[(k + 1) * blk + ns + a * (2 * Nr - a - 1) / 2 + (c2 - a - 1)];
-                    }
-                    const int *hs = tb.hes_rs + (size_t)it * 6;
-                    shs[hs[0]] = 2 * Qw[0] + sm2; shs[hs[1]] = 2 * Qw[1] + sm2;
-                    shs[hs[2]] = 2 * Qw[2] + T * v * (lx * c_ + ly * s_);
-                    shs[hs[3]] = T * (lx * s_ - ly * c_);
-                    shs[hs[4]] = 2 * Rw[0]; shs[hs[5]] = 2 * Rw[1];
-                }
-            } else if (it < nRS + nPS) {
-                const int e = it - nRS, k = e / M, q = e % M;
-                int a = 0, rem = q;
-                while (rem >= Nr - 1 - a) { rem -= Nr - 1 - a; a++; }
-                const int c2 = a + 1 + rem;
-                const double dx = sw[k * ns + 3 * a] - sw[k * ns + 3 * c2], dy = sw[k * ns + 3 * a + 1] - sw[k * ns + 3 * c2 + 1];
-                sg[(k + 1) * blk + ns + q] = dx * dx + dy * dy;
-                const int *js = tb.jac_ps + (size_t)e * 4;
-                sj[js[0]] = 2 * dx; sj[js[1]] = -2 * dx; sj[js[2]] = 2 * dy; sj[js[3]] = -2 * dy;
-                if (lam && hess) {
-                    const double mu = sl[(k + 1) * blk + ns + q];
-                    const int *hs = tb.hes_ps + (size_t)e * 2;
-                    shs[hs[0]] = -2 * mu; shs[hs[1]] = -2 * mu;
-                }
-            } else if (it < nRS + nPS + ns) {
-                const int r = it - nRS - nPS;
-                sg[r] = sw[r] - sp[r];
-                sj[tb.jac_init[r]] = 1.0;
-            } else if (it < nRS + nPS + ns + M) {
-                sg[ns + (it - nRS - nPS - ns)] = NMPC_DUMMY_ROW_VALUE;
-            } else {
-                sgrad[N * ns + (it - nRS - nPS - ns - M)] = 0.0;  // X_N is not in the cost
-            }
-        }
+        double facc = eval_point_items(Nr, N, T, Qw, Rw, sw, sl, sp, sgrad, sg, sj, shs, tb, lam != nullptr, hess != nullptr);
         // block reduction of f
         for (int m = 16; m > 0; m >>= 1) facc += __shfl_xor_sync(0xffffffffu, facc, m);
         if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = facc;
@@ -183,6 +202,34 @@ __global__ void __launch_bounds__(256) eval_kernel(int Nr, int N, double T, doub
         __syncthreads();
     }
     if (threadIdx.x == 0) bulk_wait_read_all();   // shared memory must outlive the last bulk stores
+}
+
+// Records that do not fit shared memory (more than ~11 robots at N = 20): same work items, written straight to global memory.
+__global__ void __launch_bounds__(256) eval_kernel_big(int Nr, int N, double T, double Q0, double Q1, double Q2, double R0, double R1, int B,
+                                                       const double *__restrict__ w, const double *__restrict__ p,
+                                                       const double *__restrict__ lam, double *__restrict__ f, double *__restrict__ grad,
+                                                       double *__restrict__ g, double *__restrict__ jac, double *__restrict__ hess,
+                                                       NmpcEvalTables tb)
+{
+    __shared__ double sred[8];
+    const int ns = 3 * Nr, nc = 2 * Nr, M = Nr * (Nr - 1) / 2, S = N + 1;
+    const size_t n = (size_t)ns * S + (size_t)nc * N, mg = (size_t)S * (ns + M);
+    const size_t nj = 3 * (size_t)Nr + (size_t)N * (11 * Nr + 4 * M), nh = (size_t)N * (6 * Nr + 2 * M);
+    const double Qw[3] = {Q0, Q1, Q2}, Rw[2] = {R0, R1};
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        double facc = eval_point_items(Nr, N, T, Qw, Rw, w + b * n, lam ? lam + b * mg : nullptr, p + (size_t)b * 2 * ns,
+                                       grad ? grad + b * n : nullptr, g ? g + b * mg : nullptr, jac ? jac + b * nj : nullptr,
+                                       hess ? hess + b * nh : nullptr, tb, lam != nullptr, hess != nullptr);
+        for (int m = 16; m > 0; m >>= 1) facc += __shfl_xor_sync(0xffffffffu, facc, m);
+        if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = facc;
+        __syncthreads();
+        if (threadIdx.x == 0 && f) {
+            double t = 0.0;
+            for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += sred[i];
+            f[b] = t;
+        }
+        __syncthreads();
+    }
 }
 
 // u0 = [u[1:]; u[-1]]  and  X0 = [X[1:]; X[N-1]]   (row N-1, not N: the reference's quirk)

@@ -521,8 +521,14 @@ extern "C" int nmpc_eval(nmpc_handle *h, int B, const double *w, const double *p
 {
     if (!h || !w || !p || B <= 0) return fail(NMPC_EINVAL, "nmpc_eval: bad argument");
     if (hess && !lam_g) return fail(NMPC_EINVAL, "nmpc_eval: hess needs lam_g");
-    if (!h->eval_ok) return fail(NMPC_ENOTSUP, h->family ? "nmpc_eval: not available for the static-obstacle family"
-                                                        : "nmpc_eval: the evaluation record of a %d-robot problem (%zu B) exceeds shared memory", h->d.Nr, h->eval_smem);
+    if (h->family) return fail(NMPC_ENOTSUP, "nmpc_eval: not available for this problem family");
+    if (!h->eval_ok) {   // record larger than shared memory: global-memory variant
+        eval_kernel_big<<<std::min(B, h->sm_count * 8), 256, 0, (cudaStream_t)stream>>>(h->d.Nr, h->d.N, h->d.T, h->d.Q[0], h->d.Q[1], h->d.Q[2],
+                                                                                        h->d.R[0], h->d.R[1], B, w, p, lam_g, f, grad, g, jac, hess, h->tb);
+        h->launches++;
+        CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     int per_sm = (int)std::max<size_t>(1, (size_t)(220 * 1024) / h->eval_smem);
     int blocks = std::min(B, h->sm_count * per_sm);
     const int pf = (std::max(h->n, h->mg) + 255) / 256;

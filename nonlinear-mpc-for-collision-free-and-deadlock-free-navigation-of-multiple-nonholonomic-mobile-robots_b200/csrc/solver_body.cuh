@@ -45,14 +45,7 @@
     auto frow = [=](int k, int i) -> double * { return ws + ((long long)R_COUNT * S + (long long)k * NS + i) * LW; }; \
     auto zvalid = [=](int k) -> bool { return l < (k < N ? NZ : NS); };                                \
     auto gradf = [=](int k, double z) -> double { return (k < N && isz) ? qw * (z - xs_l) : 0.0; };    \
-    /* prefetch up to 16 scratch rows of stage k into L1: lane pair p takes the p-th row of `mask` */ \
-    auto prefetch_lane = [=](unsigned mask) -> int { return (int)wp::nth_set_bit(mask, l / LPR); };     \
-    auto prefetch_at = [=](int rid, int k) {                                                           \
-        if (rid >= 0 && rid < 32 && k >= 0 && k <= N) wp::prefetch(ws + ((long long)rid * S + k) * LW + (l % LPR) * 16); \
-    };                                                                                                 \
-    auto prefetch_rows = [=](unsigned mask, int k) { prefetch_at(prefetch_lane(mask), k); };           \
-    (void)prefetch_lane; (void)prefetch_at;                                                            \
-    (void)row; (void)frow; (void)zvalid; (void)gradf; (void)prefetch_rows;
+    (void)row; (void)frow; (void)zvalid; (void)gradf;
 
 struct alignas(16) NmpcD2 { double x, y; };   // one 128-bit shared-memory load
 

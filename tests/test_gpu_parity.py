@@ -25,7 +25,8 @@ def _t(torch, a):
     return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device="cuda")
 
 
-@pytest.mark.parametrize("Nr,N,T", [(1, 25, 0.25), (2, 7, 0.1), (3, 5, 0.05), (6, 20, 0.3), (6, 35, 0.3), (8, 5, 0.02), (10, 20, 0.1)])
+@pytest.mark.parametrize("Nr,N,T", [(1, 25, 0.25), (2, 7, 0.1), (3, 5, 0.05), (6, 20, 0.3), (6, 35, 0.3), (8, 5, 0.02), (10, 20, 0.1),
+                                    (16, 20, 0.3), (32, 6, 0.1)])   # the last two: records larger than shared memory (eval_kernel_big)
 def test_eval_kernel_matches_oracle(pkg, torch_cuda, Nr, N, T):
     torch = torch_cuda
     rng = np.random.default_rng(Nr + N)
