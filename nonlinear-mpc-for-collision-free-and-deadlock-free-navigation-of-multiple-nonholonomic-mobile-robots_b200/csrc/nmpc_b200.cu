@@ -96,6 +96,10 @@ struct nmpc_handle {
     const int *d_order;                       // optional processing order (device, caller owned), see nmpc_set_order
     int nobs, family, rk_steps;               // static obstacles per robot; family: 0 centralized, 1 obstacles, 2 small OCP (thread per instance)
     double *d_obs;                            // [nobs][3] on the device
+    bool thread_ok;                           // a thread-per-instance kernel exists for this problem (small-OCP family; one robot with
+                                              // static obstacles): used for the small-OCP family always, else from thread_min_batch on
+    size_t t_ws_doubles;                      // its scratch per instance
+    int thread_min_batch;
     bool block_path, eval_ok;                 // Nr > 10: CTA-per-instance dense-block solver; eval record fits shared memory
     int *d_pairs;                             // pair table (i, j) of the inequality rows, block path
     // host-pointer API staging
@@ -206,11 +210,11 @@ extern "C" int nmpc_create_ocp(int model, int N, double T, int rk_steps, const n
     h->ns = TS::NX; h->nc = TS::NU; h->M = 0; h->S = N + 1; h->nobs = 0; h->family = 2; h->rk_steps = rk_steps;
     h->n = TS::NZ * N + TS::NX; h->mg = TS::NX * N; h->np = 0; h->nnzj = 0; h->nnzh = 0;
     h->launches = 0; h->d_buf = nullptr; h->d_bytes = 0; h->stream = nullptr; h->d_tables = nullptr; h->d_pairs = nullptr;
-    h->d_order = nullptr; h->d_obs = nullptr; h->block_path = false; h->eval_ok = false;
+    h->d_order = nullptr; h->d_obs = nullptr; h->block_path = false; h->eval_ok = false; h->thread_ok = true; h->thread_min_batch = 1;
     cudaGetDevice(&h->dev);
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->dev);
-    h->ws_doubles_per_slot = (size_t)TS::ws_doubles(N);
-    h->lw = 0; h->teams_per_cta = 64; h->threads = 64; h->ctas_per_sm = 1 << 16; h->solve_smem = 0; h->eval_smem = 0;
+    h->ws_doubles_per_slot = 0; h->t_ws_doubles = (size_t)TS::ws_doubles(N);
+    h->lw = 0; h->teams_per_cta = 1; h->threads = 64; h->ctas_per_sm = 1; h->solve_smem = 0; h->eval_smem = 0;
     *out = h;
     return 0;
 }
@@ -241,6 +245,14 @@ static int create_impl(const nmpc_desc *d, const nmpc_opts *o, int nobs, const d
     h->d_pairs = nullptr; h->d_order = nullptr;
     // the obstacle family runs on the dense-block path for every Nr; NMPC_FORCE_BLOCK: test hook, any Nr on that path
     h->block_path = d->Nr > 10 || h->family != 0 || getenv("NMPC_FORCE_BLOCK") != nullptr; h->eval_ok = h->family == 0;
+    // A single robot with static obstacles (the reference's obstacle scripts) also runs on the thread-per-instance small-OCP
+    // solver (UnicycleObstacles model), parity-tested, but measured slower than the CTA-per-instance path both alone (88 ms
+    // against 49 ms per solve at N = 100) and in batches (9.2 k against 23.0 k solves/s, B = 8192, N = 20: its per-thread
+    // scratch is not coalesced across instances), so it is off unless NMPC_THREAD_MIN_BATCH sets a switch-over batch size.
+    h->thread_ok = h->family == 1 && d->Nr == 1;
+    h->t_ws_doubles = h->thread_ok ? (size_t)ThreadSolver<UnicycleObstacles>::ws_doubles(d->N) : 0;
+    h->thread_min_batch = 0x7fffffff;
+    if (const char *ov = getenv("NMPC_THREAD_MIN_BATCH")) h->thread_min_batch = atoi(ov) > 0 ? atoi(ov) : 1;
     DBG("device count ok");
     cudaGetDevice(&h->dev);
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->dev);
@@ -354,8 +366,10 @@ static int solve_grid(const nmpc_handle *h, int B)
     return need < cap ? (need > 0 ? need : 1) : cap;
 }
 static size_t bound_rows_bytes(const nmpc_handle *h, int nb) { return (size_t)nb * NMPC_BR_COUNT * h->S * h->lw * sizeof(double); }
+static bool use_thread(const nmpc_handle *h, int B) { return h->thread_ok && B >= h->thread_min_batch; }
 static size_t ws_bytes_for(const nmpc_handle *h, int B, int nb)
 {
+    if (use_thread(h, B)) return 256 + (size_t)((B + 63) / 64 * 64) * h->t_ws_doubles * sizeof(double);
     return 256 + bound_rows_bytes(h, nb) + (size_t)solve_grid(h, B) * h->teams_per_cta * h->ws_doubles_per_slot * sizeof(double);
 }
 extern "C" size_t nmpc_workspace_bytes(const nmpc_handle *h, int B) { return h && B > 0 ? ws_bytes_for(h, B, 1) : 0; }
@@ -371,12 +385,13 @@ static int solve_impl(nmpc_handle *h, int B, const double *x0, const double *p, 
     const int nb = bounds_batched ? B : 1;
     const size_t need = ws_bytes_for(h, B, nb);
     if (workspace_bytes < need) return fail(NMPC_ENOMEM, "nmpc_solve: workspace %zu B < %zu B required", workspace_bytes, need);
+    const bool thr = use_thread(h, B);
     char *base = (char *)workspace;
     int *counter = (int *)base, *berr = counter + 1;
     double *brows = (double *)(base + 256);
-    double *slots = (double *)(base + 256 + bound_rows_bytes(h, nb));
+    double *slots = (double *)(base + 256 + (thr ? 0 : bound_rows_bytes(h, nb)));
     CUDA_OK(cudaMemsetAsync(base, 0, 256, st));
-    if (h->family != 2) {
+    if (!thr) {
         long long total = (long long)nb * h->S * h->lw;
         int blocks = (int)std::min<long long>((total + 255) / 256, 4096);
         prep_bounds_kernel<<<blocks, 256, 0, st>>>(h->d.Nr, h->d.N, h->o.bound_relax_factor, nb, h->lw, lbx, ubx, lbg, ubg, brows, berr, h->nobs, h->family);
@@ -389,11 +404,12 @@ static int solve_impl(nmpc_handle *h, int B, const double *x0, const double *p, 
     P.o = h->o; P.x0 = x0; P.p = p; P.brows = brows;
     P.bstride = bounds_batched ? (long long)NMPC_BR_COUNT * h->S * h->lw : 0;
     P.bound_err = berr; P.x = x; P.f = f; P.g = g; P.lam_x = lam_x; P.lam_g = lam_g; P.status = status; P.iters = iters;
-    P.stats = stats; P.trace = trace; P.max_trace = max_trace; P.ws = slots; P.ws_stride = (long long)h->ws_doubles_per_slot;
+    P.stats = stats; P.trace = trace; P.max_trace = max_trace; P.ws = slots; P.ws_stride = (long long)(thr ? h->t_ws_doubles : h->ws_doubles_per_slot);
     P.counter = counter; P.pairs = h->d_pairs; P.order = h->d_order; P.nobs = h->nobs; P.family = h->family; P.obs = h->d_obs;
-    P.lbx = lbx; P.ubx = ubx; P.lbg = lbg; P.ubg = ubg; P.bounds_batched = bounds_batched; P.rk_steps = h->rk_steps;
-    const int grid = solve_grid(h, B);
-    if (h->family == 2) solve_kernel_small_ocp<VanDerPol><<<grid, h->threads, 0, st>>>(P);
+    P.lbx = lbx; P.ubx = ubx; P.lbg = lbg; P.ubg = ubg; P.bounds_batched = bounds_batched; P.rk_steps = h->rk_steps; P.np = h->np;
+    const int grid = thr ? (B + 63) / 64 : solve_grid(h, B);
+    if (thr && h->family == 2) solve_kernel_small_ocp<VanDerPol><<<grid, 64, 0, st>>>(P);
+    else if (thr) solve_kernel_small_ocp<UnicycleObstacles><<<grid, 64, 0, st>>>(P);
     else if (h->block_path) solve_kernel_block<<<grid, h->threads, h->solve_smem, st>>>(P);
     else switch (h->d.Nr) {
         case 1: solve_kernel<1><<<grid, h->threads, h->solve_smem, st>>>(P); break;

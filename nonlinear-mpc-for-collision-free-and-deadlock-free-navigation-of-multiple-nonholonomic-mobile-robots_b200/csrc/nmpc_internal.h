@@ -37,7 +37,7 @@ typedef struct NmpcSolveParams {
     int nobs, family;                /* static obstacles per robot; row layout (0 / 1)   */
     const double *obs;               /* [nobs][3] centre x, y, clearance radius (device) */
     const double *lbx, *ubx, *lbg, *ubg;  /* flat bounds (small-OCP family reads them directly) */
-    int bounds_batched, rk_steps;
+    int bounds_batched, rk_steps, np;
 } NmpcSolveParams;
 
 #endif

@@ -54,9 +54,14 @@ def _t(torch, a):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("path", ["cta", "thread"])
 @pytest.mark.parametrize("case", ["one", "six"])
-def test_gpu_obstacle_family_matches_slsqp(pkg, torch_cuda, case):
+def test_gpu_obstacle_family_matches_slsqp(pkg, torch_cuda, case, path, monkeypatch):
+    """Both kernels that serve this family: the CTA-per-instance dense-block solver (small batches) and the
+    thread-per-instance small-OCP solver (large batches; forced here with NMPC_THREAD_MIN_BATCH=1)."""
     torch = torch_cuda
+    if path == "thread":
+        monkeypatch.setenv("NMPC_THREAD_MIN_BATCH", "1")
     if case == "one":      # first scenario geometry, shortened horizon: obstacle between start and goal
         N, T, obs, margin = 15, 0.3, np.array([[0.45, 0.5, 0.3]]), 0.05
         P = np.array([[0.0, 0.0, 0.6, 1.2, 1.3, 0.0], [0.1, -0.1, 0.9, 1.0, 1.4, 0.3]])
