@@ -614,12 +614,15 @@ struct BlockSolver {
                 if (wid < nblk) {
                     const int o = wid * 32;
                     double x[32];
+                    const int nb_ = nc - o < 32 ? nc - o : 32;   // rows of this block that exist (the padding is an identity)
 #pragma unroll
                     for (int i = 0; i < 32; i++) {
                         double acc = i == lane ? 1.0 : 0.0;
+                        if (i < nb_) {
 #pragma unroll
-                        for (int jj = 0; jj < i; jj++) acc -= Ls[(o + i) * ncp + o + jj] * x[jj];   // x[jj] = 0 for jj < lane
-                        x[i] = i >= lane ? acc / Ls[(o + i) * ncp + o + i] : 0.0;
+                            for (int jj = 0; jj < i; jj++) acc -= Ls[(o + i) * ncp + o + jj] * x[jj];   // x[jj] = 0 for jj < lane
+                            x[i] = i >= lane ? acc / Ls[(o + i) * ncp + o + i] : 0.0;
+                        } else x[i] = acc;
                     }
                     __syncwarp();
 #pragma unroll
@@ -815,7 +818,9 @@ struct BlockSolver {
                         double ti = gi < nc ? tb[gi] : 0.0;
                         for (int w = 0; w < nw; w++) ti -= red[w * 32 + i];
                         double acc = ti / __ldg(Lk + (long long)gi * ncp + gi);
-                        for (int u = 1; u < 32; u++) {
+                        const int nb_ = nc - 32 * I < 32 ? nc - 32 * I : 32;   // rows of this block that exist
+#pragma unroll 8
+                        for (int u = 1; u < nb_; u++) {   // (independent loads: the unrolled loop keeps eight in flight)
                             const double tu = __shfl_sync(0xffffffffu, ti, u);
                             const double lv = u > i ? __ldg(Lk + (long long)gi * ncp + 32 * I + u) : 0.0;
                             acc += lv * tu;

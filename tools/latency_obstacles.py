@@ -19,3 +19,7 @@ for step in range(40):
     p[0, 0] += T * U[0, 0] * np.cos(th); p[0, 1] += T * U[0, 0] * np.sin(th); p[0, 2] += T * U[0, 1]
     w = np.concatenate([np.concatenate([X[1:], X[N - 1:N]]).ravel(), np.concatenate([U[1:], U[-1:]]).ravel()])[None]
 print("N=%d: p50 %.2f ms  p95 %.2f ms  first(cold) %.1f ms  mean warm iters %.1f  status %s" % (N, 1e3 * np.median(times[1:]), 1e3 * np.percentile(times[1:], 95), 1e3 * times[0], np.mean(its[1:]), o["status"]))
+import ctypes
+prof = (ctypes.c_longlong * 16)()
+prob.L.nmpc_debug_block_profile(prof, 1)
+print("phase Mcycles [prepass, matvec, build, cholesky, trsm, syrk, forward, eval]:", [round(v / 1e6, 1) for v in prof[:8]])
