@@ -176,6 +176,8 @@ class Problem:
         x0, p = np.atleast_2d(f64(x0)), np.atleast_2d(f64(p))
         lbx, ubx, lbg, ubg = f64(lbx), f64(ubx), f64(lbg), f64(ubg)
         B = x0.shape[0]
+        if getattr(self, "_order", None) is not None and self._order.numel() != B:
+            raise ValueError("the scheduling order set with set_order() has %d entries, the batch has %d" % (self._order.numel(), B))
         if x0.shape[1] != self.n or p.shape != (B, self.np_):
             raise ValueError("x0 must be [B,%d] and p [B,%d]" % (self.n, self.np_))
         batched = 1 if lbx.ndim == 2 else 0
@@ -216,6 +218,8 @@ class Problem:
         for t in (x0, p, lbx, ubx, lbg, ubg):
             if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
                 raise ValueError("inputs must be contiguous float64 CUDA tensors")
+        if getattr(self, "_order", None) is not None and self._order.numel() != B:
+            raise ValueError("the scheduling order set with set_order() has %d entries, the batch has %d" % (self._order.numel(), B))
         batched = 1 if lbx.dim() == 2 else 0
         ws = self.workspace(B, bool(batched))
         o = out if out is not None else {}
@@ -298,6 +302,8 @@ def closed_loop(prob, P, lbx, ubx, lbg, ubg, steps, tol=1e-1, dmin=None):
     traj[0] = p[:, :ns]
     out = {}
     for t in range(steps):
+        if t == 0:
+            prob.set_order(None)
         active = (p[:, :ns] - p[:, ns:]).norm(dim=1) > tol
         act[t] = active
         prob.solve(x0, p, lbx, ubx, lbg, ubg, want=(), out=out)
