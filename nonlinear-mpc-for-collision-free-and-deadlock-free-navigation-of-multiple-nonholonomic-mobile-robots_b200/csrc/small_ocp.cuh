@@ -88,6 +88,7 @@ struct OcpCtx {
 struct VanDerPol {
     static constexpr int NX = 2, NU = 1, MAXI = 0;
     static constexpr bool INIT_ROWS = false;      // the initial state is fixed through its bounds (:79-80)
+    static constexpr int EQ_SIGN = 1;             // shooting rows are reported as F(X_k, U_k) - X_{k+1} (:104)
     template <class S> static __host__ __device__ void f(const S *x, const S *u, S *xdot, S &L)
     {
         const S one = S::constant(1.0);
@@ -110,6 +111,7 @@ struct VanDerPol {
 struct UnicycleObstacles {
     static constexpr int NX = 3, NU = 2, MAXI = NMPC_MAX_OBSTACLES;
     static constexpr bool INIT_ROWS = true;       // g starts with X_0 - x0bar (:109)
+    static constexpr int EQ_SIGN = -1;            // shooting rows are reported as X_{k+1} - (X_k + T f) (:122-123)
     template <class S> static __device__ void step(const OcpCtx &c, int, const S *x, const S *u, S *xf, S &q)
     {
         const S cs = jcos(x[2]), sn = jsin(x[2]);
@@ -290,7 +292,7 @@ struct ThreadSolver {
     // equality residual of stage k: F(z_{k-1}) - X_k - ce (k >= 1), x0bar - X_0 - ce (k = 0, INIT_ROWS)
     __device__ __forceinline__ double eqres(int k, int i, const double *xk) const
     {
-        return (k == 0 ? Model::x0bar(ctx, i) : cst(k - 1)[C_F + i]) - xk[i] - (k == 0 ? -row(R_CE, 0)[i] : row(R_CE, k)[i]);
+        return (k == 0 ? Model::x0bar(ctx, i) : cst(k - 1)[C_F + i]) - xk[i] - (k == 0 ? -1.0 : (double)Model::EQ_SIGN) * row(R_CE, k)[i];
     }
 
     __device__ __noinline__ void init_point()
@@ -639,7 +641,7 @@ struct ThreadSolver {
                 model(k, zt);
                 for (int i = 0; i < LD; i++)
                     row(R_DS, k)[i] = (i < ni && qact(k, i)) ? WS::push_in(cin(k, i)[0], row(R_DL, k)[i], row(R_DU, k)[i], o.bound_push, o.bound_frac) - row(R_S, k)[i] : 0.0;
-                for (int i = 0; i < NX; i++) zt[i] = WS::push_in(cst(k)[C_F + i] - row(R_CE, k + 1)[i], row(R_BL, k + 1)[i], row(R_BU, k + 1)[i], o.bound_push, o.bound_frac);
+                for (int i = 0; i < NX; i++) zt[i] = WS::push_in(cst(k)[C_F + i] - Model::EQ_SIGN * row(R_CE, k + 1)[i], row(R_BL, k + 1)[i], row(R_BU, k + 1)[i], o.bound_push, o.bound_frac);
                 for (int u = 0; u < NU; u++) zt[NX + u] = k + 1 < N ? row(R_Z, k + 1)[NX + u] : 0.0;
             }
         }
@@ -699,7 +701,7 @@ struct ThreadSolver {
         for (int k = kfirst(); k <= N; k++)
             for (int i = 0; i < NX; i++) {
                 const long long r = inst * mg + Model::grow_eq(ctx, k, i);
-                const double sgn = k == 0 ? -1.0 : 1.0;   // the initial rows are reported as X_0 - x0bar
+                const double sgn = k == 0 ? -1.0 : (double)Model::EQ_SIGN;   // the initial rows are reported as X_0 - x0bar
                 if (P.g) P.g[r] = sgn * ((k == 0 ? Model::x0bar(ctx, i) : cst(k - 1)[C_F + i]) - row(R_Z, k)[i]);
                 if (P.lam_g) P.lam_g[r] = sgn * row(R_YC, k)[i] / df;
             }

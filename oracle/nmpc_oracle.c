@@ -27,24 +27,51 @@
 /* ------------------------------------------------------------------------------------ */
 typedef struct {
     int Nr, N, ns, nc, nz, M, n, mg, blk, nX, nI, nE;
+    int Mp, nobs;      /* M = Mp pair rows + Nr * nobs obstacle rows per block */
+    const double *obs;
     double T, Q[3], R[2];
     int *pi, *pj; /* lexicographic pairs i<j  (...six...py:288-306) */
 } dims_t;
+
+/* offset of block b in the flat g / lbg / ubg / lam_g vectors: the obstacle family has no inequality rows in block 0 */
+static inline int goff(const dims_t *D, int b) { return D->nobs ? (b == 0 ? 0 : D->ns + (b - 1) * D->blk) : b * D->blk; }
+
+/* inequality row q of a block on the stage vector zk: value, gradient w.r.t. (x_i, y_i) (negated for robot j of a pair;
+ * j = -1 for an obstacle row, first_scenario_mpc_obstacle_avoidance.py:125) and its second derivatives */
+typedef struct { double dv, gx, gy, hxx, hyy, hxy; int i, j; } rowg_t;
+static inline rowg_t row_geom(const dims_t *D, const double *zk, int q)
+{
+    rowg_t r;
+    if (q < D->Mp) {
+        r.i = D->pi[q]; r.j = D->pj[q];
+        double dx = zk[3 * r.i] - zk[3 * r.j], dy = zk[3 * r.i + 1] - zk[3 * r.j + 1];
+        r.dv = dx * dx + dy * dy; r.gx = 2 * dx; r.gy = 2 * dy; r.hxx = 2; r.hyy = 2; r.hxy = 0;
+    } else {
+        int e = q - D->Mp, o = e % D->nobs;
+        r.i = e / D->nobs; r.j = -1;
+        double dx = zk[3 * r.i] - D->obs[3 * o], dy = zk[3 * r.i + 1] - D->obs[3 * o + 1];
+        double rho = sqrt(dx * dx + dy * dy);
+        r.gx = dx / rho; r.gy = dy / rho; r.dv = rho - D->obs[3 * o + 2];
+        r.hxx = (1 - r.gx * r.gx) / rho; r.hyy = (1 - r.gy * r.gy) / rho; r.hxy = -r.gx * r.gy / rho;
+    }
+    return r;
+}
 
 static void dims_init(dims_t *D, const orc_desc *d)
 {
     D->Nr = d->Nr; D->N = d->N; D->T = d->T;
     memcpy(D->Q, d->Q, sizeof D->Q); memcpy(D->R, d->R, sizeof D->R);
     D->ns = 3 * d->Nr; D->nc = 2 * d->Nr; D->nz = 5 * d->Nr;
-    D->M = d->Nr * (d->Nr - 1) / 2;
+    D->Mp = d->Nr * (d->Nr - 1) / 2; D->nobs = d->obs ? d->nobs : 0; D->obs = d->obs;
+    D->M = D->Mp + d->Nr * D->nobs;
     D->nX = D->ns * (D->N + 1);
     D->n = D->nX + D->nc * D->N;
     D->blk = D->ns + D->M;
-    D->mg = (D->N + 1) * D->blk;
+    D->mg = D->nobs ? D->ns + D->N * D->blk : (D->N + 1) * D->blk;
     D->nI = (D->N + 1) * D->M;
     D->nE = (D->N + 1) * D->ns;
-    D->pi = (int *)malloc(sizeof(int) * (D->M + 1));
-    D->pj = (int *)malloc(sizeof(int) * (D->M + 1));
+    D->pi = (int *)malloc(sizeof(int) * (D->Mp + 1));
+    D->pj = (int *)malloc(sizeof(int) * (D->Mp + 1));
     int q = 0;
     for (int i = 0; i < D->Nr; i++)
         for (int j = i + 1; j < D->Nr; j++) { D->pi[q] = i; D->pj[q] = j; q++; }
@@ -52,7 +79,12 @@ static void dims_init(dims_t *D, const orc_desc *d)
 static void dims_free(dims_t *D) { free(D->pi); free(D->pj); }
 
 int orc_n(const orc_desc *d) { return 3 * d->Nr * (d->N + 1) + 2 * d->Nr * d->N; }
-int orc_mg(const orc_desc *d) { return (d->N + 1) * (3 * d->Nr + d->Nr * (d->Nr - 1) / 2); }
+int orc_mg(const orc_desc *d)
+{
+    int M = d->Nr * (d->Nr - 1) / 2;
+    if (d->obs && d->nobs > 0) return 3 * d->Nr + d->N * (3 * d->Nr + M + d->Nr * d->nobs);
+    return (d->N + 1) * (3 * d->Nr + M);
+}
 int orc_nnz_jac(const orc_desc *d)
 { int M = d->Nr * (d->Nr - 1) / 2; return 3 * d->Nr + d->N * (11 * d->Nr + 4 * M); }
 int orc_nnz_hess(const orc_desc *d)
@@ -298,11 +330,7 @@ static void eval_cons(const ctx_t *C, const double *z, double *c, double *dv)
             ck[3 * i + 2] = zn[3 * i + 2] - (th + T * om) - ce[3 * i + 2];
         }
         double *dk = dv + (k + 1) * M;
-        for (int q = 0; q < M; q++) {
-            int i = D->pi[q], j = D->pj[q];
-            double dx = zk[3 * i] - zk[3 * j], dy = zk[3 * i + 1] - zk[3 * j + 1];
-            dk[q] = dx * dx + dy * dy;
-        }
+        for (int q = 0; q < M; q++) dk[q] = row_geom(D, zk, q).dv;
     }
 }
 
@@ -351,10 +379,9 @@ static void eval_jtv(const ctx_t *C, const double *z, const double *yc, const do
             ok[ns + 2 * i + 1] -= T * lt;
         }
         for (int q = 0; q < M; q++) {
-            int i = D->pi[q], j = D->pj[q];
-            double dx = zk[3 * i] - zk[3 * j], dy = zk[3 * i + 1] - zk[3 * j + 1];
-            ok[3 * i] += 2 * dx * mu[q]; ok[3 * j] -= 2 * dx * mu[q];
-            ok[3 * i + 1] += 2 * dy * mu[q]; ok[3 * j + 1] -= 2 * dy * mu[q];
+            rowg_t g = row_geom(D, zk, q);
+            ok[3 * g.i] += g.gx * mu[q]; ok[3 * g.i + 1] += g.gy * mu[q];
+            if (g.j >= 0) { ok[3 * g.j] -= g.gx * mu[q]; ok[3 * g.j + 1] -= g.gy * mu[q]; }
         }
     }
 }
@@ -427,11 +454,17 @@ static int kkt_solve(ctx_t *C, const double *z, const double *ycW, const double 
         for (int q = 0; q < M; q++) {
             int r = (k + 1) * M + q;
             if (!act[r]) continue;
-            int i = D->pi[q], j = D->pj[q];
-            double gxq = 2 * (zk[3 * i] - zk[3 * j]), gyq = 2 * (zk[3 * i + 1] - zk[3 * j + 1]);
-            double Dq = sigs[r] + delta, mu2 = 2 * ydW[r], hq = Dq * rd[r] + gs[r];
-            double xx = Dq * gxq * gxq + mu2, yy = Dq * gyq * gyq + mu2, xy = Dq * gxq * gyq;
+            rowg_t rg = row_geom(D, zk, q);
+            int i = rg.i, j = rg.j;
+            double gxq = rg.gx, gyq = rg.gy;
+            double Dq = sigs[r] + delta, hq = Dq * rd[r] + gs[r];
+            double xx = Dq * gxq * gxq + ydW[r] * rg.hxx, yy = Dq * gyq * gyq + ydW[r] * rg.hyy, xy = Dq * gxq * gyq + ydW[r] * rg.hxy;
             int xi = 3 * i, yi = 3 * i + 1, xj = 3 * j, yj = 3 * j + 1;
+            if (j < 0) { /* obstacle row: only robot i's own block */
+                Mw[xi * nz + xi] += xx; Mw[yi * nz + yi] += yy; Mw[xi * nz + yi] += xy; Mw[yi * nz + xi] += xy;
+                m[xi] += gxq * hq; m[yi] += gyq * hq;
+                continue;
+            }
             Mw[xi * nz + xi] += xx; Mw[xj * nz + xj] += xx; Mw[xi * nz + xj] -= xx; Mw[xj * nz + xi] -= xx;
             Mw[yi * nz + yi] += yy; Mw[yj * nz + yj] += yy; Mw[yi * nz + yj] -= yy; Mw[yj * nz + yi] -= yy;
             Mw[xi * nz + yi] += xy; Mw[yi * nz + xi] += xy; Mw[xj * nz + yj] += xy; Mw[yj * nz + xj] += xy;
@@ -503,9 +536,9 @@ static int kkt_solve(ctx_t *C, const double *z, const double *ycW, const double 
         for (int q = 0; q < M; q++) {
             int r = (k + 1) * M + q;
             if (!act[r]) { ds[r] = 0; ytd[r] = 0; continue; }
-            int i = D->pi[q], j = D->pj[q];
-            double gxq = 2 * (zk[3 * i] - zk[3 * j]), gyq = 2 * (zk[3 * i + 1] - zk[3 * j + 1]);
-            ds[r] = gxq * (dk[3 * i] - dk[3 * j]) + gyq * (dk[3 * i + 1] - dk[3 * j + 1]) + rd[r];
+            rowg_t rg = row_geom(D, zk, q);
+            double ddx = dk[3 * rg.i] - (rg.j >= 0 ? dk[3 * rg.j] : 0.0), ddy = dk[3 * rg.i + 1] - (rg.j >= 0 ? dk[3 * rg.j + 1] : 0.0);
+            ds[r] = rg.gx * ddx + rg.gy * ddy + rd[r];
             ytd[r] = (sigs[r] + delta) * ds[r] + gs[r];
         }
     }
@@ -738,12 +771,14 @@ static int solve_one(const orc_desc *d, const orc_opts *o, const double *x0, con
         }
         for (int b = 0; b <= N; b++) {
             for (int j = 0; j < ns; j++) {
-                double l = lbg[b * D->blk + j], u = ubg[b * D->blk + j];
+                double l = lbg[goff(D, b) + j], u = ubg[goff(D, b) + j];
                 if (!(l == u) || !isfinite(l)) { rc = -4; goto done; } /* dynamics rows must be equalities */
                 C.ceq[b * ns + j] = l;
             }
             for (int qq = 0; qq < M; qq++) {
-                double l = lbg[b * D->blk + ns + qq], u = ubg[b * D->blk + ns + qq]; int e = b * M + qq;
+                int e = b * M + qq;
+                if (D->nobs && b == 0) { C.dl[e] = -INFINITY; C.du[e] = INFINITY; V.act[e] = 0; continue; } /* no such rows */
+                double l = lbg[goff(D, b) + ns + qq], u = ubg[goff(D, b) + ns + qq];
                 if (!(l <= u)) { rc = -2; goto done; }
                 if (l == u) { rc = -5; goto done; } /* equality on a distance row: unsupported */
                 C.dl[e] = l > -INFINITY ? l - o->bound_relax_factor * fmax(1.0, fabs(l)) : -INFINITY;
@@ -1150,15 +1185,25 @@ finished:
     /* ---- outputs in the reference layout, multipliers in CasADi's sign convention ---- */
     stage_to_flat(D, V.z, x);
     if (f) *f = eval_obj(&C, V.z);
-    if (g) orc_eval(d, x, p, NULL, NULL, NULL, g, NULL, NULL);
+    if (g && !D->nobs) orc_eval(d, x, p, NULL, NULL, NULL, g, NULL, NULL);
+    if (g && D->nobs) { /* the obstacle family is outside orc_eval: rows from the stage-layout evaluation */
+        double *cc = (double *)malloc(sizeof(double) * (nE + nI + 1)), *dd = cc + nE;
+        const double *ce0 = C.ceq; double *zero = (double *)calloc(nE, sizeof(double));
+        C.ceq = zero; eval_cons(&C, V.z, cc, dd); C.ceq = (double *)ce0;
+        for (int b = 0; b <= N; b++) {
+            for (int j = 0; j < ns; j++) g[goff(D, b) + j] = cc[b * ns + j];
+            if (b > 0) for (int qq = 0; qq < M; qq++) g[goff(D, b) + ns + qq] = dd[b * M + qq];
+        }
+        free(cc); free(zero);
+    }
     if (lam_x) {
         for (size_t e = 0; e < nZ; e++) V.zt[e] = (V.zU[e] - V.zL[e]) / C.df;
         stage_to_flat(D, V.zt, lam_x);
     }
     if (lam_g)
         for (int b = 0; b <= N; b++) {
-            for (int j = 0; j < ns; j++) lam_g[b * D->blk + j] = V.yc[b * ns + j] / C.df;
-            for (int qq = 0; qq < M; qq++) lam_g[b * D->blk + ns + qq] = V.yd[b * M + qq] / C.df;
+            for (int j = 0; j < ns; j++) lam_g[goff(D, b) + j] = V.yc[b * ns + j] / C.df;
+            if (!(D->nobs && b == 0)) for (int qq = 0; qq < M; qq++) lam_g[goff(D, b) + ns + qq] = V.yd[b * M + qq] / C.df;
         }
     if (status) *status = st;
     if (iters) *iters = iter;

@@ -27,6 +27,12 @@ typedef struct {
     double T;     /* sampling period                                              */
     double Q[3];  /* diag state weights  (1,5,0.1)  ...six...py:252-259            */
     double R[2];  /* diag control weights (0.5,0.05) ...six...py:261-266           */
+    /* static circular obstacles (first_/third_scenario_mpc_obstacle_avoidance.py:96-152); 0 / NULL = the centralized family.
+     * With nobs > 0 every robot gets nobs rows per stage  sqrt((x-ox)^2+(y-oy)^2) - clearance  after the pair rows, block 0 of
+     * g holds the initial condition only (no dummy rows), mg = 3Nr + N(3Nr + M + Nr nobs); orc_eval and the CCS patterns do
+     * not cover this family (orc_solve / orc_solve_batch do). */
+    int nobs;
+    const double *obs;  /* [nobs][3] = centre x, y, clearance (rob_dim + r_obs) */
 } orc_desc;
 
 typedef struct {

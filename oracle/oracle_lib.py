@@ -20,7 +20,8 @@ STATUS = {0: "SOLVED", 1: "ACCEPTABLE", 2: "MAX_ITER", 3: "INFEASIBLE", 4: "NUME
 
 
 class Desc(C.Structure):
-    _fields_ = [("Nr", C.c_int), ("N", C.c_int), ("T", C.c_double), ("Q", C.c_double * 3), ("R", C.c_double * 2)]
+    _fields_ = [("Nr", C.c_int), ("N", C.c_int), ("T", C.c_double), ("Q", C.c_double * 3), ("R", C.c_double * 2),
+                ("nobs", C.c_int), ("obs", C.c_void_p)]
 
 
 class Opts(C.Structure):
@@ -85,9 +86,13 @@ def _f64(a):
 class Oracle:
     """Nr-robot, horizon-N unicycle NLP + restated IPOPT on the CPU."""
 
-    def __init__(self, Nr, N, T, Q=(1.0, 5.0, 0.1), R=(0.5, 0.05), **opts):
+    def __init__(self, Nr, N, T, Q=(1.0, 5.0, 0.1), R=(0.5, 0.05), obstacles=None, **opts):
+        """obstacles: [n_obs, 3] (centre x, y, clearance): the static-obstacle family (first_scenario_mpc_obstacle_avoidance.py)."""
         self.L = lib()
-        self.d = Desc(int(Nr), int(N), float(T), (C.c_double * 3)(*Q), (C.c_double * 2)(*R))
+        self.obstacles = None if obstacles is None else np.ascontiguousarray(np.asarray(obstacles, dtype=np.float64).reshape(-1, 3))
+        self.d = Desc(int(Nr), int(N), float(T), (C.c_double * 3)(*Q), (C.c_double * 2)(*R),
+                      0 if self.obstacles is None else int(self.obstacles.shape[0]),
+                      None if self.obstacles is None else self.obstacles.ctypes.data)
         self.o = Opts()
         self.L.orc_default_opts(C.byref(self.o))
         for k, v in opts.items():

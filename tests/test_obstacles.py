@@ -42,6 +42,36 @@ def test_slsqp_reference_solution_avoids_the_obstacle():
     assert (g[lbg != ubg] < 0.05 + 1e-6).any(), "the obstacle should be active on the way to the goal"
 
 
+def _cases():
+    one = dict(N=15, T=0.3, obs=np.array([[0.45, 0.5, 0.3]]), margin=0.05,
+               P=np.array([[0.0, 0.0, 0.6, 1.2, 1.3, 0.0], [0.1, -0.1, 0.9, 1.0, 1.4, 0.3]]))
+    six = dict(N=20, T=0.3, obs=_obs(THIRD), margin=0.1,
+               P=np.array([[0.0, 0.6, 1.57, 0.1, 3.9, 1.57], [0.3, 0.7, 1.2, -0.2, 3.6, 1.57]]))
+    return {"one": one, "six": six}
+
+
+@pytest.mark.parametrize("case", ["one", "six"])
+def test_c_oracle_covers_the_obstacle_family(case):
+    """oracle/nmpc_oracle.c with obstacle rows (restated IPOPT, same algorithm as for the robot pairs): its solution is a KKT point
+    of the NumPy restatement, in the scripts' row layout, and agrees with the independent SLSQP solve."""
+    from oracle.oracle_lib import Oracle
+    c = _cases()[case]
+    nlp, orc = ObstacleNLP(c["N"], c["T"], c["obs"]), Oracle(1, c["N"], c["T"], obstacles=c["obs"])
+    assert (orc.n, orc.mg) == (nlp.n, nlp.mg)
+    lbx, ubx, lbg, ubg = nlp.bounds(c["margin"], 0.2, np.pi / 4)
+    for p in c["P"]:
+        r = orc.solve(nlp.cold_start(p[:3]), p, lbx, ubx, lbg, ubg)
+        assert r["status"] == 0 and r["stats"][0] <= 1e-8
+        np.testing.assert_allclose(r["g"], nlp.g(r["x"], p), atol=1e-12)
+        assert abs(r["f"] - nlp.f(r["x"], p)) <= 1e-10 * max(1.0, abs(r["f"]))
+        ref = nlp.solve_slsqp(nlp.cold_start(p[:3]), p, lbx, ubx, lbg, ubg)
+        if np.abs(ref.x - r["x"])[nlp.nX:].max() > 1e-4:
+            ref = nlp.solve_slsqp(r["x"], p, lbx, ubx, lbg, ubg)
+            assert ref.fun >= r["f"] - 1e-9 * max(1.0, abs(r["f"]))
+        assert abs(ref.fun - r["f"]) <= 1e-6 * max(1.0, abs(r["f"]))
+        assert np.abs(ref.x - r["x"])[nlp.nX:].max() <= 1e-4
+
+
 @pytest.fixture(scope="module")
 def torch_cuda():
     import torch
@@ -95,6 +125,15 @@ def test_gpu_obstacle_family_matches_slsqp(pkg, torch_cuda, case, path, monkeypa
             assert ref.fun >= f[b] - 1e-9 * max(1.0, abs(f[b])), (ref.fun, f[b])
         assert abs(ref.fun - f[b]) <= 1e-6 * max(1.0, abs(f[b])), (ref.fun, f[b])
         assert du <= 1e-4, du
+    # and against the C oracle (the same restated IPOPT algorithm): same point, same multipliers, iteration counts within 3
+    from oracle.oracle_lib import Oracle
+    orc = Oracle(1, N, T, obstacles=obs)
+    refb = orc.solve_batch(x0, P, lbx, ubx, lbg, ubg, want_duals=True)
+    assert (refb["status"] == 0).all()
+    assert np.abs(refb["x"] - x)[:, nlp.nX:].max() <= 1e-4
+    assert (np.abs(refb["f"] - f) <= 1e-6 * np.maximum(1.0, np.abs(f))).all()
+    assert np.abs(out["iters"].cpu().numpy() - refb["iters"]).max() <= 3, (out["iters"].cpu().numpy(), refb["iters"])
+    np.testing.assert_allclose(out["lam_g"].cpu().numpy(), refb["lam_g"], rtol=0, atol=1e-5 * max(1.0, np.abs(refb["lam_g"]).max()))
 
 
 @pytest.mark.gpu
