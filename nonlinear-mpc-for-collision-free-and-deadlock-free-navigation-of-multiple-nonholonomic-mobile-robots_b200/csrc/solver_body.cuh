@@ -85,7 +85,7 @@ struct WarpSolver {
     // slots of the forward pass's staging buffer (sm + SM_MC, NZ + STG_ROWS rows): NS factor rows, vectors of stage k, then of block k+1
     enum { WS_LIN = NS, WS_DG, WS_Z, WS_ZL, WS_ZU, WS_BL, WS_BU, WS_GX, WS_COEF, WS_RC, WS_DL, WS_DU, WS_GS, WS_GXQ, WS_GYQ, WS_RD, WS_DQ,
            WS_S, WS_VL, WS_VU, WS_COUNT };
-    static_assert(FS_COUNT <= STG_ROWS && WS_COUNT <= NZ + STG_ROWS && WS_COUNT <= 64, "staging buffers");
+    static_assert((int)FS_COUNT <= (int)STG_ROWS && (int)WS_COUNT <= NZ + (int)STG_ROWS && (int)WS_COUNT <= 64, "staging buffers");
 
     // Issue the asynchronous copies of one stage's rows: slot s <- tab[s] + (k + (s >= kofs_from)) rows, stage clamped to N.
     // Two rows per warp instruction (16 bytes per lane); completion: wp::cp_async_wait() + tsync().
