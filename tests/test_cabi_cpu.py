@@ -35,6 +35,12 @@ def test_no_cpu_fallback(pkg):
         pytest.skip("GPU present")
     with pytest.raises(pkg.NmpcError):
         pkg.Problem(2, 5, 0.1)
+    with pytest.raises(pkg.NmpcError):
+        pkg.Problem(1, 5, 0.1, obstacles=[[0.5, 0.5, 0.3]])      # static-obstacle family
+    with pytest.raises(pkg.NmpcError):
+        pkg.Problem(16, 5, 0.1)                                   # dense-block path
+    with pytest.raises(pkg.NmpcError):
+        pkg.SmallOcp("van_der_pol")                               # small-OCP family
 
 
 def test_casadi_helpers_are_column_major(pkg):
