@@ -481,12 +481,20 @@ struct BlockSolver {
             // A. pr = p_{k+1} - P_{k+1} rc_{k+1}   (one warp per row)
             {
                 const double *rcn = row(R_RC, k + 1), *pn = row(R_LIN, k + 1);
-                for (int r = wid; r < ns; r += nw) {
-                    double acc = 0.0;
-                    for (int j = lane; j < ns; j += 32) acc += Pn[r * ns + j] * rcn[j];
+                for (int r0 = wid; r0 < ns; r0 += 4 * nw) {   // four rows per warp at a time: four times the loads in flight
+                    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+                    for (int j = lane; j < ns; j += 32) {
+                        const double v = rcn[j];
 #pragma unroll
-                    for (int m = 16; m > 0; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
-                    if (lane == 0) prv[r] = pn[r] - acc;
+                        for (int q = 0; q < 4; q++) { const int r = r0 + q * nw; if (r < ns) acc[q] += Pn[r * ns + j] * v; }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+#pragma unroll
+                        for (int m = 16; m > 0; m >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], m);
+                        const int r = r0 + q * nw;
+                        if (lane == 0 && r < ns) prv[r] = pn[r] - acc[q];
+                    }
                 }
             }
             // per-robot sums of the condensed collision blocks (curvature and gradient), one (array, robot) per thread
@@ -719,9 +727,12 @@ struct BlockSolver {
             // F. P_k = M_xx - Y'Y (upper 4x4 tiles over Y resident in shared memory, mirrored), p_k = m_x - Y' y_m
             {
                 const int ns4 = (ns + 3) & ~3, nt4 = ns4 / 4;
-                for (int e = tid; e < nt4 * nt4; e += nt) {
-                    const int tr = e / nt4, tc = e - tr * nt4;
-                    if (tc < tr) continue;
+                const int ntri = nt4 * (nt4 + 1) / 2;   // upper-triangular tiles, enumerated densely: every thread gets its share
+                for (int e = tid; e < ntri; e += nt) {
+                    int tr = (int)(((2 * nt4 + 1) - sqrt((double)(2 * nt4 + 1) * (2 * nt4 + 1) - 8.0 * e)) * 0.5);
+                    while (tr > 0 && tr * (2 * nt4 - tr + 1) / 2 > e) tr--;
+                    while ((tr + 1) * (2 * nt4 - tr) / 2 <= e) tr++;
+                    const int tc = e - tr * (2 * nt4 - tr + 1) / 2 + tr;
                     const int r0 = 4 * tr, c0 = 4 * tc;
                     double acc[4][4], pv[4][4];
 #pragma unroll
@@ -793,15 +804,29 @@ struct BlockSolver {
             const double *Pk = Pall + (long long)k * ns * ns;
             const double *Yk = Yall + (long long)(k < N ? k : 0) * nc * ldy, *Lk = Lall + (long long)(k < N ? k : 0) * ncp * ncp;
             // y~c_k = -(P_k dx + p_k);  t = Y_k dx + y_m      (one warp per row)
-            for (int r = wid; r < ns + (k < N ? nc : 0); r += nw) {
-                const double *mr = r < ns ? Pk + (long long)r * ns : Yk + (long long)(r - ns) * ldy;
-                double acc = 0.0;
-                for (int j = lane; j < ns; j += 32) acc += mr[j] * dzb[j];
+            const int nrows = ns + (k < N ? nc : 0);
+            for (int r0 = wid; r0 < nrows; r0 += 4 * nw) {   // four rows per warp at a time
+                const double *mr[4];
+                double acc[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-                for (int m = 16; m > 0; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
-                if (lane == 0) {
-                    if (r < ns) row(rytc, k)[r] = -(acc + row(R_LIN, k)[r]);
-                    else tb[r - ns] = acc + mr[ns];
+                for (int q = 0; q < 4; q++) {
+                    const int r = r0 + q * nw < nrows ? r0 + q * nw : r0;
+                    mr[q] = r < ns ? Pk + (long long)r * ns : Yk + (long long)(r - ns) * ldy;
+                }
+                for (int j = lane; j < ns; j += 32) {
+                    const double v = dzb[j];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) acc[q] += mr[q][j] * v;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+#pragma unroll
+                    for (int m = 16; m > 0; m >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], m);
+                    const int r = r0 + q * nw;
+                    if (lane == 0 && r < nrows) {
+                        if (r < ns) row(rytc, k)[r] = -(acc[q] + row(R_LIN, k)[r]);
+                        else tb[r - ns] = acc[q] + mr[q][ns];
+                    }
                 }
             }
             __syncthreads();
