@@ -330,7 +330,13 @@ static void eval_cons(const ctx_t *C, const double *z, double *c, double *dv)
             ck[3 * i + 2] = zn[3 * i + 2] - (th + T * om) - ce[3 * i + 2];
         }
         double *dk = dv + (k + 1) * M;
-        for (int q = 0; q < M; q++) dk[q] = row_geom(D, zk, q).dv;
+        /* (pair rows keep their original expression: exactly symmetric scenarios decide their branch by round-off) */
+        for (int q = 0; q < D->Mp; q++) {
+            int i = D->pi[q], j = D->pj[q];
+            double dx = zk[3 * i] - zk[3 * j], dy = zk[3 * i + 1] - zk[3 * j + 1];
+            dk[q] = dx * dx + dy * dy;
+        }
+        for (int q = D->Mp; q < M; q++) dk[q] = row_geom(D, zk, q).dv;
     }
 }
 
@@ -378,10 +384,15 @@ static void eval_jtv(const ctx_t *C, const double *z, const double *yc, const do
             ok[ns + 2 * i] -= T * (c * lx + s * ly);
             ok[ns + 2 * i + 1] -= T * lt;
         }
-        for (int q = 0; q < M; q++) {
+        for (int q = 0; q < D->Mp; q++) {
+            int i = D->pi[q], j = D->pj[q];
+            double dx = zk[3 * i] - zk[3 * j], dy = zk[3 * i + 1] - zk[3 * j + 1];
+            ok[3 * i] += 2 * dx * mu[q]; ok[3 * j] -= 2 * dx * mu[q];
+            ok[3 * i + 1] += 2 * dy * mu[q]; ok[3 * j + 1] -= 2 * dy * mu[q];
+        }
+        for (int q = D->Mp; q < M; q++) {
             rowg_t g = row_geom(D, zk, q);
             ok[3 * g.i] += g.gx * mu[q]; ok[3 * g.i + 1] += g.gy * mu[q];
-            if (g.j >= 0) { ok[3 * g.j] -= g.gx * mu[q]; ok[3 * g.j + 1] -= g.gy * mu[q]; }
         }
     }
 }
@@ -454,17 +465,20 @@ static int kkt_solve(ctx_t *C, const double *z, const double *ycW, const double 
         for (int q = 0; q < M; q++) {
             int r = (k + 1) * M + q;
             if (!act[r]) continue;
-            rowg_t rg = row_geom(D, zk, q);
-            int i = rg.i, j = rg.j;
-            double gxq = rg.gx, gyq = rg.gy;
-            double Dq = sigs[r] + delta, hq = Dq * rd[r] + gs[r];
-            double xx = Dq * gxq * gxq + ydW[r] * rg.hxx, yy = Dq * gyq * gyq + ydW[r] * rg.hyy, xy = Dq * gxq * gyq + ydW[r] * rg.hxy;
-            int xi = 3 * i, yi = 3 * i + 1, xj = 3 * j, yj = 3 * j + 1;
-            if (j < 0) { /* obstacle row: only robot i's own block */
-                Mw[xi * nz + xi] += xx; Mw[yi * nz + yi] += yy; Mw[xi * nz + yi] += xy; Mw[yi * nz + xi] += xy;
-                m[xi] += gxq * hq; m[yi] += gyq * hq;
+            if (q >= D->Mp) { /* obstacle row: only robot i's own block, curvature (I - n n')/rho */
+                rowg_t rg = row_geom(D, zk, q);
+                double Dq = sigs[r] + delta, hq = Dq * rd[r] + gs[r];
+                double oxx = Dq * rg.gx * rg.gx + ydW[r] * rg.hxx, oyy = Dq * rg.gy * rg.gy + ydW[r] * rg.hyy, oxy = Dq * rg.gx * rg.gy + ydW[r] * rg.hxy;
+                int xi = 3 * rg.i, yi = 3 * rg.i + 1;
+                Mw[xi * nz + xi] += oxx; Mw[yi * nz + yi] += oyy; Mw[xi * nz + yi] += oxy; Mw[yi * nz + xi] += oxy;
+                m[xi] += rg.gx * hq; m[yi] += rg.gy * hq;
                 continue;
             }
+            int i = D->pi[q], j = D->pj[q];
+            double gxq = 2 * (zk[3 * i] - zk[3 * j]), gyq = 2 * (zk[3 * i + 1] - zk[3 * j + 1]);
+            double Dq = sigs[r] + delta, mu2 = 2 * ydW[r], hq = Dq * rd[r] + gs[r];
+            double xx = Dq * gxq * gxq + mu2, yy = Dq * gyq * gyq + mu2, xy = Dq * gxq * gyq;
+            int xi = 3 * i, yi = 3 * i + 1, xj = 3 * j, yj = 3 * j + 1;
             Mw[xi * nz + xi] += xx; Mw[xj * nz + xj] += xx; Mw[xi * nz + xj] -= xx; Mw[xj * nz + xi] -= xx;
             Mw[yi * nz + yi] += yy; Mw[yj * nz + yj] += yy; Mw[yi * nz + yj] -= yy; Mw[yj * nz + yi] -= yy;
             Mw[xi * nz + yi] += xy; Mw[yi * nz + xi] += xy; Mw[xj * nz + yj] += xy; Mw[yj * nz + xj] += xy;
@@ -536,9 +550,14 @@ static int kkt_solve(ctx_t *C, const double *z, const double *ycW, const double 
         for (int q = 0; q < M; q++) {
             int r = (k + 1) * M + q;
             if (!act[r]) { ds[r] = 0; ytd[r] = 0; continue; }
-            rowg_t rg = row_geom(D, zk, q);
-            double ddx = dk[3 * rg.i] - (rg.j >= 0 ? dk[3 * rg.j] : 0.0), ddy = dk[3 * rg.i + 1] - (rg.j >= 0 ? dk[3 * rg.j + 1] : 0.0);
-            ds[r] = rg.gx * ddx + rg.gy * ddy + rd[r];
+            if (q >= D->Mp) {
+                rowg_t rg = row_geom(D, zk, q);
+                ds[r] = rg.gx * dk[3 * rg.i] + rg.gy * dk[3 * rg.i + 1] + rd[r];
+            } else {
+                int i = D->pi[q], j = D->pj[q];
+                double gxq = 2 * (zk[3 * i] - zk[3 * j]), gyq = 2 * (zk[3 * i + 1] - zk[3 * j + 1]);
+                ds[r] = gxq * (dk[3 * i] - dk[3 * j]) + gyq * (dk[3 * i + 1] - dk[3 * j + 1]) + rd[r];
+            }
             ytd[r] = (sigs[r] + delta) * ds[r] + gs[r];
         }
     }
