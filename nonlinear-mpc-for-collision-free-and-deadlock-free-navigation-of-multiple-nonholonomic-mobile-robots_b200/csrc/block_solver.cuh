@@ -98,6 +98,8 @@ struct BlockSolver {
     static __device__ __forceinline__ void tsync() { __syncthreads(); }
     __device__ __forceinline__ double *row(int r, int k) const { return ws + ((long long)r * S + k) * W; }
     __device__ __forceinline__ bool is_lead() const { return tid == 0; }
+    __device__ __forceinline__ void iter_sync() const {}
+    __device__ __forceinline__ void mid_sync() const {}
     __device__ __forceinline__ int pairidx(int a, int b) const { return a * (2 * Nr - a - 1) / 2 + (b - a - 1); }
     __device__ __forceinline__ double qw(int l) const { return l < ns ? 2.0 * P.Q[l % 3] : 2.0 * P.R[(l - ns) & 1]; }
     __device__ __forceinline__ double xs(int l) const { return l < ns ? pp[ns + l] : 0.0; }

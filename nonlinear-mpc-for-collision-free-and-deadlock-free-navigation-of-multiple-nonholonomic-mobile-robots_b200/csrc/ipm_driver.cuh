@@ -29,12 +29,13 @@ NMPC_DEV void ipm_run(S &s)
     double mu = o.mu_init, tau = fmax(o.tau_min, 1.0 - mu);
     double theta_max = -1.0, theta_min = -1.0, delta_last = 0.0, f_prev = 0.0;
     int iter = 0, st = NMPC_MAX_ITER, n_acc = 0;
-    bool tiny_prev = false;
+    bool tiny_prev = false, at_top = false;   // at_top: between the two convoy barriers of an iteration
     double E0 = 0.0;
     const double mu_floor = fmin(o.tol, o.compl_inf_tol) / (o.barrier_tol_factor + 1.0);
     typename S::EvalOut E;
     E.dinf = E.c0 = E.cmu = E.ysum = E.zsum = 0.0;
     for (;;) {
+        s.iter_sync(); at_top = true;
         s.eval(true, mu, 0.0, 0, 0, false, false, 0.0, E);
         const double smax = 100.0;
         const double sd = fmax(smax, (E.ysum + E.zsum) / fmax(1.0, s.ny_nzb)) / smax;
@@ -72,6 +73,7 @@ NMPC_DEV void ipm_run(S &s)
             if (delta > 1e20) { need_resto = true; break; }
         }
         if (delta > 0.0 && !need_resto) { delta_last = delta; s.n_reg++; }
+        s.mid_sync(); at_top = false;
         double alpha = 0.0, alpha_z = 0.0;
         int ls_count = 0;
         if (!need_resto) {
@@ -175,5 +177,6 @@ NMPC_DEV void ipm_run(S &s)
         iter++;
     }
 finished:
+    if (at_top) s.mid_sync();   // two barriers per iteration on every path: the group stays in phase
     s.write_outputs(st, iter, E0, E.pinf, E.dinf, E.c0, mu);
 }

@@ -17,10 +17,10 @@
 #include "aux_kernels.cuh"
 
 #ifndef SOLVE_WARPS
-#define SOLVE_WARPS 4
+#define SOLVE_WARPS 3     // warps (instances) per CTA = the convoy group, see WarpSolver::iter_sync
 #endif
 #ifndef SOLVE_MIN_CTAS
-#define SOLVE_MIN_CTAS 3   // 12 resident instances per SM (15 KB of shared memory each, <= 168 registers per thread)
+#define SOLVE_MIN_CTAS 4   // 12 resident instances per SM (15 KB of shared memory each, <= 168 registers per thread)
 #endif
 
 static thread_local char g_err[512] = "";
@@ -53,7 +53,7 @@ extern "C" void nmpc_default_opts(nmpc_opts *o)
 // ------------------------------------------------------------------------------------------------
 // the persistent solve kernel: one warp per instance, instances pulled from an atomic queue
 // ------------------------------------------------------------------------------------------------
-// threads per CTA and instances ("teams") per CTA: one warp per instance up to 6 robots (4 per CTA);
+// threads per CTA and instances ("teams") per CTA: one warp per instance up to 6 robots (3 per CTA);
 // 7..10 robots use the two-warp team (one instance per 64-thread CTA)
 template <int NR> struct SolveCfg {
     static constexpr int LW = WarpSolver<NR>::LW;
@@ -76,7 +76,11 @@ __global__ void __launch_bounds__(SolveCfg<NR>::THREADS, SolveCfg<NR>::MIN_CTAS)
         if (tl == 0) sm[WarpSolver<NR>::SM_MISC + 1] = (double)atomicAdd(P.counter, 1);
         WarpSolver<NR>::tsync();
         const int slot = (int)sm[WarpSolver<NR>::SM_MISC + 1];
-        if (slot >= P.B) break;
+        if (slot >= P.B) {
+            // convoy mode: keep answering the group's barriers until every warp of the CTA has run out of work
+            if (LW == 32 && P.convoy) while (wp::cta_count(false) != 0) {}
+            break;
+        }
         const int inst = P.order ? P.order[slot] : slot;   // longest-first scheduling when the caller has a predictor
         s.setup(inst);
         s.run();
@@ -100,6 +104,7 @@ struct nmpc_handle {
                                               // static obstacles): used for the small-OCP family always, else from thread_min_batch on
     size_t t_ws_doubles;                      // its scratch per instance
     int thread_min_batch;
+    int convoy;                               // warp path: iteration-level convoy of the CTA's warps (instruction-cache locality)
     bool block_path, eval_ok;                 // Nr > 10: CTA-per-instance dense-block solver; eval record fits shared memory
     int *d_pairs;                             // pair table (i, j) of the inequality rows, block path
     // host-pointer API staging
@@ -252,6 +257,8 @@ static int create_impl(const nmpc_desc *d, const nmpc_opts *o, int nobs, const d
     h->thread_ok = h->family == 1 && d->Nr == 1;
     h->t_ws_doubles = h->thread_ok ? (size_t)ThreadSolver<UnicycleObstacles>::ws_doubles(d->N) : 0;
     h->thread_min_batch = 0x7fffffff;
+    h->convoy = 2;   // 0 off, 1 barrier per iteration, 2 also before the forward pass (measured: +14 % cold throughput)
+    if (const char *ov = getenv("NMPC_CONVOY")) h->convoy = atoi(ov);
     if (const char *ov = getenv("NMPC_THREAD_MIN_BATCH")) h->thread_min_batch = atoi(ov) > 0 ? atoi(ov) : 1;
     DBG("device count ok");
     cudaGetDevice(&h->dev);
@@ -406,6 +413,7 @@ static int solve_impl(nmpc_handle *h, int B, const double *x0, const double *p, 
     P.bound_err = berr; P.x = x; P.f = f; P.g = g; P.lam_x = lam_x; P.lam_g = lam_g; P.status = status; P.iters = iters;
     P.stats = stats; P.trace = trace; P.max_trace = max_trace; P.ws = slots; P.ws_stride = (long long)(thr ? h->t_ws_doubles : h->ws_doubles_per_slot);
     P.counter = counter; P.pairs = h->d_pairs; P.order = h->d_order; P.nobs = h->nobs; P.family = h->family; P.obs = h->d_obs;
+    P.convoy = B > solve_grid(h, B) ? h->convoy : 0;   // pointless while every CTA has at most one working warp
     P.lbx = lbx; P.ubx = ubx; P.lbg = lbg; P.ubg = ubg; P.bounds_batched = bounds_batched; P.rk_steps = h->rk_steps; P.np = h->np;
     const int grid = thr ? (B + 63) / 64 : solve_grid(h, B);
     if (thr && h->family == 2) solve_kernel_small_ocp<VanDerPol><<<grid, 64, 0, st>>>(P);

@@ -34,6 +34,7 @@ typedef struct NmpcSolveParams {
     int *counter;                    /* work queue                                       */
     const int *pairs;                /* [M][2] pair table (dense-block path only)        */
     const int *order;                /* optional [B] processing order of the instances   */
+    int convoy;                      /* warp path: the CTA's warps start every IPM iteration together */
     int nobs, family;                /* static obstacles per robot; row layout (0 / 1)   */
     const double *obs;               /* [nobs][3] centre x, y, clearance radius (device) */
     const double *lbx, *ubx, *lbg, *ubg;  /* flat bounds (small-OCP family reads them directly) */

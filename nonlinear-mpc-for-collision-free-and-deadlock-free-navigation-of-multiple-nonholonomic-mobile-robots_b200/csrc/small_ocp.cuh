@@ -196,6 +196,8 @@ struct ThreadSolver {
     __device__ ThreadSolver(const NmpcSolveParams &p, double *wsp) : P(p), ws(wsp) {}
     static __device__ __forceinline__ void tsync() {}
     __device__ __forceinline__ bool is_lead() const { return true; }
+    __device__ __forceinline__ void iter_sync() const {}
+    __device__ __forceinline__ void mid_sync() const {}
     __device__ __forceinline__ double *row(int r, int k) const { return ws + ((long long)r * S + k) * LD; }
     __device__ __forceinline__ double *cst(int k) const { return cache + (long long)k * C_COUNT; }
     __device__ __forceinline__ double *cin(int k, int i) const { return cst(k) + C_I + i * CI_STRIDE; }

@@ -15,6 +15,7 @@ namespace wp {
 NMPC_DEV int lane() { return threadIdx.x & 31; }
 NMPC_DEV int team_lane(int lw) { return threadIdx.x & (lw - 1); }   // lane inside a 32- or 64-thread team
 NMPC_DEV void sync_cta() { __syncthreads(); }
+NMPC_DEV int cta_count(bool pred) { return __syncthreads_count(pred); }   // CTA barrier + number of threads with pred
 NMPC_DEV void sync() { __syncwarp(); }
 NMPC_DEV double shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 NMPC_DEV double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
