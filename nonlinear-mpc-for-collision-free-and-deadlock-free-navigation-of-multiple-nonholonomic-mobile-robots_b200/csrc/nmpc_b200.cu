@@ -53,13 +53,14 @@ extern "C" void nmpc_default_opts(nmpc_opts *o)
 // ------------------------------------------------------------------------------------------------
 // the persistent solve kernel: one warp per instance, instances pulled from an atomic queue
 // ------------------------------------------------------------------------------------------------
-// threads per CTA and instances ("teams") per CTA: one warp per instance up to 6 robots (3 per CTA);
-// 7..10 robots use the two-warp team (one instance per 64-thread CTA)
+// threads per CTA and instances ("teams") per CTA: one warp per instance up to 6 robots (3 per CTA, 4 CTAs per SM);
+// 7..10 robots use the two-warp team (2 per CTA on named barriers, 2 CTAs per SM: 255 registers per thread).  The
+// one-warp teams of a CTA are a convoy group (WarpSolver::iter_sync).
 template <int NR> struct SolveCfg {
     static constexpr int LW = WarpSolver<NR>::LW;
-    static constexpr int THREADS = LW == 32 ? SOLVE_WARPS * 32 : 64;
+    static constexpr int THREADS = LW == 32 ? SOLVE_WARPS * 32 : 128;
     static constexpr int TEAMS = THREADS / LW;
-    static constexpr int MIN_CTAS = LW == 32 ? SOLVE_MIN_CTAS : 1;
+    static constexpr int MIN_CTAS = LW == 32 ? SOLVE_MIN_CTAS : 2;
 };
 
 template <int NR>
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(SolveCfg<NR>::THREADS, SolveCfg<NR>::MIN_CTAS)
         const int slot = (int)sm[WarpSolver<NR>::SM_MISC + 1];
         if (slot >= P.B) {
             // convoy mode: keep answering the group's barriers until every warp of the CTA has run out of work
-            if (LW == 32 && P.convoy) while (wp::cta_count(false) != 0) {}
+            if (P.convoy) while (wp::cta_count(false) != 0) {}
             break;
         }
         const int inst = P.order ? P.order[slot] : slot;   // longest-first scheduling when the caller has a predictor
@@ -413,7 +414,9 @@ static int solve_impl(nmpc_handle *h, int B, const double *x0, const double *p, 
     P.bound_err = berr; P.x = x; P.f = f; P.g = g; P.lam_x = lam_x; P.lam_g = lam_g; P.status = status; P.iters = iters;
     P.stats = stats; P.trace = trace; P.max_trace = max_trace; P.ws = slots; P.ws_stride = (long long)(thr ? h->t_ws_doubles : h->ws_doubles_per_slot);
     P.counter = counter; P.pairs = h->d_pairs; P.order = h->d_order; P.nobs = h->nobs; P.family = h->family; P.obs = h->d_obs;
-    P.convoy = B > solve_grid(h, B) ? h->convoy : 0;   // pointless while every CTA has at most one working warp
+    // convoy: one-warp teams only (measured -5..-8 % for the two-warp teams of 7..10 robots, whose groups are two instances),
+    // and pointless while every CTA has at most one working team
+    P.convoy = (!h->block_path && !thr && h->lw == 32 && h->teams_per_cta > 1 && B > solve_grid(h, B)) ? h->convoy : 0;
     P.lbx = lbx; P.ubx = ubx; P.lbg = lbg; P.ubg = ubg; P.bounds_batched = bounds_batched; P.rk_steps = h->rk_steps; P.np = h->np;
     const int grid = thr ? (B + 63) / 64 : solve_grid(h, B);
     if (thr && h->family == 2) solve_kernel_small_ocp<VanDerPol><<<grid, 64, 0, st>>>(P);

@@ -113,7 +113,7 @@ struct WarpSolver {
     NMPC_DEV WarpSolver(const NmpcSolveParams &p, double *smem, double *wsp) : P(p), sm(smem), ws(wsp) {}
 
     // team-wide barrier and all-reduce (a team is one warp, or the two warps of a 64-thread CTA)
-    static NMPC_DEV void tsync() { if (LW == 32) wp::sync(); else wp::sync_cta(); }
+    static NMPC_DEV void tsync() { if (LW == 32) wp::sync(); else wp::sync_team64(); }
     NMPC_DEV double tred(double v, int op) const
     {
         double r = op == 0 ? wp::red_sum(v) : (op == 1 ? wp::red_max(v) : wp::red_min(v));
@@ -1101,12 +1101,12 @@ struct WarpSolver {
     // hooks used by the shared interior-point driver (ipm_driver.cuh)
     // ---------------------------------------------------------------------------------------
     NMPC_DEV bool is_lead() const { return l == 0; }
-    // Convoy mode (one warp per instance, P.convoy > 0): the warps of a CTA meet at the start of every IPM iteration and
+    // Convoy mode (P.convoy > 0): the teams of a CTA meet at the start of every IPM iteration and
     // (P.convoy > 1) again before the forward pass, so that they run the same pass at about the same time and share its
     // instructions in the SM's instruction cache.  Every barrier also counts the working warps (an idle warp
     // contributes 0) -- see solve_kernel.
-    NMPC_DEV void iter_sync() const { if (LW == 32 && P.convoy) wp::cta_count(l == 0); }
-    NMPC_DEV void mid_sync() const { if (LW == 32 && P.convoy > 1) wp::cta_count(l == 0); }
+    NMPC_DEV void iter_sync() const { if (P.convoy) wp::cta_count(l == 0); }
+    NMPC_DEV void mid_sync() const { if (P.convoy > 1) wp::cta_count(l == 0); }
     NMPC_DEV bool factor_m(int mode, double mu, double delta, bool soc)
     {
         return mode == 0 ? factor<0>(mu, delta, soc) : (mode == 1 ? factor<1>(mu, delta, soc) : factor<2>(mu, delta, soc));

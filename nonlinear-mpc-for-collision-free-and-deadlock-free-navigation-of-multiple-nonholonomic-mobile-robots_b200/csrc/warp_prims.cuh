@@ -15,6 +15,8 @@ namespace wp {
 NMPC_DEV int lane() { return threadIdx.x & 31; }
 NMPC_DEV int team_lane(int lw) { return threadIdx.x & (lw - 1); }   // lane inside a 32- or 64-thread team
 NMPC_DEV void sync_cta() { __syncthreads(); }
+// barrier of one 64-thread team (named barrier 1 + team index; barrier 0 stays free for the whole CTA)
+NMPC_DEV void sync_team64() { asm volatile("bar.sync %0, 64;" ::"r"(1 + (int)(threadIdx.x >> 6)) : "memory"); }
 NMPC_DEV int cta_count(bool pred) { return __syncthreads_count(pred); }   // CTA barrier + number of threads with pred
 NMPC_DEV void sync() { __syncwarp(); }
 NMPC_DEV double shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }

@@ -27,6 +27,7 @@ inline int lane() { return emu->cur & 31; }
 inline int team_lane(int lw) { return emu->cur & (lw - 1); }
 inline void sync() { swapcontext(&emu->ctx[emu->cur], &emu->main); }
 inline void sync_cta() { sync(); }
+inline void sync_team64() { sync(); }
 inline int cta_count(bool pred) { return pred ? 1 : 0; }
 inline double shfl(double v, int src) { emu->xd[emu->cur] = v; sync(); double r = emu->xd[(emu->cur & 32) | (src & 31)]; sync(); return r; }
 inline double shfl_xor(double v, int m) { return shfl(v, (emu->cur & 31) ^ m); }
