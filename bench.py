@@ -23,9 +23,9 @@ sys.path.insert(0, ROOT)
 NR, NH, T, DMIN, VMAX, WMAX = 6, 20, 0.3, 0.3, 0.22, 2.84      # sixth_scenario.py:127-135, N overridden to 20
 PER_GPU = 8192
 ALG_BYTES_PER_SOLVE = 15728       # p + w0 in, x + f + g out
-# dram__bytes_read.sum + dram__bytes_write.sum of solve_kernel<6> per solve, from the ncu --set full capture of v17
-# (profiles/ncu_solve_kernel_r1_v17.txt: 92.05 + 63.46 GB for 3552 cold-start instances): scratch rows stream through HBM
-TRAFFIC_BYTES_PER_SOLVE = int((92.046642e9 + 63.455251e9) / 3552)
+# dram__bytes_read.sum + dram__bytes_write.sum of solve_kernel<6> per solve, from the ncu --set full capture of v22
+# (profiles/ncu_solve_kernel_r1_v22.txt: 90.08 + 63.32 GB for 3552 cold-start instances): scratch rows stream through HBM
+TRAFFIC_BYTES_PER_SOLVE = int((90.082462e9 + 63.322748e9) / 3552)
 F_FACT, F_SOLVE, F_EVAL = 1100160, 92160, 14700   # SURVEY.md 8d dense-stage FP64 flop counts @ Nr=6, N=20
 
 
