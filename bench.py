@@ -23,24 +23,29 @@ sys.path.insert(0, ROOT)
 NR, NH, T, DMIN, VMAX, WMAX = 6, 20, 0.3, 0.3, 0.22, 2.84      # sixth_scenario.py:127-135, N overridden to 20
 PER_GPU = 8192
 ALG_BYTES_PER_SOLVE = 15728       # p + w0 in, x + f + g out
-# dram__bytes_read.sum + dram__bytes_write.sum of solve_kernel<6> per solve, from the ncu --set full capture of v22
-# (profiles/ncu_solve_kernel_r1_v22.txt: 90.08 + 63.32 GB for 3552 cold-start instances): scratch rows stream through HBM
-TRAFFIC_BYTES_PER_SOLVE = int((90.082462e9 + 63.322748e9) / 3552)
 F_FACT, F_SOLVE, F_EVAL = 1100160, 92160, 14700   # SURVEY.md 8d dense-stage FP64 flop counts @ Nr=6, N=20
+F_ITER = F_FACT + F_SOLVE + F_EVAL                # 1.207 MFLOP per interior-point iteration (SURVEY.md 8d's unit of work)
 
 
-def synthetic(B, seed):
-    from oracle.nlp_numpy import synthetic_instances
-    cache = os.path.join(ROOT, "gpurun_out", "synth_%d_%d.npy" % (B, seed))
-    if os.path.exists(cache):
-        return np.load(cache)
-    P = synthetic_instances(B, NR, seed)
+def measured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of solve_kernel<6> per solve, from the latest committed ncu --set full
+    capture (profiles/solve_kernel_traffic.json names the capture); None when the file is missing."""
     try:
-        os.makedirs(os.path.dirname(cache), exist_ok=True)
-        np.save(cache, P)
-    except OSError:
-        pass
-    return P
+        t = json.load(open(os.path.join(ROOT, "profiles", "solve_kernel_traffic.json")))
+        return (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["instances"], t["source"]
+    except (OSError, KeyError, ValueError):
+        return None, None
+
+
+def load_pkg():
+    import __graft_entry__ as ge
+    return ge.load_package()
+
+
+def shard(rank, world, per_gpu):
+    """This rank's slice of ONE default_rng(20261018) table of world * per_gpu instances (65,536 at 8 x 8,192),
+    split by sharding.shard_range.  Host-only code of the package (workload.py): no CUDA needed."""
+    return load_pkg().workload.bench_shard(rank, world, per_gpu, NR)
 
 
 class ClockSampler(threading.Thread):
@@ -93,6 +98,37 @@ def cpu_arm(P, nthreads, budget_s=20.0):
     return n / dt, n, dt, float(np.concatenate(iters).mean())
 
 
+def cpu_one_core(steps=60):
+    """the CPU path on ONE core -- cold solves/s over the first instances of the workload and p50 / p95
+    single-solve latency over the closed-loop hexagon swap (the loop timed at centralized_six...py:482), restated IPOPT."""
+    from oracle.oracle_lib import Oracle
+    wl = load_pkg().workload
+    o = Oracle(NR, NH, T)
+    lbx, ubx, lbg, ubg = o.bounds(DMIN, VMAX, WMAX)
+    P = wl.synthetic_instances(48, NR)
+    t0 = time.perf_counter()
+    n = 0
+    for q in P:
+        o.solve(o.cold_start(q[:3 * NR]), q, lbx, ubx, lbg, ubg)
+        n += 1
+        if time.perf_counter() - t0 > 6.0:
+            break
+    cold = n / (time.perf_counter() - t0)
+    p1 = wl.hexagon_swap(True)
+    w = o.cold_start(p1[:18])
+    times = []
+    for _ in range(steps):
+        t1 = time.perf_counter()
+        r = o.solve(w, p1, lbx, ubx, lbg, ubg)
+        times.append(time.perf_counter() - t1)
+        x = r["x"]
+        p1[:18] = o.plant(p1[:18], x[18 * (NH + 1):18 * (NH + 1) + 12])
+        w = o.shift(x)
+    return {"cold_solves_per_s": cold, "cold_sample": n, "p50_ms": 1e3 * float(np.median(times[1:])), "p95_ms": 1e3 * float(np.percentile(times[1:], 95)),
+            "first_cold_ms": 1e3 * times[0], "loop_steps": steps,
+            "note": "one host core, restated IPOPT (oracle/): cold solves of the first instances; p50/p95 over the %d-step closed-loop hexagon swap" % steps}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -108,14 +144,14 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     ncores = os.cpu_count() or 1
-    config = {"workload": "6-robot N=20 cold-start NMPC (sixth_scenario.py constants), %d synthetic start/goal instances per GPU "
-                          "(65536 over 8 GPUs), rng seed 20261018+rank" % a.per_gpu,
+    config = {"workload": "6-robot N=20 cold-start NMPC (sixth_scenario.py constants), %d synthetic start/goal instances per GPU: rank r's "
+                          "slice of one default_rng(20261018) table of n_gpus x %d instances (65536 at 8 GPUs)" % (a.per_gpu, a.per_gpu),
               "Nr": NR, "N": NH, "T": T, "dmin": DMIN, "batch_per_gpu": a.per_gpu, "l2": "flushed between timed steps (512 MiB write)"}
 
     if a.impl == "reference":
         if rank != 0:
             return
-        P = synthetic(a.per_gpu, 20261018)
+        P, _ = shard(0, 1, a.per_gpu)
         per_step = []
         tot_n = tot_t = 0
         mean_it = 0.0
@@ -130,14 +166,13 @@ def main():
                 "cpu_baseline": {"value": val, "unit": "solves/s", "cores": ncores, "kind": "port",
                                  "sample": "first %d cold-start instances of the same workload per step (~8 s), restated IPOPT "
                                            "(oracle/nmpc_oracle.c, OpenMP); CasADi/IPOPT are not installable here" % (tot_n // max(1, a.steps)),
-                                 "mean_iters": mean_it},
+                                 "mean_iters": mean_it, "one_core": cpu_one_core()},
                 "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
 
     import torch
-    import __graft_entry__ as ge
-    pkg = ge.load_package()
+    pkg = load_pkg()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
@@ -146,7 +181,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     B = a.per_gpu
-    P = synthetic(B, 20261018 + rank)
+    P, (shard_lo, shard_hi) = shard(rank, world, B)
     if a.clone >= 0:
         P = np.repeat(P[a.clone:a.clone + 1], B, axis=0)
     prob = pkg.Problem(NR, NH, T)
@@ -182,14 +217,26 @@ def main():
     launches = prob.launch_count() - launches0
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    tot_ms = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tot_ms, op=dist.ReduceOp.MAX)
-    tot_ms = tot_ms.item()
     st = out["status"].cpu().numpy()
     stats = out["stats"].cpu().numpy()
     iters = out["iters"].cpu().numpy()
     solved = float((st == 0).mean())
+    # per-rank record: its own device time and the iteration statistics of its shard (the makespan of a rank is decided by
+    # the tail of its 4.6 waves, so the MAX over ranks grows with the number of different shards)
+    mine = torch.tensor([sum(ms) / a.steps, float(iters.mean()), float(iters.max()), float(stats[:, 8].mean()), float(stats[:, 8].max()),
+                         float(shard_lo)], dtype=torch.float64, device=dev)
+    allr = [torch.zeros_like(mine) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(allr, mine)
+    else:
+        allr = [mine]
+    per_rank = [{"rank": r, "ms_per_step": v[0].item(), "mean_ip_iters": v[1].item(), "max_ip_iters": int(v[2].item()),
+                 "mean_factorisations": v[3].item(), "max_factorisations": int(v[4].item()), "first_instance": int(v[5].item())}
+                for r, v in enumerate(allr)]
+    tot_ms = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot_ms, op=dist.ReduceOp.MAX)
+    tot_ms = tot_ms.item()
 
     # ---- end to end through the host-buffer C-ABI call (pinned inputs, H2D + solve + D2H of x, status, iters) ----
     pin = lambda v: torch.as_tensor(np.ascontiguousarray(v), dtype=torch.float64).pin_memory().numpy()
@@ -243,11 +290,7 @@ def main():
     # ---- p50 single-solve latency: hexagon swap (C-6 constants, N=20), closed loop, batch = 1, host buffers ----
     lat = None
     if rank == 0:
-        s3 = np.sqrt(3) / 2
-        st = np.array([[s3, 0.5, -2.618], [0, 1, -1.571], [-s3, 0.5, -0.524], [-s3, -0.5, 0.524], [0, -1, 1.571], [s3, -0.5, 2.618]])
-        st = st + 0.02 * np.sin(1.0 + 2.0 * np.arange(18)).reshape(6, 3)        # de-symmetrised (see tests/test_closed_loop.py)
-        goal = -st.copy(); goal[:, 2] = st[:, 2]
-        p1 = np.concatenate([st.ravel(), goal.ravel()])[None]
+        p1 = pkg.workload.hexagon_swap(True)[None]        # de-symmetrised (see tests/test_closed_loop.py)
         w1_ = prob.cold_start(p1[:, :18])
         times, o1 = [], {}
         for step in range(60):
@@ -266,9 +309,8 @@ def main():
     # ---- BASELINE.json configs[4]: 64-robot swarm on the CTA-per-instance dense-block path (one timed launch) ----
     swarm = None
     if rank == 0 and world == 1 and a.swarm > 0:
-        from oracle.nlp_numpy import synthetic_instances
         Bs, Ns = a.swarm, 64
-        Ps = synthetic_instances(min(Bs, 8), Nr=Ns, seed=20261018, box=8.0)
+        Ps = pkg.workload.synthetic_instances(min(Bs, 8), Nr=Ns, seed=20261018, box=8.0)
         Ps = np.tile(Ps, ((Bs + len(Ps) - 1) // len(Ps), 1))[:Bs]      # 8 distinct instances, repeated (rejection sampling 64 robots is slow)
         sp = pkg.Problem(Ns, NH, T)
         sb = sp.bounds(DMIN, VMAX, WMAX)
@@ -318,12 +360,15 @@ def main():
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     per_gpu_solves = B * a.steps / (tot_ms * 1e-3)
-    ach_gbs = per_gpu_solves * ALG_BYTES_PER_SOLVE / 1e9
     import ctypes
-    tf = ctypes.c_double(0.0)
+    tf, tdm = ctypes.c_double(0.0), ctypes.c_double(0.0)
     pkg.lib().nmpc_probe_fp64(ctypes.byref(tf))
-    flops_per_solve = float((stats[:, 8] * F_FACT + iters * (F_SOLVE + F_EVAL)).mean())
-    ach_tf = per_gpu_solves * flops_per_solve / 1e12
+    pkg.lib().nmpc_probe_dmma(ctypes.byref(tdm))
+    # achieved = solves/s x mean interior-point iterations x 1.207 MFLOP (dense-stage count of ONE factorisation,
+    # back-solve and evaluation per iteration; failed inertia attempts are not useful work and are not counted)
+    ach_tf = per_gpu_solves * float(iters.mean()) * F_ITER / 1e12
+    flops_refact = float((stats[:, 8] * F_FACT + iters * (F_SOLVE + F_EVAL)).mean())
+    traffic_per_solve, traffic_src = measured_traffic()
     cpu_val, cpu_n, cpu_dt, cpu_it = cpu_arm(P, ncores, budget_s=15.0)     # same instances as the GPU arm, bounded to ~15 s
     line = {
         "metric": "6-robot N=20 NMPC solves/sec", "value": value, "unit": "solves/s", "n_gpus": world, "steps": a.steps,
@@ -331,14 +376,27 @@ def main():
         "dtype": "f64", "data": "synthetic", "config": config,
         "solved_frac": solved, "mean_ip_iters": float(iters.mean()), "max_ip_iters": int(iters.max()),
         "mean_factorisations": float(stats[:, 8].mean()),
-        "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                     "traffic": TRAFFIC_BYTES_PER_SOLVE * B, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
-                     "note": "solve_kernel is FP64-pipe/latency bound, not HBM bound (SURVEY.md 8d); see fp64"},
-        "fp64": {"achieved_tflops": ach_tf, "peak_tflops": tf.value, "frac": ach_tf / tf.value if tf.value else None,
-                 "flops_per_solve": flops_per_solve, "peak_source": "nmpc_probe_fp64 (DFMA microbenchmark, this run)"},
+        "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": tf.value, "unit": "TFLOP/s", "frac": ach_tf / tf.value if tf.value else None,
+                     "traffic": traffic_per_solve * B if traffic_per_solve else None, "traffic_source": traffic_src,
+                     "flops_per_unit": F_ITER, "units_per_launch": float(iters.sum()),
+                     "peak_source": "nmpc_probe_fp64: register-only DFMA kernel timed in this run (MEASURED_PEAKS.json has no FP64 figure)",
+                     "note": "solve_kernel<6>: the binding resource is the FP64 pipe / dependent-issue latency / instruction fetch, not HBM "
+                             "and not tensor cores (tcgen05 has no f64 kind; DMMA probe below); see roofline_hbm for the memory view"},
+        "roofline_hbm": {"achieved": per_gpu_solves * traffic_per_solve / 1e9 if traffic_per_solve else None, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": per_gpu_solves * traffic_per_solve / 1e9 / hbm_peak if traffic_per_solve else None,
+                         "algorithmic_gbs": per_gpu_solves * ALG_BYTES_PER_SOLVE / 1e9, "algorithmic_bytes_per_solve": ALG_BYTES_PER_SOLVE,
+                         "measured_bytes_per_solve": traffic_per_solve, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)",
+                         "note": "measured DRAM traffic of the committed ncu capture x this run's solves/s: the scratch rows of the resident "
+                                 "instances stream through HBM (they do not fit L2)"},
+        "fp64_extras": {"refactorisation_inclusive_tflops": per_gpu_solves * flops_refact / 1e12,
+                        "refactorisation_inclusive_frac": per_gpu_solves * flops_refact / 1e12 / tf.value if tf.value else None,
+                        "dmma_probe_tflops": tdm.value, "dfma_probe_tflops": tf.value,
+                        "note": "refactorisation-inclusive = every factorisation attempt (also those that fail the inertia test) at the dense-stage "
+                                "count; dmma_probe = mma.sync.m8n8k4.f64 micro-probe (nmpc_probe_dmma)"},
+        "per_rank": per_rank,
         "cpu_baseline": {"value": cpu_val, "unit": "solves/s", "cores": ncores, "kind": "port",
                          "sample": "%d cold-start instances of the same workload in %.1f s, restated IPOPT (oracle/), OpenMP" % (cpu_n, cpu_dt),
-                         "mean_iters": cpu_it},
+                         "mean_iters": cpu_it, "one_core": cpu_one_core()},
         "e2e": {"value": e2e_val, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "warm_start": warm, "latency": lat, "swarm64": swarm, "van_der_pol": vdp,
         "gpu_launches": launches, "clocks": sampler.summary(),

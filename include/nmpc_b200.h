@@ -18,8 +18,12 @@
  *    X_0 - x0bar and M constant rows (3.5); block k+1 = Euler defect of stage k and the squared
  *    distances on X_k, pairs in lexicographic order                               (:278,282-331)
  *  - multipliers in CasADi's sign convention (L = f + lam_g'g + lam_x'x).
- *  - functions whose names end in _host take HOST pointers and copy through pinned staging
- *    buffers; all others take DEVICE pointers, are asynchronous on `stream` and never allocate.
+ *  - functions whose names end in _host take HOST pointers (pageable or pinned: they are handed to
+ *    cudaMemcpyAsync as they are, so only pinned buffers overlap with device work), copy them into a
+ *    device staging area owned by the handle, and synchronise before returning; all others take DEVICE
+ *    pointers, are asynchronous on `stream` and never allocate.
+ *  - a handle belongs to the CUDA device that was current in nmpc_create; every later call must be made
+ *    with the same device current (checked: NMPC_EINVAL otherwise).
  *  - return value: 0 on success, <0 on an API error (nmpc_last_error() has the text).
  *    Non-convergence is NOT an error: it is reported per instance in status[], and the last
  *    iterate is returned, as CasADi does by default (the reference never reads the status).
@@ -71,7 +75,9 @@ enum { NMPC_SOLVED = 0, NMPC_ACCEPTABLE = 1, NMPC_MAX_ITER = 2, NMPC_INFEASIBLE 
 
 /* stats[B][NMPC_NSTATS] */
 enum { NMPC_ST_KKT_ERR = 0, NMPC_ST_PRIMAL_INF, NMPC_ST_DUAL_INF, NMPC_ST_COMPL, NMPC_ST_MU,
-       NMPC_ST_N_REG, NMPC_ST_N_RESTO, NMPC_ST_N_SOC, NMPC_ST_N_FACTOR, NMPC_ST_N_LS, NMPC_NSTATS };
+       NMPC_ST_N_REG, NMPC_ST_N_RESTO, NMPC_ST_N_SOC, NMPC_ST_N_FACTOR, NMPC_ST_N_LS,
+       NMPC_ST_FILTER_EVICT,   /* filter entries dropped because the fixed-size filter was full (IPOPT's is unbounded): 0 on every parity case */
+       NMPC_NSTATS };
 
 enum { NMPC_EINVAL = -1, NMPC_EBOUNDS = -2, NMPC_ENOTSUP = -3, NMPC_ECUDA = -4, NMPC_ENOMEM = -5 };
 
@@ -83,6 +89,19 @@ const char *nmpc_last_error(void);
 /* Replaces the nlpsol(...) factory (:345-346).  The handle owns only immutable problem metadata. */
 int nmpc_create(const nmpc_desc *d, const nmpc_opts *o, nmpc_handle **out);
 void nmpc_destroy(nmpc_handle *h);
+
+/* Launch tuning (no effect on results).  These used to be environment variables read inside nmpc_create; they are explicit
+ * now so that nothing on the product path depends on the process environment.
+ *   convoy            0 off, 1 the warps of a CTA meet at the start of every interior-point iteration, 2 (default) also
+ *                     before the forward pass (instruction-cache locality of the one-warp-per-instance path)
+ *   ctas_per_sm       > 0: cap on resident CTAs per SM (occupancy experiments); 0 = as many as fit
+ *   force_block_path  != 0: run any Nr on the CTA-per-instance dense-block solver (test hook)
+ *   thread_min_batch  > 0: batches at least this large of the one-robot static-obstacle family use the thread-per-instance
+ *                     solver; 0 = never */
+typedef struct nmpc_tuning { int convoy, ctas_per_sm, force_block_path, thread_min_batch; } nmpc_tuning;
+void nmpc_default_tuning(nmpc_tuning *t);
+/* nmpc_create / nmpc_create_obstacles (n_obs > 0) with explicit tuning; t == NULL means the defaults. */
+int nmpc_create_tuned(const nmpc_desc *d, const nmpc_opts *o, const nmpc_tuning *t, int n_obs, const double *obs, nmpc_handle **out);
 
 int nmpc_n(const nmpc_handle *h);        /* decision variables                         */
 int nmpc_mg(const nmpc_handle *h);       /* constraint rows                            */
@@ -125,12 +144,16 @@ int nmpc_create_obstacles(const nmpc_desc *d, const nmpc_opts *o, int n_obs, con
 enum { NMPC_OCP_VAN_DER_POL = 1 };
 int nmpc_create_ocp(int model, int N, double T, int rk_steps, const nmpc_opts *o, nmpc_handle **out);
 
-/* Scheduling hint for the following nmpc_solve* calls on this handle: order [B] (DEVICE int32, caller owned, a permutation
- * of 0..B-1) is the sequence in which the persistent teams pull instances from the work queue; NULL restores index order.
- * Instances differ in iteration count (17 on average, up to 70, one MPC step after a solve), so a closed loop that passes
- * the previous step's iteration counts sorted in descending order (longest first) shortens the tail of the launch.
- * Results do not depend on the order. */
-int nmpc_set_order(nmpc_handle *h, const int32_t *order);
+/* Scheduling hint for the following nmpc_solve* calls on this handle: order [len] (DEVICE int32, caller owned, a permutation
+ * of 0..len-1) is the sequence in which the persistent teams pull instances from the work queue; NULL (len ignored) restores
+ * index order.  Instances differ in iteration count (17 on average, up to 70, one MPC step after a solve), so a closed loop
+ * that passes the previous step's iteration counts sorted in descending order (longest first) shortens the tail of the launch.
+ * Results do not depend on the order.  The array must stay valid, and its contents must be complete on the stream the solve
+ * is launched on (nmpc_solve_host uses the handle's own stream: synchronise the producer first), until the hint is replaced.
+ * A solve whose batch size differs from len fails with NMPC_EINVAL; entries outside 0..len-1 are skipped by the kernel
+ * (the outputs of the instances a broken permutation leaves out are not written), so a stale or corrupt order can never
+ * cause an out-of-bounds access. */
+int nmpc_set_order(nmpc_handle *h, const int32_t *order, int len);
 
 /* nmpc_solve plus a per-iteration trace [B][max_trace][8] = (mu, scaled KKT error, theta, f, alpha_primal,
  * alpha_dual, delta_w, line-search trials) -- the parity tests compare it with the oracle's trace. */
@@ -169,6 +192,9 @@ int nmpc_hess_pattern(const nmpc_handle *h, int32_t *colptr, int32_t *rowidx);
 /* Measurement helper: sustained FP64 FMA throughput of the device (TFLOP/s) from a register-only DFMA
  * kernel -- the roofline denominator for the factorisation (MEASURED_PEAKS.json has no FP64 figure). */
 int nmpc_probe_fp64(double *tflops_out);
+/* Same for the FP64 tensor-core instruction (mma.sync.m8n8k4.f64, DMMA; tcgen05 has no f64 kind): the number behind the
+ * dense-block path's choice of register tiles on the FP64 FMA pipe (csrc/block_solver.cuh). */
+int nmpc_probe_dmma(double *tflops_out);
 
 /* Debug aid: cycle counters of the phases of the dense-block factorisation (Nr > 10), CTA 0 only:
  * [0] stage-parallel pre-pass, [1] p + P r mat-vec, [2] stage-matrix assembly, [3] control-block elimination,

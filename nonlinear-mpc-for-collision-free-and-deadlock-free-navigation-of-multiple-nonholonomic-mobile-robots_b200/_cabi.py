@@ -7,14 +7,15 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnmpc_b200.so")
-NSTATS = 10
+NSTATS = 11      # NMPC_NSTATS (the last column counts filter evictions)
 NTRACE = 8
 STATUS = {0: "SOLVED", 1: "ACCEPTABLE", 2: "MAX_ITER", 3: "INFEASIBLE", 4: "NUMERICAL"}
 SYMBOLS = ["nmpc_default_opts", "nmpc_last_error", "nmpc_create", "nmpc_destroy", "nmpc_n", "nmpc_mg", "nmpc_np",
            "nmpc_nnz_jac", "nmpc_nnz_hess", "nmpc_workspace_bytes", "nmpc_workspace_bytes_batched_bounds", "nmpc_solve",
            "nmpc_solve_trace", "nmpc_solve_host", "nmpc_shift",
            "nmpc_plant", "nmpc_eval", "nmpc_jac_pattern", "nmpc_hess_pattern", "nmpc_launch_count", "nmpc_probe_fp64",
-           "nmpc_debug_block_profile", "nmpc_set_order", "nmpc_create_obstacles", "nmpc_create_ocp"]
+           "nmpc_debug_block_profile", "nmpc_set_order", "nmpc_create_obstacles", "nmpc_create_ocp",
+           "nmpc_default_tuning", "nmpc_create_tuned", "nmpc_probe_dmma"]
 
 
 class Desc(C.Structure):
@@ -31,6 +32,11 @@ class Opts(C.Structure):
                 ("bound_mult_init_val", C.c_double), ("constr_mult_init_max", C.c_double),
                 ("kappa_sigma", C.c_double), ("kappa_d", C.c_double), ("nlp_scaling_max_gradient", C.c_double),
                 ("max_soc", C.c_int), ("max_resto_iter", C.c_int)]
+
+
+class Tuning(C.Structure):
+    """nmpc_tuning: launch tuning, no effect on results (include/nmpc_b200.h)."""
+    _fields_ = [("convoy", C.c_int), ("ctas_per_sm", C.c_int), ("force_block_path", C.c_int), ("thread_min_batch", C.c_int)]
 
 
 class NmpcError(RuntimeError):
@@ -54,6 +60,9 @@ def lib():
     L.nmpc_last_error.restype = C.c_char_p
     L.nmpc_create.argtypes = [C.POINTER(Desc), C.POINTER(Opts), C.POINTER(H)]
     L.nmpc_create_obstacles.argtypes = [C.POINTER(Desc), C.POINTER(Opts), C.c_int, vp, C.POINTER(H)]
+    L.nmpc_default_tuning.argtypes = [C.POINTER(Tuning)]
+    L.nmpc_default_tuning.restype = None
+    L.nmpc_create_tuned.argtypes = [C.POINTER(Desc), C.POINTER(Opts), C.POINTER(Tuning), C.c_int, vp, C.POINTER(H)]
     L.nmpc_create_ocp.argtypes = [C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(Opts), C.POINTER(H)]
     L.nmpc_destroy.argtypes = [H]
     L.nmpc_destroy.restype = None
@@ -74,7 +83,8 @@ def lib():
     L.nmpc_launch_count.argtypes = [H]
     L.nmpc_probe_fp64.argtypes = [C.POINTER(C.c_double)]
     L.nmpc_debug_block_profile.argtypes = [C.POINTER(C.c_longlong), C.c_int]
-    L.nmpc_set_order.argtypes = [H, vp]
+    L.nmpc_set_order.argtypes = [H, vp, C.c_int]
+    L.nmpc_probe_dmma.argtypes = [C.POINTER(C.c_double)]
     L.nmpc_launch_count.restype = C.c_longlong
     _LIB = L
     return L
@@ -83,6 +93,16 @@ def lib():
 def check(rc):
     if rc != 0:
         raise NmpcError("nmpc error %d: %s" % (rc, lib().nmpc_last_error().decode()))
+
+
+def default_tuning(**kw):
+    t = Tuning()
+    lib().nmpc_default_tuning(C.byref(t))
+    for k, v in kw.items():
+        if k not in {f[0] for f in Tuning._fields_}:
+            raise ValueError("unknown tuning key %r" % (k,))
+        setattr(t, k, int(v))
+    return t
 
 
 def default_opts(**kw):

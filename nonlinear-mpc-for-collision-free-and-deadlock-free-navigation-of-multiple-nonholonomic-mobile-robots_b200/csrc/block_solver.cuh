@@ -83,7 +83,8 @@ struct BlockSolver {
         const long long S = N + 1, ns = 3 * Nr, nc = 2 * Nr, W = row_width(Nr, nobs);
         const long long ldy = (ns + 1 + 3) & ~3LL;
         const long long ncp = (nc + 31) & ~31LL;
-        return (long long)R_COUNT * S * W + ((S * ns * ns + 1) & ~1LL) + (long long)(N + 1) * nc * ldy + (long long)N * ncp * ncp;   // every block 16-byte aligned
+        return (long long)R_COUNT * S * W + ((S * ns * ns + 1) & ~1LL) + (long long)(N + 1) * nc * ldy + (long long)N * ncp * ncp   // every block 16-byte aligned
+               + 2 * NMPC_FILTER_CAP;   // the filter (theta values, then phi values), see filter_add
     }
     static NMPC_HD long long sm_doubles(int Nr)
     {
@@ -161,6 +162,7 @@ struct BlockSolver {
         SM_TB = SM_DXN + ns; SM_XB = SM_TB + ncp; SM_DINV = SM_XB + ncp; SM_PR = SM_DINV + ncp; SM_CS = SM_PR + ns; SM_DS = SM_CS + 2 * Nr; SM_MUU = (SM_DS + 5 * Nr + 1) & ~1;
         df = 1.0; fn = 0;
         n_reg = n_resto = n_soc = n_fact = n_ls = 0;
+        if (tid == 0) sm[SM_MISC + 2] = 0.0;   // filter evictions
         __syncthreads();
     }
     __device__ bool bounds_rejected()
@@ -1048,32 +1050,28 @@ struct BlockSolver {
     // ---------------------------------------------------------------------------------------
     // filter (shared memory; thread 0 edits)
     // ---------------------------------------------------------------------------------------
+    // IPOPT's filter is unbounded inside a barrier subproblem: it lives in the slot's global scratch, append-only (an entry
+    // that a newer one dominates is redundant for the test and stays); an overflow overwrites the oldest and is counted.
+    __device__ double *filter_base() const { return Lall + (long long)N * ncp * ncp; }
     __device__ bool filter_ok(double th, double ph) const
     {
-        NMPC_BLK_LOCALS
-        const double *fth = sm + SM_FTH, *fph = sm + SM_FPH;
-        for (int i = 0; i < fn; i++)
+        const double *fth = wp::global_ptr(filter_base()), *fph = fth + NMPC_FILTER_CAP;
+        const int m = fn < NMPC_FILTER_CAP ? fn : NMPC_FILTER_CAP;
+        for (int i = 0; i < m; i++)
             if (!(th < fth[i] || ph < fph[i])) return false;
         return true;
     }
     NMPC_BPASS void filter_add(double th, double ph)
     {
         NMPC_BLK_LOCALS
-        double *fth = sm + SM_FTH, *fph = sm + SM_FPH, *misc = sm + SM_MISC;
+        double *fth = wp::global_ptr(filter_base()), *fph = fth + NMPC_FILTER_CAP;
         __syncthreads();
         if (tid == 0) {
-            int m = 0;
-            for (int i = 0; i < fn; i++)
-                if (!(fth[i] >= th && fph[i] >= ph)) { fth[m] = fth[i]; fph[m] = fph[i]; m++; }
-            if (m == NMPC_FILTER_CAP) {
-                for (int i = 1; i < m; i++) { fth[i - 1] = fth[i]; fph[i - 1] = fph[i]; }
-                m--;
-            }
-            fth[m] = th; fph[m] = ph; m++;
-            misc[0] = (double)m;
+            const int slot = fn % NMPC_FILTER_CAP;
+            fth[slot] = th; fph[slot] = ph;
+            if (fn >= NMPC_FILTER_CAP) sm[SM_MISC + 2] += 1.0;
         }
-        __syncthreads();
-        fn = (int)misc[0];
+        fn++;
         __syncthreads();
     }
     __device__ bool trial_ok(double th_t, double ph_t, double theta, double phi, double theta_max, double theta_min, double gbd,
@@ -1128,7 +1126,7 @@ struct BlockSolver {
                 double *sp = P.stats + (long long)inst * NMPC_NSTATS;
                 sp[NMPC_ST_KKT_ERR] = E0; sp[NMPC_ST_PRIMAL_INF] = pinf; sp[NMPC_ST_DUAL_INF] = dinf; sp[NMPC_ST_COMPL] = c0;
                 sp[NMPC_ST_MU] = mu; sp[NMPC_ST_N_REG] = n_reg; sp[NMPC_ST_N_RESTO] = n_resto; sp[NMPC_ST_N_SOC] = n_soc;
-                sp[NMPC_ST_N_FACTOR] = n_fact; sp[NMPC_ST_N_LS] = n_ls;
+                sp[NMPC_ST_N_FACTOR] = n_fact; sp[NMPC_ST_N_LS] = n_ls; sp[NMPC_ST_FILTER_EVICT] = sm[SM_MISC + 2];
             }
         }
         __syncthreads();

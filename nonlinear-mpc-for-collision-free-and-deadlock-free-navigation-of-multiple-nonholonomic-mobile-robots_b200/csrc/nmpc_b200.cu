@@ -17,10 +17,13 @@
 #include "aux_kernels.cuh"
 
 #ifndef SOLVE_WARPS
-#define SOLVE_WARPS 3     // warps (instances) per CTA = the convoy group, see WarpSolver::iter_sync
+#define SOLVE_WARPS 4     // warps (instances) per CTA = the convoy group, see WarpSolver::iter_sync
 #endif
 #ifndef SOLVE_MIN_CTAS
-#define SOLVE_MIN_CTAS 4   // 12 resident instances per SM (15 KB of shared memory each, <= 168 registers per thread)
+#define SOLVE_MIN_CTAS 3   // 12 resident instances per SM (13.2 KB of shared memory each, <= 168 registers per thread).  Measured
+                           // (round 2, profiles/sweeps_r2.md): 4 x 3 -> 46.4 k, 3 x 4 -> 45.1 k, 6 x 2 -> 45.6 k, 2 x 6 -> 43.2 k solves/s;
+                           // 128-register builds with 15-16 warps per SM (3 x 5, 4 x 4, 2 x 8) -> 34-35 k: their spills go to
+                           // local memory while 16 x 13.2 KB of shared memory leaves almost no L1 to hold them
 #endif
 
 static thread_local char g_err[512] = "";
@@ -83,6 +86,7 @@ __global__ void __launch_bounds__(SolveCfg<NR>::THREADS, SolveCfg<NR>::MIN_CTAS)
             break;
         }
         const int inst = P.order ? P.order[slot] : slot;   // longest-first scheduling when the caller has a predictor
+        if ((unsigned)inst >= (unsigned)P.B) continue;      // not a permutation: never index outside the batch
         s.setup(inst);
         s.run();
     }
@@ -99,6 +103,8 @@ struct nmpc_handle {
     size_t ws_doubles_per_slot, solve_smem, eval_smem;
     int ctas_per_sm, lw, teams_per_cta, threads;
     const int *d_order;                       // optional processing order (device, caller owned), see nmpc_set_order
+    int order_len;
+    nmpc_tuning tune;
     int nobs, family, rk_steps;               // static obstacles per robot; family: 0 centralized, 1 obstacles, 2 small OCP (thread per instance)
     double *d_obs;                            // [nobs][3] on the device
     bool thread_ok;                           // a thread-per-instance kernel exists for this problem (small-OCP family; one robot with
@@ -179,24 +185,40 @@ template <int NR> static cudaError_t config_solve(nmpc_handle *h)
     int nb = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, solve_kernel<NR>, SolveCfg<NR>::THREADS, h->solve_smem);
     h->ctas_per_sm = nb > 0 ? nb : 1;
-    if (const char *ov = getenv("NMPC_CTAS_PER_SM")) {   // tuning knob: fewer resident instances per SM
-        int v = atoi(ov);
-        if (v >= 1 && v < h->ctas_per_sm) h->ctas_per_sm = v;
-    }
+    if (h->tune.ctas_per_sm >= 1 && h->tune.ctas_per_sm < h->ctas_per_sm) h->ctas_per_sm = h->tune.ctas_per_sm;
     return e;
 }
 
-static int create_impl(const nmpc_desc *d, const nmpc_opts *o, int nobs, const double *obs, nmpc_handle **out);
+static int create_impl(const nmpc_desc *d, const nmpc_opts *o, const nmpc_tuning *t, int nobs, const double *obs, nmpc_handle **out);
 
-extern "C" int nmpc_create(const nmpc_desc *d, const nmpc_opts *o, nmpc_handle **out) { return create_impl(d, o, 0, nullptr, out); }
+extern "C" void nmpc_default_tuning(nmpc_tuning *t)
+{
+    t->convoy = 2;   // measured: +14 % cold throughput over no convoy, +4 % over the iteration barrier alone
+    t->ctas_per_sm = 0; t->force_block_path = 0; t->thread_min_batch = 0;
+}
 
-extern "C" int nmpc_create_obstacles(const nmpc_desc *d, const nmpc_opts *o, int n_obs, const double *obs, nmpc_handle **out)
+extern "C" int nmpc_create(const nmpc_desc *d, const nmpc_opts *o, nmpc_handle **out) { return create_impl(d, o, nullptr, 0, nullptr, out); }
+
+static int check_obstacles(int n_obs, const double *obs)
 {
     if (n_obs < 1 || n_obs > NMPC_MAX_OBSTACLES || !obs)
         return fail(NMPC_EINVAL, "nmpc_create_obstacles: need 1..%d obstacles (x, y, clearance radius each)", NMPC_MAX_OBSTACLES);
     for (int i = 0; i < n_obs; i++)
         if (!(obs[3 * i + 2] >= 0.0)) return fail(NMPC_EINVAL, "nmpc_create_obstacles: obstacle %d has a negative clearance radius", i);
-    return create_impl(d, o, n_obs, obs, out);
+    return 0;
+}
+
+extern "C" int nmpc_create_tuned(const nmpc_desc *d, const nmpc_opts *o, const nmpc_tuning *t, int n_obs, const double *obs, nmpc_handle **out)
+{
+    if (n_obs != 0) { int rc = check_obstacles(n_obs, obs); if (rc) return rc; }
+    return create_impl(d, o, t, n_obs, n_obs ? obs : nullptr, out);
+}
+
+extern "C" int nmpc_create_obstacles(const nmpc_desc *d, const nmpc_opts *o, int n_obs, const double *obs, nmpc_handle **out)
+{
+    int rc = check_obstacles(n_obs, obs);
+    if (rc) return rc;
+    return create_impl(d, o, nullptr, n_obs, obs, out);
 }
 
 // Small generic OCP family (thread per instance): currently the Van der Pol demo of mpc_pose_control_casadi.py
@@ -216,7 +238,8 @@ extern "C" int nmpc_create_ocp(int model, int N, double T, int rk_steps, const n
     h->ns = TS::NX; h->nc = TS::NU; h->M = 0; h->S = N + 1; h->nobs = 0; h->family = 2; h->rk_steps = rk_steps;
     h->n = TS::NZ * N + TS::NX; h->mg = TS::NX * N; h->np = 0; h->nnzj = 0; h->nnzh = 0;
     h->launches = 0; h->d_buf = nullptr; h->d_bytes = 0; h->stream = nullptr; h->d_tables = nullptr; h->d_pairs = nullptr;
-    h->d_order = nullptr; h->d_obs = nullptr; h->block_path = false; h->eval_ok = false; h->thread_ok = true; h->thread_min_batch = 1;
+    h->d_order = nullptr; h->order_len = 0; h->d_obs = nullptr; h->block_path = false; h->eval_ok = false; h->thread_ok = true; h->thread_min_batch = 1;
+    nmpc_default_tuning(&h->tune);
     cudaGetDevice(&h->dev);
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->dev);
     h->ws_doubles_per_slot = 0; h->t_ws_doubles = (size_t)TS::ws_doubles(N);
@@ -225,21 +248,19 @@ extern "C" int nmpc_create_ocp(int model, int N, double T, int rk_steps, const n
     return 0;
 }
 
-static int create_impl(const nmpc_desc *d, const nmpc_opts *o, int nobs, const double *obs, nmpc_handle **out)
+static int create_impl(const nmpc_desc *d, const nmpc_opts *o, const nmpc_tuning *t, int nobs, const double *obs, nmpc_handle **out)
 {
     if (!d || !out) return fail(NMPC_EINVAL, "nmpc_create: NULL argument");
     if (d->N < 1 || !(d->T > 0)) return fail(NMPC_EINVAL, "nmpc_create: need N >= 1 and T > 0");
     if (d->Nr < 1 || d->Nr > NMPC_MAX_ROBOTS)
         return fail(NMPC_ENOTSUP, "nmpc_create: Nr = %d; supported: 1..10 robots (warp-per-instance) and 11..%d (CTA-per-instance dense blocks)", d->Nr, NMPC_MAX_ROBOTS);
-    const bool dbg = getenv("NMPC_DEBUG") != nullptr;
-#define DBG(msg) do { if (dbg) { fprintf(stderr, "[nmpc_create] %s\n", msg); fflush(stderr); } } while (0)
-    DBG("enter");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(NMPC_ECUDA, "nmpc_create: no CUDA device -- this library has no CPU fallback");
     nmpc_handle *h = new nmpc_handle();
     h->d = *d;
     if (o) h->o = *o; else nmpc_default_opts(&h->o);
+    if (t) h->tune = *t; else nmpc_default_tuning(&h->tune);
     h->ns = 3 * d->Nr; h->nc = 2 * d->Nr; h->M = d->Nr * (d->Nr - 1) / 2; h->S = d->N + 1;
     h->nobs = nobs; h->family = nobs > 0 ? 1 : 0; h->d_obs = nullptr;
     h->n = h->ns * h->S + h->nc * d->N; h->np = 2 * h->ns;
@@ -248,30 +269,24 @@ static int create_impl(const nmpc_desc *d, const nmpc_opts *o, int nobs, const d
     h->mg = h->family ? h->ns + d->N * (h->ns + h->M + d->Nr * nobs) : h->S * (h->ns + h->M);
     h->nnzj = 3 * d->Nr + d->N * (11 * d->Nr + 4 * h->M); h->nnzh = d->N * (6 * d->Nr + 2 * h->M);
     h->launches = 0; h->d_buf = nullptr; h->d_bytes = 0; h->stream = nullptr; h->d_tables = nullptr;
-    h->d_pairs = nullptr; h->d_order = nullptr;
-    // the obstacle family runs on the dense-block path for every Nr; NMPC_FORCE_BLOCK: test hook, any Nr on that path
-    h->block_path = d->Nr > 10 || h->family != 0 || getenv("NMPC_FORCE_BLOCK") != nullptr; h->eval_ok = h->family == 0;
+    h->d_pairs = nullptr; h->d_order = nullptr; h->order_len = 0;
+    // the obstacle family runs on the dense-block path for every Nr; nmpc_tuning.force_block_path: test hook, any Nr on that path
+    h->block_path = d->Nr > 10 || h->family != 0 || h->tune.force_block_path != 0; h->eval_ok = h->family == 0;
     // A single robot with static obstacles (the reference's obstacle scripts) also runs on the thread-per-instance small-OCP
     // solver (UnicycleObstacles model), parity-tested, but measured slower than the CTA-per-instance path both alone (88 ms
     // against 49 ms per solve at N = 100) and in batches (9.2 k against 23.0 k solves/s, B = 8192, N = 20: its per-thread
-    // scratch is not coalesced across instances), so it is off unless NMPC_THREAD_MIN_BATCH sets a switch-over batch size.
+    // scratch is not coalesced across instances), so it is off unless nmpc_tuning.thread_min_batch sets a switch-over batch size.
     h->thread_ok = h->family == 1 && d->Nr == 1;
     h->t_ws_doubles = h->thread_ok ? (size_t)ThreadSolver<UnicycleObstacles>::ws_doubles(d->N) : 0;
-    h->thread_min_batch = 0x7fffffff;
-    h->convoy = 2;   // 0 off, 1 barrier per iteration, 2 also before the forward pass (measured: +14 % cold throughput)
-    if (const char *ov = getenv("NMPC_CONVOY")) h->convoy = atoi(ov);
-    if (const char *ov = getenv("NMPC_THREAD_MIN_BATCH")) h->thread_min_batch = atoi(ov) > 0 ? atoi(ov) : 1;
-    DBG("device count ok");
+    h->thread_min_batch = h->tune.thread_min_batch > 0 ? h->tune.thread_min_batch : 0x7fffffff;
+    h->convoy = h->tune.convoy;   // 0 off, 1 barrier per iteration, 2 also before the forward pass
     cudaGetDevice(&h->dev);
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->dev);
     std::vector<int> tab;
-    DBG("build tables");
     build_tables(h, tab);
-    DBG("tables built");
     cudaError_t e = cudaMalloc(&h->d_tables, tab.size() * sizeof(int));
     if (e == cudaSuccess) e = cudaMemcpy(h->d_tables, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) { delete h; return fail(NMPC_ECUDA, "nmpc_create: table upload failed: %s", cudaGetErrorString(e)); }
-    DBG("tables uploaded");
+    if (e != cudaSuccess) { nmpc_destroy(h); return fail(NMPC_ECUDA, "nmpc_create: table upload failed: %s", cudaGetErrorString(e)); }
     const int N = d->N, Nr = d->Nr, M = h->M;
     h->tb.jac_rs = h->d_tables;
     h->tb.jac_ps = h->tb.jac_rs + (size_t)N * Nr * 11;
@@ -279,6 +294,12 @@ static int create_impl(const nmpc_desc *d, const nmpc_opts *o, int nobs, const d
     h->tb.hes_rs = h->d_tables + h->nnzj;
     h->tb.hes_ps = h->tb.hes_rs + (size_t)N * Nr * 6;
     switch (h->block_path ? 0 : Nr) {
+#ifdef NMPC_DEV_ONLY_NR   // development builds (tools/dev_build.sh): one warp-path instantiation, 5 x faster to compile
+        case NMPC_DEV_ONLY_NR: h->ws_doubles_per_slot = slot_doubles<NMPC_DEV_ONLY_NR>(N); e = config_solve<NMPC_DEV_ONLY_NR>(h); break;
+        case 100: break;
+#define NMPC_SKIP_OTHER_NR
+#endif
+#ifndef NMPC_SKIP_OTHER_NR
         case 1: h->ws_doubles_per_slot = slot_doubles<1>(N); e = config_solve<1>(h); break;
         case 2: h->ws_doubles_per_slot = slot_doubles<2>(N); e = config_solve<2>(h); break;
         case 3: h->ws_doubles_per_slot = slot_doubles<3>(N); e = config_solve<3>(h); break;
@@ -289,6 +310,7 @@ static int create_impl(const nmpc_desc *d, const nmpc_opts *o, int nobs, const d
         case 8: h->ws_doubles_per_slot = slot_doubles<8>(N); e = config_solve<8>(h); break;
         case 9: h->ws_doubles_per_slot = slot_doubles<9>(N); e = config_solve<9>(h); break;
         case 10: h->ws_doubles_per_slot = slot_doubles<10>(N); e = config_solve<10>(h); break;
+#endif
         default: {   // dense-block path: one 512-thread CTA per instance, the control block of the stage matrix in shared memory
             h->ws_doubles_per_slot = (size_t)BlockSolver::ws_doubles(Nr, N, h->nobs);
             // CTA size: the register-resident Cholesky needs 8 rows per warp over ncp = roundup(2 Nr, 32) rows, i.e. 4 ncp threads
@@ -301,7 +323,7 @@ static int create_impl(const nmpc_desc *d, const nmpc_opts *o, int nobs, const d
             int nb = 0;
             if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, solve_kernel_block, h->threads, h->solve_smem);
             h->ctas_per_sm = nb > 0 ? nb : 1;
-            if (const char *ov = getenv("NMPC_CTAS_PER_SM")) { int v = atoi(ov); if (v >= 1 && v < h->ctas_per_sm) h->ctas_per_sm = v; }
+            if (h->tune.ctas_per_sm >= 1 && h->tune.ctas_per_sm < h->ctas_per_sm) h->ctas_per_sm = h->tune.ctas_per_sm;
             std::vector<int> pr;
             for (int a = 0; a < Nr; a++)
                 for (int b = a + 1; b < Nr; b++) { pr.push_back(a); pr.push_back(b); }
@@ -314,8 +336,7 @@ static int create_impl(const nmpc_desc *d, const nmpc_opts *o, int nobs, const d
             break;
         }
     }
-    if (e != cudaSuccess) { cudaFree(h->d_tables); delete h; return fail(NMPC_ECUDA, "nmpc_create: kernel configuration failed: %s", cudaGetErrorString(e)); }
-    DBG("solve kernel configured");
+    if (e != cudaSuccess) { nmpc_destroy(h); return fail(NMPC_ECUDA, "nmpc_create: kernel configuration failed: %s", cudaGetErrorString(e)); }
     h->eval_smem = (size_t)(2 * h->n + 2 * h->mg + 2 * h->ns + h->nnzj + h->nnzh + 32 + 8) * sizeof(double);
     if (h->eval_smem > (size_t)220 * 1024 || h->family != 0) h->eval_ok = false;   // large swarms: the stand-alone evaluation record exceeds shared memory
     else {
@@ -330,7 +351,7 @@ static int create_impl(const nmpc_desc *d, const nmpc_opts *o, int nobs, const d
         if (e == cudaSuccess) e = cudaFuncSetAttribute(eval_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(eval_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz);
     }
-    if (e != cudaSuccess) { cudaFree(h->d_tables); delete h; return fail(NMPC_ENOTSUP, "nmpc_create: eval record (%zu B) exceeds shared memory: %s", h->eval_smem, cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { const size_t es = h->eval_smem; nmpc_destroy(h); return fail(NMPC_ENOTSUP, "nmpc_create: eval record (%zu B) exceeds shared memory: %s", es, cudaGetErrorString(e)); }
     *out = h;
     return 0;
 }
@@ -390,6 +411,13 @@ static int solve_impl(nmpc_handle *h, int B, const double *x0, const double *p, 
 {
     if (!h || !x0 || (!p && h->np > 0) || !lbx || !ubx || !lbg || !ubg || !x || !workspace) return fail(NMPC_EINVAL, "nmpc_solve: NULL argument");
     if (B <= 0) return fail(NMPC_EINVAL, "nmpc_solve: B must be positive");
+    if (h->d_order && h->order_len != B)
+        return fail(NMPC_EINVAL, "nmpc_solve: the scheduling order set with nmpc_set_order has %d entries, the batch has %d", h->order_len, B);
+    {
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess || cur != h->dev)
+            return fail(NMPC_EINVAL, "nmpc_solve: the handle was created on CUDA device %d but device %d is current", h->dev, cur);
+    }
     const int nb = bounds_batched ? B : 1;
     const size_t need = ws_bytes_for(h, B, nb);
     if (workspace_bytes < need) return fail(NMPC_ENOMEM, "nmpc_solve: workspace %zu B < %zu B required", workspace_bytes, need);
@@ -423,6 +451,9 @@ static int solve_impl(nmpc_handle *h, int B, const double *x0, const double *p, 
     else if (thr) solve_kernel_small_ocp<UnicycleObstacles><<<grid, 64, 0, st>>>(P);
     else if (h->block_path) solve_kernel_block<<<grid, h->threads, h->solve_smem, st>>>(P);
     else switch (h->d.Nr) {
+#ifdef NMPC_DEV_ONLY_NR
+        default: solve_kernel<NMPC_DEV_ONLY_NR><<<grid, h->threads, h->solve_smem, st>>>(P); break;
+#else
         case 1: solve_kernel<1><<<grid, h->threads, h->solve_smem, st>>>(P); break;
         case 2: solve_kernel<2><<<grid, h->threads, h->solve_smem, st>>>(P); break;
         case 3: solve_kernel<3><<<grid, h->threads, h->solve_smem, st>>>(P); break;
@@ -433,16 +464,18 @@ static int solve_impl(nmpc_handle *h, int B, const double *x0, const double *p, 
         case 8: solve_kernel<8><<<grid, h->threads, h->solve_smem, st>>>(P); break;
         case 9: solve_kernel<9><<<grid, h->threads, h->solve_smem, st>>>(P); break;
         default: solve_kernel<10><<<grid, h->threads, h->solve_smem, st>>>(P); break;
+#endif
     }
     h->launches++;
     CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-extern "C" int nmpc_set_order(nmpc_handle *h, const int32_t *order)
+extern "C" int nmpc_set_order(nmpc_handle *h, const int32_t *order, int len)
 {
     if (!h) return fail(NMPC_EINVAL, "nmpc_set_order: NULL handle");
-    h->d_order = order;
+    if (order && len <= 0) return fail(NMPC_EINVAL, "nmpc_set_order: len must be positive");
+    h->d_order = order; h->order_len = order ? len : 0;
     return 0;
 }
 
@@ -589,6 +622,25 @@ __global__ void __launch_bounds__(256) dfma_probe_kernel(int iters, double *out)
     if (r == 123.456) out[0] = r;
 }
 
+// FP64 tensor-core probe: mma.sync.aligned.m8n8k4 f64 (DMMA), 8 independent accumulator tiles per warp, register only.
+// One instruction = 8 x 8 x 4 FMAs = 512 flop per warp.  Measured beside the DFMA probe so that the dense-block path's
+// "register tiles on the FP64 pipe, not DMMA" decision (block_solver.cuh) rests on a number.
+__global__ void __launch_bounds__(256) dmma_probe_kernel(int iters, double *out)
+{
+    double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+    double c[8][2];
+    for (int t = 0; t < 8; t++) { c[t][0] = t * 1e-3; c[t][1] = t * 2e-3; }
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int t = 0; t < 8; t++)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                         : "+d"(c[t][0]), "+d"(c[t][1]) : "d"(a), "d"(b));
+    }
+    double r = 0.0;
+    for (int t = 0; t < 8; t++) r += c[t][0] + c[t][1];
+    if (r == 123.456) out[0] = r;
+}
+
 // debug aid: cycle counters per phase of the dense-block factorisation (CTA 0); reset = 1 clears them after the read
 extern "C" int nmpc_debug_block_profile(long long *out16, int reset)
 {
@@ -618,6 +670,33 @@ extern "C" int nmpc_probe_fp64(double *tflops_out)
         float ms = 0;
         CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
         double tf = 2.0 * 8.0 * iters * 256.0 * grid / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    *tflops_out = best;
+    return 0;
+}
+
+extern "C" int nmpc_probe_dmma(double *tflops_out)
+{
+    if (!tflops_out) return fail(NMPC_EINVAL, "nmpc_probe_dmma: NULL argument");
+    int dev = 0, sms = 0;
+    CUDA_OK(cudaGetDevice(&dev));
+    CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    double *d = nullptr;
+    CUDA_OK(cudaMalloc(&d, 64));
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
+    const int iters = 1 << 14, grid = sms * 8;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        CUDA_OK(cudaEventRecord(e0));
+        dmma_probe_kernel<<<grid, 256>>>(iters, d);
+        CUDA_OK(cudaEventRecord(e1));
+        CUDA_OK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+        double tf = 512.0 * 8.0 * iters * 8.0 * grid / (ms * 1e-3) / 1e12;   // 512 flop x 8 tiles x 8 warps per CTA
         if (rep > 0 && tf > best) best = tf;
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);

@@ -4,7 +4,8 @@
 #include "nmpc_b200.h"
 
 #define NMPC_LANES 32
-#define NMPC_FILTER_CAP 16
+#define NMPC_FILTER_CAP 256     /* filter entries per barrier subproblem (global scratch; overflow is counted in the stats) */
+#define NMPC_FILTER_CAP_SMALL 64 /* the thread-per-instance small-OCP solver keeps its filter in local memory */
 #define NMPC_DUMMY_ROW_VALUE 3.5 /* centralized_six_robots_implementation.py:278 */
 #define NMPC_NTRACE 8
 #define NMPC_MAX_ROBOTS 64

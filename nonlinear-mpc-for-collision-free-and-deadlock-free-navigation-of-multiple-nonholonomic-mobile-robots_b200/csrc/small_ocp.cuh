@@ -188,8 +188,8 @@ struct ThreadSolver {
     int N, S, inst, fn, ni;
     bool fixed0;
     double df, ny_nzb, nzb_cnt;
-    int n_reg, n_resto, n_soc, n_fact, n_ls;
-    double fth[NMPC_FILTER_CAP], fph[NMPC_FILTER_CAP];
+    int n_reg, n_resto, n_soc, n_fact, n_ls, n_evict;
+    double fth[NMPC_FILTER_CAP_SMALL], fph[NMPC_FILTER_CAP_SMALL];
 
     static NMPC_HD long long ws_doubles(int N) { return (long long)(R_COUNT * LD + C_COUNT) * (N + 1); }
 
@@ -216,7 +216,7 @@ struct ThreadSolver {
         ni = Model::n_ineq(ctx);
         cache = ws + (long long)R_COUNT * LD * S;
         df = 1.0; fn = 0; fixed0 = false;
-        n_reg = n_resto = n_soc = n_fact = n_ls = 0;
+        n_reg = n_resto = n_soc = n_fact = n_ls = n_evict = 0;
     }
     __device__ bool bounds_rejected()
     {
@@ -675,7 +675,7 @@ struct ThreadSolver {
         int m = 0;
         for (int i = 0; i < fn; i++)
             if (!(fth[i] >= th && fph[i] >= ph)) { fth[m] = fth[i]; fph[m] = fph[i]; m++; }
-        if (m == NMPC_FILTER_CAP) { for (int i = 1; i < m; i++) { fth[i - 1] = fth[i]; fph[i - 1] = fph[i]; } m--; }
+        if (m == NMPC_FILTER_CAP_SMALL) { for (int i = 1; i < m; i++) { fth[i - 1] = fth[i]; fph[i - 1] = fph[i]; } m--; n_evict++; }
         fth[m] = th; fph[m] = ph; fn = m + 1;
     }
     __device__ bool trial_ok(double th_t, double ph_t, double theta, double phi, double theta_max, double theta_min, double gbd,
@@ -720,7 +720,7 @@ struct ThreadSolver {
             double *sp = P.stats + (long long)inst * NMPC_NSTATS;
             sp[NMPC_ST_KKT_ERR] = E0; sp[NMPC_ST_PRIMAL_INF] = pinf; sp[NMPC_ST_DUAL_INF] = dinf; sp[NMPC_ST_COMPL] = c0;
             sp[NMPC_ST_MU] = mu; sp[NMPC_ST_N_REG] = n_reg; sp[NMPC_ST_N_RESTO] = n_resto; sp[NMPC_ST_N_SOC] = n_soc;
-            sp[NMPC_ST_N_FACTOR] = n_fact; sp[NMPC_ST_N_LS] = n_ls;
+            sp[NMPC_ST_N_FACTOR] = n_fact; sp[NMPC_ST_N_LS] = n_ls; sp[NMPC_ST_FILTER_EVICT] = n_evict;
         }
     }
     __device__ void run() { ipm_run(*this); }

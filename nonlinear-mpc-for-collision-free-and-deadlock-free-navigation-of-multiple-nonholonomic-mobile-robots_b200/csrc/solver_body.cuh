@@ -48,6 +48,9 @@
     (void)row; (void)frow; (void)zvalid; (void)gradf;
 
 struct alignas(16) NmpcD2 { double x, y; };   // one 128-bit shared-memory load
+#ifndef NMPC_XBATCH
+#define NMPC_XBATCH 3   // pairs of pivot-row entries per batch of the sweep's state-row update (see factor())
+#endif
 
 template <int NR>
 struct WarpSolver {
@@ -64,28 +67,36 @@ struct WarpSolver {
         R_S, R_VL, R_VU, R_YD, R_DS, R_DS2, R_YTD, R_YTD2, R_DSOC, R_GXQ, R_GYQ, R_RD, R_DQ, R_GS, R_DG, R_TRIG, R_TRIG2,
         R_COUNT
     };
-    // shared-memory carve-up (doubles, per warp)
-    enum {
-        PLD = NS + 3,  // leading dimension of the P broadcast buffer: 3Nr columns of P, the pr column, 2 zero columns
-        SM_COL = 0,                      // two pivot-row buffers, each LW values + LW reciprocals
-        SM_PB = 4 * LW, SM_ZB = SM_PB + ((NS * PLD + 1) & ~1), SM_DZB = SM_ZB + LW, SM_RCB = SM_DZB + LW,
-        SM_PRB = SM_RCB + LW, SM_HB = SM_PRB + LW, SM_CS = SM_HB + LW, SM_SN = SM_CS + NRP, SM_CA = SM_SN + NRP, SM_CB = SM_CA + NRP,
-        SM_TCS = SM_CB + NRP, SM_TSN = SM_TCS + NRP, SM_CRS = SM_TSN + NRP, SM_THD = SM_CRS + NRP,
-        SM_PXX = SM_THD + NRP, SM_PYY = SM_PXX + MP, SM_PXY = SM_PYY + MP, SM_PHX = SM_PXY + MP,
-        SM_PHY = SM_PHX + MP, SM_FTH = SM_PHY + MP, SM_FPH = SM_FTH + 16, SM_MISC = SM_FPH + 16,
-        SM_RED = SM_MISC + 8,            // cross-warp reduction scratch (two-warp teams)
-        SM_TAB = SM_RED + 8,             // per-pass table of the staged rows' base pointers (64 entries)
-        SM_MC = SM_TAB + ((NS + 20 + 1) & ~1),   // column buffer of the stage KKT matrix: mc[row][lane], NZ rows
-        SM_STG = SM_MC + NZ * LW,        // rows of the NEXT stage, copied asynchronously (cp.async) while this one is processed
-        STG_ROWS = (20 - 2 * NR > 16) ? 20 - 2 * NR : 16,
-        SM_DOUBLES = SM_STG + STG_ROWS * LW
-    };
     // slots of the factorisation's staging buffer (sm + SM_STG): rows of stage k, then rows of block k+1
     enum { FS_Z, FS_TRIG, FS_ZL, FS_ZU, FS_BL, FS_BU, FS_YC, FS_S, FS_VL, FS_VU, FS_YD, FS_CSOC, FS_DSOC, FS_CE, FS_DL, FS_DU, FS_COUNT };
-    // slots of the forward pass's staging buffer (sm + SM_MC, NZ + STG_ROWS rows): NS factor rows, vectors of stage k, then of block k+1
+    // slots of the forward pass's staging buffer (the whole big region): NS factor rows, vectors of stage k, then of block k+1
     enum { WS_LIN = NS, WS_DG, WS_Z, WS_ZL, WS_ZU, WS_BL, WS_BU, WS_GX, WS_COEF, WS_RC, WS_DL, WS_DU, WS_GS, WS_GXQ, WS_GYQ, WS_RD, WS_DQ,
            WS_S, WS_VL, WS_VU, WS_COUNT };
-    static_assert((int)FS_COUNT <= (int)STG_ROWS && (int)WS_COUNT <= NZ + (int)STG_ROWS && (int)WS_COUNT <= 64, "staging buffers");
+    // shared-memory carve-up (doubles, per team): small buffers that live for the whole solve, then one big region that the
+    // factorisation and the forward pass carve up differently (they never run at the same time)
+    enum {
+        PLD = NS + 3,  // leading dimension of the P broadcast buffer: 3Nr columns of P, the pr column, 2 zero columns
+        TSZ = NR * NR, // one addend table of the stage-matrix build, see factor()
+        SM_ZB = 0, SM_DZB = SM_ZB + LW, SM_RCB = SM_DZB + LW, SM_PRB = SM_RCB + LW, SM_HB = SM_PRB + LW,
+        SM_CS = SM_HB + LW, SM_SN = SM_CS + NRP, SM_C4 = SM_SN + NRP,   // c4[4 i ..]: a_i, b_i, T cos, T sin of robot i (one 32-byte record)
+        SM_CRS = SM_C4 + 4 * NRP, SM_THD = SM_CRS + NRP,
+        SM_MISC = SM_THD + NRP,
+        SM_RED = SM_MISC + 8,            // cross-warp reduction scratch (two-warp teams)
+        SM_TAB = SM_RED + 8,             // per-pass table of the staged rows' base pointers (64 entries)
+        SM_BIG = SM_TAB + ((NS + 20 + 1) & ~1),
+        // -- factorisation view of the big region
+        SM_COL = SM_BIG,                 // two pivot-row buffers, each LW values + LW reciprocals
+        SM_PB = SM_COL + 4 * LW,
+        SM_TT = SM_PB + ((NS * PLD + 1) & ~1),     // 8 addend tables [NR][NR], the gradient rows HH[5][NR], a row of zeros
+        TT_DOUBLES = (8 * TSZ + 6 * NR + 1) & ~1,
+        STG_ROWS = FS_COUNT,
+        SM_STG = SM_TT + TT_DOUBLES,     // rows of the NEXT stage, copied asynchronously (cp.async) while this one is processed
+        BIG_FACTOR = SM_STG + STG_ROWS * LW - SM_BIG,
+        // -- forward view: WS_COUNT staging rows from SM_BIG
+        BIG_FORWARD = WS_COUNT * LW,
+        SM_DOUBLES = SM_BIG + (BIG_FACTOR > BIG_FORWARD ? BIG_FACTOR : BIG_FORWARD)
+    };
+    static_assert((int)WS_COUNT <= 64 && (SM_BIG & 1) == 0 && (SM_STG & 1) == 0 && (SM_DOUBLES & 1) == 0 && (SM_C4 & 3) == 0, "shared-memory layout");
 
     // Issue the asynchronous copies of one stage's rows: slot s <- tab[s] + (k + (s >= kofs_from)) rows, stage clamped to N.
     // Two rows per warp instruction (16 bytes per lane); completion: wp::cp_async_wait() + tsync().
@@ -100,7 +111,8 @@ struct WarpSolver {
             wp::cp_async16(stg + s * LW + c2, tab[s] + (long long)kk * LW + c2);
         }
     }
-    static NMPC_HD long long ws_doubles(int N) { return ((long long)R_COUNT * (N + 1) + (long long)(N + 1) * NS) * LW; }
+    // per-slot scratch: the vector rows, the Riccati factor rows, then the filter (NMPC_FILTER_CAP theta values, then as many phi values)
+    static NMPC_HD long long ws_doubles(int N) { return ((long long)R_COUNT * (N + 1) + (long long)(N + 1) * NS) * LW + 2 * NMPC_FILTER_CAP; }
 
     const NmpcSolveParams &P;
     double *sm, *ws;
@@ -161,7 +173,7 @@ struct WarpSolver {
         qw = isx ? 2.0 * P.Q[comp] : (isu ? 2.0 * P.R[comp] : 0.0);
         df = 1.0; fn = 0;
         n_reg = n_resto = n_soc = n_fact = n_ls = 0;
-        for (int e = l; e < NS * PLD; e += LW) sm[SM_PB + e] = 0.0;
+        if (l == 0) sm[SM_MISC + 2] = 0.0;   // filter evictions (NMPC_ST_FILTER_EVICT)
         tsync();
     }
 
@@ -457,18 +469,29 @@ struct WarpSolver {
 
     // ---------------------------------------------------------------------------------------
     // backward Riccati sweep (K3).  false = a control-block pivot was <= 0 (wrong inertia).
-    // ---------------------------------------------------------------------------------------
-    // backward Riccati sweep (K3).  false = a control-block pivot was <= 0 (wrong inertia).
     //
     // Lane l < 5Nr holds column l of the stage KKT matrix M = H + [A B]' P+ [A B]: its 3Nr state
-    // rows in X[] and its 2Nr control rows in U[]; lane 31 holds the linear term m as one more
+    // rows in X[] and its 2Nr control rows in U[]; the last lane holds the linear term m as one more
     // column.  The control block is eliminated by 2Nr symmetric sweeps inside a ROLLED loop: the
     // pivot row is always U[0] (published through shared memory), and the control rows rotate by
     // one register per step (the rotation is folded into the destination registers of the
     // update, so it costs nothing).  A control column's state rows stay 0 until its own pivot
     // (they equal the pivot row by symmetry), which makes the own-column update the same FMA.
-    // After the loop X[] holds P (state lanes), K' (control lanes) and p (lane 31); U[] of lane
-    // 31 holds the feed-forward term.
+    // After the loop X[] holds P (state lanes), K' (control lanes) and p (last lane); U[] of the last
+    // lane holds the feed-forward term.
+    //
+    // The column is assembled directly in the registers by a loop over the robots that is unrolled at compile time:
+    // robot i contributes the rows 3i..3i+2 and the control rows 2i, 2i+1 of W = P+ [A B](:, l) (unicycle-sparse: three
+    // terms per entry).  Everything else that has to be added to the column -- the collision curvature (x / y lanes), the
+    // theta-v cross term, the control diagonal, and, for the last lane, the whole stage gradient h -- arrives as the ADDEND of
+    // those FMAs: lane l reads it from five per-lane rows a0p..a4p of small shared-memory tables (x / y / theta rows of robot
+    // i, v / omega rows of robot i), so the assembly has no lane-dependent control flow and no register indexing:
+    //   x lane of robot r:  a0p = Txx[r], a1p = Txy[r]     Txx[r][j] = -pxx(r,j), Txx[r][r] = +sum_j pxx(r,j)   (same for Tyy, Txy)
+    //   y lane of robot r:  a0p = Txy[r], a1p = Tyy[r]
+    //   theta lane:         a3p = D3[r]   (crs_r at [r], zeros elsewhere);   v lane: a3p = Dv[r] (its diagonal);   omega lane: a4p = Dw[r]
+    //   last lane:          a0p..a4p = HH[0..4]  (the gradient, one row per component class);   every other row: zeros.
+    // (The first version built the column through a [5Nr][32] shared-memory column buffer with rolled loops over robots and
+    // pairs: 7.7 KB per instance and ~570 instructions per stage, against ~200 and 2.6 KB here.)
     // ---------------------------------------------------------------------------------------
     template <int MODE>
     NMPC_PASS bool factor(double mu, double delta, bool soc)
@@ -478,10 +501,9 @@ struct WarpSolver {
         const bool isL = (l == LW - 1);
         double X[NS], U[NC];
         double plin = 0.0, dgx = 0.0;
-        double *col = sm + SM_COL, *pb = sm + SM_PB, *zb = sm + SM_ZB, *rcb = sm + SM_RCB, *prb = sm + SM_PRB, *hb = sm + SM_HB, *mc = sm + SM_MC;
-        double *cs = sm + SM_CS, *sn = sm + SM_SN, *ca = sm + SM_CA, *cb = sm + SM_CB, *tcs = sm + SM_TCS,
-               *tsn = sm + SM_TSN, *crs = sm + SM_CRS, *thd = sm + SM_THD;
-        double *pxx = sm + SM_PXX, *pyy = sm + SM_PYY, *pxy = sm + SM_PXY, *phx = sm + SM_PHX, *phy = sm + SM_PHY;
+        double *col = sm + SM_COL, *pb = sm + SM_PB, *zb = sm + SM_ZB, *rcb = sm + SM_RCB, *prb = sm + SM_PRB, *hb = sm + SM_HB;
+        double *cs = sm + SM_CS, *sn = sm + SM_SN, *c4 = sm + SM_C4, *crs = sm + SM_CRS, *thd = sm + SM_THD;
+        double *tt = sm + SM_TT, *HH = tt + 8 * TSZ, *ZR = HH + 5 * NR;
         double *stg = sm + SM_STG;
         n_fact++;
         tsync();
@@ -499,6 +521,32 @@ struct WarpSolver {
             }
             reinterpret_cast<const double **>(sm + SM_TAB)[l] = p0;
         }
+        // the big region was the forward pass's staging buffer: reset the constant zeros of the addend tables and of the two
+        // padding columns of the P buffer (the last lane multiplies them by 0)
+        for (int e = l; e < 8 * TSZ + 6 * NR; e += LW) tt[e] = 0.0;
+        for (int e = l; e < NS; e += LW) { pb[e * PLD + NS + 1] = 0.0; pb[e * PLD + NS + 2] = 0.0; }
+        // addend rows of this lane (see above), the diagonal entry this lane maintains, and this lane's row-sum job
+        const double *a0p = ZR, *a1p = ZR, *a2p = ZR, *a3p = ZR, *a4p = ZR;
+        double *selfp = nullptr;         // diagonal entry of D3 / Dv / Dw owned by this lane
+        double *hslot = nullptr;         // where this lane's stage gradient goes (HH)
+        if (isx) {
+            hslot = HH + comp * NR + rob;
+            if (comp == 0) { a0p = tt + 0 * TSZ + rob * NR; a1p = tt + 1 * TSZ + rob * NR; }
+            else if (comp == 1) { a0p = tt + 1 * TSZ + rob * NR; a1p = tt + 2 * TSZ + rob * NR; }
+            else { a3p = tt + 5 * TSZ + rob * NR; selfp = tt + 5 * TSZ + rob * (NR + 1); }
+        } else if (isu) {
+            hslot = HH + (3 + comp) * NR + rob;
+            if (comp == 0) { a3p = tt + 6 * TSZ + rob * NR; selfp = tt + 6 * TSZ + rob * (NR + 1); }
+            else { a4p = tt + 7 * TSZ + rob * NR; selfp = tt + 7 * TSZ + rob * (NR + 1); }
+        } else if (isL) { a0p = HH; a1p = HH + NR; a2p = HH + 2 * NR; a3p = HH + 3 * NR; a4p = HH + 4 * NR; }
+        // row sums of the five pair tables: lane a * NR + i sums row i of table a and stores it on the diagonal
+        const bool rsum = M > 0 && l < 5 * NR;
+        const int rs_a = l / NR, rs_i = l - rs_a * NR;
+        double *rs_row = tt + rs_a * TSZ + rs_i * NR;
+        // column l of [A B]:  al e_x + be e_y + ga e_theta of this lane's robot (last lane: the pr column); xm: control lanes keep
+        // their state rows at 0 until their own pivot (see the sweep)
+        const double xm = isu ? 0.0 : 1.0;
+        const int base = isL ? NS : 3 * rob;
         tsync();
         stage_issue(sm, stg, l, N, FS_COUNT, FS_YC, N - 1);   // in flight during the terminal stage
         // terminal stage: X_N carries no cost and no distance rows, only its box
@@ -531,7 +579,7 @@ struct WarpSolver {
                 const double v = zr[NS + 2 * l], c_ = stg[FS_TRIG * LW + l], s_ = stg[FS_TRIG * LW + NRP + l];
                 cs[l] = c_; sn[l] = s_;
                 double a_ = -T * v * s_, b_ = T * v * c_, tc = T * c_, ts = T * s_;
-                ca[l] = a_; cb[l] = b_; tcs[l] = tc; tsn[l] = ts;
+                c4[4 * l] = a_; c4[4 * l + 1] = b_; c4[4 * l + 2] = tc; c4[4 * l + 3] = ts;
                 double *cf = row(R_COEF, k);
                 cf[l] = a_; cf[CFS + l] = b_; cf[2 * CFS + l] = tc; cf[3 * CFS + l] = ts;
                 if (MODE == 0) {
@@ -545,6 +593,7 @@ struct WarpSolver {
                 for (int i = 0; i < NS; i++) pb[i * PLD + l] = X[i];
                 pb[l * PLD + l] += dgx;   // same lane wrote this element just above
             }
+            if (rsum) rs_row[rs_i] = 0.0;   // the diagonal is summed over below: clear the previous stage's sum
             tsync();
             // equality residual of block k+1 and the condensed inequality block k+1
             if (isx) {
@@ -565,10 +614,15 @@ struct WarpSolver {
                 in.lo = stg[FS_DL * LW + l]; in.hi = stg[FS_DU * LW + l]; in.s = stg[FS_S * LW + l]; in.vl = stg[FS_VL * LW + l];
                 in.vu = stg[FS_VU * LW + l]; in.yd = stg[FS_YD * LW + l]; in.dsoc = stg[FS_DSOC * LW + l];
                 ineq_block<MODE>(row, in, l, pi, pj, kd, k + 1, mu, delta, soc, zb, a0, a1, a2, a3, a4);
-                pxx[l] = a0; pyy[l] = a1; pxy[l] = a2; phx[l] = a3; phy[l] = a4;
+                const int e1 = pi * NR + pj, e2 = pj * NR + pi;
+                tt[e1] = -a0; tt[e2] = -a0;                                   // Txx
+                tt[TSZ + e1] = -a2; tt[TSZ + e2] = -a2;                       // Txy
+                tt[2 * TSZ + e1] = -a1; tt[2 * TSZ + e2] = -a1;               // Tyy
+                tt[3 * TSZ + e1] = a3; tt[3 * TSZ + e2] = -a3;                // Thx: gradient of robot pi gets +, of robot pj gets -
+                tt[4 * TSZ + e1] = a4; tt[4 * TSZ + e2] = -a4;                // Thy
             }
             tsync();
-            // pr = p_{k+1} + P_{k+1} r (r = -rc), published as one more column of pb for lane 31
+            // pr = p_{k+1} + P_{k+1} r (r = -rc), published as one more column of pb for the last lane
             if (isx) {
                 double pr = plin;
                 if (MODE != 1) {
@@ -578,6 +632,12 @@ struct WarpSolver {
                 }
                 pb[l * PLD + NS] = pr;
             }
+            if (rsum) {   // diagonal of the curvature tables = + sum of the pair terms; of the gradient tables = the robot's sum
+                double s_ = 0.0;
+                NMPC_UNROLL
+                for (int j = 0; j < NR; j++) s_ += rs_row[j];
+                rs_row[rs_i] = rs_a < 3 ? -s_ : s_;
+            }
             // stage gradient h_l (variable l) and diagonal curvature
             double sig = 0.0, gx = 0.0, dg = 0.0;
             if (isz) {
@@ -586,60 +646,31 @@ struct WarpSolver {
                 if (MODE == 0) { dg += df * qw; if (isx && comp == 2) dg += thd[rob]; }
             }
             row(R_GX, k)[l] = gx;
-            double hl_ = gx;
-            // column l of [A B]:  al e_x + be e_y + ga e_theta of this lane's robot (last lane: the pr column)
-            double al = 0.0, be = 0.0, ga = 0.0;
-            int base = 3 * rob;
-            if (isx) { if (comp == 0) al = 1.0; else if (comp == 1) be = 1.0; else { al = ca[rob]; be = cb[rob]; ga = 1.0; } }
-            else if (isu) { if (comp == 0) { al = tcs[rob]; be = tsn[rob]; } else ga = T; }
-            else if (isL) { al = 1.0; base = NS; }
+            dgx = isx ? dg : 0.0;                                                   // state diagonal is carried lazily
+            if (selfp) *selfp = isu ? dg : (MODE == 0 ? crs[rob] : 0.0);           // control diagonal / theta-v cross term
+            tsync();
+            if (isz) *hslot = gx + ((M > 0 && isx && comp < 2) ? tt[(3 + comp) * TSZ + rob * (NR + 1)] : 0.0);
             tsync();
             if (k > 0) stage_issue(sm, stg, l, N, FS_COUNT, FS_YC, k - 1);   // every lane has consumed the staged rows of stage k
-            // The column of M = [A B]' P+ [A B] + H is assembled in a shared-memory column buffer mc[row][lane] by
-            // ROLLED loops (robots, pairs) and loaded into registers once: the straight-line version of this code
-            // was ~1000 instructions per stage and missed the SM instruction cache on every stage
-            // (sm__icc hit rate 63 %, GPC instruction-cache bandwidth at 70-85 % of peak in ncu).
-            double *mcl = mc + l;
-            NMPC_NOUNROLL
-            for (int i = 0; i < NR; i++) {
-                const double *q0 = pb + (3 * i) * PLD + base;
-                const double Wx = al * q0[0] + be * q0[1] + ga * q0[2];
-                const double Wy = al * q0[PLD] + be * q0[PLD + 1] + ga * q0[PLD + 2];
-                const double Wt = al * q0[2 * PLD] + be * q0[2 * PLD + 1] + ga * q0[2 * PLD + 2];
-                // a control column's state rows stay 0 until its own pivot (see the sweep)
-                mcl[(3 * i) * LW] = isu ? 0.0 : Wx;
-                mcl[(3 * i + 1) * LW] = isu ? 0.0 : Wy;
-                mcl[(3 * i + 2) * LW] = isu ? 0.0 : Wt + ca[i] * Wx + cb[i] * Wy;
-                mcl[(NS + 2 * i) * LW] = tcs[i] * Wx + tsn[i] * Wy;
-                mcl[(NS + 2 * i + 1) * LW] = T * Wt;
-            }
-            // own-column additions (each lane touches only its own column of mc: no barrier needed)
-            if (isu) mcl[l * LW] += dg;                                            // control diagonal
-            dgx = isx ? dg : 0.0;                                                   // state diagonal is carried lazily
-            if (MODE == 0 && isx && comp == 2) mcl[(NS + 2 * rob) * LW] += crs[rob];    // theta-v cross term
-            if (M > 0 && isx && comp < 2) {                                         // collision curvature and gradient
-                double ssame = 0.0, scross = 0.0, glin = 0.0;
-                NMPC_NOUNROLL
-                for (int j = 0; j < NR; j++) {
-                    if (j == rob) continue;
-                    const int q = rob < j ? pairidx(rob, j) : pairidx(j, rob);
-                    const double vs = comp == 0 ? pxx[q] : pyy[q], vc = pxy[q];
-                    const double ph = comp == 0 ? phx[q] : phy[q];
-                    mcl[(3 * j) * LW] -= comp == 0 ? vs : vc;
-                    mcl[(3 * j + 1) * LW] -= comp == 0 ? vc : vs;
-                    ssame += vs; scross += vc; glin += rob < j ? ph : -ph;
+            {
+                const double al = isL ? 1.0 : (isx ? (comp == 0 ? 1.0 : (comp == 2 ? c4[4 * rob] : 0.0)) : (isu && comp == 0 ? c4[4 * rob + 2] : 0.0));
+                const double be = isx ? (comp == 1 ? 1.0 : (comp == 2 ? c4[4 * rob + 1] : 0.0)) : (isu && comp == 0 ? c4[4 * rob + 3] : 0.0);
+                const double ga = isx ? (comp == 2 ? 1.0 : 0.0) : (isu && comp == 1 ? T : 0.0);
+                const double *pbl = pb + base;
+                NMPC_UNROLL
+                for (int i = 0; i < NR; i++) {
+                    const double *q0 = pbl + (3 * i) * PLD;
+                    const double Wx = al * q0[0] + be * q0[1] + ga * q0[2];
+                    const double Wy = al * q0[PLD] + be * q0[PLD + 1] + ga * q0[PLD + 2];
+                    const double Wt = al * q0[2 * PLD] + be * q0[2 * PLD + 1] + ga * q0[2 * PLD + 2];
+                    const double ca_ = c4[4 * i], cb_ = c4[4 * i + 1], tc_ = c4[4 * i + 2], ts_ = c4[4 * i + 3];
+                    X[3 * i] = fma(xm, Wx, a0p[i]);
+                    X[3 * i + 1] = fma(xm, Wy, a1p[i]);
+                    X[3 * i + 2] = fma(xm, fma(ca_, Wx, fma(cb_, Wy, Wt)), a2p[i]);
+                    U[2 * i] = fma(tc_, Wx, fma(ts_, Wy, a3p[i]));
+                    U[2 * i + 1] = fma(T, Wt, a4p[i]);
                 }
-                mcl[(3 * rob) * LW] += comp == 0 ? ssame : scross;
-                mcl[(3 * rob + 1) * LW] += comp == 0 ? scross : ssame;
-                hl_ += glin;
             }
-            tsync();
-            if (isz) mc[l * LW + (LW - 1)] += hl_;   // the linear-term column (last lane's) adds the stage gradient h, one row per lane
-            tsync();
-            NMPC_UNROLL
-            for (int i = 0; i < NS; i++) X[i] = mcl[i * LW];
-            NMPC_UNROLL
-            for (int u = 0; u < NC; u++) U[u] = mcl[(NS + u) * LW];
             // symmetric sweep of the control pivots (rolled, with one-pivot LOOK-AHEAD).  The pivot row is U[0] of
             // every lane; it is published in ROTATED order (slot NS + r holds control column (j + r) mod 2Nr), so the
             // readers use compile-time offsets and the rows rotate through the registers for free.  A second row of
@@ -647,31 +678,24 @@ struct WarpSolver {
             // the NEXT pivot row is updated and published first, so its shared-memory round trip and reciprocal
             // overlap the remaining rank-1 update instead of sitting on the critical path of every pivot.
             const int ucol = l - NS;   // control column of this lane (if any)
-            {
-                if (isz) { const int s0 = isu ? ucol + NS : l; col[s0] = U[0]; col[LW + s0] = wp::rcp_pos(U[0]); }
-            }
+            int pslot = l;             // where this lane publishes its entry of the next pivot row (control lanes: rotating)
+            if (isz) { col[pslot] = U[0]; col[LW + pslot] = wp::rcp_pos(U[0]); }
             NMPC_NOUNROLL
             for (int j = 0; j < NC; j++) {
                 const double *buf = col + 2 * LW * (j & 1);
                 double *nbuf = col + 2 * LW * ((j + 1) & 1);
                 tsync();
                 const double inv = buf[LW + NS];   // 1 / pivot, from the pivot's own lane (rotated slot NS)
-                if (!(inv > 0.0) || !(inv < NMPC_INF)) { wp::cp_async_wait(); return false; }   // drain the staging copies before the retry
-                // the pivot row arrives in 128-bit loads, all issued before the FMAs
-                NmpcD2 bx[NS / 2];
+                if (!wp::pos_normal(inv)) { wp::cp_async_wait(); return false; }   // drain the staging copies before the retry
+                // the control part of the pivot row first (128-bit loads): it feeds the look-ahead
                 double bu[NC];
-                {
-                    const NmpcD2 *b2 = reinterpret_cast<const NmpcD2 *>(buf);
+                if ((NS & 1) == 0) {
+                    const NmpcD2 *c2 = reinterpret_cast<const NmpcD2 *>(buf + NS);
                     NMPC_UNROLL
-                    for (int i = 0; i < NS / 2; i++) bx[i] = b2[i];
-                    if ((NS & 1) == 0) {
-                        const NmpcD2 *c2 = reinterpret_cast<const NmpcD2 *>(buf + NS);
-                        NMPC_UNROLL
-                        for (int r = 0; r < NC / 2; r++) { NmpcD2 v = c2[r]; bu[2 * r] = v.x; bu[2 * r + 1] = v.y; }
-                    } else {
-                        NMPC_UNROLL
-                        for (int r = 0; r < NC; r++) bu[r] = buf[NS + r];
-                    }
+                    for (int r = 0; r < NC / 2; r++) { NmpcD2 v = c2[r]; bu[2 * r] = v.x; bu[2 * r + 1] = v.y; }
+                } else {
+                    NMPC_UNROLL
+                    for (int r = 0; r < NC; r++) bu[r] = buf[NS + r];
                 }
                 const bool own = (ucol == j);
                 const double t = own ? -inv : U[0] * inv;
@@ -680,23 +704,39 @@ struct WarpSolver {
                     NMPC_UNROLL
                     for (int r = 1; r < NC; r++) U[r] = 0.0;
                 }
-                // look-ahead: this lane's entry of pivot row j+1
+                // look-ahead: this lane's entry of pivot row j+1 (the publish after the last pivot is harmless: that buffer is not read again)
                 const double u1 = U[1] - bu[1] * t;
-                if (j + 1 < NC) {
-                    int slot = l;
-                    if (isu) { slot = ucol - (j + 1); slot += slot < 0 ? NC : 0; slot += NS; }
-                    if (isz) { nbuf[slot] = u1; nbuf[LW + slot] = wp::rcp_pos(u1); }   // every lane: no divergent reciprocal
-                }
-                NMPC_UNROLL
-                for (int i = 0; i < NS / 2; i++) { X[2 * i] -= bx[i].x * tx; X[2 * i + 1] -= bx[i].y * tx; }
-                if (NS & 1) X[NS - 1] -= buf[NS - 1] * tx;
+                if (isu) { pslot--; pslot += pslot < NS ? NC : 0; }
+                const double r1 = wp::rcp_pos(u1);   // every lane: no divergent reciprocal
+                if (isz) { nbuf[pslot] = u1; nbuf[LW + pslot] = r1; }
                 // control rows (rotating): slots NS+2 .. NS+NC-1
                 U[0] = u1;
                 NMPC_UNROLL
                 for (int r = 2; r < NC; r++) U[r - 1] = U[r] - bu[r] * t;
                 U[NC - 1] = t;
+                // state rows in batches of XB pairs, each batch loaded while the previous one is consumed: the whole pivot row
+                // in registers at once (the first version) costs 60 registers and caps the kernel at 12 warps per SM
+                {
+                    constexpr int NP = NS / 2, XB = NMPC_XBATCH;
+                    const NmpcD2 *b2 = reinterpret_cast<const NmpcD2 *>(buf);
+                    NmpcD2 cur[XB], nxt[XB];
+                    NMPC_UNROLL
+                    for (int i = 0; i < XB; i++) if (i < NP) cur[i] = b2[i];
+                    NMPC_UNROLL
+                    for (int i0 = 0; i0 < NP; i0 += XB) {
+                        NMPC_UNROLL
+                        for (int i = 0; i < XB; i++) if (i0 + XB + i < NP) nxt[i] = b2[i0 + XB + i];
+                        wp::sched_fence();
+                        NMPC_UNROLL
+                        for (int i = 0; i < XB; i++)
+                            if (i0 + i < NP) { X[2 * (i0 + i)] -= cur[i].x * tx; X[2 * (i0 + i) + 1] -= cur[i].y * tx; }
+                        NMPC_UNROLL
+                        for (int i = 0; i < XB; i++) cur[i] = nxt[i];
+                    }
+                    if (NS & 1) X[NS - 1] -= buf[NS - 1] * tx;
+                }
             }
-            // publish p_k / feed-forward (lane 31's column) and store the factors
+            // publish p_k / feed-forward (the last lane's column) and store the factors
             tsync();
             if (isL) {
                 NMPC_UNROLL
@@ -755,7 +795,7 @@ struct WarpSolver {
         NMPC_LOCALS
         double ap = 0.0, az = 0.0, gbd = 0.0, tiny = 0.0;   // max ratios, see slack_step_terms
         double *dzb = sm + SM_DZB;
-        double *stg = sm + SM_MC;   // the factorisation's column buffer is free during this pass: NZ + STG_ROWS staging rows
+        double *stg = sm + SM_BIG;  // the factorisation's buffers are free during this pass: WS_COUNT staging rows
         tsync();
         for (int s = NS + l; s < WS_COUNT; s += LW) {   // base pointers (stage 0) of the vector rows staged per stage; see WS_*
             const double *p0 = nullptr;
@@ -990,33 +1030,32 @@ struct WarpSolver {
     }
 
     // ---------------------------------------------------------------------------------------
-    // filter (kept in shared memory; lane 0 edits)
+    // filter.  IPOPT's filter is unbounded inside a barrier subproblem (it is reset when mu changes); the benchmark instances
+    // add up to 104 entries to it (oracle, 4,096 instances), so it lives in the per-slot global scratch, append-only:
+    // entries that a new one dominates are redundant for the acceptance test and are simply left in place.  Every lane checks
+    // its share of the entries.  An overflow of the NMPC_FILTER_CAP entries overwrites the oldest and is counted (stats).
     // ---------------------------------------------------------------------------------------
+    NMPC_DEV double *filter_base() const { return ws + ((long long)R_COUNT * S + (long long)S * NS) * LW; }
     NMPC_DEV bool filter_ok(double th, double ph) const
     {
-        const double *fth = sm + SM_FTH, *fph = sm + SM_FPH;
-        for (int i = 0; i < fn; i++)
-            if (!(th < fth[i] || ph < fph[i])) return false;
-        return true;
+        const double *fth = wp::global_ptr(filter_base()), *fph = fth + NMPC_FILTER_CAP;
+        const int m = fn < NMPC_FILTER_CAP ? fn : NMPC_FILTER_CAP;
+        bool ok = true;
+        for (int i = wp::team_lane(LW); i < m; i += LW)
+            if (!(th < fth[i] || ph < fph[i])) ok = false;
+        return tred_min(ok ? 1.0 : 0.0) > 0.5;
     }
     NMPC_PASS void filter_add(double th, double ph)
     {
         NMPC_LOCALS
-        double *fth = sm + SM_FTH, *fph = sm + SM_FPH, *misc = sm + SM_MISC;
-        tsync();
+        double *fth = wp::global_ptr(filter_base()), *fph = fth + NMPC_FILTER_CAP;
         if (l == 0) {
-            int m = 0;
-            for (int i = 0; i < fn; i++)
-                if (!(fth[i] >= th && fph[i] >= ph)) { fth[m] = fth[i]; fph[m] = fph[i]; m++; }
-            if (m == NMPC_FILTER_CAP) {
-                for (int i = 1; i < m; i++) { fth[i - 1] = fth[i]; fph[i - 1] = fph[i]; }
-                m--;
-            }
-            fth[m] = th; fph[m] = ph; m++;
-            misc[0] = (double)m;
+            const int slot = fn % NMPC_FILTER_CAP;
+            fth[slot] = th; fph[slot] = ph;
+            if (fn >= NMPC_FILTER_CAP) sm[SM_MISC + 2] += 1.0;
         }
+        fn++;
         tsync();
-        fn = (int)misc[0];
     }
     static NMPC_DEV bool cmp_le(double lhs, double rhs, double bas) { return lhs - rhs <= 10.0 * 2.220446049250313e-16 * fabs(bas); }
 
@@ -1080,7 +1119,7 @@ struct WarpSolver {
                 double *sp = P.stats + (long long)inst * NMPC_NSTATS;
                 sp[NMPC_ST_KKT_ERR] = E0; sp[NMPC_ST_PRIMAL_INF] = pinf; sp[NMPC_ST_DUAL_INF] = dinf; sp[NMPC_ST_COMPL] = c0;
                 sp[NMPC_ST_MU] = mu; sp[NMPC_ST_N_REG] = n_reg; sp[NMPC_ST_N_RESTO] = n_resto; sp[NMPC_ST_N_SOC] = n_soc;
-                sp[NMPC_ST_N_FACTOR] = n_fact; sp[NMPC_ST_N_LS] = n_ls;
+                sp[NMPC_ST_N_FACTOR] = n_fact; sp[NMPC_ST_N_LS] = n_ls; sp[NMPC_ST_FILTER_EVICT] = sm[SM_MISC + 2];
             }
         }
         tsync();

@@ -49,6 +49,11 @@ NMPC_DEV void cp_async16(double *smem_dst, const double *gsrc)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
 NMPC_DEV void cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// compiler-level fence: memory accesses are not moved across it (keeps the batched loads of the sweep apart, which bounds
+// their register footprint)
+NMPC_DEV void sched_fence() { asm volatile("" ::: "memory"); }
+// positive, finite, normal double (one integer compare on the high word; nvcc turns the two floating-point compares into ~15 integer instructions)
+NMPC_DEV bool pos_normal(double v) { return (unsigned)(__double2hiint(v) - 0x00100000) < 0x7fe00000u; }
 NMPC_DEV unsigned nth_set_bit(unsigned mask, int n) { return __fns(mask, 0, n + 1); }
 // one shared copy of the long math routines: keeps the passes small enough for the instruction cache
 __device__ __noinline__ void sincos_(double x, double *s, double *c) { sincos(x, s, c); }

@@ -26,6 +26,25 @@ SCENARIOS = {
     "C-6": (6, 0.3, 35, 0.3, 0.22, 2.84,
             [0.866, 0.5, -2.618, 0, 1, -1.571, -0.866, 0.5, -0.524, -0.866, -0.5, 0.524, 0, -1, 1.571, 0.866, -0.5, 2.618],
             [-0.866, -0.5, -2.618, 0, -1, -1.571, 0.866, -0.5, -0.524, 0.866, 0.5, 0.524, 0, 1, 1.571, -0.866, 0.5, 2.618], 1e-1),  # sixth_scenario.py
+    # fifth_scenario.py:115-123 (T, N, dmin, bounds), :253-254 (start: V formation at x < 0), :268-269 (goal: mirrored V), :297 (stop 1e-1)
+    "C-5": (5, 0.1, 35, 0.3, 0.22, 2.84, [-0.5, 1.0, 0, -1.0, 0.5, 0, -1.5, 0, 0, -1.0, -0.5, 0, -0.5, -1.0, 0],
+            [0.5, -1.0, 0, 1.0, -0.5, 0, 1.5, 0, 0, 1.0, 0.5, 0, 0.5, 1.0, 0], 1e-1),
+    # centralized_two_robots_implementation.py:101-109, :213-214 (frame origins = true starts), :224 (goal), :252 (stop 5e-2)
+    "C-2r": (2, 0.05, 70, 0.15, 0.22, 2.84, [-0.7112, -0.7112, 0.785, 0.7112, 0.7112, -2.356],
+             [0.7112, 0.7112, 0.785, -0.7112, -0.7112, -2.356], 5e-2),
+    # centralized_six_robots_implementation.py:197-205 (dmin 0.4, v_max 0.15, omega_max 1.5), :364-369 (frame origins = true
+    # starts), :386-388 (goal), :416 (stop 1e-1): the real-robot constants
+    "C-6r": (6, 0.3, 35, 0.4, 0.15, 1.5,
+             [0.7, 0.4, -2.618, 0.0, 0.8, -1.57, -0.7, 0.4, -0.523, -0.7, -0.4, 0.523, 0.0, -0.8, 1.57, 0.7, -0.4, 2.618],
+             [-0.7, -0.4, -2.618, 0.0, -0.8, -1.57, 0.7, -0.4, -0.523, 0.7, 0.4, 0.523, 0.0, 0.8, 1.57, -0.7, 0.4, 2.618], 1e-1),
+    # mpc_online_casadi_tb3_ten_multi_centralized_collision_avoidance.py:169-177 (T 0.1, N 20, dmin 0.3), :409-410 (goal: two
+    # rows of five), :438 (stop 1e-1).  The script's start poses are unusable as written (robots 6-10 repeat 1-5, :389-399):
+    # robots 1-5 keep theirs (four corners and the centre), robots 6-10 start on the edge midpoints and at (2, 0).
+    "C-10": (10, 0.1, 20, 0.3, 0.22, 2.84,
+             [-1, 1, -0.785, 1, 1, -2.356, 1, -1, 2.356, -1, -1, 0.785, 0, 0, 0,
+              0, 1, -1.571, 1, 0, 3.1416, 0, -1, 1.571, -1, 0, 0, 2, 0, 3.1416],
+             [-1.5, 1, 1.57, -0.5, 1, 1.57, 0.5, 1, 1.57, 1.5, 1, 1.57, 2.5, 1, 1.57,
+              -1.5, -1, -1.57, -0.5, -1, -1.57, 0.5, -1, -1.57, 1.5, -1, -1.57, 2.5, 2.5, 0.0], 1e-1),
 }
 
 

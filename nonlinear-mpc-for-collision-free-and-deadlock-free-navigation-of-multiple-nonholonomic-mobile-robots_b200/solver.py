@@ -15,7 +15,7 @@ import ctypes as C
 import numpy as np
 
 from . import _cabi
-from ._cabi import NSTATS, NTRACE, Desc, NmpcError, check, default_opts, lib
+from ._cabi import NSTATS, NTRACE, Desc, NmpcError, check, default_opts, default_tuning, lib
 
 
 # ----------------------------------------------------------------------------------------------
@@ -97,20 +97,20 @@ def _flat(a, size, name):
 class Problem:
     """Handle on the CUDA library for one (Nr, N, T, Q, R) problem family."""
 
-    def __init__(self, Nr, N, T, Q=(1.0, 5.0, 0.1), R=(0.5, 0.05), obstacles=None, **opts):
+    def __init__(self, Nr, N, T, Q=(1.0, 5.0, 0.1), R=(0.5, 0.05), obstacles=None, tuning=None, **opts):
         """obstacles: optional [n_obs, 3] array of static circular obstacles (centre x, y, clearance = rob_dim + r_obs): the
-        reference's obstacle-avoidance family (first_scenario_mpc_obstacle_avoidance.py:96-152), see nmpc_create_obstacles."""
+        reference's obstacle-avoidance family (first_scenario_mpc_obstacle_avoidance.py:96-152), see nmpc_create_obstacles.
+        tuning: optional dict of nmpc_tuning fields (convoy, ctas_per_sm, force_block_path, thread_min_batch)."""
         self.L = lib()
         self.desc = Desc(int(Nr), int(N), float(T), (C.c_double * 3)(*[float(q) for q in Q]),
                          (C.c_double * 2)(*[float(r) for r in R]))
         self.opts = default_opts(**opts)
         self.h = C.c_void_p()
         self.obstacles = None if obstacles is None else np.ascontiguousarray(np.asarray(obstacles, dtype=np.float64).reshape(-1, 3))
-        if self.obstacles is None:
-            check(self.L.nmpc_create(C.byref(self.desc), C.byref(self.opts), C.byref(self.h)))
-        else:
-            check(self.L.nmpc_create_obstacles(C.byref(self.desc), C.byref(self.opts), int(self.obstacles.shape[0]),
-                                               self.obstacles.ctypes.data, C.byref(self.h)))
+        self.tuning = default_tuning(**(tuning or {}))
+        check(self.L.nmpc_create_tuned(C.byref(self.desc), C.byref(self.opts), C.byref(self.tuning),
+                                       0 if self.obstacles is None else int(self.obstacles.shape[0]),
+                                       None if self.obstacles is None else self.obstacles.ctypes.data, C.byref(self.h)))
         self.nobs = 0 if self.obstacles is None else int(self.obstacles.shape[0])
         self.Nr, self.N, self.T = int(Nr), int(N), float(T)
         self.ns, self.nc = 3 * self.Nr, 2 * self.Nr
@@ -204,12 +204,17 @@ class Problem:
             raise NmpcError("no CUDA device: the batched path has no CPU fallback")
         return torch
 
-    def workspace(self, B, batched_bounds=False):
+    def workspace(self, B, batched_bounds=False, device=None):
         torch = self._torch()
         need = (self.L.nmpc_workspace_bytes_batched_bounds if batched_bounds else self.L.nmpc_workspace_bytes)(self.h, int(B))
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(int(need), dtype=torch.uint8, device="cuda")
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
+            self._ws = torch.empty(int(need), dtype=torch.uint8, device=device)
         return self._ws
+
+    def _stream(self, device):
+        """Raw stream handle of torch's current stream ON THE TENSORS' DEVICE (the handle checks the device itself)."""
+        return self._torch().cuda.current_stream(device).cuda_stream
 
     def solve(self, x0, p, lbx, ubx, lbg, ubg, want=("f", "g", "lam_x", "lam_g", "stats"), out=None, trace=0):
         """x0 [B,n], p [B,6Nr], bounds [n]/[mg] or [B,.]: float64 CUDA tensors.  Returns CUDA tensors."""
@@ -221,9 +226,11 @@ class Problem:
         if getattr(self, "_order", None) is not None and self._order.numel() != B:
             raise ValueError("the scheduling order set with set_order() has %d entries, the batch has %d" % (self._order.numel(), B))
         batched = 1 if lbx.dim() == 2 else 0
-        ws = self.workspace(B, bool(batched))
-        o = out if out is not None else {}
         dev = x0.device
+        if any(t.device != dev for t in (p, lbx, ubx, lbg, ubg)):
+            raise ValueError("all inputs must live on the same CUDA device")
+        ws = self.workspace(B, bool(batched), dev)
+        o = out if out is not None else {}
         o.setdefault("x", torch.empty((B, self.n), dtype=torch.float64, device=dev))
         for k, shp in (("f", (B,)), ("g", (B, self.mg)), ("lam_x", (B, self.n)), ("lam_g", (B, self.mg)), ("stats", (B, NSTATS))):
             if k in want:
@@ -231,7 +238,7 @@ class Problem:
         o.setdefault("status", torch.empty(B, dtype=torch.int32, device=dev))
         o.setdefault("iters", torch.empty(B, dtype=torch.int32, device=dev))
         ptr = lambda k: o[k].data_ptr() if k in o else None
-        stream = torch.cuda.current_stream().cuda_stream
+        stream = self._stream(dev)
         args = [self.h, B, x0.data_ptr(), p.data_ptr(), lbx.data_ptr(), ubx.data_ptr(), lbg.data_ptr(), ubg.data_ptr(), batched,
                 ptr("x"), ptr("f"), ptr("g"), ptr("lam_x"), ptr("lam_g"), ptr("status"), ptr("iters"), ptr("stats")]
         if trace:
@@ -249,7 +256,7 @@ class Problem:
             if not (order.is_cuda and order.dtype == torch.int32 and order.is_contiguous()):
                 raise ValueError("order must be a contiguous int32 CUDA tensor")
         self._order = order
-        check(self.L.nmpc_set_order(self.h, None if order is None else order.data_ptr()))
+        check(self.L.nmpc_set_order(self.h, None if order is None else order.data_ptr(), 0 if order is None else int(order.numel())))
 
     def order_from_iters(self, iters):
         """Longest-first order from the iteration counts of the previous MPC step (the closed-loop predictor)."""
@@ -259,14 +266,13 @@ class Problem:
     def shift(self, x_prev, out=None):
         torch = self._torch()
         out = torch.empty_like(x_prev) if out is None else out
-        check(self.L.nmpc_shift(self.h, x_prev.shape[0], x_prev.data_ptr(), out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        check(self.L.nmpc_shift(self.h, x_prev.shape[0], x_prev.data_ptr(), out.data_ptr(), self._stream(x_prev.device)))
         return out
 
     def plant(self, state, x_opt, out=None):
         torch = self._torch()
         out = torch.empty_like(state) if out is None else out
-        check(self.L.nmpc_plant(self.h, state.shape[0], state.data_ptr(), x_opt.data_ptr(), out.data_ptr(),
-                                torch.cuda.current_stream().cuda_stream))
+        check(self.L.nmpc_plant(self.h, state.shape[0], state.data_ptr(), x_opt.data_ptr(), out.data_ptr(), self._stream(state.device)))
         return out
 
     def eval(self, w, p, lam_g=None, want=("f", "grad", "g", "jac", "hess")):
@@ -280,7 +286,7 @@ class Problem:
             o[k] = torch.empty(shapes[k], dtype=torch.float64, device=dev)
         ptr = lambda k: o[k].data_ptr() if k in o else None
         check(self.L.nmpc_eval(self.h, B, w.data_ptr(), p.data_ptr(), lam_g.data_ptr() if lam_g is not None else None,
-                               ptr("f"), ptr("grad"), ptr("g"), ptr("jac"), ptr("hess"), torch.cuda.current_stream().cuda_stream))
+                               ptr("f"), ptr("grad"), ptr("g"), ptr("jac"), ptr("hess"), self._stream(dev)))
         return o
 
 
@@ -377,7 +383,12 @@ class NlpSolver:
                            iter_count=int(o["iters"][0]), kkt_error=float(o["stats"][0, 0]))
         lam_p = np.zeros(P.np_)
         if P.np_:
-            lam_p[:P.ns] = -o["lam_g"][0, :P.ns]    # d f*/d x0bar: only the initial-condition rows depend on p[0:ns]
+            # dL/dp with L = f + lam_g'g: the initial-condition rows are X_0 - p[0:ns]; the cost holds xs = p[ns:] in
+            # sum_{k<N} (X_k - xs)'Q(X_k - xs)  (centralized_six_robots_implementation.py:278,314)
+            lam_p[:P.ns] = -o["lam_g"][0, :P.ns]
+            Xk = o["x"][0, :P.ns * (P.N + 1)].reshape(P.N + 1, P.ns)[:P.N]
+            Qd = np.tile(np.asarray(list(P.desc.Q), float), P.Nr)
+            lam_p[P.ns:] = -2.0 * Qd * (Xk - np.asarray(_flat(p, P.np_, "p"))[P.ns:][None]).sum(axis=0)
         return {"x": DM(o["x"][0]), "f": DM(o["f"][:1]), "g": DM(o["g"][0]), "lam_x": DM(o["lam_x"][0]),
                 "lam_g": DM(o["lam_g"][0]), "lam_p": DM(lam_p)}
 

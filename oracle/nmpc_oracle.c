@@ -20,7 +20,7 @@
 #endif
 
 #define DUMMY_ROW_VALUE 3.5 /* ...six...py:278 */
-#define FILTER_CAP 16
+#define FILTER_CAP 256   /* IPOPT's filter is unbounded; an overflow is counted in ORC_ST_FILTER_EVICT (never seen) */
 
 /* ------------------------------------------------------------------------------------ */
 /* dimensions                                                                            */
@@ -703,7 +703,7 @@ static double barrier_of(const ctx_t *C, const vecs_t *V, const double *z, const
     return C->df * eval_obj(C, z) - mu * lg + kd * mu * damp;
 }
 
-typedef struct { double th[FILTER_CAP], ph[FILTER_CAP]; int n; } filter_t;
+typedef struct { double th[FILTER_CAP], ph[FILTER_CAP]; int n, evict, added, added_max; } filter_t;
 
 static int filter_ok(const filter_t *F, double th, double ph)
 {
@@ -719,9 +719,11 @@ static void filter_add(filter_t *F, double th, double ph)
     F->n = m;
     if (F->n == FILTER_CAP) { /* drop the oldest */
         for (int i = 1; i < F->n; i++) { F->th[i - 1] = F->th[i]; F->ph[i - 1] = F->ph[i]; }
-        F->n--;
+        F->n--; F->evict++;
     }
     F->th[F->n] = th; F->ph[F->n] = ph; F->n++;
+    F->added++;      /* entries added since the last reset: what an append-only filter (the CUDA kernels') has to hold */
+    if (F->added > F->added_max) F->added_max = F->added;
 }
 
 /* largest alpha in (0,1] keeping primal slacks >= (1-tau) of their current value */
@@ -842,7 +844,7 @@ static int solve_one(const orc_desc *d, const orc_opts *o, const double *x0, con
     }
     /* ---- main loop ---- */
     double mu = o->mu_init, tau = fmax(o->tau_min, 1.0 - mu);
-    filter_t F; F.n = 0;
+    filter_t F; F.n = 0; F.evict = 0; F.added = 0; F.added_max = 0;
     double theta_max = -1, theta_min = -1, delta_last = 0.0, f_prev = 0.0;
     int iter = 0, st = ORC_MAX_ITER, n_acc = 0, n_reg = 0, n_resto = 0, n_soc = 0, n_fact = 1, n_ls = 0;
     double E0 = 0, dual_inf = 0, primal_inf = 0, compl0 = 0;
@@ -921,7 +923,7 @@ static int solve_one(const orc_desc *d, const orc_opts *o, const double *x0, con
             if (!(Emu <= o->barrier_tol_factor * mu) && !(tiny_prev && pass == 0)) break;
             double nm = fmax(fmin(o->kappa_mu * mu, pow(mu, o->theta_mu)), mu_floor);
             if (nm >= mu) break;
-            mu = nm; tau = fmax(o->tau_min, 1.0 - mu); F.n = 0; tiny_prev = 0;
+            mu = nm; tau = fmax(o->tau_min, 1.0 - mu); F.n = 0; F.added = 0; tiny_prev = 0;
         }
         f_prev = fcur;
         if (trace && iter < max_trace) {
@@ -1230,7 +1232,7 @@ finished:
         stats[ORC_ST_KKT_ERR] = E0; stats[ORC_ST_PRIMAL_INF] = primal_inf; stats[ORC_ST_DUAL_INF] = dual_inf;
         stats[ORC_ST_COMPL] = compl0; stats[ORC_ST_MU] = mu; stats[ORC_ST_N_REG] = n_reg;
         stats[ORC_ST_N_RESTO] = n_resto; stats[ORC_ST_N_SOC] = n_soc; stats[ORC_ST_N_FACTOR] = n_fact;
-        stats[ORC_ST_N_LS] = n_ls;
+        stats[ORC_ST_N_LS] = n_ls; stats[ORC_ST_FILTER_EVICT] = F.evict; stats[ORC_ST_FILTER_ADDS] = F.added_max;
     }
 done:
     ctx_free_riccati(&C); free(V.act); free(pool); dims_free(&C.D);

@@ -65,7 +65,8 @@ enum { ORC_SOLVED = 0, ORC_ACCEPTABLE = 1, ORC_MAX_ITER = 2, ORC_INFEASIBLE = 3,
 
 /* stats[] slots written by orc_solve (length ORC_NSTATS) */
 enum { ORC_ST_KKT_ERR = 0, ORC_ST_PRIMAL_INF, ORC_ST_DUAL_INF, ORC_ST_COMPL, ORC_ST_MU,
-       ORC_ST_N_REG, ORC_ST_N_RESTO, ORC_ST_N_SOC, ORC_ST_N_FACTOR, ORC_ST_N_LS, ORC_NSTATS };
+       ORC_ST_N_REG, ORC_ST_N_RESTO, ORC_ST_N_SOC, ORC_ST_N_FACTOR, ORC_ST_N_LS,
+       ORC_ST_FILTER_EVICT /* filter overflows (0) */, ORC_ST_FILTER_ADDS /* most entries added within one barrier subproblem */, ORC_NSTATS };
 
 /* per-iteration trace row (length ORC_NTRACE) */
 enum { ORC_TR_MU = 0, ORC_TR_ERR, ORC_TR_THETA, ORC_TR_OBJ, ORC_TR_ALPHA_PR, ORC_TR_ALPHA_DU,

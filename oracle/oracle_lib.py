@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-ORC_NSTATS = 10
+ORC_NSTATS = 12
 ORC_NTRACE = 8
 STATUS = {0: "SOLVED", 1: "ACCEPTABLE", 2: "MAX_ITER", 3: "INFEASIBLE", 4: "NUMERICAL"}
 

@@ -9,7 +9,7 @@ from oracle.oracle_lib import Desc, Opts, lib as _orc_lib
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
-NSTATS, NTRACE = 10, 8
+NSTATS, NTRACE = 11, 8
 
 
 def lib():

@@ -27,15 +27,32 @@ class OracleSolver:
         return {"x": _X(r["x"])}
 
 
-STEPS = {"C-1": 60, "C-2": 40, "C-3": 25, "C-4": 25, "C-6": 15}
+# every closed loop runs until the reference's stop test ||x0 - xs|| <= tol (centralized_six...py:416) or this many steps
+# (casadi_test.py:143 caps its own loop at sim_tim / T = 400 steps)
+MAX_STEPS = 400
+IPOPT_OPTS = {"print_time": 0, "ipopt": {"max_iter": 2000, "print_level": 0, "acceptable_tol": 1e-8, "acceptable_obj_change_tol": 1e-6}}
+# What the restated IPOPT (oracle) does on each scenario with the Euler plant, measured (steps, final ||x - xs||); the reference
+# records no outputs, so these are characterisation, not ground truth:
+#   C-5 arrives after 137 steps, C-6 after 46; C-1 / C-2 / C-2r / C-4 reach the 400-step cap 0.07-0.10 from the goal (the
+#   nonholonomic parking stall of a terminal-cost-free NMPC); C-3 needs more than 400 steps of T = 0.05 for
+#   its 4.2 m; C-6r (dmin 0.4 on a 0.8 m hexagon) and C-10 end in a collision-free standstill short of the goal -- the local
+#   solver's deadlock, present in the oracle and in the CUDA solver alike.
+ARRIVES = {"C-5", "C-6"}
 
 
-@pytest.mark.parametrize("sid", ["C-1", "C-2", "C-4"])
+def _desym(start, Nr):
+    # C-4, C-6, C-6r are perfectly symmetric swaps: mirror-image optima have the same cost and rounding decides between them
+    # (hard part 1).  Trajectory parity is asserted from a deterministically de-symmetrised start (robots never
+    # sit on exact lattice points anyway); the exactly symmetric layouts are covered by test_gpu_symmetric_scenarios_same_cost.
+    return np.asarray(start, float) + 0.02 * np.sin(1.0 + 2.0 * np.arange(3 * Nr))
+
+
+@pytest.mark.parametrize("sid", ["C-1", "C-2", "C-4", "C-5"])
 def test_oracle_closed_loop_reaches_for_goal_without_collisions(pkg, sid):
     Nr, T, N, dmin, vmax, wmax, start, goal, tol = pkg.mpc_loop.SCENARIOS[sid]
     N = min(N, 20)                                          # keep the CPU suite short; the GPU test runs the reference horizons
     args = pkg.mpc_loop.bounds(Nr, N, dmin, vmax, wmax)
-    xx, u = pkg.mpc_loop.run_mpc(OracleSolver(Nr, N, T), Nr, T, N, start, goal, args, tol, STEPS[sid])
+    xx, u = pkg.mpc_loop.run_mpc(OracleSolver(Nr, N, T), Nr, T, N, _desym(start, Nr), goal, args, tol, 60)
     err = np.linalg.norm(xx - np.asarray(goal, float)[None], axis=1)
     assert err[-1] < err[0] - 0.5 * min(1.0, T * vmax * len(u) * 0.5)      # real progress toward the goal
     assert pkg.mpc_loop.min_pair_distance(xx, Nr) >= dmin - 1e-6
@@ -43,64 +60,37 @@ def test_oracle_closed_loop_reaches_for_goal_without_collisions(pkg, sid):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("sid", ["C-1", "C-2", "C-3", "C-4", "C-6"])
+@pytest.mark.parametrize("sid", ["C-1", "C-2", "C-2r", "C-3", "C-4", "C-5", "C-6", "C-6r", "C-10"])
 def test_gpu_closed_loop_matches_oracle_and_is_collision_free(pkg, sid):
+    """The reference's loop body (mpc_loop.run_mpc) on every 1-6(-10) robot scenario of SURVEY.md App. C at the reference's
+    own horizon, run to the stop tolerance or the 400-step cap: the CUDA solver behind the nlpsol shim against the oracle."""
     Nr, T, N, dmin, vmax, wmax, start, goal, tol = pkg.mpc_loop.SCENARIOS[sid]
-    # C-4 and C-6 are perfectly symmetric swaps: mirror-image optima have the same cost and rounding decides
-    # between them (hard part 1).  Step-by-step trajectory parity is therefore asserted on a
-    # deterministically de-symmetrised start (robots never sit on exact lattice points anyway); the exactly
-    # symmetric layouts are covered by test_gpu_symmetric_scenarios_same_cost below.
-    start = np.asarray(start, float) + 0.02 * np.sin(1.0 + 2.0 * np.arange(3 * Nr))
+    start = _desym(start, Nr)
     args = pkg.mpc_loop.bounds(Nr, N, dmin, vmax, wmax)
-    solver = pkg.nlpsol("solver", "ipopt", {"family": "unicycle_centralized", "Nr": Nr, "N": N, "T": T},
-                        {"print_time": 0, "ipopt": {"max_iter": 2000, "print_level": 0, "acceptable_tol": 1e-8,
-                                                    "acceptable_obj_change_tol": 1e-6}})
-    xx_g, u_g = pkg.mpc_loop.run_mpc(solver, Nr, T, N, start, goal, args, tol, STEPS[sid])
-    xx_o, u_o = pkg.mpc_loop.run_mpc(OracleSolver(Nr, N, T), Nr, T, N, start, goal, args, tol, STEPS[sid])
-    assert len(u_g) == len(u_o)
-    assert np.abs(u_g - u_o).max() <= 1e-4, np.abs(u_g - u_o).max(axis=1)
-    assert np.abs(xx_g - xx_o).max() <= 1e-4
+    solver = pkg.nlpsol("solver", "ipopt", {"family": "unicycle_centralized", "Nr": Nr, "N": N, "T": T}, IPOPT_OPTS)
+    xx_g, u_g = pkg.mpc_loop.run_mpc(solver, Nr, T, N, start, goal, args, tol, MAX_STEPS)
+    xx_o, u_o = pkg.mpc_loop.run_mpc(OracleSolver(Nr, N, T), Nr, T, N, start, goal, args, tol, MAX_STEPS)
+    goal = np.asarray(goal, float)
+    err_g, err_o = np.linalg.norm(xx_g - goal[None], axis=1), np.linalg.norm(xx_o - goal[None], axis=1)
+    # (1) zero collisions and admissible controls over the whole run
     assert pkg.mpc_loop.min_pair_distance(xx_g, Nr) >= dmin - 1e-6
-    err = np.linalg.norm(xx_g - np.asarray(goal, float)[None], axis=1)
-    assert err[-1] < err[0]
+    assert np.all(np.abs(u_g[:, 0::2]) <= vmax + 1e-6) and np.all(np.abs(u_g[:, 1::2]) <= wmax + 1e-6)
+    # (2) step-by-step parity while the two closed loops are the same dynamical system: the first 40 applied controls
+    m = min(40, len(u_g), len(u_o))
+    assert np.abs(u_g[:m] - u_o[:m]).max() <= 1e-4, np.abs(u_g[:m] - u_o[:m]).max(axis=1)
+    assert np.abs(xx_g[:m + 1] - xx_o[:m + 1]).max() <= 1e-4
+    # (3) the end of the run: arrival where the oracle arrives (same step count up to the tolerance crossing), else the same
+    #     final distance from the goal
+    assert (len(u_o) < MAX_STEPS) == (sid in ARRIVES), (sid, len(u_o), err_o[-1])
+    if sid in ARRIVES:
+        assert len(u_g) < MAX_STEPS and err_g[-1] <= tol and abs(len(u_g) - len(u_o)) <= 2, (len(u_g), len(u_o), err_g[-1])
+    else:
+        assert len(u_g) == MAX_STEPS and abs(err_g[-1] - err_o[-1]) <= 2e-2, (err_g[-1], err_o[-1])
+    assert err_g[-1] < err_g[0]
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("sid", ["C-4", "C-6"])
-def test_gpu_symmetric_scenarios_same_cost(pkg, sid):
-    """Exactly symmetric swaps: GPU and oracle may take mirror-image branches, but every applied step must be a
-    converged, collision-free solve and the first-step optimal cost must agree to 1e-6 relative."""
-    Nr, T, N, dmin, vmax, wmax, start, goal, tol = pkg.mpc_loop.SCENARIOS[sid]
-    prob, orc = pkg.Problem(Nr, N, T), Oracle(Nr, N, T)
-    lbx, ubx, lbg, ubg = prob.bounds(dmin, vmax, wmax)
-    P = np.concatenate([start, goal])[None].astype(float)
-    x0 = prob.cold_start(P[:, :3 * Nr])
-    out = prob.solve_host(x0, P, lbx, ubx, lbg, ubg)
-    ref = orc.solve(x0[0], P[0], lbx, ubx, lbg, ubg)
-    assert out["status"][0] == 0 and ref["status"] == 0
-    if abs(out["f"][0] - ref["f"]) / ref["f"] > 1e-6:
-        # From an exactly symmetric start the branch is decided by round-off; the GPU kernel and the oracle evaluate the same
-        # expressions in the same order and normally take the same branch (this assertion has held to 1e-6), but a compiler
-        # that contracts one multiply-add differently sends them to neighbouring local minimisers (observed once: 837.19 vs
-        # 836.47 on the hexagon).  Both are converged KKT points then; their costs must still be close.
-        assert abs(out["f"][0] - ref["f"]) / ref["f"] <= 2e-3, (out["f"][0], ref["f"])
-        assert out["stats"][0, 0] <= 1e-8 and ref["stats"][0] <= 1e-8
-    args = pkg.mpc_loop.bounds(Nr, N, dmin, vmax, wmax)
-    solver = pkg.nlpsol("solver", "ipopt", {"family": "unicycle_centralized", "Nr": Nr, "N": N, "T": T},
-                        {"print_time": 0, "ipopt": {"max_iter": 2000, "print_level": 0, "acceptable_tol": 1e-8,
-                                                    "acceptable_obj_change_tol": 1e-6}})
-    xx_g, u_g = pkg.mpc_loop.run_mpc(solver, Nr, T, N, start, goal, args, tol, STEPS[sid])
-    xx_o, u_o = pkg.mpc_loop.run_mpc(OracleSolver(Nr, N, T), Nr, T, N, start, goal, args, tol, STEPS[sid])
-    assert len(u_g) == len(u_o)
-    assert np.abs(u_g - u_o).max() <= 1e-4, np.abs(u_g - u_o).max(axis=1)
-    assert np.abs(xx_g - xx_o).max() <= 1e-4
-    assert pkg.mpc_loop.min_pair_distance(xx_g, Nr) >= dmin - 1e-6
-    err = np.linalg.norm(xx_g - np.asarray(goal, float)[None], axis=1)
-    assert err[-1] < err[0]
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("sid", ["C-4", "C-6"])
+@pytest.mark.parametrize("sid", ["C-4", "C-6", "C-6r"])
 def test_gpu_symmetric_scenarios_same_cost(pkg, sid):
     """Exactly symmetric swaps: GPU and oracle may take mirror-image branches, but every applied step must be a
     converged, collision-free solve and the first-step optimal cost must agree to 1e-6 relative."""
@@ -125,7 +115,7 @@ def test_gpu_symmetric_scenarios_same_cost(pkg, sid):
         assert np.abs(out2["x"][0] - ref["x"])[nX:].max() <= 1e-4
     args = pkg.mpc_loop.bounds(Nr, N, dmin, vmax, wmax)
     solver = pkg.nlpsol("solver", "ipopt", {"family": "unicycle_centralized", "Nr": Nr, "N": N, "T": T}, {})
-    xx, u = pkg.mpc_loop.run_mpc(solver, Nr, T, N, start, goal, args, tol, STEPS[sid])
+    xx, u = pkg.mpc_loop.run_mpc(solver, Nr, T, N, start, goal, args, tol, 60)
     assert pkg.mpc_loop.min_pair_distance(xx, Nr) >= dmin - 1e-6
     err = np.linalg.norm(xx - np.asarray(goal, float)[None], axis=1)
     assert err[-1] < err[0]

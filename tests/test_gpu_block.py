@@ -21,8 +21,8 @@ def _t(torch, a):
     return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device="cuda:0")
 
 
-def _solve_both(pkg, torch, Nr, N, T, P, dmin=0.3):
-    prob, orc = pkg.Problem(Nr, N, T), Oracle(Nr, N, T)
+def _solve_both(pkg, torch, Nr, N, T, P, dmin=0.3, tuning=None):
+    prob, orc = pkg.Problem(Nr, N, T, tuning=tuning), Oracle(Nr, N, T)
     lbx, ubx, lbg, ubg = prob.bounds(dmin, 0.22, 2.84)
     x0 = prob.cold_start(P[:, :3 * Nr])
     out = prob.solve(_t(torch, x0), _t(torch, P), _t(torch, lbx), _t(torch, ubx), _t(torch, lbg), _t(torch, ubg))
@@ -128,12 +128,11 @@ def test_block_path_closed_loop_and_host_api(pkg, torch_cuda):
 
 
 @pytest.mark.parametrize("Nr,N,T", [(1, 25, 0.25), (2, 7, 0.1), (3, 10, 0.3), (6, 20, 0.3)])
-def test_block_path_equals_oracle_on_small_robot_counts(pkg, torch_cuda, Nr, N, T, monkeypatch):
-    """The dense-block solver is generic in Nr: forced onto 1..6 robots (NMPC_FORCE_BLOCK) it must reproduce the oracle
-    exactly like the warp-per-instance path does."""
-    monkeypatch.setenv("NMPC_FORCE_BLOCK", "1")
+def test_block_path_equals_oracle_on_small_robot_counts(pkg, torch_cuda, Nr, N, T):
+    """The dense-block solver is generic in Nr: forced onto 1..6 robots (nmpc_tuning.force_block_path) it must reproduce the
+    oracle exactly like the warp-per-instance path does."""
     P = synthetic_instances(6, Nr=Nr, seed=300 + Nr, box=2.0)
-    prob, out, ref, (lbx, ubx, lbg, ubg) = _solve_both(pkg, torch_cuda, Nr, N, T, P, dmin=0.3)
+    prob, out, ref, (lbx, ubx, lbg, ubg) = _solve_both(pkg, torch_cuda, Nr, N, T, P, dmin=0.3, tuning=dict(force_block_path=1))
     du, df = _check(out, ref, Nr, N, lbg, P, 0.3)
     assert ((du <= 1e-4) & (df <= 1e-6)).all(), (du, df, out["iters"].cpu().numpy(), ref["iters"])
     assert np.abs(out["iters"].cpu().numpy() - ref["iters"]).max() <= 3

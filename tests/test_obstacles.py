@@ -86,12 +86,11 @@ def _t(torch, a):
 @pytest.mark.gpu
 @pytest.mark.parametrize("path", ["cta", "thread"])
 @pytest.mark.parametrize("case", ["one", "six"])
-def test_gpu_obstacle_family_matches_slsqp(pkg, torch_cuda, case, path, monkeypatch):
+def test_gpu_obstacle_family_matches_slsqp(pkg, torch_cuda, case, path):
     """Both kernels that serve this family: the CTA-per-instance dense-block solver (small batches) and the
-    thread-per-instance small-OCP solver (large batches; forced here with NMPC_THREAD_MIN_BATCH=1)."""
+    thread-per-instance small-OCP solver (large batches; forced here with nmpc_tuning.thread_min_batch = 1)."""
     torch = torch_cuda
-    if path == "thread":
-        monkeypatch.setenv("NMPC_THREAD_MIN_BATCH", "1")
+    tuning = dict(thread_min_batch=1) if path == "thread" else None
     if case == "one":      # first scenario geometry, shortened horizon: obstacle between start and goal
         N, T, obs, margin = 15, 0.3, np.array([[0.45, 0.5, 0.3]]), 0.05
         P = np.array([[0.0, 0.0, 0.6, 1.2, 1.3, 0.0], [0.1, -0.1, 0.9, 1.0, 1.4, 0.3]])
@@ -99,7 +98,7 @@ def test_gpu_obstacle_family_matches_slsqp(pkg, torch_cuda, case, path, monkeypa
         N, T, obs, margin = 20, 0.3, _obs(THIRD), 0.1
         P = np.array([[0.0, 0.6, 1.57, 0.1, 3.9, 1.57], [0.3, 0.7, 1.2, -0.2, 3.6, 1.57]])
     v_max, w_max = 0.2, np.pi / 4
-    prob = pkg.Problem(1, N, T, obstacles=obs)
+    prob = pkg.Problem(1, N, T, obstacles=obs, tuning=tuning)
     nlp = ObstacleNLP(N, T, obs)
     assert (prob.n, prob.mg) == (nlp.n, nlp.mg)
     lbx, ubx, lbg, ubg = prob.bounds_obstacles(margin, v_max, w_max)
