@@ -48,6 +48,10 @@
     (void)row; (void)frow; (void)zvalid; (void)gradf;
 
 struct alignas(16) NmpcD2 { double x, y; };   // one 128-bit shared-memory load
+#ifndef NMPC_PIVOT_UNROLL
+#define NMPC_PIVOT_UNROLL 1   // 2: both pivot-row buffers get compile-time addresses (6 % fewer instructions per pivot) but the loop body
+                              // doubles; measured slower (43.8 k against 46.5 k solves/s): instruction fetch, not issue, is the limit
+#endif
 #ifndef NMPC_XBATCH
 #define NMPC_XBATCH 3   // pairs of pivot-row entries per batch of the sweep's state-row update (see factor())
 #endif
@@ -118,6 +122,11 @@ struct WarpSolver {
     double *sm, *ws;
     const double *BL, *BU, *CE, *DL, *DU;
     int N, S, l, rob, comp, pi, pj, inst, fn;
+    // cos/sin rows of the iterate (r_trig is R_TRIG or R_TRIG2; the other one receives the trial points).  When a step is
+    // accepted at the trial point evaluated last, its rows BECOME the iterate's (swap) and no sincos is recomputed.
+    int r_trig, t2_rdz;
+    bool trig_valid;
+    double t2_alpha;
     bool isx, isu, isz, isq;
     double T, df, xs_l, qw, x0bar_l, ny_nzb, nzb_cnt;
     int n_reg, n_resto, n_soc, n_fact, n_ls;
@@ -241,6 +250,7 @@ struct WarpSolver {
         ny_nzb = tred_sum(cnt_y) + nzb_cnt;
         tsync();
         trig_rows(row, l, N, 0.0, 0, false, R_TRIG);
+        this->r_trig = R_TRIG; this->trig_valid = true; this->t2_rdz = -1; this->t2_alpha = 0.0;
     }
 
     // ---------------------------------------------------------------------------------------
@@ -289,8 +299,9 @@ struct WarpSolver {
         double sprod = 1.0;   // product of this stage's (<= 4) slacks; folded into (mantissa, exponent) once per stage
         auto addlog = [&](double x) { sprod *= x; };
         auto foldlog = [&]() { int e; lmant = wp::frexp_(lmant * sprod, &e); lexp += e; sprod = 1.0; };
-        const int rt = trial ? R_TRIG2 : R_TRIG;
-        trig_rows(row, l, N, alpha, rdz, trial, rt);
+        const int rt = trial ? (this->r_trig == R_TRIG ? R_TRIG2 : R_TRIG) : this->r_trig;
+        if (trial) { trig_rows(row, l, N, alpha, rdz, true, rt); this->t2_rdz = rdz; this->t2_alpha = alpha; }
+        else if (!this->trig_valid) { trig_rows(row, l, N, 0.0, 0, false, rt); this->trig_valid = true; }
         auto load_z = [&](int k) {
             ZRows r;
             k = k < N ? k : N;
@@ -510,7 +521,7 @@ struct WarpSolver {
         if (l < FS_COUNT) {   // base pointers (stage 0) of the rows staged per stage; see FS_*
             const double *p0 = nullptr;
             switch (l) {
-                case FS_Z: p0 = row(R_Z, 0); break;      case FS_TRIG: p0 = row(R_TRIG, 0); break;
+                case FS_Z: p0 = row(R_Z, 0); break;      case FS_TRIG: p0 = row(this->r_trig, 0); break;
                 case FS_ZL: p0 = row(R_ZL, 0); break;    case FS_ZU: p0 = row(R_ZU, 0); break;
                 case FS_BL: p0 = BL; break;              case FS_BU: p0 = BU; break;
                 case FS_YC: p0 = row(R_YC, 0); break;    case FS_S: p0 = row(R_S, 0); break;
@@ -679,14 +690,12 @@ struct WarpSolver {
             // overlap the remaining rank-1 update instead of sitting on the critical path of every pivot.
             const int ucol = l - NS;   // control column of this lane (if any)
             int pslot = l;             // where this lane publishes its entry of the next pivot row (control lanes: rotating)
-            if (isz) { col[pslot] = U[0]; col[LW + pslot] = wp::rcp_pos(U[0]); }
-            NMPC_NOUNROLL
-            for (int j = 0; j < NC; j++) {
-                const double *buf = col + 2 * LW * (j & 1);
-                double *nbuf = col + 2 * LW * ((j + 1) & 1);
+            col[pslot] = U[0]; col[LW + pslot] = wp::rcp_pos(U[0]);   // every lane (no branch): the slots of the lanes beyond the 5Nr columns are never read
+            // one pivot step; the loop below is unrolled by two so that both buffers have compile-time addresses
+            auto pivot = [&](const int j, const double *buf, double *nbuf) -> bool {
                 tsync();
                 const double inv = buf[LW + NS];   // 1 / pivot, from the pivot's own lane (rotated slot NS)
-                if (!wp::pos_normal(inv)) { wp::cp_async_wait(); return false; }   // drain the staging copies before the retry
+                if (!wp::pos_normal(inv)) return false;
                 // the control part of the pivot row first (128-bit loads): it feeds the look-ahead
                 double bu[NC];
                 if ((NS & 1) == 0) {
@@ -700,7 +709,8 @@ struct WarpSolver {
                 const bool own = (ucol == j);
                 const double t = own ? -inv : U[0] * inv;
                 const double tx = (ucol > j && isu) ? 0.0 : t;
-                if (own) {   // the pivot column becomes column / d: start its remaining rows from 0
+                if (own) {   // the pivot column becomes column / d: start its remaining rows from 0.  (Predicated moves instead of
+                             // this divergent branch were measured: 22 FSEL in front of the FMAs, 45.2 k -> 42.0 k solves/s.)
                     NMPC_UNROLL
                     for (int r = 1; r < NC; r++) U[r] = 0.0;
                 }
@@ -708,7 +718,7 @@ struct WarpSolver {
                 const double u1 = U[1] - bu[1] * t;
                 if (isu) { pslot--; pslot += pslot < NS ? NC : 0; }
                 const double r1 = wp::rcp_pos(u1);   // every lane: no divergent reciprocal
-                if (isz) { nbuf[pslot] = u1; nbuf[LW + pslot] = r1; }
+                nbuf[pslot] = u1; nbuf[LW + pslot] = r1;
                 // control rows (rotating): slots NS+2 .. NS+NC-1
                 U[0] = u1;
                 NMPC_UNROLL
@@ -735,7 +745,19 @@ struct WarpSolver {
                     }
                     if (NS & 1) X[NS - 1] -= buf[NS - 1] * tx;
                 }
+                return true;
+            };
+#if NMPC_PIVOT_UNROLL == 2
+            NMPC_NOUNROLL
+            for (int j = 0; j < NC; j += 2) {
+                if (!pivot(j, col, col + 2 * LW) || !pivot(j + 1, col + 2 * LW, col)) { wp::cp_async_wait(); return false; }   // drain the staging copies before the retry
             }
+#else
+            NMPC_NOUNROLL
+            for (int j = 0; j < NC; j++) {
+                if (!pivot(j, col + 2 * LW * (j & 1), col + 2 * LW * ((j + 1) & 1))) { wp::cp_async_wait(); return false; }   // drain the staging copies before the retry
+            }
+#endif
             // publish p_k / feed-forward (the last lane's column) and store the factors
             tsync();
             if (isL) {
@@ -749,8 +771,9 @@ struct WarpSolver {
                 const double v = prb[l];
                 plin = v;
                 row(R_LIN, k)[l] = v; row(R_DG, k)[l] = dgx;
+                double *fp = frow(k, 0) + l;   // one address, compile-time row offsets
                 NMPC_UNROLL
-                for (int i = 0; i < NS; i++) frow(k, i)[l] = X[i];
+                for (int i = 0; i < NS; i++) fp[i * LW] = X[i];
             }
         }
         tsync();
@@ -910,6 +933,9 @@ struct WarpSolver {
     NMPC_PASS void accept(double alpha, double az, double mu, int rdz, int rds, int rytc, int rytd)
     {
         NMPC_LOCALS
+        if (this->t2_rdz == rdz && this->t2_alpha == alpha) { this->r_trig = this->r_trig == R_TRIG ? R_TRIG2 : R_TRIG; this->trig_valid = true; }
+        else this->trig_valid = false;
+        this->t2_rdz = -1;
         const double ks = this->P.o.kappa_sigma, iks = 1.0 / ks;
         // bound multiplier after the step, kept in the kappa_sigma corridor around mu / (new slack)
         auto mult = [=](double m, double sl_old, double sl_new, double dv_signed) {
@@ -952,6 +978,7 @@ struct WarpSolver {
     NMPC_PASS void accept_primal(double alpha, int rdz, int rds)
     {
         NMPC_LOCALS
+        this->trig_valid = false; this->t2_rdz = -1;
         for (int k = 0; k <= N; k++) {
             if (zvalid(k)) row(R_Z, k)[l] += alpha * row(rdz, k)[l];
             if (M > 0 && isq && (DL[k * LW + l] > -NMPC_INF || DU[k * LW + l] < NMPC_INF)) row(R_S, k)[l] += alpha * row(rds, k)[l];
