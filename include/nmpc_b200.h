@@ -131,8 +131,9 @@ int nmpc_solve(nmpc_handle *h, int B, const double *x0, const double *p,
  * with clearance = rob_dim + r_obs (:125), bounded below by the margin the scripts put in lbg (0.05 / 0.1) and above by +inf.
  * obs: HOST array [n_obs][3] = (ox, oy, clearance).  Row layout of g / lbg / ubg / lam_g (as the scripts build it, :109-125):
  * [X_0 - x0bar (3 Nr)], then for k = 0..N-1: [defect rows (3 Nr); pair rows (M, none for one robot); obstacle rows, robot-major
- * (Nr n_obs)]; mg = 3 Nr + N (3 Nr + M + Nr n_obs).  Runs on the CTA-per-instance dense-block path for every Nr; nmpc_eval and
- * the CCS patterns are not available for this family. */
+ * (Nr n_obs)]; mg = 3 Nr + N (3 Nr + M + Nr n_obs).  Runs on the warp-per-instance path for 1..4 robots while M + Nr n_obs <= 32
+ * (one robot with up to 32 obstacles; the reference's scripts have one robot and 1, 4 or 6), else on the CTA-per-instance
+ * dense-block path; nmpc_eval and the CCS patterns are not available for this family. */
 int nmpc_create_obstacles(const nmpc_desc *d, const nmpc_opts *o, int n_obs, const double *obs, nmpc_handle **out);
 
 /* Small generic optimal-control problems, one GPU thread per instance.  model NMPC_OCP_VAN_DER_POL is the direct-multiple-shooting

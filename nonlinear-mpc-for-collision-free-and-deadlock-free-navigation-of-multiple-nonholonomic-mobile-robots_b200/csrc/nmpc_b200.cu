@@ -16,6 +16,7 @@
 #include "small_ocp.cuh"
 #include "aux_kernels.cuh"
 
+#define NMPC_OBS_WARP_MAX_ROBOTS 4   // the static-obstacle family is instantiated on the warp path for 1..4 robots
 #ifndef SOLVE_WARPS
 #define SOLVE_WARPS 4     // warps (instances) per CTA = the convoy group, see WarpSolver::iter_sync
 #endif
@@ -59,27 +60,29 @@ extern "C" void nmpc_default_opts(nmpc_opts *o)
 // threads per CTA and instances ("teams") per CTA: one warp per instance up to 6 robots (3 per CTA, 4 CTAs per SM);
 // 7..10 robots use the two-warp team (2 per CTA on named barriers, 2 CTAs per SM: 255 registers per thread).  The
 // one-warp teams of a CTA are a convoy group (WarpSolver::iter_sync).
-template <int NR> struct SolveCfg {
-    static constexpr int LW = WarpSolver<NR>::LW;
+template <int NR, bool OBS = false> struct SolveCfg {
+    static constexpr int LW = WarpSolver<NR, OBS>::LW;
     static constexpr int THREADS = LW == 32 ? SOLVE_WARPS * 32 : 128;
     static constexpr int TEAMS = THREADS / LW;
     static constexpr int MIN_CTAS = LW == 32 ? SOLVE_MIN_CTAS : 2;
 };
 
-template <int NR>
-__global__ void __launch_bounds__(SolveCfg<NR>::THREADS, SolveCfg<NR>::MIN_CTAS) solve_kernel(const NmpcSolveParams P)
+// OBS: the static-obstacle family (its own instantiation, see WarpSolver)
+template <int NR, bool OBS = false>
+__global__ void __launch_bounds__((SolveCfg<NR, OBS>::THREADS), (SolveCfg<NR, OBS>::MIN_CTAS)) solve_kernel(const NmpcSolveParams P)
 {
     extern __shared__ double smem[];
-    constexpr int LW = SolveCfg<NR>::LW;
+    typedef WarpSolver<NR, OBS> WSol;
+    constexpr int LW = SolveCfg<NR, OBS>::LW;
     const int team = threadIdx.x / LW, tl = threadIdx.x & (LW - 1);
-    double *sm = smem + (size_t)team * WarpSolver<NR>::SM_DOUBLES;
-    double *ws = P.ws + ((long long)blockIdx.x * SolveCfg<NR>::TEAMS + team) * P.ws_stride;
-    WarpSolver<NR> s(P, sm, ws);
+    double *sm = smem + (size_t)team * WSol::SM_DOUBLES;
+    double *ws = P.ws + ((long long)blockIdx.x * SolveCfg<NR, OBS>::TEAMS + team) * P.ws_stride;
+    WSol s(P, sm, ws);
     for (;;) {
-        WarpSolver<NR>::tsync();
-        if (tl == 0) sm[WarpSolver<NR>::SM_MISC + 1] = (double)atomicAdd(P.counter, 1);
-        WarpSolver<NR>::tsync();
-        const int slot = (int)sm[WarpSolver<NR>::SM_MISC + 1];
+        WSol::tsync();
+        if (tl == 0) sm[WSol::SM_MISC + 1] = (double)atomicAdd(P.counter, 1);
+        WSol::tsync();
+        const int slot = (int)sm[WSol::SM_MISC + 1];
         if (slot >= P.B) {
             // convoy mode: keep answering the group's barriers until every warp of the CTA has run out of work
             if (P.convoy) while (wp::cta_count(false) != 0) {}
@@ -175,15 +178,15 @@ static void build_tables(nmpc_handle *h, std::vector<int> &tab)
     tab.insert(tab.end(), hs.begin(), hs.end());
 }
 
-template <int NR> static size_t slot_doubles(int N) { return (size_t)WarpSolver<NR>::ws_doubles(N); }
-template <int NR> static cudaError_t config_solve(nmpc_handle *h)
+template <int NR, bool OBS = false> static size_t slot_doubles(int N) { return (size_t)WarpSolver<NR, OBS>::ws_doubles(N); }
+template <int NR, bool OBS = false> static cudaError_t config_solve(nmpc_handle *h)
 {
-    h->lw = SolveCfg<NR>::LW; h->teams_per_cta = SolveCfg<NR>::TEAMS; h->threads = SolveCfg<NR>::THREADS;
-    h->solve_smem = (size_t)SolveCfg<NR>::TEAMS * WarpSolver<NR>::SM_DOUBLES * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(solve_kernel<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->solve_smem);
+    h->lw = SolveCfg<NR, OBS>::LW; h->teams_per_cta = SolveCfg<NR, OBS>::TEAMS; h->threads = SolveCfg<NR, OBS>::THREADS;
+    h->solve_smem = (size_t)SolveCfg<NR, OBS>::TEAMS * WarpSolver<NR, OBS>::SM_DOUBLES * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(solve_kernel<NR, OBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->solve_smem);
     if (e != cudaSuccess) return e;
     int nb = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, solve_kernel<NR>, SolveCfg<NR>::THREADS, h->solve_smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, solve_kernel<NR, OBS>, SolveCfg<NR, OBS>::THREADS, h->solve_smem);
     h->ctas_per_sm = nb > 0 ? nb : 1;
     if (h->tune.ctas_per_sm >= 1 && h->tune.ctas_per_sm < h->ctas_per_sm) h->ctas_per_sm = h->tune.ctas_per_sm;
     return e;
@@ -271,7 +274,11 @@ static int create_impl(const nmpc_desc *d, const nmpc_opts *o, const nmpc_tuning
     h->launches = 0; h->d_buf = nullptr; h->d_bytes = 0; h->stream = nullptr; h->d_tables = nullptr;
     h->d_pairs = nullptr; h->d_order = nullptr; h->order_len = 0;
     // the obstacle family runs on the dense-block path for every Nr; nmpc_tuning.force_block_path: test hook, any Nr on that path
-    h->block_path = d->Nr > 10 || h->family != 0 || h->tune.force_block_path != 0; h->eval_ok = h->family == 0;
+    // the obstacle family runs on the warp-per-instance path for up to 4 robots while its rows fit the warp's lanes (pair rows +
+    // Nr n_obs <= 32: one robot with up to 32 obstacles; the reference's scripts have one robot and 1, 4 or 6), else on the dense-block path
+    const int lanes = 32;
+    const bool obs_fit = d->Nr <= NMPC_OBS_WARP_MAX_ROBOTS && h->M + d->Nr * nobs <= lanes;
+    h->block_path = d->Nr > 10 || (h->family != 0 && !obs_fit) || h->tune.force_block_path != 0; h->eval_ok = h->family == 0;
     // A single robot with static obstacles (the reference's obstacle scripts) also runs on the thread-per-instance small-OCP
     // solver (UnicycleObstacles model), parity-tested, but measured slower than the CTA-per-instance path both alone (88 ms
     // against 49 ms per solve at N = 100) and in batches (9.2 k against 23.0 k solves/s, B = 8192, N = 20: its per-thread
@@ -293,10 +300,16 @@ static int create_impl(const nmpc_desc *d, const nmpc_opts *o, const nmpc_tuning
     h->tb.jac_init = h->tb.jac_ps + (size_t)N * M * 4;
     h->tb.hes_rs = h->d_tables + h->nnzj;
     h->tb.hes_ps = h->tb.hes_rs + (size_t)N * Nr * 6;
-    switch (h->block_path ? 0 : Nr) {
+    switch (h->block_path ? 0 : (h->family ? 100 + Nr : Nr)) {
+#ifndef NMPC_DEV_ONLY_NR
+        case 101: h->ws_doubles_per_slot = slot_doubles<1, true>(N); e = config_solve<1, true>(h); break;
+        case 102: h->ws_doubles_per_slot = slot_doubles<2, true>(N); e = config_solve<2, true>(h); break;
+        case 103: h->ws_doubles_per_slot = slot_doubles<3, true>(N); e = config_solve<3, true>(h); break;
+        case 104: h->ws_doubles_per_slot = slot_doubles<4, true>(N); e = config_solve<4, true>(h); break;
+#endif
 #ifdef NMPC_DEV_ONLY_NR   // development builds (tools/dev_build.sh): one warp-path instantiation, 5 x faster to compile
         case NMPC_DEV_ONLY_NR: h->ws_doubles_per_slot = slot_doubles<NMPC_DEV_ONLY_NR>(N); e = config_solve<NMPC_DEV_ONLY_NR>(h); break;
-        case 100: break;
+        case 1000: break;
 #define NMPC_SKIP_OTHER_NR
 #endif
 #ifndef NMPC_SKIP_OTHER_NR
@@ -329,12 +342,12 @@ static int create_impl(const nmpc_desc *d, const nmpc_opts *o, const nmpc_tuning
                 for (int b = a + 1; b < Nr; b++) { pr.push_back(a); pr.push_back(b); }
             if (e == cudaSuccess) e = cudaMalloc(&h->d_pairs, (pr.size() + 2) * sizeof(int));
             if (e == cudaSuccess && !pr.empty()) e = cudaMemcpy(h->d_pairs, pr.data(), pr.size() * sizeof(int), cudaMemcpyHostToDevice);
-            if (e == cudaSuccess && h->nobs > 0) {
-                e = cudaMalloc(&h->d_obs, (size_t)3 * h->nobs * sizeof(double));
-                if (e == cudaSuccess) e = cudaMemcpy(h->d_obs, obs, (size_t)3 * h->nobs * sizeof(double), cudaMemcpyHostToDevice);
-            }
             break;
         }
+    }
+    if (e == cudaSuccess && h->nobs > 0) {
+        e = cudaMalloc(&h->d_obs, (size_t)3 * h->nobs * sizeof(double));
+        if (e == cudaSuccess) e = cudaMemcpy(h->d_obs, obs, (size_t)3 * h->nobs * sizeof(double), cudaMemcpyHostToDevice);
     }
     if (e != cudaSuccess) { nmpc_destroy(h); return fail(NMPC_ECUDA, "nmpc_create: kernel configuration failed: %s", cudaGetErrorString(e)); }
     h->eval_smem = (size_t)(2 * h->n + 2 * h->mg + 2 * h->ns + h->nnzj + h->nnzh + 32 + 8) * sizeof(double);
@@ -450,7 +463,13 @@ static int solve_impl(nmpc_handle *h, int B, const double *x0, const double *p, 
     if (thr && h->family == 2) solve_kernel_small_ocp<VanDerPol><<<grid, 64, 0, st>>>(P);
     else if (thr) solve_kernel_small_ocp<UnicycleObstacles><<<grid, 64, 0, st>>>(P);
     else if (h->block_path) solve_kernel_block<<<grid, h->threads, h->solve_smem, st>>>(P);
-    else switch (h->d.Nr) {
+    else switch (h->family ? 100 + h->d.Nr : h->d.Nr) {
+#ifndef NMPC_DEV_ONLY_NR
+        case 101: solve_kernel<1, true><<<grid, h->threads, h->solve_smem, st>>>(P); break;
+        case 102: solve_kernel<2, true><<<grid, h->threads, h->solve_smem, st>>>(P); break;
+        case 103: solve_kernel<3, true><<<grid, h->threads, h->solve_smem, st>>>(P); break;
+        case 104: solve_kernel<4, true><<<grid, h->threads, h->solve_smem, st>>>(P); break;
+#endif
 #ifdef NMPC_DEV_ONLY_NR
         default: solve_kernel<NMPC_DEV_ONLY_NR><<<grid, h->threads, h->solve_smem, st>>>(P); break;
 #else

@@ -38,6 +38,10 @@
               pi = this->pi, pj = this->pj;                                                            \
     const bool isx = this->isx, isu = this->isu, isz = this->isz, isq = this->isq;                     \
     const double T = this->T, df = this->df, xs_l = this->xs_l, qw = this->qw, x0bar_l = this->x0bar_l; \
+    const int nobs = OBS ? this->nobs : 0, family = OBS ? this->family : 0;                              \
+    const bool isobs = OBS && this->isobs;                                                              \
+    const double qox = this->qox, qoy = this->qoy, qoc = this->qoc;                                     \
+    (void)nobs; (void)family; (void)isobs; (void)qox; (void)qoy; (void)qoc;                              \
     (void)sm; (void)ws; (void)BL; (void)BU; (void)CE; (void)DL; (void)DU; (void)N; (void)S; (void)l;   \
     (void)rob; (void)comp; (void)pi; (void)pj; (void)isx; (void)isu; (void)isz; (void)isq; (void)T;    \
     (void)df; (void)xs_l; (void)qw; (void)x0bar_l;                                                     \
@@ -56,7 +60,9 @@ struct alignas(16) NmpcD2 { double x, y; };   // one 128-bit shared-memory load
 #define NMPC_XBATCH 3   // pairs of pivot-row entries per batch of the sweep's state-row update (see factor())
 #endif
 
-template <int NR>
+// OBS: the static-obstacle family (obstacle rows after the pair rows).  A separate instantiation: the generalised row geometry and
+// the wider addend tables cost the pair-only benchmark path 8 % when they are merely switched off at run time (measured).
+template <int NR, bool OBS = false>
 struct WarpSolver {
     static constexpr int NS = 3 * NR, NC = 2 * NR, NZ = 5 * NR, M = NR * (NR - 1) / 2;
     static constexpr int LIN = NZ, NM = NZ + 1;
@@ -65,7 +71,10 @@ struct WarpSolver {
     static constexpr int CFS = LW / 4;        // stride of the four coefficient groups inside a R_COEF row
     static constexpr int LPR = LW / 16;       // 128-byte lines per scratch row
     static constexpr int NRP = (NR <= 8) ? 8 : 16, MP = (M <= 16) ? 16 : 64;
-    static_assert(NZ + 1 <= 64 && M <= 64, "at most 11 robots on the lane-per-column path");
+    // static circular obstacles (family F of the reference, first_scenario_mpc_obstacle_avoidance.py:96-152): nobs rows per robot and
+    // stage after the M pair rows, one lane each, so Nr * nobs <= LW - M on this path
+    static constexpr int NOBS_MAX = OBS ? (LW - M) / NR : 0, TCOLS = NR + NOBS_MAX;
+    static_assert(NZ + 1 <= 64 && M <= LW, "at most 10 robots on the lane-per-column path");
     enum Row {
         R_Z, R_ZL, R_ZU, R_DZ, R_DZ2, R_GX, R_YC, R_YTC, R_YTC2, R_RC, R_CSOC, R_COEF, R_LIN,
         R_S, R_VL, R_VU, R_YD, R_DS, R_DS2, R_YTD, R_YTD2, R_DSOC, R_GXQ, R_GYQ, R_RD, R_DQ, R_GS, R_DG, R_TRIG, R_TRIG2,
@@ -80,7 +89,7 @@ struct WarpSolver {
     // factorisation and the forward pass carve up differently (they never run at the same time)
     enum {
         PLD = NS + 3,  // leading dimension of the P broadcast buffer: 3Nr columns of P, the pr column, 2 zero columns
-        TSZ = NR * NR, // one addend table of the stage-matrix build, see factor()
+        TSZ = NR * TCOLS, // one addend table of the stage-matrix build (rows: robots; columns: robots, then this robot's obstacles), see factor()
         SM_ZB = 0, SM_DZB = SM_ZB + LW, SM_RCB = SM_DZB + LW, SM_PRB = SM_RCB + LW, SM_HB = SM_PRB + LW,
         SM_CS = SM_HB + LW, SM_SN = SM_CS + NRP, SM_C4 = SM_SN + NRP,   // c4[4 i ..]: a_i, b_i, T cos, T sin of robot i (one 32-byte record)
         SM_CRS = SM_C4 + 4 * NRP, SM_THD = SM_CRS + NRP,
@@ -128,6 +137,11 @@ struct WarpSolver {
     bool trig_valid;
     double t2_alpha;
     bool isx, isu, isz, isq;
+    // inequality rows of a block: lanes < M are the pair rows (pi, pj); lanes M .. M + Nr nobs - 1 the static-obstacle rows, robot-major
+    // (row M + i nobs + o: robot pi = i against obstacle o = (qox, qoy, clearance qoc)); family 1 = the obstacle scripts' g layout
+    int nobs, family;
+    bool isobs;
+    double qox, qoy, qoc;
     double T, df, xs_l, qw, x0bar_l, ny_nzb, nzb_cnt;
     int n_reg, n_resto, n_soc, n_fact, n_ls;
 
@@ -158,16 +172,40 @@ struct WarpSolver {
     NMPC_DEV bool zvalid(int k) const { return l < (k < N ? NZ : NS); }
     static NMPC_DEV int pairidx(int a, int b) { return a * (2 * NR - a - 1) / 2 + (b - a - 1); }
     static NMPC_DEV bool fin(double v) { return v > -NMPC_INF && v < NMPC_INF; }
+    // One inequality row evaluated on a stage vector zr: value, gradient w.r.t. (x_pi, y_pi) (negated for robot pj of a pair row)
+    // and its own second derivatives.  Pair rows: squared distance (centralized_six_robots_implementation.py:288-306); obstacle
+    // rows: sqrt((x - ox)^2 + (y - oy)^2) - clearance (first_scenario_mpc_obstacle_avoidance.py:96-99,125).
+    struct RowG { double dv, gx, gy, hxx, hyy, hxy; };
+    static NMPC_DEV RowG rowg(const double *zr, int pi, int pj, bool isobs, double ox, double oy, double oc)
+    {
+        RowG r;
+        if (isobs) {
+            const double dx = zr[3 * pi] - ox, dy = zr[3 * pi + 1] - oy;
+            const double rho = sqrt(dx * dx + dy * dy), ir = 1.0 / rho;
+            r.gx = dx * ir; r.gy = dy * ir; r.dv = rho - oc;
+            r.hxx = (1.0 - r.gx * r.gx) * ir; r.hyy = (1.0 - r.gy * r.gy) * ir; r.hxy = -r.gx * r.gy * ir;
+        } else {
+            const double dx = zr[3 * pi] - zr[3 * pj], dy = zr[3 * pi + 1] - zr[3 * pj + 1];
+            r.dv = dx * dx + dy * dy; r.gx = 2.0 * dx; r.gy = 2.0 * dy; r.hxx = 2.0; r.hyy = 2.0; r.hxy = 0.0;
+        }
+        return r;
+    }
 
     // ---------------------------------------------------------------------------------------
     NMPC_DEV void setup(int instance)
     {
         inst = instance; N = P.N; S = N + 1; T = P.T; l = wp::team_lane(LW);
-        isx = l < NS; isu = l >= NS && l < NZ; isz = l < NZ; isq = l < M;
+        nobs = OBS ? P.nobs : 0; family = OBS ? P.family : 0;
+        isx = l < NS; isu = l >= NS && l < NZ; isz = l < NZ; isq = l < M + NR * nobs; isobs = isq && l >= M;
+        qox = qoy = qoc = 0.0;
         rob = isx ? l / 3 : (isu ? (l - NS) / 2 : 0);
         comp = isx ? l % 3 : (isu ? (l - NS) % 2 : 0);
         pi = 0; pj = 0;
-        if (isq) {
+        if (isobs) {
+            const int e = l - M, o = e % nobs;
+            pi = e / nobs; pj = pi;   // pj = pi: the "other robot" terms of a pair row cancel for an obstacle row
+            qox = P.obs[3 * o]; qoy = P.obs[3 * o + 1]; qoc = P.obs[3 * o + 2];
+        } else if (isq) {
             int q = 0;
             for (int a = 0; a < NR; a++)
                 for (int b = a + 1; b < NR; b++) { if (q == l) { pi = a; pj = b; } q++; }
@@ -234,11 +272,7 @@ struct WarpSolver {
                 double lo = DL[b * LW + l], hi = DU[b * LW + l];
                 bool hl = lo > -NMPC_INF, hu = hi < NMPC_INF;
                 double dv = NMPC_DUMMY_ROW_VALUE;
-                if (b > 0) {
-                    const double *zr = row(R_Z, b - 1);
-                    double dx = zr[3 * pi] - zr[3 * pj], dy = zr[3 * pi + 1] - zr[3 * pj + 1];
-                    dv = dx * dx + dy * dy;
-                }
+                if (b > 0) dv = rowg(row(R_Z, b - 1), pi, pj, isobs, qox, qoy, qoc).dv;
                 s = (hl || hu) ? push_in(dv, lo, hi, o.bound_push, o.bound_frac) : dv;
                 vl = hl ? o.bound_mult_init_val : 0.0; vu = hu ? o.bound_mult_init_val : 0.0;
                 cnt_z += (hl ? 1.0 : 0.0) + (hu ? 1.0 : 0.0);
@@ -345,7 +379,7 @@ struct WarpSolver {
         };
         ZRows zc = load_z(0), zn = load_z(1);
         QRows qn = load_q(1);
-        if (M > 0 && isq) { QRows q0 = load_q(0); ineq_row(0, q0, NMPC_DUMMY_ROW_VALUE); }   // block 0: the dummy rows
+        if (isq) { QRows q0 = load_q(0); ineq_row(0, q0, NMPC_DUMMY_ROW_VALUE); }   // block 0: the dummy rows
         for (int k = 0; k <= N; k++) {
             const ZRows zf = load_z(k + 2);          // in flight during this stage
             const QRows qf = load_q(k + 2);
@@ -373,10 +407,7 @@ struct WarpSolver {
                 if (FULL) ysum += fabs(zc.yc);
             }
             // ---- inequality block k+1 (distances on X_k) ----
-            if (M > 0 && isq && k < N) {
-                double dx = zb[3 * pi] - zb[3 * pj], dy = zb[3 * pi + 1] - zb[3 * pj + 1];
-                ineq_row(k + 1, qn, dx * dx + dy * dy);
-            }
+            if (isq && k < N) ineq_row(k + 1, qn, rowg(zb, pi, pj, isobs, qox, qoy, qoc).dv);
             // ---- variable bounds, objective, stationarity of stage k ----
             if (zv) {
                 const double lo = zc.lo, hi = zc.hi;
@@ -400,14 +431,20 @@ struct WarpSolver {
                                 r -= zn.yc + (-T * v * snr) * ycn[3 * rob] + (T * v * csr) * ycn[3 * rob + 1];
                             } else {
                                 r -= zn.yc;
+                                const double *ydn = ydb;
                                 if (M > 0) {
-                                    const double *ydn = ydb;
                                     NMPC_NOUNROLL
                                     for (int j = 0; j < NR; j++) {
                                         if (j == rob) continue;
                                         int q = rob < j ? pairidx(rob, j) : pairidx(j, rob);
                                         r += 2.0 * (zk - zb[3 * j + comp]) * ydn[q];
                                     }
+                                }
+                                NMPC_NOUNROLL
+                                for (int o = 0; o < nobs; o++) {   // this robot's static obstacles: gradient (dx, dy) / rho
+                                    const double *ob = wp::global_ptr(P.obs) + 3 * o;
+                                    const double dx = zb[3 * rob] - ob[0], dy = zb[3 * rob + 1] - ob[1];
+                                    r += (comp == 0 ? dx : dy) / sqrt(dx * dx + dy * dy) * ydn[M + rob * nobs + o];
                                 }
                             }
                         } else {
@@ -454,25 +491,25 @@ struct WarpSolver {
     // block's inputs (from the staging buffer inside the sweep, from global memory for block 0).
     struct QIn { double lo, hi, s, vl, vu, yd, dsoc; };
     template <int MODE, class RowFn>
-    static NMPC_DEV void ineq_block(RowFn row, const QIn &in, int l, int pi, int pj, double kd, int b, double mu,
-                                    double delta, bool soc, const double *zb, double &pxx, double &pyy, double &pxy, double &phx,
-                                    double &phy)
+    static NMPC_DEV void ineq_block(RowFn row, const QIn &in, int l, int pi, int pj, bool isobs, double ox, double oy, double oc, double kd,
+                                    int b, double mu, double delta, bool soc, const double *zb, double &pxx, double &pyy, double &pxy,
+                                    double &phx, double &phy)
     {
         pxx = pyy = pxy = phx = phy = 0.0;
         double gxq = 0, gyq = 0, rd = 0, Dq = 0, gs = 0;
         const double lo = in.lo, hi = in.hi;
         if (lo > -NMPC_INF || hi < NMPC_INF) {
-            double dv = NMPC_DUMMY_ROW_VALUE;
+            double dv = NMPC_DUMMY_ROW_VALUE, hxx = 0, hyy = 0, hxy = 0;
             if (b > 0) {
-                double dx = zb[3 * pi] - zb[3 * pj], dy = zb[3 * pi + 1] - zb[3 * pj + 1];
-                gxq = 2.0 * dx; gyq = 2.0 * dy; dv = dx * dx + dy * dy;
+                const RowG g = rowg(zb, pi, pj, isobs, ox, oy, oc);
+                gxq = g.gx; gyq = g.gy; dv = g.dv; hxx = g.hxx; hyy = g.hyy; hxy = g.hxy;
             }
             double s = in.s, sigs;
             sig_g<MODE>(kd, s, lo, hi, in.vl, in.vu, mu, 0.0, sigs, gs);
             rd = MODE == 1 ? 0.0 : (soc ? in.dsoc : dv - s);
             Dq = sigs + delta;
-            double hq = Dq * rd + gs, mu2 = MODE == 0 ? 2.0 * in.yd : 0.0;
-            pxx = Dq * gxq * gxq + mu2; pyy = Dq * gyq * gyq + mu2; pxy = Dq * gxq * gyq;
+            const double hq = Dq * rd + gs, yq = MODE == 0 ? in.yd : 0.0;   // multiplier times the row's own curvature
+            pxx = Dq * gxq * gxq + yq * hxx; pyy = Dq * gyq * gyq + yq * hyy; pxy = Dq * gxq * gyq + yq * hxy;
             phx = gxq * hq; phy = gyq * hq;
         }
         row(R_GXQ, b)[l] = gxq; row(R_GYQ, b)[l] = gyq; row(R_RD, b)[l] = rd; row(R_DQ, b)[l] = Dq; row(R_GS, b)[l] = gs;
@@ -542,18 +579,18 @@ struct WarpSolver {
         double *hslot = nullptr;         // where this lane's stage gradient goes (HH)
         if (isx) {
             hslot = HH + comp * NR + rob;
-            if (comp == 0) { a0p = tt + 0 * TSZ + rob * NR; a1p = tt + 1 * TSZ + rob * NR; }
-            else if (comp == 1) { a0p = tt + 1 * TSZ + rob * NR; a1p = tt + 2 * TSZ + rob * NR; }
-            else { a3p = tt + 5 * TSZ + rob * NR; selfp = tt + 5 * TSZ + rob * (NR + 1); }
+            if (comp == 0) { a0p = tt + 0 * TSZ + rob * TCOLS; a1p = tt + 1 * TSZ + rob * TCOLS; }
+            else if (comp == 1) { a0p = tt + 1 * TSZ + rob * TCOLS; a1p = tt + 2 * TSZ + rob * TCOLS; }
+            else { a3p = tt + 5 * TSZ + rob * TCOLS; selfp = tt + 5 * TSZ + rob * (TCOLS + 1); }
         } else if (isu) {
             hslot = HH + (3 + comp) * NR + rob;
-            if (comp == 0) { a3p = tt + 6 * TSZ + rob * NR; selfp = tt + 6 * TSZ + rob * (NR + 1); }
-            else { a4p = tt + 7 * TSZ + rob * NR; selfp = tt + 7 * TSZ + rob * (NR + 1); }
+            if (comp == 0) { a3p = tt + 6 * TSZ + rob * TCOLS; selfp = tt + 6 * TSZ + rob * (TCOLS + 1); }
+            else { a4p = tt + 7 * TSZ + rob * TCOLS; selfp = tt + 7 * TSZ + rob * (TCOLS + 1); }
         } else if (isL) { a0p = HH; a1p = HH + NR; a2p = HH + 2 * NR; a3p = HH + 3 * NR; a4p = HH + 4 * NR; }
         // row sums of the five pair tables: lane a * NR + i sums row i of table a and stores it on the diagonal
-        const bool rsum = M > 0 && l < 5 * NR;
-        const int rs_a = l / NR, rs_i = l - rs_a * NR;
-        double *rs_row = tt + rs_a * TSZ + rs_i * NR;
+        const bool rsum_any = M > 0 || nobs > 0, rsum = rsum_any && l < 5 * NR;
+        const int rs_a = l / NR, rs_i = l - rs_a * NR, rs_n = NR + nobs;
+        double *rs_row = tt + rs_a * TSZ + rs_i * TCOLS;
         // column l of [A B]:  al e_x + be e_y + ga e_theta of this lane's robot (last lane: the pr column); xm: control lanes keep
         // their state rows at 0 until their own pivot (see the sweep)
         const double xm = isu ? 0.0 : 1.0;
@@ -619,18 +656,20 @@ struct WarpSolver {
                 }
                 rcb[l] = rc; row(R_RC, k + 1)[l] = rc;
             }
-            if (M > 0 && isq) {
+            if (isq) {
                 double a0, a1, a2, a3, a4;
                 QIn in;
                 in.lo = stg[FS_DL * LW + l]; in.hi = stg[FS_DU * LW + l]; in.s = stg[FS_S * LW + l]; in.vl = stg[FS_VL * LW + l];
                 in.vu = stg[FS_VU * LW + l]; in.yd = stg[FS_YD * LW + l]; in.dsoc = stg[FS_DSOC * LW + l];
-                ineq_block<MODE>(row, in, l, pi, pj, kd, k + 1, mu, delta, soc, zb, a0, a1, a2, a3, a4);
-                const int e1 = pi * NR + pj, e2 = pj * NR + pi;
-                tt[e1] = -a0; tt[e2] = -a0;                                   // Txx
-                tt[TSZ + e1] = -a2; tt[TSZ + e2] = -a2;                       // Txy
-                tt[2 * TSZ + e1] = -a1; tt[2 * TSZ + e2] = -a1;               // Tyy
-                tt[3 * TSZ + e1] = a3; tt[3 * TSZ + e2] = -a3;                // Thx: gradient of robot pi gets +, of robot pj gets -
-                tt[4 * TSZ + e1] = a4; tt[4 * TSZ + e2] = -a4;                // Thy
+                ineq_block<MODE>(row, in, l, pi, pj, isobs, qox, qoy, qoc, kd, k + 1, mu, delta, soc, zb, a0, a1, a2, a3, a4);
+                // pair row: entries (pi, pj) and (pj, pi); obstacle row: column NR + o of robot pi (it only feeds the row sum)
+                const int e1 = isobs ? pi * TCOLS + NR + (l - M) % nobs : pi * TCOLS + pj, e2 = isobs ? e1 : pj * TCOLS + pi;
+                tt[e2] = -a0; tt[TSZ + e2] = -a2; tt[2 * TSZ + e2] = -a1; tt[3 * TSZ + e2] = -a3; tt[4 * TSZ + e2] = -a4;
+                tt[e1] = -a0;                                                 // Txx
+                tt[TSZ + e1] = -a2;                                           // Txy
+                tt[2 * TSZ + e1] = -a1;                                       // Tyy
+                tt[3 * TSZ + e1] = a3;                                        // Thx: gradient of robot pi gets +, of robot pj gets -
+                tt[4 * TSZ + e1] = a4;                                        // Thy
             }
             tsync();
             // pr = p_{k+1} + P_{k+1} r (r = -rc), published as one more column of pb for the last lane
@@ -645,8 +684,12 @@ struct WarpSolver {
             }
             if (rsum) {   // diagonal of the curvature tables = + sum of the pair terms; of the gradient tables = the robot's sum
                 double s_ = 0.0;
-                NMPC_UNROLL
-                for (int j = 0; j < NR; j++) s_ += rs_row[j];
+                if (NOBS_MAX == 0 || nobs == 0) {
+                    NMPC_UNROLL
+                    for (int j = 0; j < NR; j++) s_ += rs_row[j];
+                } else {
+                    for (int j = 0; j < rs_n; j++) s_ += rs_row[j];
+                }
                 rs_row[rs_i] = rs_a < 3 ? -s_ : s_;
             }
             // stage gradient h_l (variable l) and diagonal curvature
@@ -660,7 +703,7 @@ struct WarpSolver {
             dgx = isx ? dg : 0.0;                                                   // state diagonal is carried lazily
             if (selfp) *selfp = isu ? dg : (MODE == 0 ? crs[rob] : 0.0);           // control diagonal / theta-v cross term
             tsync();
-            if (isz) *hslot = gx + ((M > 0 && isx && comp < 2) ? tt[(3 + comp) * TSZ + rob * (NR + 1)] : 0.0);
+            if (isz) *hslot = gx + ((rsum_any && isx && comp < 2) ? tt[(3 + comp) * TSZ + rob * (TCOLS + 1)] : 0.0);
             tsync();
             if (k > 0) stage_issue(sm, stg, l, N, FS_COUNT, FS_YC, k - 1);   // every lane has consumed the staged rows of stage k
             {
@@ -778,12 +821,12 @@ struct WarpSolver {
         }
         tsync();
         if (isx) row(R_RC, 0)[l] = MODE == 1 ? 0.0 : (soc ? row(R_CSOC, 0)[l] : row(R_Z, 0)[l] - x0bar_l - CE[l]);
-        if (M > 0 && isq) {
+        if (isq) {
             double a0, a1, a2, a3, a4;
             QIn in;
             in.lo = DL[l]; in.hi = DU[l]; in.s = row(R_S, 0)[l]; in.vl = row(R_VL, 0)[l]; in.vu = row(R_VU, 0)[l];
             in.yd = MODE == 0 ? row(R_YD, 0)[l] : 0.0; in.dsoc = soc ? row(R_DSOC, 0)[l] : 0.0;
-            ineq_block<MODE>(row, in, l, pi, pj, kd, 0, mu, delta, soc, zb, a0, a1, a2, a3, a4);
+            ineq_block<MODE>(row, in, l, pi, pj, isobs, qox, qoy, qoc, kd, 0, mu, delta, soc, zb, a0, a1, a2, a3, a4);
         }
         tsync();
         return true;
@@ -852,7 +895,7 @@ struct WarpSolver {
         };
         issue(0);
         double dx = isx ? -row(R_RC, 0)[l] : 0.0;
-        if (M > 0 && isq) {
+        if (isq) {
             double rd = row(R_RD, 0)[l], Dq = row(R_DQ, 0)[l], gs = row(R_GS, 0)[l];
             bool act = DL[l] > -NMPC_INF || DU[l] < NMPC_INF;
             double ds = act ? rd : 0.0, ytd = act ? Dq * ds + gs : 0.0;
@@ -907,12 +950,12 @@ struct WarpSolver {
                 tsync();
                 double dn = 0.0;
                 if (isx) dn = dzb[l] + cA * dzb[3 * rob + 2] + cB * dzb[NS + 2 * rob + (comp == 2 ? 1 : 0)] - v_rc;
-                if (M > 0 && isq) {
+                if (isq) {
                     const int b = k + 1;
                     bool act = q_lo > -NMPC_INF || q_hi < NMPC_INF;
                     double ds = 0.0, ytd = 0.0;
                     if (act) {
-                        ds = q_gx * (dzb[3 * pi] - dzb[3 * pj]) + q_gy * (dzb[3 * pi + 1] - dzb[3 * pj + 1]) + q_rd;
+                        ds = q_gx * (dzb[3 * pi] - (isobs ? 0.0 : dzb[3 * pj])) + q_gy * (dzb[3 * pi + 1] - (isobs ? 0.0 : dzb[3 * pj + 1])) + q_rd;
                         ytd = q_dq * ds + q_gs;
                         slack_step_terms(q_s, ds, q_lo, q_hi, q_vl, q_vu, mu, ap, az);
                         gbd += q_gs * ds; tiny = fmax(tiny, fabs(ds) / (1.0 + fabs(q_s)));
@@ -963,7 +1006,7 @@ struct WarpSolver {
                 row(R_Z, k)[l] = zn;
             }
             if (isx) row(R_YC, k)[l] = c.yc + alpha * (c.ytc - c.yc);
-            if (M > 0 && isq && (c.dlo > -NMPC_INF || c.dhi < NMPC_INF)) {
+            if (isq && (c.dlo > -NMPC_INF || c.dhi < NMPC_INF)) {
                 const double sn_ = c.s + alpha * c.ds;
                 if (c.dlo > -NMPC_INF) row(R_VL, k)[l] = mult(c.vl, c.s - c.dlo, sn_ - c.dlo, -c.ds);
                 if (c.dhi < NMPC_INF) row(R_VU, k)[l] = mult(c.vu, c.dhi - c.s, c.dhi - sn_, c.ds);
@@ -981,7 +1024,7 @@ struct WarpSolver {
         this->trig_valid = false; this->t2_rdz = -1;
         for (int k = 0; k <= N; k++) {
             if (zvalid(k)) row(R_Z, k)[l] += alpha * row(rdz, k)[l];
-            if (M > 0 && isq && (DL[k * LW + l] > -NMPC_INF || DU[k * LW + l] < NMPC_INF)) row(R_S, k)[l] += alpha * row(rds, k)[l];
+            if (isq && (DL[k * LW + l] > -NMPC_INF || DU[k * LW + l] < NMPC_INF)) row(R_S, k)[l] += alpha * row(rds, k)[l];
         }
         tsync();
     }
@@ -998,7 +1041,7 @@ struct WarpSolver {
                 if (hi < NMPC_INF) { double s2 = hi - z; row(R_ZU, k)[l] = fmax(fmin(row(R_ZU, k)[l], ks * mu / s2), mu / (ks * s2)); }
             }
             row(R_YC, k)[l] = 0.0; row(R_YD, k)[l] = 0.0;
-            if (M > 0 && isq) {
+            if (isq) {
                 double s = row(R_S, k)[l], lo = DL[k * LW + l], hi = DU[k * LW + l];
                 if (lo > -NMPC_INF) { double s2 = s - lo; row(R_VL, k)[l] = fmax(fmin(row(R_VL, k)[l], ks * mu / s2), mu / (ks * s2)); }
                 if (hi < NMPC_INF) { double s2 = hi - s; row(R_VU, k)[l] = fmax(fmin(row(R_VU, k)[l], ks * mu / s2), mu / (ks * s2)); }
@@ -1021,12 +1064,12 @@ struct WarpSolver {
             zb[l] = zv ? zt : 0.0;
             tsync();
             if (k < N && l < NR) { double s_, c_; wp::sincos_(zb[3 * l + 2], &s_, &c_); cs[l] = c_; sn[l] = s_; }
-            if (M > 0 && isq) {
+            if (isq) {
                 for (int pass = (k == 0 ? 0 : 1); pass < 2; pass++) {
                     if (pass == 1 && k == N) break;
                     const int b = pass == 0 ? 0 : k + 1;
                     double lo = DL[b * LW + l], hi = DU[b * LW + l], dv = NMPC_DUMMY_ROW_VALUE;
-                    if (pass == 1) { double dx = zb[3 * pi] - zb[3 * pj], dy = zb[3 * pi + 1] - zb[3 * pj + 1]; dv = dx * dx + dy * dy; }
+                    if (pass == 1) dv = rowg(zb, pi, pj, isobs, qox, qoy, qoc).dv;
                     bool act = lo > -NMPC_INF || hi < NMPC_INF;
                     row(R_DS, b)[l] = act ? push_in(dv, lo, hi, o.bound_push, o.bound_frac) - row(R_S, b)[l] : 0.0;
                 }
@@ -1051,7 +1094,7 @@ struct WarpSolver {
         NMPC_LOCALS
         for (int k = 0; k <= N; k++) {
             row(R_CSOC, k)[l] = isx ? row(R_RC, k)[l] : 0.0;
-            row(R_DSOC, k)[l] = (M > 0 && isq) ? row(R_RD, k)[l] : 0.0;
+            row(R_DSOC, k)[l] = (isq) ? row(R_RD, k)[l] : 0.0;
         }
         tsync();
     }
@@ -1092,7 +1135,11 @@ struct WarpSolver {
     NMPC_PASS void write_outputs(int st, int iter, double E0, double pinf, double dinf, double c0, double mu)
     {
         NMPC_LOCALS
-        const long long n = (long long)NS * S + (long long)NC * N, mg = (long long)S * (NS + M);
+        // g / lam_g layout: N + 1 blocks of [NS equality rows ; MQ inequality rows]; the obstacle scripts (family 1) have no inequality
+        // rows in block 0 (first_scenario_mpc_obstacle_avoidance.py:109-125), so block k >= 1 starts at NS + (k - 1)(NS + MQ)
+        const long long MQ = M + (long long)NR * nobs, n = (long long)NS * S + (long long)NC * N;
+        const long long mg = family ? NS + (long long)N * (NS + MQ) : (long long)S * (NS + MQ);
+        auto goff = [=](int b) -> long long { return family ? (b == 0 ? 0 : NS + (long long)(b - 1) * (NS + MQ)) : (long long)b * (NS + MQ); };
         double *x = P.x + inst * n;
         double *lx = P.lam_x ? P.lam_x + inst * n : nullptr;
         double *g = P.g ? P.g + inst * mg : nullptr;
@@ -1121,19 +1168,18 @@ struct WarpSolver {
                 if (k < N) {
                     double v = zb[NS + 2 * rob];
                     double pred = comp == 0 ? zk + T * v * cs[rob] : (comp == 1 ? zk + T * v * sn[rob] : zk + T * zb[NS + 2 * rob + 1]);
-                    if (g) g[(long long)(k + 1) * (NS + M) + l] = row(R_Z, k + 1)[l] - pred;
-                    if (lg) lg[(long long)(k + 1) * (NS + M) + l] = row(R_YC, k + 1)[l] / df;
+                    if (g) g[goff(k + 1) + l] = row(R_Z, k + 1)[l] - pred;
+                    if (lg) lg[goff(k + 1) + l] = row(R_YC, k + 1)[l] / df;
                 }
             }
-            if (M > 0 && isq) {
-                if (k == 0) {
+            if (isq) {
+                if (k == 0 && !family) {
                     if (g) g[NS + l] = NMPC_DUMMY_ROW_VALUE;
                     if (lg) lg[NS + l] = row(R_YD, 0)[l] / df;
                 }
                 if (k < N) {
-                    double dx = zb[3 * pi] - zb[3 * pj], dy = zb[3 * pi + 1] - zb[3 * pj + 1];
-                    if (g) g[(long long)(k + 1) * (NS + M) + NS + l] = dx * dx + dy * dy;
-                    if (lg) lg[(long long)(k + 1) * (NS + M) + NS + l] = row(R_YD, k + 1)[l] / df;
+                    if (g) g[goff(k + 1) + NS + l] = rowg(zb, pi, pj, isobs, qox, qoy, qoc).dv;
+                    if (lg) lg[goff(k + 1) + NS + l] = row(R_YD, k + 1)[l] / df;
                 }
             }
         }
@@ -1185,7 +1231,7 @@ struct WarpSolver {
     NMPC_DEV double mult_absmax()
     {
         double ymax = 0.0;
-        for (int k = 0; k <= N; k++) ymax = fmax(ymax, fmax(isx ? fabs(row(R_YC, k)[l]) : 0.0, (M > 0 && isq) ? fabs(row(R_YD, k)[l]) : 0.0));
+        for (int k = 0; k <= N; k++) ymax = fmax(ymax, fmax(isx ? fabs(row(R_YC, k)[l]) : 0.0, (isq) ? fabs(row(R_YD, k)[l]) : 0.0));
         return tred_max(ymax);
     }
     NMPC_DEV void mult_zero()

@@ -19,7 +19,7 @@ def lib():
         _LIB = C.CDLL(os.path.join(_HERE, "libnmpc_emul.so"))
         dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
         _LIB.emu_solve.argtypes = ([C.POINTER(Desc), C.POINTER(Opts), C.c_int] + [dp] * 6 + [C.c_int] + [dp] * 5
-                                   + [ip, ip, dp, dp, C.c_int, C.c_int])
+                                   + [ip, ip, dp, dp, C.c_int, C.c_int, C.c_int, dp])
     return _LIB
 
 
@@ -27,8 +27,10 @@ def _dp(a):
     return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
 
 
-def emu_solve(Nr, N, T, x0, p, lbx, ubx, lbg, ubg, Q=(1.0, 5.0, 0.1), R=(0.5, 0.05), trace=False, reverse=0, **opts):
+def emu_solve(Nr, N, T, x0, p, lbx, ubx, lbg, ubg, Q=(1.0, 5.0, 0.1), R=(0.5, 0.05), trace=False, reverse=0, obstacles=None, **opts):
+    """obstacles: [n_obs, 3] (centre x, y, clearance) -> the static-obstacle family (its own g layout, see nmpc_create_obstacles)."""
     L = lib()
+    obs = None if obstacles is None else np.ascontiguousarray(np.asarray(obstacles, dtype=np.float64).reshape(-1, 3))
     d = Desc(int(Nr), int(N), float(T), (C.c_double * 3)(*Q), (C.c_double * 2)(*R))
     o = Opts()
     _orc_lib().orc_default_opts(C.byref(o))   # nmpc_opts and orc_opts have the same layout
@@ -48,5 +50,5 @@ def emu_solve(Nr, N, T, x0, p, lbx, ubx, lbg, ubg, Q=(1.0, 5.0, 0.1), R=(0.5, 0.
     rc = L.emu_solve(C.byref(d), C.byref(o), B, _dp(x0), _dp(p), _dp(lbx), _dp(ubx), _dp(lbg), _dp(ubg),
                      1 if lbx.ndim == 2 else 0, _dp(x), _dp(f), _dp(g), _dp(lam_x), _dp(lam_g),
                      st.ctypes.data_as(C.POINTER(C.c_int)), it.ctypes.data_as(C.POINTER(C.c_int)), _dp(stats),
-                     _dp(tr), ntr, int(reverse))
+                     _dp(tr), ntr, int(reverse), 0 if obs is None else int(obs.shape[0]), _dp(obs))
     return dict(rc=rc, x=x, f=f, g=g, lam_x=lam_x, lam_g=lam_g, status=st, iters=it, stats=stats, trace=tr)

@@ -16,6 +16,12 @@ thread_local Job job;
 
 template <int NR> void lane_body()
 {
+    if (NR <= 4 && job.P->nobs > 0) {   // the static-obstacle family has its own instantiation (1..4 robots on the warp path)
+        WarpSolver<(NR <= 4 ? NR : 1), true> s(*job.P, job.sm, job.ws);
+        s.setup(job.inst);
+        s.run();
+        return;
+    }
     WarpSolver<NR> s(*job.P, job.sm, job.ws);
     s.setup(job.inst);
     s.run();
@@ -30,18 +36,18 @@ void fibre_main()
     wp::emu->done[wp::emu->cur] = true;
     swapcontext(&wp::emu->ctx[wp::emu->cur], &wp::emu->main);
 }
-template <int NR> long long ws_doubles(int N) { return WarpSolver<NR>::ws_doubles(N); }
-template <int NR> int sm_doubles() { return WarpSolver<NR>::SM_DOUBLES; }
+template <int NR> long long ws_doubles(int N) { return WarpSolver<NR, NR <= 4>::ws_doubles(N); }   // the larger of the two instantiations
+template <int NR> int sm_doubles() { return WarpSolver<NR, NR <= 4>::SM_DOUBLES; }
 }  // namespace
 
 extern "C" int emu_solve(const nmpc_desc *d, const nmpc_opts *o, int B, const double *x0, const double *p,
                          const double *lbx, const double *ubx, const double *lbg, const double *ubg,
                          int bounds_batched, double *x, double *f, double *g, double *lam_x, double *lam_g,
-                         int *status, int *iters, double *stats, double *trace, int max_trace, int reverse)
+                         int *status, int *iters, double *stats, double *trace, int max_trace, int reverse, int nobs, const double *obs)
 {
     if (!d || d->Nr < 1 || d->Nr > 10 || d->N < 1) return NMPC_EINVAL;
-    const int Nr = d->Nr, N = d->N, S = N + 1, ns = 3 * Nr, nc = 2 * Nr, M = Nr * (Nr - 1) / 2;
-    const long long n = (long long)ns * S + (long long)nc * N, mg = (long long)S * (ns + M);
+    const int Nr = d->Nr, N = d->N, S = N + 1, ns = 3 * Nr, nc = 2 * Nr, M = Nr * (Nr - 1) / 2 + Nr * nobs, family = nobs > 0 ? 1 : 0;
+    const long long n = (long long)ns * S + (long long)nc * N, mg = family ? ns + (long long)N * (ns + M) : (long long)S * (ns + M);
     const int nb = bounds_batched ? B : 1;
     const int LWd = (5 * Nr + 1 <= 32) ? 32 : 64;
     const long long bstride = (long long)NMPC_BR_COUNT * S * LWd;
@@ -51,7 +57,7 @@ extern "C" int emu_solve(const nmpc_desc *d, const nmpc_opts *o, int B, const do
         for (int k = 0; k < S; k++)
             for (int l = 0; l < LWd; l++) {
                 int e = nmpc_prep_bounds_elem(Nr, N, o->bound_relax_factor, lbx + b * n, ubx + b * n, lbg + b * mg,
-                                              ubg + b * mg, k, l, LWd, brows.data() + (size_t)b * bstride);
+                                              ubg + b * mg, k, l, LWd, brows.data() + (size_t)b * bstride, nobs, family);
                 if (e && !berr) berr = e;
             }
     long long wsd = 0; int smd = 0;
@@ -70,6 +76,7 @@ extern "C" int emu_solve(const nmpc_desc *d, const nmpc_opts *o, int B, const do
     P.o = *o; P.x0 = x0; P.p = p; P.brows = brows.data(); P.bstride = bounds_batched ? bstride : 0;
     P.bound_err = &berr; P.x = x; P.f = f; P.g = g; P.lam_x = lam_x; P.lam_g = lam_g; P.status = status; P.iters = iters;
     P.stats = stats; P.trace = trace; P.max_trace = max_trace; P.ws = ws.data(); P.ws_stride = wsd;
+    P.nobs = nobs; P.family = family; P.obs = obs;
     const size_t STK = 512 * 1024;
     std::vector<char> stacks(64 * STK);
     wp::Emu emu;

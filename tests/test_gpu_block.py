@@ -79,6 +79,20 @@ def test_block_path_64_robot_swarm(pkg, torch_cuda):
     # above, <= 1e-8) whose objectives agree, but robots that must turn by ~pi may turn either way (symmetric local
     # minimisers), so the control tolerance of the small cases does not apply here.
     assert (df <= 1e-4).all(), (du, df, out["iters"].cpu().numpy(), ref["iters"])
+    print("swarm64 cold: GPU vs oracle fixture  du", du, " df", df, " iters", out["iters"].cpu().numpy(), ref["iters"])
+    # Restarted FROM the oracle's point the CUDA solver re-converges in a few dozen iterations (not ~450) to a KKT point of
+    # practically the same objective.  Measured (round 2): df 1.5e-6 / 1.4e-5 with controls that differ by > 1 -- at this size the
+    # NLP has many neighbouring local minimisers and flat control directions (robots that stand still may point anywhere), so
+    # north_star's control tolerance is asserted on the small cases (test_block_path_matches_oracle) and only the objective here.
+    pol = prob.solve(_t(torch, gold["x"]), _t(torch, P), _t(torch, lbx), _t(torch, ubx), _t(torch, lbg), _t(torch, ubg))
+    torch.cuda.synchronize()
+    assert (pol["status"].cpu().numpy() == 0).all() and pol["stats"][:, 0].max().item() <= 1e-8
+    dfp = np.abs(pol["f"].cpu().numpy() - gold["f"]) / np.abs(gold["f"])
+    print("swarm64 restart from the oracle's point: df", dfp, " iters", pol["iters"].cpu().numpy())
+    assert (dfp <= 1e-4).all() and (pol["iters"].cpu().numpy() <= 80).all(), (dfp, pol["iters"].cpu().numpy())
+    # where the cold-start paths end in the same basin the objective tolerance is north_star's
+    same = du <= 1e-4
+    assert (df[same] <= 1e-6).all(), (du, df)
     # pairwise distances of the predicted trajectory respect dmin at every stage the NLP constrains
     x = out["x"].cpu().numpy()[:, :3 * Nr * (N + 1)].reshape(2, N + 1, Nr, 3)[:, :N, :, :2]
     d = np.linalg.norm(x[:, :, :, None] - x[:, :, None], axis=-1) + np.eye(Nr)[None, None] * 1e9

@@ -75,3 +75,41 @@ def test_emulated_two_warp_team_eight_robots():
         e = emu_solve(Nr, N, T, w0, p, lbx, ubx, lbg, ubg, reverse=rev)
         assert e["status"][0] == r["status"] == 0 and int(e["iters"][0]) == r["iters"]
         assert np.abs(e["x"][0] - r["x"]).max() <= 1e-9
+
+
+@pytest.mark.parametrize("case", ["one", "six", "two_robots"])
+@pytest.mark.parametrize("reverse", [0, 1])
+def test_emulated_kernel_obstacle_family(case, reverse):
+    """Static circular obstacles (first_/third_scenario_mpc_obstacle_avoidance.py:96-152) on the warp-per-instance path: the
+    obstacle rows occupy the lanes after the pair rows.  Same iterates as the C oracle (its restated IPOPT with obstacle rows),
+    in the scripts' g layout (no inequality rows in block 0)."""
+    third = [(-0.6, 3.3, 0.2), (0.6, 3.3, 0.125), (0.0, 2.3, 0.15), (1.0, 2.3, 0.15), (-0.6, 1.3, 0.2), (0.6, 1.3, 0.175)]
+    if case == "one":
+        Nr, N, T, obs, margin, dmin = 1, 15, 0.3, np.array([[0.45, 0.5, 0.3]]), 0.05, 0.0
+        p = np.array([0.0, 0.0, 0.6, 1.2, 1.3, 0.0])
+    elif case == "six":
+        Nr, N, T, obs, margin, dmin = 1, 20, 0.3, np.array([[x, y, r + 0.15] for x, y, r in third]), 0.1, 0.0
+        p = np.array([0.0, 0.6, 1.57, 0.1, 3.9, 1.57])
+    else:      # two robots swapping sides around two obstacles: pair row + 2 x 2 obstacle rows per stage
+        Nr, N, T, obs, margin, dmin = 2, 12, 0.3, np.array([[0.0, 0.35, 0.25], [0.0, -0.4, 0.25]]), 0.05, 0.3
+        p = np.array([-0.8, 0.05, 0.0, 0.8, -0.05, 3.1, 0.8, 0.0, 0.0, -0.8, 0.0, 3.1])
+    o = Oracle(Nr, N, T, obstacles=obs)
+    ns, M, nobs = 3 * Nr, Nr * (Nr - 1) // 2, len(obs)
+    inf = np.inf
+    lbx = np.concatenate([np.tile([-10.0, -10.0, -2 * np.pi], Nr * (N + 1)), np.tile([-0.2, -np.pi / 4], Nr * N)])
+    ubx = -lbx
+    blk_lo = np.concatenate([np.zeros(ns), np.full(M, dmin * dmin), np.full(Nr * nobs, margin)])
+    blk_hi = np.concatenate([np.zeros(ns), np.full(M + Nr * nobs, inf)])
+    lbg, ubg = np.concatenate([np.zeros(ns), np.tile(blk_lo, N)]), np.concatenate([np.zeros(ns), np.tile(blk_hi, N)])
+    assert o.mg == len(lbg)
+    w0 = o.cold_start(p[:ns])
+    r = o.solve(w0, p, lbx, ubx, lbg, ubg)
+    e = emu_solve(Nr, N, T, w0, p, lbx, ubx, lbg, ubg, reverse=reverse, obstacles=obs)
+    assert e["rc"] == 0 and e["status"][0] == r["status"] == 0
+    assert abs(int(e["iters"][0]) - r["iters"]) <= 2
+    nX = ns * (N + 1)
+    assert np.abs(e["x"][0] - r["x"])[nX:].max() <= 1e-7
+    assert abs(e["f"][0] - r["f"]) / max(1.0, r["f"]) <= 1e-9
+    np.testing.assert_allclose(e["g"][0], r["g"], atol=1e-9)
+    np.testing.assert_allclose(e["lam_g"][0], r["lam_g"], atol=1e-5)
+    assert e["g"][0][lbg != ubg].min() >= margin * 0 + min(margin, dmin * dmin if M else margin) - 1e-8

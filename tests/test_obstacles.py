@@ -84,13 +84,14 @@ def _t(torch, a):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("path", ["cta", "thread"])
+@pytest.mark.parametrize("path", ["warp", "cta", "thread"])
 @pytest.mark.parametrize("case", ["one", "six"])
 def test_gpu_obstacle_family_matches_slsqp(pkg, torch_cuda, case, path):
-    """Both kernels that serve this family: the CTA-per-instance dense-block solver (small batches) and the
-    thread-per-instance small-OCP solver (large batches; forced here with nmpc_tuning.thread_min_batch = 1)."""
+    """The three kernels that serve this family: the warp-per-instance solver (the default: the obstacle rows take the lanes
+    after the pair rows), the CTA-per-instance dense-block solver (nmpc_tuning.force_block_path; the default when the rows do
+    not fit a team's lanes) and the thread-per-instance small-OCP solver (nmpc_tuning.thread_min_batch = 1)."""
     torch = torch_cuda
-    tuning = dict(thread_min_batch=1) if path == "thread" else None
+    tuning = {"warp": None, "cta": dict(force_block_path=1), "thread": dict(thread_min_batch=1)}[path]
     if case == "one":      # first scenario geometry, shortened horizon: obstacle between start and goal
         N, T, obs, margin = 15, 0.3, np.array([[0.45, 0.5, 0.3]]), 0.05
         P = np.array([[0.0, 0.0, 0.6, 1.2, 1.3, 0.0], [0.1, -0.1, 0.9, 1.0, 1.4, 0.3]])
@@ -176,3 +177,36 @@ def test_gpu_obstacle_family_through_the_nlpsol_shim(pkg, torch_cuda):
     np.testing.assert_allclose(np.asarray(sol["g"].full()).ravel(), nlp.g(w, p), atol=1e-10)
     with pytest.raises(pkg.NmpcError):
         solver.problem.jac_pattern()       # the stand-alone derivative record is not offered for this family
+
+
+@pytest.mark.gpu
+def test_gpu_two_robots_with_obstacles_on_the_warp_path(pkg, torch_cuda):
+    """Pair rows and obstacle rows together (one pair row + 2 x 2 obstacle rows per stage) on the warp-per-instance path, against
+    the C oracle and, forced onto it, the dense-block path: two robots swap sides around two obstacles."""
+    from oracle.oracle_lib import Oracle
+    torch = torch_cuda
+    Nr, N, T, margin, dmin = 2, 12, 0.3, 0.05, 0.3
+    obs = np.array([[0.0, 0.35, 0.25], [0.0, -0.4, 0.25]])
+    rng = np.random.default_rng(2)
+    P = np.array([[-0.8, 0.05, 0.0, 0.8, -0.05, 3.1, 0.8, 0.0, 0.0, -0.8, 0.0, 3.1]]) + np.concatenate([0.05 * rng.normal(size=(6, 6)), np.zeros((6, 6))], axis=1)
+    outs = []
+    for tuning in (None, dict(force_block_path=1)):
+        prob = pkg.Problem(Nr, N, T, obstacles=obs, tuning=tuning)
+        lbx, ubx, lbg, ubg = prob.bounds_obstacles(margin, 0.2, np.pi / 4, dmin=dmin)
+        x0 = prob.cold_start(P[:, :6])
+        out = prob.solve(_t(torch, x0), _t(torch, P), _t(torch, lbx), _t(torch, ubx), _t(torch, lbg), _t(torch, ubg))
+        torch.cuda.synchronize()
+        outs.append(out)
+    orc = Oracle(Nr, N, T, obstacles=obs)
+    ref = orc.solve_batch(x0, P, lbx, ubx, lbg, ubg, want_duals=True)
+    assert (ref["status"] == 0).all()
+    nX = 6 * (N + 1)
+    for out in outs:
+        assert (out["status"].cpu().numpy() == 0).all() and out["stats"][:, 0].max().item() <= 1e-8
+        x, f, g = out["x"].cpu().numpy(), out["f"].cpu().numpy(), out["g"].cpu().numpy()
+        assert np.abs(x - ref["x"])[:, nX:].max() <= 1e-4
+        assert (np.abs(f - ref["f"]) <= 1e-6 * np.maximum(1.0, np.abs(ref["f"]))).all()
+        np.testing.assert_allclose(g, ref["g"], atol=1e-7)
+        assert np.abs(out["iters"].cpu().numpy() - ref["iters"]).max() <= 3
+        ineq = lbg != ubg
+        assert (g[:, ineq] >= lbg[ineq][None] - 1e-6).all()
