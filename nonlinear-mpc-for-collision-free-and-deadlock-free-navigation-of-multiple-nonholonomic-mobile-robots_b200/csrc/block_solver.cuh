@@ -89,7 +89,7 @@ struct BlockSolver {
     static NMPC_HD long long sm_doubles(int Nr)
     {
         const long long ns = 3 * Nr, nc = 2 * Nr, nz = 5 * Nr, ncp = (nc + 31) & ~31LL, ns4 = (ns + 3) & ~3LL;
-        const long long a = ncp * ncp, b = nc * ((ns + 1 + 3) & ~3LL);   // Cholesky factor, then Y resident for the triangular solve and the rank-k update
+        const long long a = ncp * (ncp + 1), b = nc * ((ns + 1 + 3) & ~3LL);   // Cholesky factor (leading dimension ncp + 1: conflict-free columns), then Y resident for the triangular solve and the rank-k update
         (void)ns4;
         return 32 * 12 + 16 + 16 + 8 + nz + ns + 3 * ncp + ns + 7 * Nr + (a > b ? a : b) + 16;
     }
@@ -572,6 +572,8 @@ struct BlockSolver {
             //    trailing matrix in registers; the pivot column is broadcast through a double-buffered shared vector; L goes to
             //    shared memory (leading dimension ncp, identity padding).  Pivot <= 0: wrong inertia.
             double *Ls = Muu;
+            const int lds = ncp + 1;   // shared-memory leading dimension of L: the per-pivot column store and the transposed
+                                       // write of the diagonal-block inverses had 32-way bank conflicts at ncp (23 M conflicts per short solve)
             {
                 const int ti = tid >> 5, tj = tid & 31;
                 double tile[8][4];
@@ -583,7 +585,7 @@ struct BlockSolver {
                         tile[a][q] = (r < nc && c < nc) ? Muu[r * nc + c] : 0.0;
                     }
                 __syncthreads();
-                for (int e = tid; e < ncp * ncp; e += nt) { const int r = e / ncp, c = e - r * ncp; Ls[e] = (r == c && r >= nc) ? 1.0 : 0.0; }
+                for (int e = tid; e < ncp * ncp; e += nt) { const int r = e / ncp, c = e - r * ncp; Ls[r * lds + c] = (r == c && r >= nc) ? 1.0 : 0.0; }
                 if (tj == 0 && 8 * ti < ncp) {
 #pragma unroll
                     for (int a = 0; a < 8; a++) colb[8 * ti + a] = tile[a][0];
@@ -594,7 +596,7 @@ struct BlockSolver {
                     double *cbn = colb + ((j + 1) & 1) * ncp;
                     const double d = cb[j];
                     if (!(d > 0.0) || !(d < NMPC_INF)) return false;   // uniform: every thread reads the same value
-                    const double inv = 1.0 / d, rinv = rsqrt(d);
+                    const double inv = wp::rcp_pos(d), rinv = rsqrt(d);   // d is positive and finite here: MUFU seed + two Newton steps instead of the IEEE division sequence
                     if (8 * ti + 7 > j) {   // warp-uniform: this warp still owns rows of the trailing matrix
                         double ca[8], cc[4];
 #pragma unroll
@@ -606,7 +608,7 @@ struct BlockSolver {
 #pragma unroll
                             for (int q = 0; q < 4; q++) tile[a][q] -= ca[a] * cc[q];
                     }
-                    for (int t = tid; t < nc; t += nt) Ls[t * ncp + j] = t >= j ? cb[t] * rinv : 0.0;
+                    for (int t = tid; t < nc; t += nt) Ls[t * lds + j] = t >= j ? cb[t] * rinv : 0.0;   // column j: stride lds = ncp + 1 doubles, no bank conflict
                     if (j + 1 < nc && tj == ((j + 1) & 31) && 8 * ti < ncp) {   // owners of the next pivot column publish it
                         const int jq = (j + 1) >> 5;
 #pragma unroll
@@ -632,20 +634,20 @@ struct BlockSolver {
                         double acc = i == lane ? 1.0 : 0.0;
                         if (i < nb_) {
 #pragma unroll
-                            for (int jj = 0; jj < i; jj++) acc -= Ls[(o + i) * ncp + o + jj] * x[jj];   // x[jj] = 0 for jj < lane
-                            x[i] = i >= lane ? acc / Ls[(o + i) * ncp + o + i] : 0.0;
+                            for (int jj = 0; jj < i; jj++) acc -= Ls[(o + i) * lds + o + jj] * x[jj];   // x[jj] = 0 for jj < lane
+                            x[i] = i >= lane ? acc / Ls[(o + i) * lds + o + i] : 0.0;
                         } else x[i] = acc;
                     }
                     __syncwarp();
 #pragma unroll
                     for (int i = 0; i < 32; i++) {
-                        if (i > lane) Ls[(o + lane) * ncp + o + i] = x[i];   // Linv[i][lane], transposed into the upper triangle
+                        if (i > lane) Ls[(o + lane) * lds + o + i] = x[i];   // Linv[i][lane], transposed into the upper triangle
                         if (i == lane) dinv[o + lane] = x[i];
                     }
                 }
             }
             __syncthreads();
-            for (int e = tid; e < ncp * ncp; e += nt) Lk[e] = Ls[e];   // kept for the forward pass (lower triangle)
+            for (int e = tid; e < ncp * ncp; e += nt) { const int r = e / ncp, c = e - r * ncp; Lk[e] = Ls[r * lds + c]; }   // kept for the forward pass (lower triangle), leading dimension ncp in global memory
             NMPC_PROF(3);
             // D. Y = L^-1 [M_ux | m_u] with Y resident in shared memory (it stays there for the rank-k update): blocked forward
             //    substitution over 32-row blocks, 4x4 register tiles; L (and the inverses of its diagonal blocks, stored

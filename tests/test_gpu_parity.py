@@ -164,6 +164,14 @@ def test_host_api_equals_device_api_and_nlpsol_shim(pkg, torch_cuda):
     assert solver.stats()["success"]
     u_mat = np.transpose(pkg.reshape(np.transpose(u), 2 * Nr, N))          # the reference's unpack (:436-437)
     assert u_mat.shape == (N, 2 * Nr)
+    # lam_p = dL/dp with L = f + lam_g'g (CasADi's convention), checked against central differences of the NumPy restatement
+    from oracle.nlp_numpy import UnicycleNLP
+    nlp = UnicycleNLP(Nr, N, T)
+    w, lg = np.asarray(sol["x"].full()).ravel(), np.asarray(sol["lam_g"].full()).ravel()
+    L = lambda pp: nlp.f(w, pp) + lg @ nlp.g(w, pp)
+    eps = 1e-6
+    fd = np.array([(L(P[0] + eps * e) - L(P[0] - eps * e)) / (2 * eps) for e in np.eye(6 * Nr)])
+    np.testing.assert_allclose(np.asarray(sol["lam_p"].full()).ravel(), fd, rtol=1e-6, atol=1e-6)
 
 
 def test_bound_errors_and_unsupported(pkg, torch_cuda):
