@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnmpc_b200.so")
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libnmpc_b200.so")      # built by __graft_entry__.build()
 NSTATS = 11      # NMPC_NSTATS (the last column counts filter evictions)
 NTRACE = 8
 STATUS = {0: "SOLVED", 1: "ACCEPTABLE", 2: "MAX_ITER", 3: "INFEASIBLE", 4: "NUMERICAL"}

@@ -349,3 +349,43 @@ def test_six_robots_all_at_origin_first_step(pkg, torch_cuda):
     ref = orc.solve(x0[0], P[0], lbx, ubx, lbg, ubg)
     assert out["status"][0] in (2, 3, 4) and out["status"][0] == ref["status"], (out["status"], ref["status"])
     assert np.all(np.isfinite(out["x"])) and out["iters"][0] <= 300
+
+
+def test_randomised_configurations_match_oracle(pkg, torch_cuda):
+    """Fuzz over the descriptor space the reference's scripts span (1-10 robots, horizons 1-40, T 0.02-0.5, dmin 0.15-0.4, the
+    TurtleBot and the real-robot control bounds, tight and wide position boxes): every configuration through the C-ABI against the
+    oracle -- same status, north_star's tolerances where both land on the same point, a KKT point and no collision everywhere."""
+    torch = torch_cuda
+    rng = np.random.default_rng(20261018)
+    n_same = n_tot = 0
+    for case in range(36):
+        Nr = int(rng.integers(1, 11))
+        N = int(rng.choice([1, 2, 3, 5, 8, 13, 20, 27, 40]))
+        T = float(rng.choice([0.02, 0.05, 0.1, 0.25, 0.3, 0.5]))
+        dmin = float(rng.choice([0.15, 0.25, 0.3, 0.4]))
+        vmax, wmax = [(0.22, 2.84), (0.15, 1.5)][int(rng.integers(0, 2))]
+        box = float(rng.choice([3.0, 10.0]))
+        B = 4
+        P = synthetic_instances(B, Nr=Nr, seed=1000 + case, box=min(2.0 + 0.3 * Nr, box - 0.5), sep=dmin + 0.2)
+        prob, orc = pkg.Problem(Nr, N, T), Oracle(Nr, N, T)
+        lbx, ubx, lbg, ubg = prob.bounds(dmin, vmax, wmax, xy_box=box)
+        x0 = prob.cold_start(P[:, :3 * Nr])
+        out = prob.solve(_t(torch, x0), _t(torch, P), _t(torch, lbx), _t(torch, ubx), _t(torch, lbg), _t(torch, ubg))
+        torch.cuda.synchronize()
+        ref = orc.solve_batch(x0, P, lbx, ubx, lbg, ubg)
+        st = out["status"].cpu().numpy()
+        assert (st == ref["status"]).all(), (case, Nr, N, T, st, ref["status"])
+        ok = st == 0
+        if ok.any():
+            assert out["stats"][:, 0].cpu().numpy()[ok].max() <= 1e-8, (case, Nr, N)
+            g = out["g"].cpu().numpy()[ok]
+            assert np.maximum(lbg[None] - g, 0.0).max() <= C_TOL, (case, Nr, N)
+        nX = 3 * Nr * (N + 1)
+        du = np.abs(out["x"].cpu().numpy() - ref["x"])[:, nX:].max(axis=1)
+        df = np.abs(out["f"].cpu().numpy() - ref["f"]) / np.maximum(1.0, np.abs(ref["f"]))
+        same = (du <= U_TOL) & (df <= F_RTOL)
+        n_same += int(same[ok].sum()); n_tot += int(ok.sum())
+        assert np.abs(out["iters"].cpu().numpy() - ref["iters"])[same & ok].max(initial=0) <= 5, (case, Nr, N, out["iters"].cpu().numpy(), ref["iters"])
+        assert out["stats"][:, 10].max().item() == 0
+    print("fuzz: %d / %d solved instances on the oracle's point" % (n_same, n_tot))
+    assert n_tot >= 100 and n_same >= 0.97 * n_tot, (n_same, n_tot)

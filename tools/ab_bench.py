@@ -1,5 +1,5 @@
 """Quick A/B timing of the benchmark workload (6 robots, N = 20, cold start; bench.py's instances) on whatever
-libnmpc_b200.so is in the package directory:   python tools/ab_bench.py [B] [convoy] [ctas_per_sm] [label]
+lib/libnmpc_b200.so is in the tree:   python tools/ab_bench.py [B] [convoy] [ctas_per_sm] [label]
 Prints one line: cold solves/s (CUDA events, best and mean of 3, L2 flushed), warm solves/s, iterations."""
 import sys
 import numpy as np

@@ -1,7 +1,7 @@
 #!/bin/sh
 # Development build of libnmpc_b200.so with a single warp-path instantiation (default Nr = 6) and extra -D flags:
 #   tools/dev_build.sh out.so [-DSOLVE_WARPS=4 -DSOLVE_MIN_CTAS=4 ...]
-# Used for launch-configuration experiments (bench.py picks the library from NMPC_B200_LIB); never shipped.
+# Used for launch-configuration experiments (copy the variant over lib/libnmpc_b200.so on the GPU box); never shipped.
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 PKG="$ROOT/nonlinear-mpc-for-collision-free-and-deadlock-free-navigation-of-multiple-nonholonomic-mobile-robots_b200"
 OUT=$1; shift
