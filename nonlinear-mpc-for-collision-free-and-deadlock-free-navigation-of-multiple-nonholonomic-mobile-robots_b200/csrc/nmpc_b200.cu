@@ -57,7 +57,7 @@ extern "C" void nmpc_default_opts(nmpc_opts *o)
 // ------------------------------------------------------------------------------------------------
 // the persistent solve kernel: one warp per instance, instances pulled from an atomic queue
 // ------------------------------------------------------------------------------------------------
-// threads per CTA and instances ("teams") per CTA: one warp per instance up to 6 robots (3 per CTA, 4 CTAs per SM);
+// threads per CTA and instances ("teams") per CTA: one warp per instance up to 6 robots (4 per CTA, 3 CTAs per SM);
 // 7..10 robots use the two-warp team (2 per CTA on named barriers, 2 CTAs per SM: 255 registers per thread).  The
 // one-warp teams of a CTA are a convoy group (WarpSolver::iter_sync).
 template <int NR, bool OBS = false> struct SolveCfg {

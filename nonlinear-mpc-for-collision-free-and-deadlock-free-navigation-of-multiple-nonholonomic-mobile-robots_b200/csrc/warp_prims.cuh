@@ -52,12 +52,6 @@ NMPC_DEV void cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory");
 // compiler-level fence: memory accesses are not moved across it (keeps the batched loads of the sweep apart, which bounds
 // their register footprint)
 NMPC_DEV void sched_fence() { asm volatile("" ::: "memory"); }
-// v, or 0 when p: one predicated 64-bit move (the compiler otherwise builds a divergent branch around a block of such moves)
-NMPC_DEV double zero_if(bool p, double v)
-{
-    asm("{.reg .pred q; setp.ne.s32 q, %1, 0; @q mov.f64 %0, 0d0000000000000000;}" : "+d"(v) : "r"((int)p));
-    return v;
-}
 // positive, finite, normal double (one integer compare on the high word; nvcc turns the two floating-point compares into ~15 integer instructions)
 NMPC_DEV bool pos_normal(double v) { return (unsigned)(__double2hiint(v) - 0x00100000) < 0x7fe00000u; }
 NMPC_DEV unsigned nth_set_bit(unsigned mask, int n) { return __fns(mask, 0, n + 1); }

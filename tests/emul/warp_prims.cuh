@@ -39,7 +39,6 @@ inline double *shared_ptr(double *p) { return p; }
 template <class Tp> inline Tp *global_ptr(Tp *p) { return p; }
 inline double rcp_pos(double d) { return 1.0 / d; }
 inline void sched_fence() {}
-inline double zero_if(bool p, double v) { return p ? 0.0 : v; }
 inline bool pos_normal(double v) { return v >= 2.2250738585072014e-308 && v < INFINITY; }
 inline void prefetch(const void *) {}
 inline void cp_async16(double *dst, const double *src) { dst[0] = src[0]; dst[1] = src[1]; }

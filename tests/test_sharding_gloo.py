@@ -69,3 +69,17 @@ def test_shard_range_properties(pkg):
             assert all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
             sizes = [hi - lo for lo, hi in edges]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_benchmark_table_is_one_stream_and_shards_tile_it(pkg):
+    """ONE default_rng(20261018) table; the package's generator (used by bench.py) and the oracle's copy (used by
+    the tests) are the same function, instance b does not depend on the table size, and the ranks' shards tile the table."""
+    import numpy as np
+    from oracle.nlp_numpy import synthetic_instances as oracle_gen
+    wl = pkg.workload
+    full = wl.synthetic_instances(96, 6)
+    np.testing.assert_array_equal(full, oracle_gen(96, 6, 20261018))
+    np.testing.assert_array_equal(full[:40], wl.synthetic_instances(40, 6))
+    parts = [wl.bench_shard(r, 4, per_gpu=24)[0] for r in range(4)]
+    np.testing.assert_array_equal(np.concatenate(parts), full)
+    assert wl.bench_shard(2, 4, per_gpu=24)[1] == (48, 72)
