@@ -140,3 +140,24 @@ def test_batched_device_closed_loop_is_collision_and_deadlock_free(pkg):
     moved = np.abs(res["u"].cpu().numpy()[-5:]).max(axis=(0, 2))
     assert np.all((moved > 1e-3) | (err[-1] <= 1e-1))                        # ... and none is deadlocked short of it
     assert res["iters"].double()[1:].mean().item() < 0.5 * res["iters"].double()[0].mean().item()   # warm starts pay off
+
+
+@pytest.mark.gpu
+def test_gpu_scenario_first_steps_match_independent_polish(pkg):
+    """The CUDA solver's first MPC step on the reference's scenarios at their own horizons against the SciPy SLSQP fixture
+    (tests/golden/polish_scenarios_scipy.npz): north_star's tolerances against a solver that shares no code with it."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "polish_scenarios_scipy.npz"))
+    for sid in gold["sids"]:
+        k = str(sid).replace("-", "")
+        Nr, T, N, dmin, vmax, wmax, start, goal, tol = pkg.mpc_loop.SCENARIOS[str(sid)]
+        prob = pkg.Problem(Nr, N, T)
+        lbx, ubx, lbg, ubg = prob.bounds(dmin, vmax, wmax)
+        p = gold["p_" + k][None]
+        out = prob.solve_host(prob.cold_start(p[:, :3 * Nr]), p, lbx, ubx, lbg, ubg)
+        assert out["status"][0] == 0, sid
+        nX = 3 * Nr * (N + 1)
+        du = np.abs(out["x"][0] - gold["x_slsqp_" + k])[nX:].max()
+        df = abs(out["f"][0] - float(gold["f_slsqp_" + k])) / max(1.0, abs(out["f"][0]))
+        assert du <= 1e-4 and df <= 1e-6, (sid, du, df)
+        assert np.maximum(lbg - out["g"][0], 0.0).max() <= 1e-6, sid

@@ -239,3 +239,22 @@ def test_benchmark_config_oracle_point_is_the_independently_polished_minimiser()
     # informational: SLSQP from the reference's COLD start lands in the oracle's basin on only a minority of instances --
     # the NLP is multi-modal, which is why parity is stated per basin
     assert gold["cold_same_basin"].sum() >= 1
+
+
+def test_scenario_first_steps_are_slsqp_minimisers(pkg):
+    """tests/golden/polish_scenarios_scipy.npz (tests/golden/make_scenario_polish_golden.py): the first MPC step of the reference's
+    scenarios C-1 ... C-6, C-2r, C-6r at the reference's own horizons (up to N = 70, 1,068 variables).  SciPy SLSQP started from
+    the restated IPOPT's x* stays there: controls within 1e-4, objective within 1e-6 (measured: <= 2.8e-6 and <= 6.2e-8)."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "polish_scenarios_scipy.npz"))
+    for sid in gold["sids"]:
+        k = str(sid).replace("-", "")
+        Nr, T, N, dmin, vmax, wmax, start, goal, tol = pkg.mpc_loop.SCENARIOS[str(sid)]
+        o = Oracle(Nr, N, T)
+        lbx, ubx, lbg, ubg = o.bounds(dmin, vmax, wmax)
+        p = gold["p_" + k]
+        r = o.solve(o.cold_start(p[:3 * Nr]), p, lbx, ubx, lbg, ubg)
+        assert r["status"] == 0
+        nX = 3 * Nr * (N + 1)
+        assert np.abs(r["x"] - gold["x_slsqp_" + k])[nX:].max() <= 1e-4, sid
+        assert abs(r["f"] - float(gold["f_slsqp_" + k])) <= 1e-6 * max(1.0, abs(r["f"])), sid
