@@ -45,8 +45,8 @@
     (void)sm; (void)ws; (void)BL; (void)BU; (void)CE; (void)DL; (void)DU; (void)N; (void)S; (void)l;   \
     (void)rob; (void)comp; (void)pi; (void)pj; (void)isx; (void)isu; (void)isz; (void)isq; (void)T;    \
     (void)df; (void)xs_l; (void)qw; (void)x0bar_l;                                                     \
-    auto row = [=](int r, int k) -> double * { return ws + ((long long)r * S + k) * LW; };            \
-    auto frow = [=](int k, int i) -> double * { return ws + ((long long)R_COUNT * S + (long long)k * NS + i) * LW; }; \
+    auto row = [=](int r, int k) -> double * { return ws + ((long long)k * R_COUNT + r) * LW; };       \
+    auto frow = [=](int k, int i) -> double * { return ws + ((long long)k * R_COUNT + R_F0 + i) * LW; }; \
     auto zvalid = [=](int k) -> bool { return l < (k < N ? NZ : NS); };                                \
     auto gradf = [=](int k, double z) -> double { return (k < N && isz) ? qw * (z - xs_l) : 0.0; };    \
     (void)row; (void)frow; (void)zvalid; (void)gradf;
@@ -75,16 +75,27 @@ struct WarpSolver {
     // stage after the M pair rows, one lane each, so Nr * nobs <= LW - M on this path
     static constexpr int NOBS_MAX = OBS ? (LW - M) / NR : 0, TCOLS = NR + NOBS_MAX;
     static_assert(NZ + 1 <= 64 && M <= LW, "at most 10 robots on the lane-per-column path");
+    // Scratch layout: one RECORD of R_COUNT rows (LW doubles each) per stage, records consecutive in memory.  The rows are ordered
+    // so that what a pass stages for one stage is two contiguous ranges: rows indexed by the stage k (from record k) and rows indexed
+    // by the block k + 1 (from record k + 1):
+    //     factorisation:  record k  [R_TRIG2 .. R_BU]                record k + 1  [R_YC .. R_DU]
+    //     forward pass:   record k  [R_Z .. R_F0 + NS - 1]           record k + 1  [R_S .. R_DQ]
+    // (round 1 kept one array per row, [row][stage][LW]: the 16 rows a stage needs were 16 separate 256-byte pieces 5 KB apart).
+    // The bound rows of the instance are copied into its records by init_point, so every staged row comes from the record.
     enum Row {
-        R_Z, R_ZL, R_ZU, R_DZ, R_DZ2, R_GX, R_YC, R_YTC, R_YTC2, R_RC, R_CSOC, R_COEF, R_LIN,
-        R_S, R_VL, R_VU, R_YD, R_DS, R_DS2, R_YTD, R_YTD2, R_DSOC, R_GXQ, R_GYQ, R_RD, R_DQ, R_GS, R_DG, R_TRIG, R_TRIG2,
+        R_TRIG2, R_TRIG, R_Z, R_ZL, R_ZU, R_BL, R_BU, R_LIN, R_DG, R_GX, R_COEF, R_F0,          // R_F0 .. R_F0 + NS - 1: Riccati factor rows
+        R_YC = R_F0 + NS, R_YD, R_CSOC, R_DSOC, R_CE, R_S, R_VL, R_VU, R_DL, R_DU, R_RC, R_GS, R_GXQ, R_GYQ, R_RD, R_DQ,
+        R_DZ, R_DZ2, R_YTC, R_YTC2, R_DS, R_DS2, R_YTD, R_YTD2,
         R_COUNT
     };
-    // slots of the factorisation's staging buffer (sm + SM_STG): rows of stage k, then rows of block k+1
-    enum { FS_Z, FS_TRIG, FS_ZL, FS_ZU, FS_BL, FS_BU, FS_YC, FS_S, FS_VL, FS_VU, FS_YD, FS_CSOC, FS_DSOC, FS_CE, FS_DL, FS_DU, FS_COUNT };
-    // slots of the forward pass's staging buffer (the whole big region): NS factor rows, vectors of stage k, then of block k+1
-    enum { WS_LIN = NS, WS_DG, WS_Z, WS_ZL, WS_ZU, WS_BL, WS_BU, WS_GX, WS_COEF, WS_RC, WS_DL, WS_DU, WS_GS, WS_GXQ, WS_GYQ, WS_RD, WS_DQ,
-           WS_S, WS_VL, WS_VU, WS_COUNT };
+    // slots of the factorisation's staging buffer (sm + SM_STG): rows [R_TRIG2 .. R_BU] of stage k, then rows [R_YC .. R_DU] of block k+1
+    enum { FS_TRIG2, FS_TRIG, FS_Z, FS_ZL, FS_ZU, FS_BL, FS_BU, FS_K_ROWS,
+           FS_YC = FS_K_ROWS, FS_YD, FS_CSOC, FS_DSOC, FS_CE, FS_S, FS_VL, FS_VU, FS_DL, FS_DU, FS_COUNT, FS_B_ROWS = FS_COUNT - FS_K_ROWS };
+    // slots of the forward pass's staging buffer (the whole big region): rows [R_Z .. last factor row] of stage k, then [R_S .. R_DQ] of block k+1
+    enum { WS_Z, WS_ZL, WS_ZU, WS_BL, WS_BU, WS_LIN, WS_DG, WS_GX, WS_COEF, WS_F0, WS_K_ROWS = WS_F0 + NS,
+           WS_S = WS_K_ROWS, WS_VL, WS_VU, WS_DL, WS_DU, WS_RC, WS_GS, WS_GXQ, WS_GYQ, WS_RD, WS_DQ, WS_COUNT, WS_B_ROWS = WS_COUNT - WS_K_ROWS };
+    static_assert(R_BU - R_TRIG2 + 1 == FS_K_ROWS && R_DU - R_YC + 1 == FS_B_ROWS && R_F0 + NS - R_Z == WS_K_ROWS && R_DQ - R_S + 1 == WS_B_ROWS,
+                  "staging slots follow the record layout");
     // shared-memory carve-up (doubles, per team): small buffers that live for the whole solve, then one big region that the
     // factorisation and the forward pass carve up differently (they never run at the same time)
     enum {
@@ -95,8 +106,7 @@ struct WarpSolver {
         SM_CRS = SM_C4 + 4 * NRP, SM_THD = SM_CRS + NRP,
         SM_MISC = SM_THD + NRP,
         SM_RED = SM_MISC + 8,            // cross-warp reduction scratch (two-warp teams)
-        SM_TAB = SM_RED + 8,             // per-pass table of the staged rows' base pointers (64 entries)
-        SM_BIG = SM_TAB + ((NS + 20 + 1) & ~1),
+        SM_BIG = SM_RED + 8,
         // -- factorisation view of the big region
         SM_COL = SM_BIG,                 // two pivot-row buffers, each LW values + LW reciprocals
         SM_PB = SM_COL + 4 * LW,
@@ -111,21 +121,15 @@ struct WarpSolver {
     };
     static_assert((int)WS_COUNT <= 64 && (SM_BIG & 1) == 0 && (SM_STG & 1) == 0 && (SM_DOUBLES & 1) == 0 && (SM_C4 & 3) == 0, "shared-memory layout");
 
-    // Issue the asynchronous copies of one stage's rows: slot s <- tab[s] + (k + (s >= kofs_from)) rows, stage clamped to N.
-    // Two rows per warp instruction (16 bytes per lane); completion: wp::cp_async_wait() + tsync().
-    static NMPC_DEV void stage_issue(double *sm, double *stg, int l, int N, int nslot, int kofs_from, int k)
+    // Asynchronous copy of `nrows` consecutive rows of a record into the staging buffer: 16 bytes per lane and instruction (two rows
+    // per warp instruction), completion: wp::cp_async_wait() + tsync().
+    static NMPC_DEV void copy_rows(double *dst, const double *src, int l, int nrows)
     {
-        const double *const *tab = reinterpret_cast<const double *const *>(sm + SM_TAB);
-        const int half = l / (LW / 2), c2 = (l % (LW / 2)) * 2;
         NMPC_NOUNROLL
-        for (int s = half; s < nslot; s += 2) {
-            int kk = k + (s >= kofs_from ? 1 : 0);
-            kk = kk < N ? kk : N;
-            wp::cp_async16(stg + s * LW + c2, tab[s] + (long long)kk * LW + c2);
-        }
+        for (int c = 2 * l; c < nrows * LW; c += 2 * LW) wp::cp_async16(dst + c, src + c);
     }
-    // per-slot scratch: the vector rows, the Riccati factor rows, then the filter (NMPC_FILTER_CAP theta values, then as many phi values)
-    static NMPC_HD long long ws_doubles(int N) { return ((long long)R_COUNT * (N + 1) + (long long)(N + 1) * NS) * LW + 2 * NMPC_FILTER_CAP; }
+    // per-slot scratch: the stage records, then the filter (NMPC_FILTER_CAP theta values, then as many phi values)
+    static NMPC_HD long long ws_doubles(int N) { return (long long)R_COUNT * (N + 1) * LW + 2 * NMPC_FILTER_CAP; }
 
     const NmpcSolveParams &P;
     double *sm, *ws;
@@ -167,8 +171,8 @@ struct WarpSolver {
     NMPC_DEV double tred_max(double v) const { return tred(v, 1); }
     NMPC_DEV double tred_min(double v) const { return tred(v, 2); }
 
-    NMPC_DEV double *row(int r, int k) const { return ws + ((long long)r * S + k) * LW; }
-    NMPC_DEV double *frow(int k, int i) const { return ws + ((long long)R_COUNT * S + (long long)k * NS + i) * LW; }
+    NMPC_DEV double *row(int r, int k) const { return ws + ((long long)k * R_COUNT + r) * LW; }
+    NMPC_DEV double *frow(int k, int i) const { return ws + ((long long)k * R_COUNT + R_F0 + i) * LW; }
     NMPC_DEV bool zvalid(int k) const { return l < (k < N ? NZ : NS); }
     static NMPC_DEV int pairidx(int a, int b) { return a * (2 * NR - a - 1) / 2 + (b - a - 1); }
     static NMPC_DEV bool fin(double v) { return v > -NMPC_INF && v < NMPC_INF; }
@@ -249,12 +253,15 @@ struct WarpSolver {
             double z = isx ? x0[k * NS + l] : ((isu && k < N) ? x0[NS * S + k * NC + (l - NS)] : 0.0);
             gmax = fmax(gmax, fabs(gradf(k, z)));
             row(R_Z, k)[l] = z;
+            // the instance's (relaxed) bound rows join its records, so that a pass stages them together with the iterate
+            row(R_BL, k)[l] = BL[k * LW + l]; row(R_BU, k)[l] = BU[k * LW + l]; row(R_CE, k)[l] = CE[k * LW + l];
+            row(R_DL, k)[l] = DL[k * LW + l]; row(R_DU, k)[l] = DU[k * LW + l];
         }
         gmax = tred_max(gmax);
         this->df = gmax > o.nlp_scaling_max_gradient ? fmax(o.nlp_scaling_max_gradient / gmax, 1e-8) : 1.0;
         double cnt_z = 0.0;
         for (int k = 0; k <= N; k++) {
-            double lo = BL[k * LW + l], hi = BU[k * LW + l];
+            double lo = row(R_BL, k)[l], hi = row(R_BU, k)[l];
             double z = push_in(row(R_Z, k)[l], lo, hi, o.bound_push, o.bound_frac);
             row(R_Z, k)[l] = z;
             bool hl = lo > -NMPC_INF, hu = hi < NMPC_INF;
@@ -269,7 +276,7 @@ struct WarpSolver {
         for (int b = 0; b <= N; b++) {
             double s = 0.0, vl = 0.0, vu = 0.0;
             if (isq) {
-                double lo = DL[b * LW + l], hi = DU[b * LW + l];
+                double lo = row(R_DL, b)[l], hi = row(R_DU, b)[l];
                 bool hl = lo > -NMPC_INF, hu = hi < NMPC_INF;
                 double dv = NMPC_DUMMY_ROW_VALUE;
                 if (b > 0) dv = rowg(row(R_Z, b - 1), pi, pj, isobs, qox, qoy, qoc).dv;
@@ -341,7 +348,7 @@ struct WarpSolver {
             k = k < N ? k : N;
             r.cs = row(rt, k < N ? k : N - 1)[rob]; r.sn = row(rt, k < N ? k : N - 1)[NRP + rob];
             r.z = row(R_Z, k)[l]; r.dz = trial ? row(rdz, k)[l] : 0.0;
-            r.lo = BL[k * LW + l]; r.hi = BU[k * LW + l]; r.ce = CE[k * LW + l];
+            r.lo = row(R_BL, k)[l]; r.hi = row(R_BU, k)[l]; r.ce = row(R_CE, k)[l];
             r.zl = FULL ? row(R_ZL, k)[l] : 0.0; r.zu = FULL ? row(R_ZU, k)[l] : 0.0; r.yc = FULL ? row(R_YC, k)[l] : 0.0;
             r.csoc = socacc ? row(R_CSOC, k)[l] : 0.0;
             return r;
@@ -350,7 +357,7 @@ struct WarpSolver {
             QRows r;
             b = b < N ? b : N;
             r.s = row(R_S, b)[l]; r.ds = trial ? row(rds, b)[l] : 0.0;
-            r.lo = DL[b * LW + l]; r.hi = DU[b * LW + l];
+            r.lo = row(R_DL, b)[l]; r.hi = row(R_DU, b)[l];
             r.yd = FULL ? row(R_YD, b)[l] : 0.0; r.vl = FULL ? row(R_VL, b)[l] : 0.0; r.vu = FULL ? row(R_VU, b)[l] : 0.0;
             r.dsoc = socacc ? row(R_DSOC, b)[l] : 0.0;
             return r;
@@ -555,20 +562,6 @@ struct WarpSolver {
         double *stg = sm + SM_STG;
         n_fact++;
         tsync();
-        if (l < FS_COUNT) {   // base pointers (stage 0) of the rows staged per stage; see FS_*
-            const double *p0 = nullptr;
-            switch (l) {
-                case FS_Z: p0 = row(R_Z, 0); break;      case FS_TRIG: p0 = row(this->r_trig, 0); break;
-                case FS_ZL: p0 = row(R_ZL, 0); break;    case FS_ZU: p0 = row(R_ZU, 0); break;
-                case FS_BL: p0 = BL; break;              case FS_BU: p0 = BU; break;
-                case FS_YC: p0 = row(R_YC, 0); break;    case FS_S: p0 = row(R_S, 0); break;
-                case FS_VL: p0 = row(R_VL, 0); break;    case FS_VU: p0 = row(R_VU, 0); break;
-                case FS_YD: p0 = row(R_YD, 0); break;    case FS_CSOC: p0 = row(R_CSOC, 0); break;
-                case FS_DSOC: p0 = row(R_DSOC, 0); break; case FS_CE: p0 = CE; break;
-                case FS_DL: p0 = DL; break;              default: p0 = DU; break;
-            }
-            reinterpret_cast<const double **>(sm + SM_TAB)[l] = p0;
-        }
         // the big region was the forward pass's staging buffer: reset the constant zeros of the addend tables and of the two
         // padding columns of the P buffer (the last lane multiplies them by 0)
         for (int e = l; e < 8 * TSZ + 6 * NR; e += LW) tt[e] = 0.0;
@@ -596,11 +589,17 @@ struct WarpSolver {
         const double xm = isu ? 0.0 : 1.0;
         const int base = isL ? NS : 3 * rob;
         tsync();
-        stage_issue(sm, stg, l, N, FS_COUNT, FS_YC, N - 1);   // in flight during the terminal stage
+        // staging of stage k: rows [R_TRIG2 .. R_BU] of record k and rows [R_YC .. R_DU] of record k + 1 (two contiguous ranges)
+        auto stage_issue = [&](int k) {
+            copy_rows(stg, row(R_TRIG2, k), l, FS_K_ROWS);
+            copy_rows(stg + FS_K_ROWS * LW, row(R_YC, k + 1), l, FS_B_ROWS);
+        };
+        const int fs_trig = FS_TRIG2 + (this->r_trig - R_TRIG2);   // which of the two trig rows belongs to the iterate
+        stage_issue(N - 1);   // in flight during the terminal stage
         // terminal stage: X_N carries no cost and no distance rows, only its box
         {
             double sig = 0.0, gx = 0.0;
-            if (isx) sig_g<MODE>(kd, row(R_Z, N)[l], BL[N * LW + l], BU[N * LW + l], row(R_ZL, N)[l], row(R_ZU, N)[l], mu, 0.0, sig, gx);
+            if (isx) sig_g<MODE>(kd, row(R_Z, N)[l], row(R_BL, N)[l], row(R_BU, N)[l], row(R_ZL, N)[l], row(R_ZU, N)[l], mu, 0.0, sig, gx);
             hb[l] = isx ? gx : 0.0;
             tsync();
             NMPC_UNROLL
@@ -624,7 +623,7 @@ struct WarpSolver {
             zb[l] = zk;
             if (l < NR) {
                 const double *zr = stg + FS_Z * LW;
-                const double v = zr[NS + 2 * l], c_ = stg[FS_TRIG * LW + l], s_ = stg[FS_TRIG * LW + NRP + l];
+                const double v = zr[NS + 2 * l], c_ = stg[fs_trig * LW + l], s_ = stg[fs_trig * LW + NRP + l];
                 cs[l] = c_; sn[l] = s_;
                 double a_ = -T * v * s_, b_ = T * v * c_, tc = T * c_, ts = T * s_;
                 c4[4 * l] = a_; c4[4 * l + 1] = b_; c4[4 * l + 2] = tc; c4[4 * l + 3] = ts;
@@ -705,7 +704,7 @@ struct WarpSolver {
             tsync();
             if (isz) *hslot = gx + ((rsum_any && isx && comp < 2) ? tt[(3 + comp) * TSZ + rob * (TCOLS + 1)] : 0.0);
             tsync();
-            if (k > 0) stage_issue(sm, stg, l, N, FS_COUNT, FS_YC, k - 1);   // every lane has consumed the staged rows of stage k
+            if (k > 0) stage_issue(k - 1);   // every lane has consumed the staged rows of stage k
             {
                 const double al = isL ? 1.0 : (isx ? (comp == 0 ? 1.0 : (comp == 2 ? c4[4 * rob] : 0.0)) : (isu && comp == 0 ? c4[4 * rob + 2] : 0.0));
                 const double be = isx ? (comp == 1 ? 1.0 : (comp == 2 ? c4[4 * rob + 1] : 0.0)) : (isu && comp == 0 ? c4[4 * rob + 3] : 0.0);
@@ -820,11 +819,11 @@ struct WarpSolver {
             }
         }
         tsync();
-        if (isx) row(R_RC, 0)[l] = MODE == 1 ? 0.0 : (soc ? row(R_CSOC, 0)[l] : row(R_Z, 0)[l] - x0bar_l - CE[l]);
+        if (isx) row(R_RC, 0)[l] = MODE == 1 ? 0.0 : (soc ? row(R_CSOC, 0)[l] : row(R_Z, 0)[l] - x0bar_l - row(R_CE, 0)[l]);
         if (isq) {
             double a0, a1, a2, a3, a4;
             QIn in;
-            in.lo = DL[l]; in.hi = DU[l]; in.s = row(R_S, 0)[l]; in.vl = row(R_VL, 0)[l]; in.vu = row(R_VU, 0)[l];
+            in.lo = row(R_DL, 0)[l]; in.hi = row(R_DU, 0)[l]; in.s = row(R_S, 0)[l]; in.vl = row(R_VL, 0)[l]; in.vu = row(R_VU, 0)[l];
             in.yd = MODE == 0 ? row(R_YD, 0)[l] : 0.0; in.dsoc = soc ? row(R_DSOC, 0)[l] : 0.0;
             ineq_block<MODE>(row, in, l, pi, pj, isobs, qox, qoy, qoc, kd, 0, mu, delta, soc, zb, a0, a1, a2, a3, a4);
         }
@@ -863,46 +862,21 @@ struct WarpSolver {
         double *dzb = sm + SM_DZB;
         double *stg = sm + SM_BIG;  // the factorisation's buffers are free during this pass: WS_COUNT staging rows
         tsync();
-        for (int s = NS + l; s < WS_COUNT; s += LW) {   // base pointers (stage 0) of the vector rows staged per stage; see WS_*
-            const double *p0 = nullptr;
-            switch (s) {
-                case WS_LIN: p0 = row(R_LIN, 0); break;  case WS_DG: p0 = row(R_DG, 0); break;
-                case WS_Z: p0 = row(R_Z, 0); break;      case WS_ZL: p0 = row(R_ZL, 0); break;
-                case WS_ZU: p0 = row(R_ZU, 0); break;    case WS_BL: p0 = BL; break;
-                case WS_BU: p0 = BU; break;              case WS_GX: p0 = row(R_GX, 0); break;
-                case WS_COEF: p0 = row(R_COEF, 0); break; case WS_RC: p0 = row(R_RC, 0); break;
-                case WS_DL: p0 = DL; break;              case WS_DU: p0 = DU; break;
-                case WS_GS: p0 = row(R_GS, 0); break;    case WS_GXQ: p0 = row(R_GXQ, 0); break;
-                case WS_GYQ: p0 = row(R_GYQ, 0); break;  case WS_RD: p0 = row(R_RD, 0); break;
-                case WS_DQ: p0 = row(R_DQ, 0); break;    case WS_S: p0 = row(R_S, 0); break;
-                case WS_VL: p0 = row(R_VL, 0); break;    default: p0 = row(R_VU, 0); break;
-            }
-            reinterpret_cast<const double **>(sm + SM_TAB)[s] = p0;
-        }
-        tsync();
-        // factor rows advance by NS rows per stage, vectors by one: the factor rows are issued separately
+        // staging of stage k: rows [R_Z .. last factor row] of record k and rows [R_S .. R_DQ] of record min(k + 1, N)
         auto issue = [&](int k) {
-            const int half = l / (LW / 2), c2 = (l % (LW / 2)) * 2;
-            NMPC_NOUNROLL
-            for (int i = half; i < NS; i += 2) wp::cp_async16(stg + i * LW + c2, frow(k, i) + c2);
-            const double *const *tab = reinterpret_cast<const double *const *>(sm + SM_TAB);
-            NMPC_NOUNROLL
-            for (int s = NS + half; s < WS_COUNT; s += 2) {
-                int kk = k + (s >= WS_RC ? 1 : 0);
-                kk = kk < N ? kk : N;
-                wp::cp_async16(stg + s * LW + c2, tab[s] + (long long)kk * LW + c2);
-            }
+            copy_rows(stg, row(R_Z, k), l, WS_K_ROWS);
+            copy_rows(stg + WS_K_ROWS * LW, row(R_S, k < N ? k + 1 : N), l, WS_B_ROWS);
         };
         issue(0);
         double dx = isx ? -row(R_RC, 0)[l] : 0.0;
         if (isq) {
             double rd = row(R_RD, 0)[l], Dq = row(R_DQ, 0)[l], gs = row(R_GS, 0)[l];
-            bool act = DL[l] > -NMPC_INF || DU[l] < NMPC_INF;
+            bool act = row(R_DL, 0)[l] > -NMPC_INF || row(R_DU, 0)[l] < NMPC_INF;
             double ds = act ? rd : 0.0, ytd = act ? Dq * ds + gs : 0.0;
             row(rds, 0)[l] = ds; row(rytd, 0)[l] = ytd;
             if (act) {
                 double s = row(R_S, 0)[l];
-                slack_step_terms(s, ds, DL[l], DU[l], row(R_VL, 0)[l], row(R_VU, 0)[l], mu, ap, az);
+                slack_step_terms(s, ds, row(R_DL, 0)[l], row(R_DU, 0)[l], row(R_VL, 0)[l], row(R_VU, 0)[l], mu, ap, az);
                 gbd += gs * ds; tiny = fmax(tiny, fabs(ds) / (1.0 + fabs(s)));
             }
         }
@@ -914,7 +888,7 @@ struct WarpSolver {
             // for stage k+1 while this stage computes
             double fv[NS];
             NMPC_UNROLL
-            for (int i = 0; i < NS; i++) fv[i] = stg[i * LW + l];
+            for (int i = 0; i < NS; i++) fv[i] = stg[(WS_F0 + i) * LW + l];
             const double v_lin = stg[WS_LIN * LW + l], v_dg = stg[WS_DG * LW + l], v_z = stg[WS_Z * LW + l], v_zl = stg[WS_ZL * LW + l],
                          v_zu = stg[WS_ZU * LW + l], v_bl = stg[WS_BL * LW + l], v_bu = stg[WS_BU * LW + l], v_gx = stg[WS_GX * LW + l];
             const double *cf = stg + WS_COEF * LW;
@@ -990,9 +964,9 @@ struct WarpSolver {
         auto load = [&](int k) {   // all rows of stage / block k, issued together one stage ahead of their use
             AR r;
             k = k < N ? k : N;
-            r.z = row(R_Z, k)[l]; r.dz = row(rdz, k)[l]; r.lo = BL[k * LW + l]; r.hi = BU[k * LW + l];
+            r.z = row(R_Z, k)[l]; r.dz = row(rdz, k)[l]; r.lo = row(R_BL, k)[l]; r.hi = row(R_BU, k)[l];
             r.zl = row(R_ZL, k)[l]; r.zu = row(R_ZU, k)[l]; r.yc = row(R_YC, k)[l]; r.ytc = row(rytc, k)[l];
-            r.s = row(R_S, k)[l]; r.ds = row(rds, k)[l]; r.dlo = DL[k * LW + l]; r.dhi = DU[k * LW + l];
+            r.s = row(R_S, k)[l]; r.ds = row(rds, k)[l]; r.dlo = row(R_DL, k)[l]; r.dhi = row(R_DU, k)[l];
             r.vl = row(R_VL, k)[l]; r.vu = row(R_VU, k)[l]; r.yd = row(R_YD, k)[l]; r.ytd = row(rytd, k)[l];
             return r;
         };
@@ -1024,7 +998,7 @@ struct WarpSolver {
         this->trig_valid = false; this->t2_rdz = -1;
         for (int k = 0; k <= N; k++) {
             if (zvalid(k)) row(R_Z, k)[l] += alpha * row(rdz, k)[l];
-            if (isq && (DL[k * LW + l] > -NMPC_INF || DU[k * LW + l] < NMPC_INF)) row(R_S, k)[l] += alpha * row(rds, k)[l];
+            if (isq && (row(R_DL, k)[l] > -NMPC_INF || row(R_DU, k)[l] < NMPC_INF)) row(R_S, k)[l] += alpha * row(rds, k)[l];
         }
         tsync();
     }
@@ -1036,13 +1010,13 @@ struct WarpSolver {
         const double ks = P.o.kappa_sigma;
         for (int k = 0; k <= N; k++) {
             if (zvalid(k)) {
-                double z = row(R_Z, k)[l], lo = BL[k * LW + l], hi = BU[k * LW + l];
+                double z = row(R_Z, k)[l], lo = row(R_BL, k)[l], hi = row(R_BU, k)[l];
                 if (lo > -NMPC_INF) { double s2 = z - lo; row(R_ZL, k)[l] = fmax(fmin(row(R_ZL, k)[l], ks * mu / s2), mu / (ks * s2)); }
                 if (hi < NMPC_INF) { double s2 = hi - z; row(R_ZU, k)[l] = fmax(fmin(row(R_ZU, k)[l], ks * mu / s2), mu / (ks * s2)); }
             }
             row(R_YC, k)[l] = 0.0; row(R_YD, k)[l] = 0.0;
             if (isq) {
-                double s = row(R_S, k)[l], lo = DL[k * LW + l], hi = DU[k * LW + l];
+                double s = row(R_S, k)[l], lo = row(R_DL, k)[l], hi = row(R_DU, k)[l];
                 if (lo > -NMPC_INF) { double s2 = s - lo; row(R_VL, k)[l] = fmax(fmin(row(R_VL, k)[l], ks * mu / s2), mu / (ks * s2)); }
                 if (hi < NMPC_INF) { double s2 = hi - s; row(R_VU, k)[l] = fmax(fmin(row(R_VU, k)[l], ks * mu / s2), mu / (ks * s2)); }
             }
@@ -1057,7 +1031,7 @@ struct WarpSolver {
         NMPC_LOCALS
         const nmpc_opts &o = this->P.o;
         double *zb = sm + SM_ZB, *cs = sm + SM_CS, *sn = sm + SM_SN;
-        double zt = isx ? push_in(x0bar_l + CE[l], BL[l], BU[l], o.bound_push, o.bound_frac) : (isu ? row(R_Z, 0)[l] : 0.0);
+        double zt = isx ? push_in(x0bar_l + row(R_CE, 0)[l], row(R_BL, 0)[l], row(R_BU, 0)[l], o.bound_push, o.bound_frac) : (isu ? row(R_Z, 0)[l] : 0.0);
         for (int k = 0; k <= N; k++) {
             const bool zv = zvalid(k);
             row(R_DZ, k)[l] = zv ? zt - row(R_Z, k)[l] : 0.0;
@@ -1068,7 +1042,7 @@ struct WarpSolver {
                 for (int pass = (k == 0 ? 0 : 1); pass < 2; pass++) {
                     if (pass == 1 && k == N) break;
                     const int b = pass == 0 ? 0 : k + 1;
-                    double lo = DL[b * LW + l], hi = DU[b * LW + l], dv = NMPC_DUMMY_ROW_VALUE;
+                    double lo = row(R_DL, b)[l], hi = row(R_DU, b)[l], dv = NMPC_DUMMY_ROW_VALUE;
                     if (pass == 1) dv = rowg(zb, pi, pj, isobs, qox, qoy, qoc).dv;
                     bool act = lo > -NMPC_INF || hi < NMPC_INF;
                     row(R_DS, b)[l] = act ? push_in(dv, lo, hi, o.bound_push, o.bound_frac) - row(R_S, b)[l] : 0.0;
@@ -1080,7 +1054,7 @@ struct WarpSolver {
                 if (isx) {
                     double v = zb[NS + 2 * rob];
                     zn = comp == 0 ? zt + T * v * cs[rob] : (comp == 1 ? zt + T * v * sn[rob] : zt + T * zb[NS + 2 * rob + 1]);
-                    zn = push_in(zn + CE[(k + 1) * LW + l], BL[(k + 1) * LW + l], BU[(k + 1) * LW + l], o.bound_push, o.bound_frac);
+                    zn = push_in(zn + row(R_CE, k + 1)[l], row(R_BL, k + 1)[l], row(R_BU, k + 1)[l], o.bound_push, o.bound_frac);
                 } else if (isu && k + 1 < N) zn = row(R_Z, k + 1)[l];
                 zt = zn;
             }
@@ -1105,7 +1079,7 @@ struct WarpSolver {
     // entries that a new one dominates are redundant for the acceptance test and are simply left in place.  Every lane checks
     // its share of the entries.  An overflow of the NMPC_FILTER_CAP entries overwrites the oldest and is counted (stats).
     // ---------------------------------------------------------------------------------------
-    NMPC_DEV double *filter_base() const { return ws + ((long long)R_COUNT * S + (long long)S * NS) * LW; }
+    NMPC_DEV double *filter_base() const { return ws + (long long)R_COUNT * S * LW; }
     NMPC_DEV bool filter_ok(double th, double ph) const
     {
         const double *fth = wp::global_ptr(filter_base()), *fph = fth + NMPC_FILTER_CAP;
