@@ -289,7 +289,7 @@ __global__ void plant_kernel(int Nr, int N, double T, int B, const double *__res
 
 __global__ void prep_bounds_kernel(int Nr, int N, double relax, int nb, int lw, const double *__restrict__ lbx, const double *__restrict__ ubx,
                                    const double *__restrict__ lbg, const double *__restrict__ ubg, double *__restrict__ rows, int *err,
-                                   int nobs = 0, int family = 0)
+                                   int nobs = 0, int family = 0, int stage_major = 0)
 {
     const int S = N + 1, ns = 3 * Nr, nc = 2 * Nr, M = Nr * (Nr - 1) / 2 + Nr * nobs;
     const long long n = (long long)ns * S + (long long)nc * N, mg = family ? ns + (long long)N * (ns + M) : (long long)S * (ns + M);
@@ -297,7 +297,7 @@ __global__ void prep_bounds_kernel(int Nr, int N, double relax, int nb, int lw, 
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const long long b = e / (S * lw);
         const int k = (int)((e / lw) % S), lane = (int)(e % lw);
-        int rc = nmpc_prep_bounds_elem(Nr, N, relax, lbx + b * n, ubx + b * n, lbg + b * mg, ubg + b * mg, k, lane, lw, rows + b * bstride, nobs, family);
+        int rc = nmpc_prep_bounds_elem(Nr, N, relax, lbx + b * n, ubx + b * n, lbg + b * mg, ubg + b * mg, k, lane, lw, rows + b * bstride, nobs, family, stage_major);
         if (rc) atomicCAS(err, 0, rc);
     }
 }

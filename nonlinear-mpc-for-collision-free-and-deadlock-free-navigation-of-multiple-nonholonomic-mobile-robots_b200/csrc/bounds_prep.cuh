@@ -18,17 +18,19 @@
 NMPC_HD inline double nmpc_relax_lo(double v, double f) { return v > -NMPC_INF ? v - f * fmax(1.0, fabs(v)) : -NMPC_INF; }
 NMPC_HD inline double nmpc_relax_hi(double v, double f) { return v < NMPC_INF ? v + f * fmax(1.0, fabs(v)) : NMPC_INF; }
 
-// rows: [NMPC_BR_COUNT][S][lw] of this bound set (lw = 32 or 64 lanes per instance).  Returns 0 or a negative NMPC_E* code.
+// rows: [NMPC_BR_COUNT][S][lw] (or, stage_major, [S][NMPC_BR_COUNT][lw]) of this bound set (lw = 32 or 64 lanes per instance).  Returns 0 or a negative NMPC_E* code.
 // nobs / family: rows per block = pair rows + Nr * nobs obstacle rows; family 1 (static obstacles,
 // first_scenario_mpc_obstacle_avoidance.py:150) has no inequality rows in block 0, so block k starts at ns + (k-1)(ns+M).
 NMPC_HD inline int nmpc_prep_bounds_elem(int Nr, int N, double relax, const double *lbx, const double *ubx,
                                          const double *lbg, const double *ubg, int k, int lane, int lw, double *rows,
-                                         int nobs = 0, int family = 0)
+                                         int nobs = 0, int family = 0, int stage_major = 0)
 {
     const int ns = 3 * Nr, nc = 2 * Nr, nz = 5 * Nr, M = Nr * (Nr - 1) / 2 + Nr * nobs, S = N + 1;
     const long long goff = family ? (k == 0 ? 0 : ns + (long long)(k - 1) * (ns + M)) : (long long)k * (ns + M);
-    const long long rs = (long long)S * lw;
-    const int e = k * lw + lane;
+    // row x of stage k: one array per row ([x][S][lw], the dense-block path) or one record of NMPC_BR_COUNT rows per stage
+    // ([S][x][lw], the warp-per-instance path, which stages [BL, BU] and [CE, DL, DU] as contiguous ranges)
+    const long long rs = stage_major ? (long long)lw : (long long)S * lw;
+    const long long e = stage_major ? (long long)k * NMPC_BR_COUNT * lw + lane : (long long)k * lw + lane;
     int err = 0;
     double lo = -NMPC_INF, hi = NMPC_INF;
     if (lane < ns) { lo = lbx[k * ns + lane]; hi = ubx[k * ns + lane]; }

@@ -78,6 +78,7 @@ __global__ void __launch_bounds__((SolveCfg<NR, OBS>::THREADS), (SolveCfg<NR, OB
     double *sm = smem + (size_t)team * WSol::SM_DOUBLES;
     double *ws = P.ws + ((long long)blockIdx.x * SolveCfg<NR, OBS>::TEAMS + team) * P.ws_stride;
     WSol s(P, sm, ws);
+    s.init_team();
     for (;;) {
         WSol::tsync();
         if (tl == 0) sm[WSol::SM_MISC + 1] = (double)atomicAdd(P.counter, 1);
@@ -443,7 +444,7 @@ static int solve_impl(nmpc_handle *h, int B, const double *x0, const double *p, 
     if (!thr) {
         long long total = (long long)nb * h->S * h->lw;
         int blocks = (int)std::min<long long>((total + 255) / 256, 4096);
-        prep_bounds_kernel<<<blocks, 256, 0, st>>>(h->d.Nr, h->d.N, h->o.bound_relax_factor, nb, h->lw, lbx, ubx, lbg, ubg, brows, berr, h->nobs, h->family);
+        prep_bounds_kernel<<<blocks, 256, 0, st>>>(h->d.Nr, h->d.N, h->o.bound_relax_factor, nb, h->lw, lbx, ubx, lbg, ubg, brows, berr, h->nobs, h->family, h->block_path ? 0 : 1);
         h->launches++;
     }
     NmpcSolveParams P;

@@ -31,9 +31,7 @@
 #define NMPC_LOCALS                                                                                   \
     double *const sm = wp::shared_ptr(this->sm);                                                      \
     double *const ws = wp::global_ptr(this->ws);                                                      \
-    const double *const BL = wp::global_ptr(this->BL), *const BU = wp::global_ptr(this->BU),           \
-                 *const CE = wp::global_ptr(this->CE), *const DL = wp::global_ptr(this->DL),           \
-                 *const DU = wp::global_ptr(this->DU);                                                 \
+    const double *const br = wp::global_ptr(this->br);                                                 \
     const int N = this->N, S = this->S, l = this->l, rob = this->rob, comp = this->comp,               \
               pi = this->pi, pj = this->pj;                                                            \
     const bool isx = this->isx, isu = this->isu, isz = this->isz, isq = this->isq;                     \
@@ -42,11 +40,13 @@
     const bool isobs = OBS && this->isobs;                                                              \
     const double qox = this->qox, qoy = this->qoy, qoc = this->qoc;                                     \
     (void)nobs; (void)family; (void)isobs; (void)qox; (void)qoy; (void)qoc;                              \
-    (void)sm; (void)ws; (void)BL; (void)BU; (void)CE; (void)DL; (void)DU; (void)N; (void)S; (void)l;   \
+    (void)sm; (void)ws; (void)br; (void)N; (void)S; (void)l;                                            \
     (void)rob; (void)comp; (void)pi; (void)pj; (void)isx; (void)isu; (void)isz; (void)isq; (void)T;    \
     (void)df; (void)xs_l; (void)qw; (void)x0bar_l;                                                     \
     auto row = [=](int r, int k) -> double * { return ws + ((long long)k * R_COUNT + r) * LW; };       \
     auto frow = [=](int k, int i) -> double * { return ws + ((long long)k * R_COUNT + R_F0 + i) * LW; }; \
+    auto brow = [=](int x, int k) -> const double * { return br + ((long long)k * NMPC_BR_COUNT + x) * LW; }; \
+    (void)brow;                                                                                        \
     auto zvalid = [=](int k) -> bool { return l < (k < N ? NZ : NS); };                                \
     auto gradf = [=](int k, double z) -> double { return (k < N && isz) ? qw * (z - xs_l) : 0.0; };    \
     (void)row; (void)frow; (void)zvalid; (void)gradf;
@@ -78,24 +78,27 @@ struct WarpSolver {
     // Scratch layout: one RECORD of R_COUNT rows (LW doubles each) per stage, records consecutive in memory.  The rows are ordered
     // so that what a pass stages for one stage is two contiguous ranges: rows indexed by the stage k (from record k) and rows indexed
     // by the block k + 1 (from record k + 1):
-    //     factorisation:  record k  [R_TRIG2 .. R_BU]                record k + 1  [R_YC .. R_DU]
+    //     factorisation:  record k  [R_TRIG2 .. R_ZU]                record k + 1  [R_YC .. R_VU]
     //     forward pass:   record k  [R_Z .. R_F0 + NS - 1]           record k + 1  [R_S .. R_DQ]
     // (round 1 kept one array per row, [row][stage][LW]: the 16 rows a stage needs were 16 separate 256-byte pieces 5 KB apart).
-    // The bound rows of the instance are copied into its records by init_point, so every staged row comes from the record.
+    // The (relaxed) bound rows are laid out the same way by prep_bounds_kernel ([stage][BL, BU, CE, DL, DU][LW]); they are shared by the
+    // batch unless bounds_batched and stay L2 resident (copying them into every instance's records cost 10 MB of DRAM traffic per solve).
     enum Row {
-        R_TRIG2, R_TRIG, R_Z, R_ZL, R_ZU, R_BL, R_BU, R_LIN, R_DG, R_GX, R_COEF, R_F0,          // R_F0 .. R_F0 + NS - 1: Riccati factor rows
-        R_YC = R_F0 + NS, R_YD, R_CSOC, R_DSOC, R_CE, R_S, R_VL, R_VU, R_DL, R_DU, R_RC, R_GS, R_GXQ, R_GYQ, R_RD, R_DQ,
+        R_TRIG2, R_TRIG, R_Z, R_ZL, R_ZU, R_LIN, R_DG, R_GX, R_COEF, R_F0,          // R_F0 .. R_F0 + NS - 1: Riccati factor rows
+        R_YC = R_F0 + NS, R_YD, R_CSOC, R_DSOC, R_S, R_VL, R_VU, R_RC, R_GS, R_GXQ, R_GYQ, R_RD, R_DQ,
         R_DZ, R_DZ2, R_YTC, R_YTC2, R_DS, R_DS2, R_YTD, R_YTD2,
         R_COUNT
     };
-    // slots of the factorisation's staging buffer (sm + SM_STG): rows [R_TRIG2 .. R_BU] of stage k, then rows [R_YC .. R_DU] of block k+1
-    enum { FS_TRIG2, FS_TRIG, FS_Z, FS_ZL, FS_ZU, FS_BL, FS_BU, FS_K_ROWS,
-           FS_YC = FS_K_ROWS, FS_YD, FS_CSOC, FS_DSOC, FS_CE, FS_S, FS_VL, FS_VU, FS_DL, FS_DU, FS_COUNT, FS_B_ROWS = FS_COUNT - FS_K_ROWS };
-    // slots of the forward pass's staging buffer (the whole big region): rows [R_Z .. last factor row] of stage k, then [R_S .. R_DQ] of block k+1
-    enum { WS_Z, WS_ZL, WS_ZU, WS_BL, WS_BU, WS_LIN, WS_DG, WS_GX, WS_COEF, WS_F0, WS_K_ROWS = WS_F0 + NS,
-           WS_S = WS_K_ROWS, WS_VL, WS_VU, WS_DL, WS_DU, WS_RC, WS_GS, WS_GXQ, WS_GYQ, WS_RD, WS_DQ, WS_COUNT, WS_B_ROWS = WS_COUNT - WS_K_ROWS };
-    static_assert(R_BU - R_TRIG2 + 1 == FS_K_ROWS && R_DU - R_YC + 1 == FS_B_ROWS && R_F0 + NS - R_Z == WS_K_ROWS && R_DQ - R_S + 1 == WS_B_ROWS,
-                  "staging slots follow the record layout");
+    // slots of the factorisation's staging buffer (sm + SM_STG): rows [R_TRIG2 .. R_ZU] of record k, bound rows [BL, BU] of stage k,
+    // rows [R_YC .. R_VU] of record k + 1, bound rows [CE, DL, DU] of block k + 1
+    enum { FS_TRIG2, FS_TRIG, FS_Z, FS_ZL, FS_ZU, FS_BL, FS_BU, FS_YC, FS_YD, FS_CSOC, FS_DSOC, FS_S, FS_VL, FS_VU, FS_CE, FS_DL, FS_DU, FS_COUNT };
+    // slots of the forward pass's staging buffer (the whole big region): rows [R_Z .. last factor row] of record k, [BL, BU] of stage k,
+    // rows [R_S .. R_DQ] of record k + 1, [DL, DU] of block k + 1
+    enum { WS_Z, WS_ZL, WS_ZU, WS_LIN, WS_DG, WS_GX, WS_COEF, WS_F0, WS_BL = WS_F0 + NS, WS_BU,
+           WS_S, WS_VL, WS_VU, WS_RC, WS_GS, WS_GXQ, WS_GYQ, WS_RD, WS_DQ, WS_DL, WS_DU, WS_COUNT };
+    static_assert(R_ZU - R_TRIG2 == FS_ZU - FS_TRIG2 && R_VU - R_YC == FS_VU - FS_YC && R_F0 + NS - 1 - R_Z == WS_F0 + NS - 1 - WS_Z &&
+                  R_DQ - R_S == WS_DQ - WS_S && NMPC_BR_BU == NMPC_BR_BL + 1 && NMPC_BR_DL == NMPC_BR_CE + 1 && NMPC_BR_DU == NMPC_BR_DL + 1,
+                  "staging slots follow the record layouts");
     // shared-memory carve-up (doubles, per team): small buffers that live for the whole solve, then one big region that the
     // factorisation and the forward pass carve up differently (they never run at the same time)
     enum {
@@ -105,6 +108,7 @@ struct WarpSolver {
         SM_CS = SM_HB + LW, SM_SN = SM_CS + NRP, SM_C4 = SM_SN + NRP,   // c4[4 i ..]: a_i, b_i, T cos, T sin of robot i (one 32-byte record)
         SM_CRS = SM_C4 + 4 * NRP, SM_THD = SM_CRS + NRP,
         SM_MISC = SM_THD + NRP,
+        SM_MBAR = SM_MISC + 4,           // the team's mbarrier (8 bytes) for the bulk-copy staging
         SM_RED = SM_MISC + 8,            // cross-warp reduction scratch (two-warp teams)
         SM_BIG = SM_RED + 8,
         // -- factorisation view of the big region
@@ -121,23 +125,36 @@ struct WarpSolver {
     };
     static_assert((int)WS_COUNT <= 64 && (SM_BIG & 1) == 0 && (SM_STG & 1) == 0 && (SM_DOUBLES & 1) == 0 && (SM_C4 & 3) == 0, "shared-memory layout");
 
-    // Asynchronous copy of `nrows` consecutive rows of a record into the staging buffer: 16 bytes per lane and instruction (two rows
-    // per warp instruction), completion: wp::cp_async_wait() + tsync().
-    static NMPC_DEV void copy_rows(double *dst, const double *src, int l, int nrows)
+    // Staging of a pass: up to four contiguous ranges of rows per stage, each ONE TMA bulk copy (cp.async.bulk global -> shared) issued
+    // by lane 0 of the team, all of them completing on the team's mbarrier (sm[SM_MBAR]); stage_wait() is the consumer side.  (The
+    // first record-layout version copied the ranges with cp.async, 16 bytes per lane: 10 + 20 loop iterations per stage pair.)
+    static NMPC_DEV void bulk_rows(double *bar, double *dst, const double *src, int nrows)
     {
-        NMPC_NOUNROLL
-        for (int c = 2 * l; c < nrows * LW; c += 2 * LW) wp::cp_async16(dst + c, src + c);
+        wp::bulk_g2s(dst, src, (unsigned)(nrows * LW * sizeof(double)), bar);
+    }
+    // once per team and kernel: the staging barrier (one arriving thread per phase: the issuing lane's expect_tx)
+    NMPC_DEV void init_team()
+    {
+        if (wp::team_lane(LW) == 0) wp::mbar_init(wp::shared_ptr(this->sm) + SM_MBAR);
+        mbar_phase = 0;
+        tsync();
+    }
+    NMPC_DEV void stage_wait()
+    {
+        wp::mbar_wait(wp::shared_ptr(this->sm) + SM_MBAR, (unsigned)mbar_phase);
+        mbar_phase ^= 1;
     }
     // per-slot scratch: the stage records, then the filter (NMPC_FILTER_CAP theta values, then as many phi values)
     static NMPC_HD long long ws_doubles(int N) { return (long long)R_COUNT * (N + 1) * LW + 2 * NMPC_FILTER_CAP; }
 
     const NmpcSolveParams &P;
     double *sm, *ws;
-    const double *BL, *BU, *CE, *DL, *DU;
+    const double *br;   // this instance's bound rows, [stage][BL, BU, CE, DL, DU][LW]
     int N, S, l, rob, comp, pi, pj, inst, fn;
     // cos/sin rows of the iterate (r_trig is R_TRIG or R_TRIG2; the other one receives the trial points).  When a step is
     // accepted at the trial point evaluated last, its rows BECOME the iterate's (swap) and no sincos is recomputed.
     int r_trig, t2_rdz;
+    int mbar_phase;   // parity of the staging mbarrier's current phase
     bool trig_valid;
     double t2_alpha;
     bool isx, isu, isz, isq;
@@ -214,10 +231,7 @@ struct WarpSolver {
             for (int a = 0; a < NR; a++)
                 for (int b = a + 1; b < NR; b++) { if (q == l) { pi = a; pj = b; } q++; }
         }
-        const double *br = P.brows + (long long)inst * P.bstride;
-        BL = br + (long long)NMPC_BR_BL * S * LW; BU = br + (long long)NMPC_BR_BU * S * LW;
-        CE = br + (long long)NMPC_BR_CE * S * LW; DL = br + (long long)NMPC_BR_DL * S * LW;
-        DU = br + (long long)NMPC_BR_DU * S * LW;
+        br = P.brows + (long long)inst * P.bstride;
         const double *pp = P.p + (long long)inst * 2 * NS;
         x0bar_l = isx ? pp[l] : 0.0;
         xs_l = isx ? pp[NS + l] : 0.0;
@@ -253,15 +267,12 @@ struct WarpSolver {
             double z = isx ? x0[k * NS + l] : ((isu && k < N) ? x0[NS * S + k * NC + (l - NS)] : 0.0);
             gmax = fmax(gmax, fabs(gradf(k, z)));
             row(R_Z, k)[l] = z;
-            // the instance's (relaxed) bound rows join its records, so that a pass stages them together with the iterate
-            row(R_BL, k)[l] = BL[k * LW + l]; row(R_BU, k)[l] = BU[k * LW + l]; row(R_CE, k)[l] = CE[k * LW + l];
-            row(R_DL, k)[l] = DL[k * LW + l]; row(R_DU, k)[l] = DU[k * LW + l];
         }
         gmax = tred_max(gmax);
         this->df = gmax > o.nlp_scaling_max_gradient ? fmax(o.nlp_scaling_max_gradient / gmax, 1e-8) : 1.0;
         double cnt_z = 0.0;
         for (int k = 0; k <= N; k++) {
-            double lo = row(R_BL, k)[l], hi = row(R_BU, k)[l];
+            double lo = brow(NMPC_BR_BL, k)[l], hi = brow(NMPC_BR_BU, k)[l];
             double z = push_in(row(R_Z, k)[l], lo, hi, o.bound_push, o.bound_frac);
             row(R_Z, k)[l] = z;
             bool hl = lo > -NMPC_INF, hu = hi < NMPC_INF;
@@ -276,7 +287,7 @@ struct WarpSolver {
         for (int b = 0; b <= N; b++) {
             double s = 0.0, vl = 0.0, vu = 0.0;
             if (isq) {
-                double lo = row(R_DL, b)[l], hi = row(R_DU, b)[l];
+                double lo = brow(NMPC_BR_DL, b)[l], hi = brow(NMPC_BR_DU, b)[l];
                 bool hl = lo > -NMPC_INF, hu = hi < NMPC_INF;
                 double dv = NMPC_DUMMY_ROW_VALUE;
                 if (b > 0) dv = rowg(row(R_Z, b - 1), pi, pj, isobs, qox, qoy, qoc).dv;
@@ -348,7 +359,7 @@ struct WarpSolver {
             k = k < N ? k : N;
             r.cs = row(rt, k < N ? k : N - 1)[rob]; r.sn = row(rt, k < N ? k : N - 1)[NRP + rob];
             r.z = row(R_Z, k)[l]; r.dz = trial ? row(rdz, k)[l] : 0.0;
-            r.lo = row(R_BL, k)[l]; r.hi = row(R_BU, k)[l]; r.ce = row(R_CE, k)[l];
+            r.lo = brow(NMPC_BR_BL, k)[l]; r.hi = brow(NMPC_BR_BU, k)[l]; r.ce = brow(NMPC_BR_CE, k)[l];
             r.zl = FULL ? row(R_ZL, k)[l] : 0.0; r.zu = FULL ? row(R_ZU, k)[l] : 0.0; r.yc = FULL ? row(R_YC, k)[l] : 0.0;
             r.csoc = socacc ? row(R_CSOC, k)[l] : 0.0;
             return r;
@@ -357,7 +368,7 @@ struct WarpSolver {
             QRows r;
             b = b < N ? b : N;
             r.s = row(R_S, b)[l]; r.ds = trial ? row(rds, b)[l] : 0.0;
-            r.lo = row(R_DL, b)[l]; r.hi = row(R_DU, b)[l];
+            r.lo = brow(NMPC_BR_DL, b)[l]; r.hi = brow(NMPC_BR_DU, b)[l];
             r.yd = FULL ? row(R_YD, b)[l] : 0.0; r.vl = FULL ? row(R_VL, b)[l] : 0.0; r.vu = FULL ? row(R_VU, b)[l] : 0.0;
             r.dsoc = socacc ? row(R_DSOC, b)[l] : 0.0;
             return r;
@@ -589,17 +600,24 @@ struct WarpSolver {
         const double xm = isu ? 0.0 : 1.0;
         const int base = isL ? NS : 3 * rob;
         tsync();
-        // staging of stage k: rows [R_TRIG2 .. R_BU] of record k and rows [R_YC .. R_DU] of record k + 1 (two contiguous ranges)
+        // staging of stage k: four contiguous ranges (see FS_*)
+        double *const bar = sm + SM_MBAR;
         auto stage_issue = [&](int k) {
-            copy_rows(stg, row(R_TRIG2, k), l, FS_K_ROWS);
-            copy_rows(stg + FS_K_ROWS * LW, row(R_YC, k + 1), l, FS_B_ROWS);
+            if (l == 0) {
+                wp::fence_proxy_async();
+                wp::bulk_expect(bar, (unsigned)(FS_COUNT * LW * sizeof(double)));
+                bulk_rows(bar, stg + FS_TRIG2 * LW, row(R_TRIG2, k), FS_BL - FS_TRIG2);
+                bulk_rows(bar, stg + FS_BL * LW, brow(NMPC_BR_BL, k), 2);
+                bulk_rows(bar, stg + FS_YC * LW, row(R_YC, k + 1), FS_CE - FS_YC);
+                bulk_rows(bar, stg + FS_CE * LW, brow(NMPC_BR_CE, k + 1), 3);
+            }
         };
         const int fs_trig = FS_TRIG2 + (this->r_trig - R_TRIG2);   // which of the two trig rows belongs to the iterate
         stage_issue(N - 1);   // in flight during the terminal stage
         // terminal stage: X_N carries no cost and no distance rows, only its box
         {
             double sig = 0.0, gx = 0.0;
-            if (isx) sig_g<MODE>(kd, row(R_Z, N)[l], row(R_BL, N)[l], row(R_BU, N)[l], row(R_ZL, N)[l], row(R_ZU, N)[l], mu, 0.0, sig, gx);
+            if (isx) sig_g<MODE>(kd, row(R_Z, N)[l], brow(NMPC_BR_BL, N)[l], brow(NMPC_BR_BU, N)[l], row(R_ZL, N)[l], row(R_ZU, N)[l], mu, 0.0, sig, gx);
             hb[l] = isx ? gx : 0.0;
             tsync();
             NMPC_UNROLL
@@ -616,7 +634,7 @@ struct WarpSolver {
         }
         NMPC_NOUNROLL
         for (int k = N - 1; k >= 0; k--) {
-            wp::cp_async_wait();
+            stage_wait();
             tsync();
             const double zk = isz ? stg[FS_Z * LW + l] : 0.0;
             const double znx = zb[l];   // X_{k+1} (this lane's component): what the previous stage left here
@@ -792,12 +810,12 @@ struct WarpSolver {
 #if NMPC_PIVOT_UNROLL == 2
             NMPC_NOUNROLL
             for (int j = 0; j < NC; j += 2) {
-                if (!pivot(j, col, col + 2 * LW) || !pivot(j + 1, col + 2 * LW, col)) { wp::cp_async_wait(); return false; }   // drain the staging copies before the retry
+                if (!pivot(j, col, col + 2 * LW) || !pivot(j + 1, col + 2 * LW, col)) { if (k > 0) stage_wait(); return false; }   // drain the staging copy in flight before the retry
             }
 #else
             NMPC_NOUNROLL
             for (int j = 0; j < NC; j++) {
-                if (!pivot(j, col + 2 * LW * (j & 1), col + 2 * LW * ((j + 1) & 1))) { wp::cp_async_wait(); return false; }   // drain the staging copies before the retry
+                if (!pivot(j, col + 2 * LW * (j & 1), col + 2 * LW * ((j + 1) & 1))) { if (k > 0) stage_wait(); return false; }   // drain the staging copy in flight before the retry
             }
 #endif
             // publish p_k / feed-forward (the last lane's column) and store the factors
@@ -819,11 +837,11 @@ struct WarpSolver {
             }
         }
         tsync();
-        if (isx) row(R_RC, 0)[l] = MODE == 1 ? 0.0 : (soc ? row(R_CSOC, 0)[l] : row(R_Z, 0)[l] - x0bar_l - row(R_CE, 0)[l]);
+        if (isx) row(R_RC, 0)[l] = MODE == 1 ? 0.0 : (soc ? row(R_CSOC, 0)[l] : row(R_Z, 0)[l] - x0bar_l - brow(NMPC_BR_CE, 0)[l]);
         if (isq) {
             double a0, a1, a2, a3, a4;
             QIn in;
-            in.lo = row(R_DL, 0)[l]; in.hi = row(R_DU, 0)[l]; in.s = row(R_S, 0)[l]; in.vl = row(R_VL, 0)[l]; in.vu = row(R_VU, 0)[l];
+            in.lo = brow(NMPC_BR_DL, 0)[l]; in.hi = brow(NMPC_BR_DU, 0)[l]; in.s = row(R_S, 0)[l]; in.vl = row(R_VL, 0)[l]; in.vu = row(R_VU, 0)[l];
             in.yd = MODE == 0 ? row(R_YD, 0)[l] : 0.0; in.dsoc = soc ? row(R_DSOC, 0)[l] : 0.0;
             ineq_block<MODE>(row, in, l, pi, pj, isobs, qox, qoy, qoc, kd, 0, mu, delta, soc, zb, a0, a1, a2, a3, a4);
         }
@@ -861,27 +879,35 @@ struct WarpSolver {
         double ap = 0.0, az = 0.0, gbd = 0.0, tiny = 0.0;   // max ratios, see slack_step_terms
         double *dzb = sm + SM_DZB;
         double *stg = sm + SM_BIG;  // the factorisation's buffers are free during this pass: WS_COUNT staging rows
+        double *const bar = sm + SM_MBAR;
         tsync();
-        // staging of stage k: rows [R_Z .. last factor row] of record k and rows [R_S .. R_DQ] of record min(k + 1, N)
+        // staging of stage k: four contiguous ranges (see WS_*); block k + 1 clamped to N
         auto issue = [&](int k) {
-            copy_rows(stg, row(R_Z, k), l, WS_K_ROWS);
-            copy_rows(stg + WS_K_ROWS * LW, row(R_S, k < N ? k + 1 : N), l, WS_B_ROWS);
+            const int kb = k < N ? k + 1 : N;
+            if (l == 0) {
+                wp::fence_proxy_async();
+                wp::bulk_expect(bar, (unsigned)(WS_COUNT * LW * sizeof(double)));
+                bulk_rows(bar, stg + WS_Z * LW, row(R_Z, k), WS_BL - WS_Z);
+                bulk_rows(bar, stg + WS_BL * LW, brow(NMPC_BR_BL, k), 2);
+                bulk_rows(bar, stg + WS_S * LW, row(R_S, kb), WS_DL - WS_S);
+                bulk_rows(bar, stg + WS_DL * LW, brow(NMPC_BR_DL, kb), 2);
+            }
         };
         issue(0);
         double dx = isx ? -row(R_RC, 0)[l] : 0.0;
         if (isq) {
             double rd = row(R_RD, 0)[l], Dq = row(R_DQ, 0)[l], gs = row(R_GS, 0)[l];
-            bool act = row(R_DL, 0)[l] > -NMPC_INF || row(R_DU, 0)[l] < NMPC_INF;
+            bool act = brow(NMPC_BR_DL, 0)[l] > -NMPC_INF || brow(NMPC_BR_DU, 0)[l] < NMPC_INF;
             double ds = act ? rd : 0.0, ytd = act ? Dq * ds + gs : 0.0;
             row(rds, 0)[l] = ds; row(rytd, 0)[l] = ytd;
             if (act) {
                 double s = row(R_S, 0)[l];
-                slack_step_terms(s, ds, row(R_DL, 0)[l], row(R_DU, 0)[l], row(R_VL, 0)[l], row(R_VU, 0)[l], mu, ap, az);
+                slack_step_terms(s, ds, brow(NMPC_BR_DL, 0)[l], brow(NMPC_BR_DU, 0)[l], row(R_VL, 0)[l], row(R_VU, 0)[l], mu, ap, az);
                 gbd += gs * ds; tiny = fmax(tiny, fabs(ds) / (1.0 + fabs(s)));
             }
         }
         for (int k = 0; k <= N; k++) {
-            wp::cp_async_wait();
+            stage_wait();
             if (isx) dzb[l] = dx;
             tsync();
             // everything this stage needs moves from the staging buffer to registers, then the buffer is refilled
@@ -964,9 +990,9 @@ struct WarpSolver {
         auto load = [&](int k) {   // all rows of stage / block k, issued together one stage ahead of their use
             AR r;
             k = k < N ? k : N;
-            r.z = row(R_Z, k)[l]; r.dz = row(rdz, k)[l]; r.lo = row(R_BL, k)[l]; r.hi = row(R_BU, k)[l];
+            r.z = row(R_Z, k)[l]; r.dz = row(rdz, k)[l]; r.lo = brow(NMPC_BR_BL, k)[l]; r.hi = brow(NMPC_BR_BU, k)[l];
             r.zl = row(R_ZL, k)[l]; r.zu = row(R_ZU, k)[l]; r.yc = row(R_YC, k)[l]; r.ytc = row(rytc, k)[l];
-            r.s = row(R_S, k)[l]; r.ds = row(rds, k)[l]; r.dlo = row(R_DL, k)[l]; r.dhi = row(R_DU, k)[l];
+            r.s = row(R_S, k)[l]; r.ds = row(rds, k)[l]; r.dlo = brow(NMPC_BR_DL, k)[l]; r.dhi = brow(NMPC_BR_DU, k)[l];
             r.vl = row(R_VL, k)[l]; r.vu = row(R_VU, k)[l]; r.yd = row(R_YD, k)[l]; r.ytd = row(rytd, k)[l];
             return r;
         };
@@ -998,7 +1024,7 @@ struct WarpSolver {
         this->trig_valid = false; this->t2_rdz = -1;
         for (int k = 0; k <= N; k++) {
             if (zvalid(k)) row(R_Z, k)[l] += alpha * row(rdz, k)[l];
-            if (isq && (row(R_DL, k)[l] > -NMPC_INF || row(R_DU, k)[l] < NMPC_INF)) row(R_S, k)[l] += alpha * row(rds, k)[l];
+            if (isq && (brow(NMPC_BR_DL, k)[l] > -NMPC_INF || brow(NMPC_BR_DU, k)[l] < NMPC_INF)) row(R_S, k)[l] += alpha * row(rds, k)[l];
         }
         tsync();
     }
@@ -1010,13 +1036,13 @@ struct WarpSolver {
         const double ks = P.o.kappa_sigma;
         for (int k = 0; k <= N; k++) {
             if (zvalid(k)) {
-                double z = row(R_Z, k)[l], lo = row(R_BL, k)[l], hi = row(R_BU, k)[l];
+                double z = row(R_Z, k)[l], lo = brow(NMPC_BR_BL, k)[l], hi = brow(NMPC_BR_BU, k)[l];
                 if (lo > -NMPC_INF) { double s2 = z - lo; row(R_ZL, k)[l] = fmax(fmin(row(R_ZL, k)[l], ks * mu / s2), mu / (ks * s2)); }
                 if (hi < NMPC_INF) { double s2 = hi - z; row(R_ZU, k)[l] = fmax(fmin(row(R_ZU, k)[l], ks * mu / s2), mu / (ks * s2)); }
             }
             row(R_YC, k)[l] = 0.0; row(R_YD, k)[l] = 0.0;
             if (isq) {
-                double s = row(R_S, k)[l], lo = row(R_DL, k)[l], hi = row(R_DU, k)[l];
+                double s = row(R_S, k)[l], lo = brow(NMPC_BR_DL, k)[l], hi = brow(NMPC_BR_DU, k)[l];
                 if (lo > -NMPC_INF) { double s2 = s - lo; row(R_VL, k)[l] = fmax(fmin(row(R_VL, k)[l], ks * mu / s2), mu / (ks * s2)); }
                 if (hi < NMPC_INF) { double s2 = hi - s; row(R_VU, k)[l] = fmax(fmin(row(R_VU, k)[l], ks * mu / s2), mu / (ks * s2)); }
             }
@@ -1031,7 +1057,7 @@ struct WarpSolver {
         NMPC_LOCALS
         const nmpc_opts &o = this->P.o;
         double *zb = sm + SM_ZB, *cs = sm + SM_CS, *sn = sm + SM_SN;
-        double zt = isx ? push_in(x0bar_l + row(R_CE, 0)[l], row(R_BL, 0)[l], row(R_BU, 0)[l], o.bound_push, o.bound_frac) : (isu ? row(R_Z, 0)[l] : 0.0);
+        double zt = isx ? push_in(x0bar_l + brow(NMPC_BR_CE, 0)[l], brow(NMPC_BR_BL, 0)[l], brow(NMPC_BR_BU, 0)[l], o.bound_push, o.bound_frac) : (isu ? row(R_Z, 0)[l] : 0.0);
         for (int k = 0; k <= N; k++) {
             const bool zv = zvalid(k);
             row(R_DZ, k)[l] = zv ? zt - row(R_Z, k)[l] : 0.0;
@@ -1042,7 +1068,7 @@ struct WarpSolver {
                 for (int pass = (k == 0 ? 0 : 1); pass < 2; pass++) {
                     if (pass == 1 && k == N) break;
                     const int b = pass == 0 ? 0 : k + 1;
-                    double lo = row(R_DL, b)[l], hi = row(R_DU, b)[l], dv = NMPC_DUMMY_ROW_VALUE;
+                    double lo = brow(NMPC_BR_DL, b)[l], hi = brow(NMPC_BR_DU, b)[l], dv = NMPC_DUMMY_ROW_VALUE;
                     if (pass == 1) dv = rowg(zb, pi, pj, isobs, qox, qoy, qoc).dv;
                     bool act = lo > -NMPC_INF || hi < NMPC_INF;
                     row(R_DS, b)[l] = act ? push_in(dv, lo, hi, o.bound_push, o.bound_frac) - row(R_S, b)[l] : 0.0;
@@ -1054,7 +1080,7 @@ struct WarpSolver {
                 if (isx) {
                     double v = zb[NS + 2 * rob];
                     zn = comp == 0 ? zt + T * v * cs[rob] : (comp == 1 ? zt + T * v * sn[rob] : zt + T * zb[NS + 2 * rob + 1]);
-                    zn = push_in(zn + row(R_CE, k + 1)[l], row(R_BL, k + 1)[l], row(R_BU, k + 1)[l], o.bound_push, o.bound_frac);
+                    zn = push_in(zn + brow(NMPC_BR_CE, k + 1)[l], brow(NMPC_BR_BL, k + 1)[l], brow(NMPC_BR_BU, k + 1)[l], o.bound_push, o.bound_frac);
                 } else if (isu && k + 1 < N) zn = row(R_Z, k + 1)[l];
                 zt = zn;
             }

@@ -18,11 +18,13 @@ template <int NR> void lane_body()
 {
     if (NR <= 4 && job.P->nobs > 0) {   // the static-obstacle family has its own instantiation (1..4 robots on the warp path)
         WarpSolver<(NR <= 4 ? NR : 1), true> s(*job.P, job.sm, job.ws);
+        s.init_team();
         s.setup(job.inst);
         s.run();
         return;
     }
     WarpSolver<NR> s(*job.P, job.sm, job.ws);
+    s.init_team();
     s.setup(job.inst);
     s.run();
 }
@@ -57,7 +59,7 @@ extern "C" int emu_solve(const nmpc_desc *d, const nmpc_opts *o, int B, const do
         for (int k = 0; k < S; k++)
             for (int l = 0; l < LWd; l++) {
                 int e = nmpc_prep_bounds_elem(Nr, N, o->bound_relax_factor, lbx + b * n, ubx + b * n, lbg + b * mg,
-                                              ubg + b * mg, k, l, LWd, brows.data() + (size_t)b * bstride, nobs, family);
+                                              ubg + b * mg, k, l, LWd, brows.data() + (size_t)b * bstride, nobs, family, 1);
                 if (e && !berr) berr = e;
             }
     long long wsd = 0; int smd = 0;

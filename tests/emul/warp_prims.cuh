@@ -5,6 +5,7 @@
 // __syncwarp() bugs show up as wrong results (and `reverse` flips the lane order).
 #pragma once
 #include <math.h>
+#include <string.h>
 #include <ucontext.h>
 
 #define NMPC_DEV inline
@@ -43,6 +44,11 @@ inline bool pos_normal(double v) { return v >= 2.2250738585072014e-308 && v < IN
 inline void prefetch(const void *) {}
 inline void cp_async16(double *dst, const double *src) { dst[0] = src[0]; dst[1] = src[1]; }
 inline void cp_async_wait() {}
+inline void mbar_init(double *) {}
+inline void fence_proxy_async() {}
+inline void bulk_expect(double *, unsigned) {}
+inline void bulk_g2s(double *dst, const double *src, unsigned bytes, double *) { memcpy(dst, src, bytes); }
+inline void mbar_wait(double *, unsigned) {}
 inline unsigned nth_set_bit(unsigned mask, int n) { for (unsigned b = 0; b < 32; b++) if (mask >> b & 1u) { if (n == 0) return b; n--; } return 0xffffffffu; }
 inline double log_(double x) { return ::log(x); }
 inline double frexp_(double x, int *e) { return ::frexp(x, e); }
