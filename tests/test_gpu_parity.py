@@ -389,3 +389,62 @@ def test_randomised_configurations_match_oracle(pkg, torch_cuda):
         assert out["stats"][:, 10].max().item() == 0
     print("fuzz: %d / %d solved instances on the oracle's point" % (n_same, n_tot))
     assert n_tot >= 100 and n_same >= 0.97 * n_tot, (n_same, n_tot)
+
+
+def test_per_instance_bounds_match_oracle(pkg, torch_cuda):
+    """bounds_batched = 1: every instance carries its own lbx/ubx/lbg/ubg rows ([B, n] / [B, mg]) -- different safety distances,
+    speed limits and position boxes inside one launch (the reference builds one `args` dict per script:
+    sixth_scenario.py:127-135 dmin 0.3, second_scenario.py:118-120 dmin 0.25, decentralized_first_scenario.py:190-192 box +-2).
+    The oracle is given the same per-instance rows; and the batched call must equal B shared-bounds calls."""
+    torch = torch_cuda
+    Nr, N, T, B = 4, 12, 0.2, 24
+    rng = np.random.default_rng(77)
+    prob, orc = pkg.Problem(Nr, N, T), Oracle(Nr, N, T)
+    P = synthetic_instances(B, Nr, 4242)
+    rows = [prob.bounds(dmin, vmax, wmax, xy_box=box) for dmin, vmax, wmax, box in
+            zip(rng.uniform(0.15, 0.35, B), rng.uniform(0.15, 0.4, B), rng.uniform(1.0, 2.84, B), rng.choice([3.0, 10.0], B))]
+    lbx, ubx, lbg, ubg = (np.stack([r[i] for r in rows]) for i in range(4))
+    x0 = prob.cold_start(P[:, :3 * Nr])
+    out = prob.solve(_t(torch, x0), _t(torch, P), _t(torch, lbx), _t(torch, ubx), _t(torch, lbg), _t(torch, ubg))
+    torch.cuda.synchronize()
+    ref = orc.solve_batch(x0, P, lbx, ubx, lbg, ubg)
+    nX = 3 * Nr * (N + 1)
+    x, f, g = out["x"].cpu().numpy(), out["f"].cpu().numpy(), out["g"].cpu().numpy()
+    assert np.all(out["status"].cpu().numpy() == ref["status"])
+    du = np.abs(x - ref["x"])[:, nX:].max(axis=1)
+    df = np.abs(f - ref["f"]) / np.maximum(1.0, np.abs(ref["f"]))
+    assert ((du <= U_TOL) & (df <= F_RTOL)).mean() >= 0.95, (du, df)
+    ok = ref["status"] == 0
+    assert ok.sum() >= B - 2
+    assert np.maximum(lbg - g, 0.0)[ok].max() <= C_TOL
+    relax = 1.01e-8 * np.maximum(1.0, np.abs(ubx))      # IPOPT's bound_relax_factor: bounds are relaxed by 1e-8 max(1, |b|) (restated in bounds_prep.cuh)
+    assert np.all(np.maximum(lbx - x, 0.0)[ok] <= relax[ok]) and np.all(np.maximum(x - ubx, 0.0)[ok] <= relax[ok])
+    # each instance's own speed limit is what binds: the largest |v| of instance b reaches vmax_b but never exceeds it
+    v = np.abs(x[:, nX::2]).max(axis=1)
+    assert np.all(v[ok] <= ubx[ok, nX] + 1.01e-8) and (v[ok] >= ubx[ok, nX] - 1e-6).mean() >= 0.8
+    for b in (0, 7, 23):       # the same instance through the shared-bounds entry: identical arithmetic, identical result
+        one = prob.solve(_t(torch, x0[b:b + 1]), _t(torch, P[b:b + 1]), _t(torch, lbx[b]), _t(torch, ubx[b]), _t(torch, lbg[b]), _t(torch, ubg[b]))
+        np.testing.assert_array_equal(one["x"].cpu().numpy()[0], x[b])
+        assert one["iters"].item() == out["iters"][b].item()
+
+
+def test_single_robot_long_horizon_goal_sequence(pkg, torch_cuda):
+    """Family E (decentralized_first_scenario.py:94-95,190-192,246-260): one robot, N = 200 stages of T = 0.05 s, positions boxed
+    to +-2, v <= 0.22, |omega| <= 2.84, solved for each pose of the script's goal list from the previous goal -- a horizon ten
+    times the benchmark's, so the stage records (not the robots) fill the scratch.  Each is checked against the oracle."""
+    torch = torch_cuda
+    Nr, N, T = 1, 200, 0.05
+    prob, orc = pkg.Problem(Nr, N, T), Oracle(Nr, N, T)
+    lbx, ubx, lbg, ubg = prob.bounds(0.15, 0.22, 2.84, xy_box=2.0)
+    goals = np.array([[0, 0, 0], [1.0, 0.5, 0.0], [0.0, 0.75, -1.57], [-0.5, 0.5, 3.14], [-0.5, -0.75, 0.785], [0.75, -0.75, -0.785], [0, 0, 0]])
+    P = np.concatenate([goals[:-1], goals[1:]], axis=1)
+    x0 = prob.cold_start(P[:, :3])
+    out = prob.solve(_t(torch, x0), _t(torch, P), _t(torch, lbx), _t(torch, ubx), _t(torch, lbg), _t(torch, ubg))
+    torch.cuda.synchronize()
+    ref = orc.solve_batch(x0, P, lbx, ubx, lbg, ubg)
+    same, du, df, it = _compare(out, ref, Nr, N, lbg, "family E")
+    assert np.all(ref["status"] == 0), ref["status"]
+    assert same.all(), (du, df, it, ref["iters"])
+    assert np.abs(it - ref["iters"]).max() <= 3
+    x = out["x"].cpu().numpy()
+    assert np.abs(x[:, :3 * (N + 1)].reshape(-1, N + 1, 3)[:, :, :2]).max() <= 2.0 + 2.1e-8

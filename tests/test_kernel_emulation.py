@@ -113,3 +113,40 @@ def test_emulated_kernel_obstacle_family(case, reverse):
     np.testing.assert_allclose(e["g"][0], r["g"], atol=1e-9)
     np.testing.assert_allclose(e["lam_g"][0], r["lam_g"], atol=1e-5)
     assert e["g"][0][lbg != ubg].min() >= margin * 0 + min(margin, dmin * dmin if M else margin) - 1e-8
+
+
+def test_emulated_kernel_long_horizon_single_robot():
+    """decentralized_first_scenario.py:94-95,190-192: N = 200, T = 0.05, positions boxed to +-2 -- 201 stage records per instance."""
+    Nr, N, T = 1, 200, 0.05
+    o = Oracle(Nr, N, T)
+    lbx, ubx, lbg, ubg = o.bounds(0.15, 0.22, 2.84)
+    lbx[:3 * (N + 1)].reshape(-1, 3)[:, :2] = -2.0
+    ubx[:3 * (N + 1)].reshape(-1, 3)[:, :2] = 2.0
+    P = np.array([[0, 0, 0, 1.0, 0.5, 0.0], [-0.5, 0.5, 3.14, -0.5, -0.75, 0.785]])
+    w0 = np.stack([o.cold_start(q[:3]) for q in P])
+    r = o.solve_batch(w0, P, lbx, ubx, lbg, ubg)
+    e = emu_solve(Nr, N, T, w0, P, lbx, ubx, lbg, ubg)
+    assert e["rc"] == 0 and np.all(e["status"] == 0) and np.all(r["status"] == 0)
+    assert np.abs(e["iters"] - r["iters"]).max() <= 2
+    assert np.abs(e["x"] - r["x"])[:, 3 * (N + 1):].max() <= 1e-6
+    assert (np.abs(e["f"] - r["f"]) / r["f"]).max() <= 1e-9
+
+
+def test_emulated_kernel_per_instance_bounds():
+    """bounds_batched = 1: each instance reads its own bound rows (its own stage-major copy in the scratch)."""
+    Nr, N, T = 3, 6, 0.2
+    o = Oracle(Nr, N, T)
+    rows = [o.bounds(dmin, v, w) for dmin, v, w in ((0.3, 0.22, 2.84), (0.15, 0.4, 1.0), (0.35, 0.1, 2.0))]
+    lbx, ubx, lbg, ubg = (np.stack([q[i] for q in rows]) for i in range(4))
+    p = np.array([-1, -1, 1.57, 0, -1, 1.57, 1, -1, 1.57, 1, 2, 0, 0, 1, 0, -1, 0.5, 0], float)
+    P = np.stack([p, p, p])
+    w0 = np.stack([o.cold_start(p[:9])] * 3)
+    r = o.solve_batch(w0, P, lbx, ubx, lbg, ubg)
+    e = emu_solve(Nr, N, T, w0, P, lbx, ubx, lbg, ubg)
+    assert e["rc"] == 0 and np.all(e["status"] == r["status"]) and np.all(r["status"] == 0)
+    nX = 3 * Nr * (N + 1)
+    assert np.abs(e["x"] - r["x"])[:, nX:].max() <= 1e-6
+    assert np.abs(e["x"][:, nX::2]).max(axis=1) == pytest.approx([0.22, 0.4, 0.1], abs=1e-6)
+    for b in range(3):     # and the shared-bounds entry gives the same numbers
+        one = emu_solve(Nr, N, T, w0[b], P[b], lbx[b], ubx[b], lbg[b], ubg[b])
+        np.testing.assert_array_equal(one["x"][0], e["x"][b])
