@@ -71,7 +71,7 @@ struct BlockSolver {
     const int *pairs;
     double *Pall, *Yall, *Lall, *Bm;
     int ncp;   // nc rounded up to a multiple of 32 (blocked triangular solves)
-    int ldy;   // leading dimension of Z_k and of [M_ux | m_u]: ns + 1 rounded up to a multiple of 4
+    int ldy;   // leading dimension of Y_k and of [M_ux | m_u]: the smallest value >= ns + 1 that is 4 mod 8 (conflict-free DMMA fragment loads)
     double T, df, ny_nzb, nzb_cnt;
     int n_reg, n_resto, n_soc, n_fact, n_ls;
     // shared-memory carve-up (doubles)
@@ -81,7 +81,7 @@ struct BlockSolver {
     static NMPC_HD long long ws_doubles(int Nr, int N, int nobs = 0)
     {
         const long long S = N + 1, ns = 3 * Nr, nc = 2 * Nr, W = row_width(Nr, nobs);
-        const long long ldy = (ns + 1 + 3) & ~3LL;
+        const long long ldy = ((ns + 4) & ~7LL) + 4;
         const long long ncp = (nc + 31) & ~31LL;
         return (long long)R_COUNT * S * W + ((S * ns * ns + 1) & ~1LL) + (long long)(N + 1) * nc * ldy + (long long)N * ncp * ncp   // every block 16-byte aligned
                + 2 * NMPC_FILTER_CAP;   // the filter (theta values, then phi values), see filter_add
@@ -89,7 +89,7 @@ struct BlockSolver {
     static NMPC_HD long long sm_doubles(int Nr)
     {
         const long long ns = 3 * Nr, nc = 2 * Nr, nz = 5 * Nr, ncp = (nc + 31) & ~31LL, ns4 = (ns + 3) & ~3LL;
-        const long long a = ncp * (ncp + 1), b = nc * ((ns + 1 + 3) & ~3LL);   // Cholesky factor (leading dimension ncp + 1: conflict-free columns), then Y resident for the triangular solve and the rank-k update
+        const long long a = ncp * (ncp + 4), b = ((nc + 3) & ~3LL) * (((ns + 4) & ~7LL) + 4);   // Cholesky factor (leading dimension ncp + 1: conflict-free columns), then Y resident for the triangular solve and the rank-k update
         (void)ns4;
         return 32 * 12 + 16 + 16 + 8 + nz + ns + 3 * ncp + ns + 7 * Nr + (a > b ? a : b) + 16;
     }
@@ -106,6 +106,13 @@ struct BlockSolver {
     __device__ __forceinline__ double xs(int l) const { return l < ns ? pp[ns + l] : 0.0; }
     __device__ __forceinline__ double gradf(int k, int l, double z) const { return k < N ? qw(l) * (z - xs(l)) : 0.0; }
     __device__ __forceinline__ int nvalid(int k) const { return k < N ? nz : ns; }
+
+    // FP64 tensor instruction: D (8 x 8) += A (8 x 4) B (4 x 8) over a warp.  Lane l = 4 g + t holds A[g][t], B[t][g] and D[g][2 t], D[g][2 t + 1].
+    // On B200 it has the DFMA pipe's peak (nmpc_probe_dmma) but needs a quarter of the operand traffic of 4 x 4 register tiles.
+    static __device__ __forceinline__ void dmma(double (&c)[2], double a, double b)
+    {
+        asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+    }
 
     // block-wide reduction of K values at once; bit i of maxmask: max (else sum); bit i of minmask: min
     template <int K>
@@ -154,7 +161,7 @@ struct BlockSolver {
         pp = P.p + (long long)inst * 2 * ns;
         pairs = P.pairs;
         Pall = ws + (long long)R_COUNT * S * W;
-        ldy = (ns + 1 + 3) & ~3; ncp = (nc + 31) & ~31;
+        ldy = ((ns + 4) & ~7) + 4; ncp = (nc + 31) & ~31;
         Yall = Pall + (((long long)S * ns * ns + 1) & ~1LL);
         Bm = Yall + (long long)N * nc * ldy;
         Lall = Bm + (long long)nc * ldy;
@@ -482,6 +489,7 @@ struct BlockSolver {
             const double *Pn = Pall + (long long)(k + 1) * ns * ns;
             double *Pk = Pall + (long long)k * ns * ns, *Yk = Yall + (long long)k * nc * ldy, *Lk = Lall + (long long)k * ncp * ncp;
             const double *cf = row(R_COEF, k), *cf2 = row(R_COEF2, k);
+            const int lds = ncp + 4;   // shared-memory leading dimension of M_uu / L: 4 mod 16, so the 8 x 4 DMMA fragment loads are conflict-free
             // A. pr = p_{k+1} - P_{k+1} rc_{k+1}   (one warp per row)
             {
                 const double *rcn = row(R_RC, k + 1), *pn = row(R_LIN, k + 1);
@@ -563,62 +571,116 @@ struct BlockSolver {
 #pragma unroll
                     for (int c = 0; c < 3; c++) Bm[(long long)(2 * i + a) * ldy + 3 * j + c] = G[3 + a][c];
 #pragma unroll
-                    for (int c = 0; c < 2; c++) Muu[(2 * i + a) * nc + 2 * j + c] = G[3 + a][3 + c];
+                    for (int c = 0; c < 2; c++) Muu[(2 * i + a) * lds + 2 * j + c] = G[3 + a][3 + c];
                 }
             }
+            for (int e = nc * ncp + tid; e < ncp * ncp; e += nt) { const int r = e / ncp, c = e - r * ncp; Muu[r * lds + c] = r == c ? 1.0 : 0.0; }   // identity padding up to a multiple of 32
             __syncthreads();
             NMPC_PROF(2);
-            // C. right-looking Cholesky M_uu = L L'.  Thread (ti, tj) keeps rows 8 ti .. 8 ti + 7 and columns tj + 32 q of the
-            //    trailing matrix in registers; the pivot column is broadcast through a double-buffered shared vector; L goes to
-            //    shared memory (leading dimension ncp, identity padding).  Pivot <= 0: wrong inertia.
+            // C. blocked right-looking Cholesky M_uu = L L', in place in shared memory (lower triangle, leading dimension lds), by
+            //    32-column panels: (1) warp 0 factors the 32 x 32 diagonal block in registers (lane = row, pivot rows exchanged by
+            //    shuffles: no CTA barrier inside a panel); (2) one thread per row below it solves x L11' = a by substitution
+            //    (L11 broadcast from shared memory); (3) the trailing matrix takes its rank-32 update as 8 x 8 tiles on the FP64
+            //    tensor instruction.  Three CTA barriers per panel instead of one per column.  Pivot <= 0: wrong inertia.
             double *Ls = Muu;
-            const int lds = ncp + 1;   // shared-memory leading dimension of L: the per-pivot column store and the transposed
-                                       // write of the diagonal-block inverses had 32-way bank conflicts at ncp (23 M conflicts per short solve)
             {
-                const int ti = tid >> 5, tj = tid & 31;
-                double tile[8][4];
+                const int g4 = lane >> 2, t4 = lane & 3;
+                const int nc8 = (nc + 7) >> 3;   // 8-row tiles that hold rows of M_uu
+                for (int j0 = 0; j0 < nc; j0 += 32) {
+                    if (wid == 0) {
+                        double a[32];
+                        double *rp = Ls + (j0 + lane) * lds + j0;
 #pragma unroll
-                for (int a = 0; a < 8; a++)
+                        for (int c = 0; c < 32; c++) a[c] = rp[c];
+                        double myrinv = 1.0;
+                        bool ok = true;
+                        // One straight-line block (a bad pivot only clears `ok`; the NaNs it produces are discarded): step j first brings
+                        // column j + 1 up to date and starts its reciprocal square root, then applies the other 30 - j updates of
+                        // column j underneath that latency.
+                        double d = __shfl_sync(0xffffffffu, a[0], 0);
+                        ok = d > 0.0 && d < NMPC_INF;
+                        double rinv = wp::rsqrt_pos(d);
+                        double *cb = colb + 32;   // two 32-entry column buffers (colb .. colb + 3 ncp is scratch here: the reciprocal diagonals sit in colb[0 .. 31])
 #pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const int r = 8 * ti + a, c = tj + 32 * q;
-                        tile[a][q] = (r < nc && c < nc) ? Muu[r * nc + c] : 0.0;
+                        for (int j = 0; j < 32; j++) {
+                            const double lij = a[j] * rinv;   // L[lane][j], meaningful for lane >= j
+                            a[j] = lij;
+                            if (lane == j) myrinv = rinv;
+                            double *cj = cb + (j & 1) * 32;
+                            cj[lane] = lij;                   // column j for everybody: shuffles would cost two issue slots per entry
+                            if (j + 1 < 32) {
+                                a[j + 1] = fma(-lij, __shfl_sync(0xffffffffu, lij, j + 1), a[j + 1]);   // the critical entry does not wait for shared memory
+                                d = __shfl_sync(0xffffffffu, a[j + 1], j + 1);
+                                ok = ok && d > 0.0 && d < NMPC_INF;   // uniform: every lane holds the same value
+                                rinv = wp::rsqrt_pos(d);
+                            }
+                            __syncwarp();
+#pragma unroll
+                            for (int c = j + 2; c < 32; c++) a[c] = fma(-lij, cj[c], a[c]);   // meaningful for lane >= c
+                        }
+                        if (ok) {
+#pragma unroll
+                            for (int c = 0; c < 32; c++)
+                                if (c <= lane) rp[c] = a[c];
+                            colb[lane] = myrinv;
+                        }
+                        if (lane == 0) sm[SM_MISC + 3] = ok ? 1.0 : 0.0;
                     }
-                __syncthreads();
-                for (int e = tid; e < ncp * ncp; e += nt) { const int r = e / ncp, c = e - r * ncp; Ls[r * lds + c] = (r == c && r >= nc) ? 1.0 : 0.0; }
-                if (tj == 0 && 8 * ti < ncp) {
+                    __syncthreads();
+                    NMPC_PROF(8);
+                    if (sm[SM_MISC + 3] == 0.0) return false;   // uniform
+                    // (2) rows below the diagonal block: x <- x L11^-T, right-looking so that the 31 updates of a step are independent
+                    {
+                        const int r = j0 + 32 + tid;
+                        if (r < nc) {
+                            double x[32];
+                            double *rp = Ls + r * lds + j0;
+                            const double *l11 = Ls + j0 * lds + j0;
 #pragma unroll
-                    for (int a = 0; a < 8; a++) colb[8 * ti + a] = tile[a][0];
-                }
-                __syncthreads();
-                for (int j = 0; j < nc; j++) {
-                    const double *cb = colb + (j & 1) * ncp;
-                    double *cbn = colb + ((j + 1) & 1) * ncp;
-                    const double d = cb[j];
-                    if (!(d > 0.0) || !(d < NMPC_INF)) return false;   // uniform: every thread reads the same value
-                    const double inv = wp::rcp_pos(d), rinv = rsqrt(d);   // d is positive and finite here: MUFU seed + two Newton steps instead of the IEEE division sequence
-                    if (8 * ti + 7 > j) {   // warp-uniform: this warp still owns rows of the trailing matrix
-                        double ca[8], cc[4];
+                            for (int c = 0; c < 32; c++) x[c] = rp[c];
 #pragma unroll
-                        for (int a = 0; a < 8; a++) { const int r = 8 * ti + a; ca[a] = r > j ? cb[r] : 0.0; }
+                            for (int c = 0; c < 32; c++) {
+                                x[c] *= colb[c];
 #pragma unroll
-                        for (int q = 0; q < 4; q++) { const int c = tj + 32 * q; cc[q] = c > j ? cb[c] * inv : 0.0; }
+                                for (int c2 = c + 1; c2 < 32; c2++) x[c2] = fma(-x[c], l11[c2 * lds + c], x[c2]);
+                            }
 #pragma unroll
-                        for (int a = 0; a < 8; a++)
-#pragma unroll
-                            for (int q = 0; q < 4; q++) tile[a][q] -= ca[a] * cc[q];
+                            for (int c = 0; c < 32; c++) rp[c] = x[c];
+                        }
                     }
-                    for (int t = tid; t < nc; t += nt) Ls[t * lds + j] = t >= j ? cb[t] * rinv : 0.0;   // column j: stride lds = ncp + 1 doubles, no bank conflict
-                    if (j + 1 < nc && tj == ((j + 1) & 31) && 8 * ti < ncp) {   // owners of the next pivot column publish it
-                        const int jq = (j + 1) >> 5;
+                    __syncthreads();
+                    NMPC_PROF(9);
+                    // (3) trailing update A22 -= L21 L21' on the lower 8 x 8 tiles: unit = one tile row x up to four tile columns
+                    {
+                        const int t0 = (j0 >> 3) + 4;
+                        int cnt = 0;
+                        for (int ti = t0; ti < nc8; ti++)
+                            for (int tj0 = t0; tj0 <= ti; tj0 += 4, cnt++) {
+                                if (cnt % nw != wid) continue;
+                                double acc[4][2];
+                                double *cp = Ls + (8 * ti + g4) * lds + 8 * tj0 + 2 * t4;
 #pragma unroll
-                        for (int q = 0; q < 4; q++)
-                            if (q == jq) {
+                                for (int q = 0; q < 4; q++) {
+                                    const double2 v = tj0 + q <= ti ? *reinterpret_cast<const double2 *>(cp + 8 * q) : make_double2(0.0, 0.0);
+                                    acc[q][0] = v.x; acc[q][1] = v.y;
+                                }
+                                const double *la = Ls + (8 * ti + g4) * lds + j0 + t4, *lb = Ls + (8 * tj0 + g4) * lds + j0 + t4;
 #pragma unroll
-                                for (int a = 0; a < 8; a++) cbn[8 * ti + a] = tile[a][q];
+                                for (int s4 = 0; s4 < 8; s4++) {
+                                    const double av = -la[4 * s4];
+#pragma unroll
+                                    for (int q = 0; q < 4; q++) {
+                                        const double bv = tj0 + q <= ti ? lb[8 * q * lds + 4 * s4] : 0.0;
+                                        dmma(acc[q], av, bv);
+                                    }
+                                }
+#pragma unroll
+                                for (int q = 0; q < 4; q++)
+                                    if (tj0 + q <= ti) *reinterpret_cast<double2 *>(cp + 8 * q) = make_double2(acc[q][0], acc[q][1]);
                             }
                     }
                     __syncthreads();
+                    NMPC_PROF(10);
                 }
             }
             // inverses of the 32 x 32 diagonal blocks of L (one warp per block, one column per lane), stored transposed in
@@ -650,131 +712,163 @@ struct BlockSolver {
             for (int e = tid; e < ncp * ncp; e += nt) { const int r = e / ncp, c = e - r * ncp; Lk[e] = Ls[r * lds + c]; }   // kept for the forward pass (lower triangle), leading dimension ncp in global memory
             NMPC_PROF(3);
             // D. Y = L^-1 [M_ux | m_u] with Y resident in shared memory (it stays there for the rank-k update): blocked forward
-            //    substitution over 32-row blocks, 4x4 register tiles; L (and the inverses of its diagonal blocks, stored
-            //    transposed in the upper triangles) is read back from global memory through L1
+            //    substitution over 32-row blocks on the FP64 tensor instruction (mma.sync m8n8k4, see dmma()).  A unit of work is one
+            //    8-row tile row of the block times four 8-column tiles; its accumulators stay in registers over the whole
+            //    contraction.  L (and the inverses of its diagonal blocks, stored transposed in the upper triangles) is read back
+            //    from global memory as A fragments; the B fragments come from the rows of Y that are already final.
             __syncthreads();   // Ls has been copied to Lk by every thread: its shared memory now becomes Y
             double *Ys = Muu;
+            const int nt8 = (ns + 1 + 7) >> 3;   // 8-column tiles of [Y | y_m]
+            const int g4 = lane >> 2, t4 = lane & 3;
             {
                 const double *Lg = Lk;
                 for (int e = tid; e < nc * (ldy / 2); e += nt)
                     reinterpret_cast<double2 *>(Ys)[e] = reinterpret_cast<const double2 *>(Bm)[e];
+                for (int e = nc * ldy + tid; e < ((nc + 3) & ~3) * ldy; e += nt) Ys[e] = 0.0;   // rows up to a multiple of four: zero (k-steps of the rank-k update)
                 __syncthreads();
-                const int tcn = ldy / 4, nblk = ncp >> 5;
-                const int tr = tid / tcn, tc = tid - tr * tcn;   // 8 tile rows x (ldy / 4) tile columns per 32-row block
-                const bool act = tr < 8;
-                const int c0 = 4 * tc;
+                NMPC_PROF(11);
+                const int nblk = ncp >> 5, ngrp = (nt8 + 3) >> 2;
+                // warp -> (tile row, column groups): the four warps wid = 4 h .. 4 h + 3 take the four tile rows (rotated, so that the
+                // warps of one scheduler hold different tile rows: phase 2's work grows with the tile row) of the column groups
+                // g = h, h + nw / 4 (ngrp <= nw / 2 for every Nr: at most two groups per warp)
+                const int ta = (wid + (wid >> 2)) & 3, gh = wid >> 2, gstep = nw >> 2;
                 for (int I = 0; I < nblk; I++) {
-                    const int r0 = 32 * I + 4 * tr;
-                    double acc[4][4];
-                    if (act && r0 < nc) {
+                    const bool rowact = 32 * I + 8 * ta < nc;   // warp-uniform: this tile row holds rows of Y
+                    const int r = 32 * I + 8 * ta + g4;         // this thread's row of the C fragments
+                    double acc[2][4][2];
+                    double al[8];
+                    if (rowact) {
+                        // phase 1: T_I = B_I - L_{I, 0:I} Y_{0:I}, written back in place (every unit owns its tile).  The A fragments
+                        // -L[r][4 s + t4] do not depend on Y: all of them are requested at once (one L2 round trip per block).
+                        if (I > 0) {
+                            double af[24];
+                            const double *la = Lg + (long long)r * ncp + t4;
 #pragma unroll
-                        for (int a = 0; a < 4; a++) {
-                            const double2 *yo = reinterpret_cast<const double2 *>(Ys + (r0 + a) * ldy + c0);
-                            const double2 o01 = r0 + a < nc ? yo[0] : make_double2(0.0, 0.0), o23 = r0 + a < nc ? yo[1] : make_double2(0.0, 0.0);
-                            acc[a][0] = o01.x; acc[a][1] = o01.y; acc[a][2] = o23.x; acc[a][3] = o23.y;
-                        }
-#pragma unroll 4
-                        for (int u = 0; u < 32 * I; u++) {
-                            const double2 *yu = reinterpret_cast<const double2 *>(Ys + u * ldy + c0);
-                            const double2 y01 = yu[0], y23 = yu[1];
-                            const double yv[4] = {y01.x, y01.y, y23.x, y23.y};
+                            for (int s4 = 0; s4 < 24; s4++) af[s4] = s4 < 8 * I ? -__ldg(la + 4 * s4) : 0.0;
 #pragma unroll
-                            for (int a = 0; a < 4; a++) {
-                                const double lv = __ldg(Lg + (long long)(r0 + a) * ncp + u);
+                            for (int rd = 0; rd < 2; rd++) {
+                                const int g = gh + rd * gstep, j0 = 4 * g;
+                                if (g >= ngrp) continue;   // warp-uniform
+                                double c1[4][2];
 #pragma unroll
-                                for (int c = 0; c < 4; c++) acc[a][c] -= lv * yv[c];
+                                for (int q = 0; q < 4; q++) {
+                                    const int cc = 8 * (j0 + q) + 2 * t4;
+                                    const bool ok = r < nc && j0 + q < nt8 && cc < ldy;
+                                    const double2 v = ok ? *reinterpret_cast<const double2 *>(Ys + r * ldy + cc) : make_double2(0.0, 0.0);
+                                    c1[q][0] = v.x; c1[q][1] = v.y;
+                                }
+                                const double *yb = Ys + t4 * ldy + 8 * j0 + g4;   // B fragment: Y[4 s + t4][8 (j0 + q) + g4]
+#pragma unroll
+                                for (int s4 = 0; s4 < 24; s4++) {
+                                    if (s4 < 8 * I) {
+#pragma unroll
+                                        for (int q = 0; q < 4; q++) {
+                                            const double b = j0 + q < nt8 ? yb[4 * s4 * ldy + 8 * q] : 0.0;
+                                            dmma(c1[q], af[s4], b);
+                                        }
+                                    }
+                                }
+#pragma unroll
+                                for (int q = 0; q < 4; q++) {
+                                    const int cc = 8 * (j0 + q) + 2 * t4;
+                                    if (r < nc && j0 + q < nt8 && cc < ldy)
+                                        *reinterpret_cast<double2 *>(Ys + r * ldy + cc) = make_double2(c1[q][0], c1[q][1]);
+                                }
                             }
                         }
+                        // A fragments of phase 2, requested before the barrier: Linv_II[i][u] (u < i) sits at L[32 I + u][32 I + i], its diagonal in dinv
+                        const int rl = 8 * ta + g4;   // block-local row
 #pragma unroll
-                        for (int a = 0; a < 4; a++)
-                            if (r0 + a < nc) {
-                                double2 *yw = reinterpret_cast<double2 *>(Ys + (r0 + a) * ldy + c0);
-                                yw[0] = make_double2(acc[a][0], acc[a][1]); yw[1] = make_double2(acc[a][2], acc[a][3]);
-                            }
+                        for (int s4 = 0; s4 < 8; s4++) {
+                            const int u = 4 * s4 + t4;
+                            al[s4] = s4 < 2 * ta + 2 ? (u < rl ? __ldg(Lg + (long long)(32 * I + u) * ncp + 32 * I + rl) : (u == rl ? dinv[32 * I + rl] : 0.0)) : 0.0;
+                        }
                     }
                     __syncthreads();
-                    double out[4][4];
-                    if (act && r0 < nc) {   // y = Linv_II t;  Linv_II[i][u] (u < i) sits at L[32 I + u][32 I + i], its diagonal in dinv
+                    NMPC_PROF(12);
+                    // phase 2: Y_I = Linv_II T_I (lower triangular: tile row ta contracts over 8 ta + 8 rows).  Results are held until
+                    // every unit has read T_I.
+                    if (rowact) {
 #pragma unroll
-                        for (int a = 0; a < 4; a++) {
-                            const double di = dinv[r0 + a];
+                        for (int rd = 0; rd < 2; rd++) {
+                            const int g = gh + rd * gstep, j0 = 4 * g;
+                            if (g >= ngrp) continue;
 #pragma unroll
-                            for (int c = 0; c < 4; c++) out[a][c] = acc[a][c] * di;
-                        }
-                        const int rl = 4 * tr;   // local row of the tile inside the block
-                        const int ub = rl + 3 < nc - 32 * I ? rl + 3 : nc - 32 * I;   // rows of Y beyond nc do not exist
-                        for (int u = 0; u < ub; u++) {
-                            const double2 *yu = reinterpret_cast<const double2 *>(Ys + (32 * I + u) * ldy + c0);
-                            const double2 y01 = yu[0], y23 = yu[1];
-                            const double yv[4] = {y01.x, y01.y, y23.x, y23.y};
+                            for (int q = 0; q < 4; q++) { acc[rd][q][0] = 0.0; acc[rd][q][1] = 0.0; }
+                            const double *yb = Ys + (32 * I + t4) * ldy + 8 * j0 + g4;
 #pragma unroll
-                            for (int a = 0; a < 4; a++) {
-                                const double lv = u < rl + a ? __ldg(Lg + (long long)(32 * I + u) * ncp + r0 + a) : 0.0;
+                            for (int s4 = 0; s4 < 8; s4++) {
+                                if (s4 < 2 * ta + 2) {
+                                    const bool rowok = 32 * I + 4 * s4 + t4 < nc;
 #pragma unroll
-                                for (int c = 0; c < 4; c++) out[a][c] += lv * yv[c];
+                                    for (int q = 0; q < 4; q++) {
+                                        const double b = rowok && j0 + q < nt8 ? yb[4 * s4 * ldy + 8 * q] : 0.0;
+                                        dmma(acc[rd][q], al[s4], b);
+                                    }
+                                }
                             }
                         }
                     }
                     __syncthreads();
-                    if (act && r0 < nc) {
+                    if (rowact) {
 #pragma unroll
-                        for (int a = 0; a < 4; a++)
-                            if (r0 + a < nc) {
-                                double2 *yw = reinterpret_cast<double2 *>(Ys + (r0 + a) * ldy + c0);
-                                yw[0] = make_double2(out[a][0], out[a][1]); yw[1] = make_double2(out[a][2], out[a][3]);
+                        for (int rd = 0; rd < 2; rd++) {
+                            const int g = gh + rd * gstep, j0 = 4 * g;
+                            if (g >= ngrp) continue;
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                const int cc = 8 * (j0 + q) + 2 * t4;
+                                if (r < nc && j0 + q < nt8 && cc < ldy)
+                                    *reinterpret_cast<double2 *>(Ys + r * ldy + cc) = make_double2(acc[rd][q][0], acc[rd][q][1]);
                             }
+                        }
                     }
                     __syncthreads();
+                    NMPC_PROF(13);
                 }
                 for (int e = tid; e < nc * (ldy / 2); e += nt)   // kept for the forward pass
                     reinterpret_cast<double2 *>(Yk)[e] = reinterpret_cast<const double2 *>(Ys)[e];
             }
             NMPC_PROF(4);
-            // F. P_k = M_xx - Y'Y (upper 4x4 tiles over Y resident in shared memory, mirrored), p_k = m_x - Y' y_m
+            // F. [P_k | p_k] = [M_xx | m_x] - Y' [Y | y_m]: the upper 8 x 8 tiles of the Gram matrix of the resident Y on the FP64 tensor
+            //    instruction, one tile row times four tile columns per unit (A fragment shared by the four), mirrored on the store
             {
-                const int ns4 = (ns + 3) & ~3, nt4 = ns4 / 4;
-                const int ntri = nt4 * (nt4 + 1) / 2;   // upper-triangular tiles, enumerated densely: every thread gets its share
-                for (int e = tid; e < ntri; e += nt) {
-                    int tr = (int)(((2 * nt4 + 1) - sqrt((double)(2 * nt4 + 1) * (2 * nt4 + 1) - 8.0 * e)) * 0.5);
-                    while (tr > 0 && tr * (2 * nt4 - tr + 1) / 2 > e) tr--;
-                    while ((tr + 1) * (2 * nt4 - tr) / 2 <= e) tr++;
-                    const int tc = e - tr * (2 * nt4 - tr + 1) / 2 + tr;
-                    const int r0 = 4 * tr, c0 = 4 * tc;
-                    double acc[4][4], pv[4][4];
+                int cnt = 0;
+                const int nk4 = (nc + 3) >> 2;
+                for (int ti = 0; ti < nt8; ti++)
+                    for (int j0 = ti; j0 < nt8; j0 += 4, cnt++) {
+                        if (cnt % nw != wid) continue;
+                        const int r = 8 * ti + g4;
+                        double acc[4][2], pv[4][2];
 #pragma unroll
-                    for (int a = 0; a < 4; a++)
+                        for (int q = 0; q < 4; q++)
 #pragma unroll
-                        for (int c = 0; c < 4; c++) {   // M_xx tile: issued before the contraction so that its latency overlaps
-                            acc[a][c] = 0.0;
-                            pv[a][c] = (r0 + a < ns && c0 + c < ns) ? Pk[(long long)(r0 + a) * ns + c0 + c] : 0.0;
-                        }
+                            for (int e = 0; e < 2; e++) {   // M_xx tile: issued before the contraction so that its latency overlaps
+                                const int cc = 8 * (j0 + q) + 2 * t4 + e;
+                                acc[q][e] = 0.0;
+                                pv[q][e] = (r < ns && cc < ns && r <= cc) ? Pk[(long long)r * ns + cc] : 0.0;
+                            }
+                        const double *ya = Ys + t4 * ldy + 8 * ti + g4, *yb = Ys + t4 * ldy + 8 * j0 + g4;
 #pragma unroll 4
-                    for (int u = 0; u < nc; u++) {
-                        const double2 *yr = reinterpret_cast<const double2 *>(Ys + u * ldy + r0);
-                        const double2 *yc = reinterpret_cast<const double2 *>(Ys + u * ldy + c0);
-                        const double2 y01 = yr[0], y23 = yr[1], z01 = yc[0], z23 = yc[1];
-                        const double ya[4] = {y01.x, y01.y, y23.x, y23.y}, zc[4] = {z01.x, z01.y, z23.x, z23.y};
+                        for (int s4 = 0; s4 < nk4; s4++) {
+                            const double a = ya[4 * s4 * ldy];
 #pragma unroll
-                        for (int a = 0; a < 4; a++)
-#pragma unroll
-                            for (int c = 0; c < 4; c++) acc[a][c] += ya[a] * zc[c];
-                    }
-#pragma unroll
-                    for (int a = 0; a < 4; a++)
-#pragma unroll
-                        for (int c = 0; c < 4; c++) {
-                            const int r = r0 + a, cc = c0 + c;
-                            if (r < ns && cc < ns && r <= cc) {
-                                const double v = pv[a][c] - acc[a][c];
-                                Pk[(long long)r * ns + cc] = v; Pk[(long long)cc * ns + r] = v;
+                            for (int q = 0; q < 4; q++) {
+                                const double b = j0 + q < nt8 ? yb[4 * s4 * ldy + 8 * q] : 0.0;
+                                dmma(acc[q], a, b);
                             }
                         }
-                }
-                for (int r = tid; r < ns; r += nt) {
-                    double acc = 0.0;
-                    for (int u = 0; u < nc; u++) acc += Ys[u * ldy + r] * Ys[u * ldy + ns];
-                    row(R_LIN, k)[r] -= acc;
-                }
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+#pragma unroll
+                            for (int e = 0; e < 2; e++) {
+                                const int cc = 8 * (j0 + q) + 2 * t4 + e;
+                                if (r < ns && cc < ns && r <= cc) {
+                                    const double v = pv[q][e] - acc[q][e];
+                                    Pk[(long long)r * ns + cc] = v; Pk[(long long)cc * ns + r] = v;
+                                } else if (r < ns && cc == ns) row(R_LIN, k)[r] -= acc[q][e];
+                            }
+                    }
             }
             __syncthreads();
             NMPC_PROF(5);

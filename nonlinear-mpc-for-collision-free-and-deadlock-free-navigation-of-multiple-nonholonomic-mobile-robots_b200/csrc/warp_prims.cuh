@@ -39,6 +39,16 @@ NMPC_DEV double rcp_pos(double d)
     e = fma(-d, r, 1.0);
     return fma(r, e, r);
 }
+// 1 / sqrt(d) for a positive, finite, normal d: MUFU seed (2^-22) and two Newton steps, no special-case branches
+NMPC_DEV double rsqrt_pos(double d)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double e = fma(-d * y, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    e = fma(-d * y, y, 1.0);
+    return fma(0.5 * y, e, y);
+}
 // L2 prefetch of a line that a later stage of the same pass will read (the per-warp scratch does not fit L1)
 NMPC_DEV void prefetch(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // asynchronous 16-byte global -> shared copy (LDGSTS, L2-only caching): stages the scratch rows of the NEXT Riccati
