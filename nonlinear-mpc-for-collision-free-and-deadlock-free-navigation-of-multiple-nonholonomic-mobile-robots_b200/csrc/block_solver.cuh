@@ -43,12 +43,13 @@ __device__ long long g_block_prof[16];
     const double *const obs = wp::global_ptr(this->obs);                                                               \
     const int Mp = this->Mp, nobs = this->nobs;                                                                        \
     double *const Pall = wp::global_ptr(this->Pall), *const Yall = wp::global_ptr(this->Yall),                          \
-                 *const Lall = wp::global_ptr(this->Lall), *const Bm = wp::global_ptr(this->Bm);                        \
+                 *const Lall = wp::global_ptr(this->Lall), *const Bm = wp::global_ptr(this->Bm),                        \
+                 *const Wg = wp::global_ptr(this->Wg);                                                                 \
     const int S = this->S, W = this->W, N = this->N, Nr = this->Nr, ns = this->ns, nc = this->nc, nz = this->nz,        \
               M = this->M, tid = this->tid, nt = this->nt;                                                             \
     auto row = [=](int r, int k) -> double * { return ws + ((long long)r * S + k) * W; };                              \
     (void)sm; (void)ws; (void)BL; (void)BU; (void)CE; (void)DL; (void)DU; (void)pp; (void)pairs; (void)Pall;            \
-    (void)Yall; (void)Lall; (void)Bm; (void)S; (void)W; (void)N; (void)Nr; (void)ns; (void)nc; (void)nz; (void)M;       \
+    (void)Yall; (void)Lall; (void)Bm; (void)Wg; (void)S; (void)W; (void)N; (void)Nr; (void)ns; (void)nc; (void)nz; (void)M;       \
     (void)tid; (void)nt; (void)row; (void)obs; (void)Mp; (void)nobs;
 
 struct BlockSolver {
@@ -69,12 +70,14 @@ struct BlockSolver {
     const double *obs;                                    // [nobs][3]: centre x, y, clearance radius
     const double *BL, *BU, *CE, *DL, *DU, *pp;
     const int *pairs;
-    double *Pall, *Yall, *Lall, *Bm;
+    double *Pall, *Yall, *Lall, *Bm, *Wg;   // Wg: Linv_II L_IJ blocks of the stage being factored (see factor, step D)
     int ncp;   // nc rounded up to a multiple of 32 (blocked triangular solves)
     int ldy;   // leading dimension of Y_k and of [M_ux | m_u]: the smallest value >= ns + 1 that is 4 mod 8 (conflict-free DMMA fragment loads)
     double T, df, ny_nzb, nzb_cnt;
     int n_reg, n_resto, n_soc, n_fact, n_ls;
     // shared-memory carve-up (doubles)
+    static constexpr int SM_MBAR = 32 * 12 + 16 + 16 + 4;   // = SM_MISC + 4: the CTA's mbarrier (initialised once per kernel)
+    unsigned bar_phase = 0;
     int SM_RED, SM_FTH, SM_FPH, SM_MISC, SM_DZB, SM_DXN, SM_TB, SM_XB, SM_DINV, SM_PR, SM_CS, SM_DS, SM_MUU;
 
     static NMPC_HD int row_width(int Nr, int nobs = 0) { int nz = 5 * Nr, M = Nr * (Nr - 1) / 2 + Nr * nobs, w = nz > M ? nz : M; return (w + 31) & ~31; }
@@ -84,7 +87,7 @@ struct BlockSolver {
         const long long ldy = ((ns + 4) & ~7LL) + 4;
         const long long ncp = (nc + 31) & ~31LL;
         return (long long)R_COUNT * S * W + ((S * ns * ns + 1) & ~1LL) + (long long)(N + 1) * nc * ldy + (long long)N * ncp * ncp   // every block 16-byte aligned
-               + 2 * NMPC_FILTER_CAP;   // the filter (theta values, then phi values), see filter_add
+               + (ncp / 32) * (ncp / 32 - 1) / 2 * 1024 + 2 * NMPC_FILTER_CAP;   // the filter (theta values, then phi values), see filter_add
     }
     static NMPC_HD long long sm_doubles(int Nr)
     {
@@ -165,6 +168,7 @@ struct BlockSolver {
         Yall = Pall + (((long long)S * ns * ns + 1) & ~1LL);
         Bm = Yall + (long long)N * nc * ldy;
         Lall = Bm + (long long)nc * ldy;
+        Wg = Lall + (long long)N * ncp * ncp;
         SM_RED = 0; SM_FTH = 32 * 12; SM_FPH = SM_FTH + 16; SM_MISC = SM_FPH + 16; SM_DZB = SM_MISC + 8; SM_DXN = SM_DZB + nz;
         SM_TB = SM_DXN + ns; SM_XB = SM_TB + ncp; SM_DINV = SM_XB + ncp; SM_PR = SM_DINV + ncp; SM_CS = SM_PR + ns; SM_DS = SM_CS + 2 * Nr; SM_MUU = (SM_DS + 5 * Nr + 1) & ~1;
         df = 1.0; fn = 0;
@@ -509,7 +513,9 @@ struct BlockSolver {
                     }
                 }
             }
-            // per-robot sums of the condensed collision blocks (curvature and gradient), one (array, robot) per thread
+            // per-robot sums of the condensed collision blocks (curvature and gradient), one (array, robot) per thread: consecutive
+            // lanes are consecutive robots, so the gathers of a warp fall into few sectors (a warp-per-sum variant with the partners
+            // spread over the lanes was measured twice as slow: its gathers are strided)
             {
                 double *dsum = sm + SM_DS;
                 for (int idx = tid; idx < 5 * Nr; idx += nt) {
@@ -710,6 +716,33 @@ struct BlockSolver {
             }
             __syncthreads();
             for (int e = tid; e < ncp * ncp; e += nt) { const int r = e / ncp, c = e - r * ncp; Lk[e] = Ls[r * lds + c]; }   // kept for the forward pass (lower triangle), leading dimension ncp in global memory
+            // W_IJ = Linv_II L_IJ for the blocks below the diagonal (I > J), while L is still in shared memory: with V = blockdiag(Linv) B
+            // the forward substitution becomes Y_I = V_I - sum_{J < I} W_IJ Y_J, one contraction and one barrier per block row instead of
+            // a contraction, a barrier, a triangular product and two more barriers.  W goes to the CTA's scratch (A fragments later).
+            {
+                const int g4 = lane >> 2, t4 = lane & 3, nblk = ncp >> 5;
+                const int nunit = 2 * nblk * (nblk - 1);   // (block pair, tile row)
+                for (int unit = wid; unit < nunit; unit += nw) {
+                    const int ta = (unit + (unit >> 2)) & 3, bp = unit >> 2;
+                    int I = 1;
+                    while ((I + 1) * I / 2 <= bp) I++;
+                    const int J = bp - I * (I - 1) / 2;
+                    const int rl = 8 * ta + g4;
+                    double acc[4][2];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) { acc[q][0] = 0.0; acc[q][1] = 0.0; }
+                    const double *lb = Ls + (32 * I + t4) * lds + 32 * J + g4;   // B fragment: L[32 I + 4 s + t4][32 J + 8 q + g4]
+                    for (int s4 = 0; s4 < 2 * ta + 2; s4++) {
+                        const int u = 4 * s4 + t4;
+                        const double a = u < rl ? Ls[(32 * I + u) * lds + 32 * I + rl] : (u == rl ? dinv[32 * I + rl] : 0.0);
+#pragma unroll
+                        for (int q = 0; q < 4; q++) dmma(acc[q], a, lb[4 * s4 * lds + 8 * q]);
+                    }
+                    double *wp_ = Wg + (long long)bp * 1024 + rl * 32 + 2 * t4;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) *reinterpret_cast<double2 *>(wp_ + 8 * q) = make_double2(acc[q][0], acc[q][1]);
+                }
+            }
             NMPC_PROF(3);
             // D. Y = L^-1 [M_ux | m_u] with Y resident in shared memory (it stays there for the rank-k update): blocked forward
             //    substitution over 32-row blocks on the FP64 tensor instruction (mma.sync m8n8k4, see dmma()).  A unit of work is one
@@ -722,110 +755,107 @@ struct BlockSolver {
             const int g4 = lane >> 2, t4 = lane & 3;
             {
                 const double *Lg = Lk;
-                for (int e = tid; e < nc * (ldy / 2); e += nt)
-                    reinterpret_cast<double2 *>(Ys)[e] = reinterpret_cast<const double2 *>(Bm)[e];
+                // [M_ux | m_u] (written by the build step with ordinary stores) comes in as ONE bulk copy (TMA, completion on the CTA's
+                // mbarrier): a thread-strided copy loop spent 10-18 k cycles per stage on L2 / DRAM round trips
+                if (tid == 0) {
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    const unsigned bytes = (unsigned)(nc * ldy) * 8u;
+                    wp::bulk_expect(sm + SM_MBAR, bytes);
+                    wp::bulk_g2s(Ys, Bm, bytes, sm + SM_MBAR);
+                }
                 for (int e = nc * ldy + tid; e < ((nc + 3) & ~3) * ldy; e += nt) Ys[e] = 0.0;   // rows up to a multiple of four: zero (k-steps of the rank-k update)
+                wp::mbar_wait(sm + SM_MBAR, bar_phase);
+                bar_phase ^= 1u;
                 __syncthreads();
                 NMPC_PROF(11);
                 const int nblk = ncp >> 5, ngrp = (nt8 + 3) >> 2;
-                // warp -> (tile row, column groups): the four warps wid = 4 h .. 4 h + 3 take the four tile rows (rotated, so that the
-                // warps of one scheduler hold different tile rows: phase 2's work grows with the tile row) of the column groups
-                // g = h, h + nw / 4 (ngrp <= nw / 2 for every Nr: at most two groups per warp)
-                const int ta = (wid + (wid >> 2)) & 3, gh = wid >> 2, gstep = nw >> 2;
-                for (int I = 0; I < nblk; I++) {
-                    const bool rowact = 32 * I + 8 * ta < nc;   // warp-uniform: this tile row holds rows of Y
-                    const int r = 32 * I + 8 * ta + g4;         // this thread's row of the C fragments
-                    double acc[2][4][2];
-                    double al[8];
-                    if (rowact) {
-                        // phase 1: T_I = B_I - L_{I, 0:I} Y_{0:I}, written back in place (every unit owns its tile).  The A fragments
-                        // -L[r][4 s + t4] do not depend on Y: all of them are requested at once (one L2 round trip per block).
-                        if (I > 0) {
-                            double af[24];
-                            const double *la = Lg + (long long)r * ncp + t4;
+                // V = blockdiag(Linv_II) B in place.  Unit = (block row I, group of four tile columns); the warp walks the four tile
+                // rows from the bottom up: tile row ta reads rows <= 8 ta + 7 of the block and writes its own, so the rows it leaves
+                // behind are still the original B.  Linv_II[i][u] (u < i) sits at L[32 I + u][32 I + i], its diagonal in dinv.
+                for (int unit = wid; unit < nblk * ngrp; unit += nw) {
+                    const int I = unit % nblk, j0 = 4 * (unit / nblk);
+                    double al[4][8];
 #pragma unroll
-                            for (int s4 = 0; s4 < 24; s4++) af[s4] = s4 < 8 * I ? -__ldg(la + 4 * s4) : 0.0;
-#pragma unroll
-                            for (int rd = 0; rd < 2; rd++) {
-                                const int g = gh + rd * gstep, j0 = 4 * g;
-                                if (g >= ngrp) continue;   // warp-uniform
-                                double c1[4][2];
-#pragma unroll
-                                for (int q = 0; q < 4; q++) {
-                                    const int cc = 8 * (j0 + q) + 2 * t4;
-                                    const bool ok = r < nc && j0 + q < nt8 && cc < ldy;
-                                    const double2 v = ok ? *reinterpret_cast<const double2 *>(Ys + r * ldy + cc) : make_double2(0.0, 0.0);
-                                    c1[q][0] = v.x; c1[q][1] = v.y;
-                                }
-                                const double *yb = Ys + t4 * ldy + 8 * j0 + g4;   // B fragment: Y[4 s + t4][8 (j0 + q) + g4]
-#pragma unroll
-                                for (int s4 = 0; s4 < 24; s4++) {
-                                    if (s4 < 8 * I) {
-#pragma unroll
-                                        for (int q = 0; q < 4; q++) {
-                                            const double b = j0 + q < nt8 ? yb[4 * s4 * ldy + 8 * q] : 0.0;
-                                            dmma(c1[q], af[s4], b);
-                                        }
-                                    }
-                                }
-#pragma unroll
-                                for (int q = 0; q < 4; q++) {
-                                    const int cc = 8 * (j0 + q) + 2 * t4;
-                                    if (r < nc && j0 + q < nt8 && cc < ldy)
-                                        *reinterpret_cast<double2 *>(Ys + r * ldy + cc) = make_double2(c1[q][0], c1[q][1]);
-                                }
-                            }
-                        }
-                        // A fragments of phase 2, requested before the barrier: Linv_II[i][u] (u < i) sits at L[32 I + u][32 I + i], its diagonal in dinv
-                        const int rl = 8 * ta + g4;   // block-local row
+                    for (int ta = 0; ta < 4; ta++)
 #pragma unroll
                         for (int s4 = 0; s4 < 8; s4++) {
-                            const int u = 4 * s4 + t4;
-                            al[s4] = s4 < 2 * ta + 2 ? (u < rl ? __ldg(Lg + (long long)(32 * I + u) * ncp + 32 * I + rl) : (u == rl ? dinv[32 * I + rl] : 0.0)) : 0.0;
+                            const int rl = 8 * ta + g4, u = 4 * s4 + t4;
+                            al[ta][s4] = s4 < 2 * ta + 2 ? (u < rl ? Lg[(long long)(32 * I + u) * ncp + 32 * I + rl] : (u == rl ? dinv[32 * I + rl] : 0.0)) : 0.0;
                         }
-                    }
-                    __syncthreads();
-                    NMPC_PROF(12);
-                    // phase 2: Y_I = Linv_II T_I (lower triangular: tile row ta contracts over 8 ta + 8 rows).  Results are held until
-                    // every unit has read T_I.
-                    if (rowact) {
+                    const double *yb = Ys + (32 * I + t4) * ldy + 8 * j0 + g4;
 #pragma unroll
-                        for (int rd = 0; rd < 2; rd++) {
-                            const int g = gh + rd * gstep, j0 = 4 * g;
-                            if (g >= ngrp) continue;
+                    for (int ta = 3; ta >= 0; ta--) {
+                        if (32 * I + 8 * ta >= nc) continue;   // warp-uniform: no rows of Y in this tile row
+                        const int r = 32 * I + 8 * ta + g4;
+                        double acc[4][2];
 #pragma unroll
-                            for (int q = 0; q < 4; q++) { acc[rd][q][0] = 0.0; acc[rd][q][1] = 0.0; }
-                            const double *yb = Ys + (32 * I + t4) * ldy + 8 * j0 + g4;
+                        for (int q = 0; q < 4; q++) { acc[q][0] = 0.0; acc[q][1] = 0.0; }
 #pragma unroll
-                            for (int s4 = 0; s4 < 8; s4++) {
-                                if (s4 < 2 * ta + 2) {
-                                    const bool rowok = 32 * I + 4 * s4 + t4 < nc;
+                        for (int s4 = 0; s4 < 8; s4++) {
+                            if (s4 < 2 * ta + 2) {
+                                const bool rowok = 32 * I + 4 * s4 + t4 < nc;
 #pragma unroll
-                                    for (int q = 0; q < 4; q++) {
-                                        const double b = rowok && j0 + q < nt8 ? yb[4 * s4 * ldy + 8 * q] : 0.0;
-                                        dmma(acc[rd][q], al[s4], b);
-                                    }
+                                for (int q = 0; q < 4; q++) {
+                                    const double b = rowok && j0 + q < nt8 ? yb[4 * s4 * ldy + 8 * q] : 0.0;
+                                    dmma(acc[q], al[ta][s4], b);
                                 }
                             }
                         }
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const int cc = 8 * (j0 + q) + 2 * t4;
+                            if (r < nc && j0 + q < nt8 && cc < ldy)
+                                *reinterpret_cast<double2 *>(Ys + r * ldy + cc) = make_double2(acc[q][0], acc[q][1]);
+                        }
                     }
-                    __syncthreads();
-                    if (rowact) {
+                }
+                __syncthreads();
+                NMPC_PROF(12);
+                // Y_I = V_I - sum_{J < I} W_IJ Y_J, block row by block row.  warp -> (tile row, column groups): the four warps
+                // wid = 4 h .. 4 h + 3 take the four tile rows of the column groups g = h, h + nw / 4 (ngrp <= nw / 2 for every Nr).  The
+                // A fragments -W[r][.] do not depend on Y: all of them are requested at once (one L2 round trip per block row).
+                const int ta = (wid + (wid >> 2)) & 3, gh = wid >> 2, gstep = nw >> 2;
+                for (int I = 1; I < nblk; I++) {
+                    const int r = 32 * I + 8 * ta + g4;   // this thread's row of the C fragments
+                    if (32 * I + 8 * ta < nc) {           // warp-uniform
+                        double af[24];
+                        const double *wa = Wg + (long long)(I * (I - 1) / 2) * 1024 + (8 * ta + g4) * 32 + t4;
+#pragma unroll
+                        for (int s4 = 0; s4 < 24; s4++) af[s4] = s4 < 8 * I ? -wa[(s4 >> 3) * 1024 + 4 * (s4 & 7)] : 0.0;
 #pragma unroll
                         for (int rd = 0; rd < 2; rd++) {
                             const int g = gh + rd * gstep, j0 = 4 * g;
-                            if (g >= ngrp) continue;
+                            if (g >= ngrp) continue;   // warp-uniform
+                            double c1[4][2];
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                const int cc = 8 * (j0 + q) + 2 * t4;
+                                const bool ok = r < nc && j0 + q < nt8 && cc < ldy;
+                                const double2 v = ok ? *reinterpret_cast<const double2 *>(Ys + r * ldy + cc) : make_double2(0.0, 0.0);
+                                c1[q][0] = v.x; c1[q][1] = v.y;
+                            }
+                            const double *yb = Ys + t4 * ldy + 8 * j0 + g4;   // B fragment: Y[4 s + t4][8 (j0 + q) + g4]
+#pragma unroll
+                            for (int s4 = 0; s4 < 24; s4++) {
+                                if (s4 < 8 * I) {
+#pragma unroll
+                                    for (int q = 0; q < 4; q++) {
+                                        const double b = j0 + q < nt8 ? yb[4 * s4 * ldy + 8 * q] : 0.0;
+                                        dmma(c1[q], af[s4], b);
+                                    }
+                                }
+                            }
 #pragma unroll
                             for (int q = 0; q < 4; q++) {
                                 const int cc = 8 * (j0 + q) + 2 * t4;
                                 if (r < nc && j0 + q < nt8 && cc < ldy)
-                                    *reinterpret_cast<double2 *>(Ys + r * ldy + cc) = make_double2(acc[rd][q][0], acc[rd][q][1]);
+                                    *reinterpret_cast<double2 *>(Ys + r * ldy + cc) = make_double2(c1[q][0], c1[q][1]);
                             }
                         }
                     }
                     __syncthreads();
-                    NMPC_PROF(13);
                 }
+                NMPC_PROF(13);
                 for (int e = tid; e < nc * (ldy / 2); e += nt)   // kept for the forward pass
                     reinterpret_cast<double2 *>(Yk)[e] = reinterpret_cast<const double2 *>(Ys)[e];
             }
@@ -903,6 +933,14 @@ struct BlockSolver {
         for (int k = 0; k <= N; k++) {
             const double *Pk = Pall + (long long)k * ns * ns;
             const double *Yk = Yall + (long long)(k < N ? k : 0) * nc * ldy, *Lk = Lall + (long long)(k < N ? k : 0) * ncp * ncp;
+            // the stage's Cholesky factor comes into shared memory as one bulk copy (TMA) underneath the mat-vecs below: the back
+            // substitution is a chain of dependent reads, which out of global memory cost an L2 / DRAM round trip per link
+            if (k < N && tid == 0) {
+                asm volatile("fence.proxy.async;" ::: "memory");
+                const unsigned bytes = (unsigned)(ncp * ncp) * 8u;
+                wp::bulk_expect(sm + SM_MBAR, bytes);
+                wp::bulk_g2s(Ls, Lk, bytes, sm + SM_MBAR);
+            }
             // y~c_k = -(P_k dx + p_k);  t = Y_k dx + y_m      (one warp per row)
             const int nrows = ns + (k < N ? nc : 0);
             for (int r0 = wid; r0 < nrows; r0 += 4 * nw) {   // four rows per warp at a time
@@ -930,24 +968,26 @@ struct BlockSolver {
                 }
             }
             __syncthreads();
-            if (k < N) {   // L' x = t by 32-row blocks: x_I = Linv_II' (t_I - sum_{J > I} L_JI' x_J), du = -x.  L comes straight
-                           // from global memory (coalesced along its rows); Linv_II sits transposed in the upper triangle of block (I, I)
-                double *red = Ls;   // nw x 32 partial sums
+            if (k < N) {   // L' x = t by 32-row blocks: x_I = Linv_II' (t_I - sum_{J > I} L_JI' x_J), du = -x.  L is read from its
+                           // shared-memory image (leading dimension ncp); Linv_II sits transposed in the upper triangle of block (I, I)
+                wp::mbar_wait(sm + SM_MBAR, bar_phase);
+                bar_phase ^= 1u;
+                double *red = Ls + ncp * ncp;   // nw x 32 partial sums (ncp (ncp + 4) doubles are reserved: 4 ncp = 32 nw)
                 for (int I = (ncp >> 5) - 1; I >= 0; I--) {
                     const int i = lane, gi = 32 * I + lane;
                     double part = 0.0;
-                    for (int u = 32 * (I + 1) + wid; u < nc; u += nw) part += __ldg(Lk + (long long)u * ncp + gi) * xb[u];
+                    for (int u = 32 * (I + 1) + wid; u < nc; u += nw) part += Ls[u * ncp + gi] * xb[u];
                     red[wid * 32 + i] = part;
                     __syncthreads();
                     if (wid == 0) {
                         double ti = gi < nc ? tb[gi] : 0.0;
                         for (int w = 0; w < nw; w++) ti -= red[w * 32 + i];
-                        double acc = ti / __ldg(Lk + (long long)gi * ncp + gi);
+                        double acc = ti / Ls[gi * ncp + gi];
                         const int nb_ = nc - 32 * I < 32 ? nc - 32 * I : 32;   // rows of this block that exist
 #pragma unroll 8
-                        for (int u = 1; u < nb_; u++) {   // (independent loads: the unrolled loop keeps eight in flight)
+                        for (int u = 1; u < nb_; u++) {
                             const double tu = __shfl_sync(0xffffffffu, ti, u);
-                            const double lv = u > i ? __ldg(Lk + (long long)gi * ncp + 32 * I + u) : 0.0;
+                            const double lv = u > i ? Ls[gi * ncp + 32 * I + u] : 0.0;
                             acc += lv * tu;
                         }
                         if (gi < nc) xb[gi] = acc;
@@ -1148,7 +1188,7 @@ struct BlockSolver {
     // ---------------------------------------------------------------------------------------
     // IPOPT's filter is unbounded inside a barrier subproblem: it lives in the slot's global scratch, append-only (an entry
     // that a newer one dominates is redundant for the test and stays); an overflow overwrites the oldest and is counted.
-    __device__ double *filter_base() const { return Lall + (long long)N * ncp * ncp; }
+    __device__ double *filter_base() const { return Wg + (long long)((ncp >> 5) * ((ncp >> 5) - 1) / 2) * 1024; }
     __device__ bool filter_ok(double th, double ph) const
     {
         const double *fth = wp::global_ptr(filter_base()), *fph = fth + NMPC_FILTER_CAP;
@@ -1238,6 +1278,7 @@ __global__ void __launch_bounds__(NMPC_BLOCK_THREADS, 1) solve_kernel_block(cons
     double *ws = P.ws + (long long)blockIdx.x * P.ws_stride;
     BlockSolver s(P, smem, ws);
     __shared__ int next_inst;
+    if (threadIdx.x == 0) wp::mbar_init(smem + BlockSolver::SM_MBAR);
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) next_inst = atomicAdd(P.counter, 1);

@@ -17,5 +17,5 @@ for rep in range(2):
     torch.cuda.synchronize(); dt = time.time() - t0
     prof = (__import__("ctypes").c_longlong * 16)()
     prob.L.nmpc_debug_block_profile(prof, 1)
-    print("phase Mcycles [prepass, matvec, build, chol-rest, trsm, syrk, forward, eval | chol: diag, rows, trailing | trsm: copy-in, phase 1, phase 2]:", [round(v / 1e6, 1) for v in prof[:14]])
+    print("phase Mcycles [prepass, matvec, build, chol-rest, trsm, syrk, forward, eval | chol: diag, rows, trailing | trsm: copy-in, V, main]:", [round(v / 1e6, 1) for v in prof[:14]])
     print("B=%d  %.3f s  status %s iters %s nfact %s kkt %.2e" % (B, dt, out['status'].cpu().numpy()[:8], out['iters'].cpu().numpy()[:8], out['stats'][:8, 8].cpu().numpy(), out['stats'][:, 0].max().item()), flush=True)
