@@ -11,14 +11,15 @@
 // flat thread-strided loops over (stage, variable / pair).  The Riccati factorisation keeps the control block of the
 // stage matrix in shared memory:
 //     M = H~ + [A B]' P+ [A B]     assembled per robot pair from the 3x3 blocks of P+ (A, B are unicycle-sparse)
-//     M_uu = L L'                  right-looking Cholesky, the matrix distributed over the registers of the CTA (8 x 4 entries
-//                                  per thread), pivot column broadcast through shared memory; a pivot <= 0 is IPOPT's
-//                                  wrong-inertia signal
-//     Y = L^-1 [M_ux | m_u]        blocked forward substitution on shared-memory column panels (32 x 32 diagonal blocks of
-//                                  L inverted once per stage, everything else is a contraction)
-//     P = M_xx - Y'Y, p = m_x - Y' y_m     4x4 register tiles over Y resident in shared memory
-// and the forward pass applies  du = -L^-T (Y dx + y_m).  FP64 has no tcgen05 kind, and the legacy DMMA (mma.sync m8n8k4)
-// has the same peak as the DFMA pipe on B200, so the contractions run as register tiles on the FP64 pipe.
+//     M_uu = L L'                  blocked right-looking Cholesky in place in shared memory, 32-column panels: the diagonal block by
+//                                  one warp in registers, the rows below by substitution, the trailing update as 8 x 8 tiles on the
+//                                  FP64 tensor instruction; a pivot <= 0 is IPOPT's wrong-inertia signal
+//     Y = L^-1 [M_ux | m_u]        Y resident in shared memory; with the inverses of the 32 x 32 diagonal blocks, V = blockdiag(Linv) B
+//                                  and W_IJ = Linv_II L_IJ, the block rows are Y_I = V_I - sum_{J < I} W_IJ Y_J (tensor instruction)
+//     P = M_xx - Y'Y, p = m_x - Y' y_m     upper 8 x 8 tiles of the Gram matrix of [Y | y_m] (tensor instruction), mirrored
+// and the forward pass applies  du = -L^-T (Y dx + y_m)  with L staged into shared memory by a bulk copy.  FP64 has no tcgen05 kind; the
+// legacy DMMA (mma.sync m8n8k4 f64) shares the DFMA pipe and its peak on B200 (tools/probe_fp64_mix.cu), so it does not raise the
+// roofline -- it is used because its fragments need a quarter of the shared-memory traffic of 4 x 4 register tiles.
 #pragma once
 #include "nmpc_internal.h"
 #include "ipm_driver.cuh"

@@ -643,8 +643,9 @@ __global__ void __launch_bounds__(256) dfma_probe_kernel(int iters, double *out)
 }
 
 // FP64 tensor-core probe: mma.sync.aligned.m8n8k4 f64 (DMMA), 8 independent accumulator tiles per warp, register only.
-// One instruction = 8 x 8 x 4 FMAs = 512 flop per warp.  Measured beside the DFMA probe so that the dense-block path's
-// "register tiles on the FP64 pipe, not DMMA" decision (block_solver.cuh) rests on a number.
+// One instruction = 8 x 8 x 4 FMAs = 512 flop per warp.  Measured beside the DFMA probe: on B200 the two have the same peak and share one pipe
+// (tools/probe_fp64_mix.cu), so DMMA does not raise the FP64 roofline; the dense-block path (block_solver.cuh) uses it for its
+// contractions because it needs a quarter of the operand traffic of 4 x 4 register tiles.
 __global__ void __launch_bounds__(256) dmma_probe_kernel(int iters, double *out)
 {
     double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
