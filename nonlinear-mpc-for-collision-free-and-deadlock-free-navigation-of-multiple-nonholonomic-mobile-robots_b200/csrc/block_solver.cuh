@@ -44,13 +44,13 @@ __device__ long long g_block_prof[16];
     const double *const obs = wp::global_ptr(this->obs);                                                               \
     const int Mp = this->Mp, nobs = this->nobs;                                                                        \
     double *const Pall = wp::global_ptr(this->Pall), *const Yall = wp::global_ptr(this->Yall),                          \
-                 *const Lall = wp::global_ptr(this->Lall), *const Bm = wp::global_ptr(this->Bm),                        \
+                 *const Lall = wp::global_ptr(this->Lall),                                                             \
                  *const Wg = wp::global_ptr(this->Wg);                                                                 \
     const int S = this->S, W = this->W, N = this->N, Nr = this->Nr, ns = this->ns, nc = this->nc, nz = this->nz,        \
               M = this->M, tid = this->tid, nt = this->nt;                                                             \
     auto row = [=](int r, int k) -> double * { return ws + ((long long)r * S + k) * W; };                              \
     (void)sm; (void)ws; (void)BL; (void)BU; (void)CE; (void)DL; (void)DU; (void)pp; (void)pairs; (void)Pall;            \
-    (void)Yall; (void)Lall; (void)Bm; (void)Wg; (void)S; (void)W; (void)N; (void)Nr; (void)ns; (void)nc; (void)nz; (void)M;       \
+    (void)Yall; (void)Lall; (void)Wg; (void)S; (void)W; (void)N; (void)Nr; (void)ns; (void)nc; (void)nz; (void)M;       \
     (void)tid; (void)nt; (void)row; (void)obs; (void)Mp; (void)nobs;
 
 struct BlockSolver {
@@ -71,7 +71,7 @@ struct BlockSolver {
     const double *obs;                                    // [nobs][3]: centre x, y, clearance radius
     const double *BL, *BU, *CE, *DL, *DU, *pp;
     const int *pairs;
-    double *Pall, *Yall, *Lall, *Bm, *Wg;   // Wg: Linv_II L_IJ blocks of the stage being factored (see factor, step D)
+    double *Pall, *Yall, *Lall, *Wg;   // Wg: Linv_II L_IJ blocks of the stage being factored (see factor, step D)
     int ncp;   // nc rounded up to a multiple of 32 (blocked triangular solves)
     int ldy;   // leading dimension of Y_k and of [M_ux | m_u]: the smallest value >= ns + 1 that is 4 mod 8 (conflict-free DMMA fragment loads)
     double T, df, ny_nzb, nzb_cnt;
@@ -87,7 +87,7 @@ struct BlockSolver {
         const long long S = N + 1, ns = 3 * Nr, nc = 2 * Nr, W = row_width(Nr, nobs);
         const long long ldy = ((ns + 4) & ~7LL) + 4;
         const long long ncp = (nc + 31) & ~31LL;
-        return (long long)R_COUNT * S * W + ((S * ns * ns + 1) & ~1LL) + (long long)(N + 1) * nc * ldy + (long long)N * ncp * ncp   // every block 16-byte aligned
+        return (long long)R_COUNT * S * W + ((S * ns * ns + 1) & ~1LL) + (long long)N * nc * ldy + (long long)N * ncp * ncp   // every block 16-byte aligned
                + (ncp / 32) * (ncp / 32 - 1) / 2 * 1024 + 2 * NMPC_FILTER_CAP;   // the filter (theta values, then phi values), see filter_add
     }
     static NMPC_HD long long sm_doubles(int Nr)
@@ -167,8 +167,7 @@ struct BlockSolver {
         Pall = ws + (long long)R_COUNT * S * W;
         ldy = ((ns + 4) & ~7) + 4; ncp = (nc + 31) & ~31;
         Yall = Pall + (((long long)S * ns * ns + 1) & ~1LL);
-        Bm = Yall + (long long)N * nc * ldy;
-        Lall = Bm + (long long)nc * ldy;
+        Lall = Yall + (long long)N * nc * ldy;
         Wg = Lall + (long long)N * ncp * ncp;
         SM_RED = 0; SM_FTH = 32 * 12; SM_FPH = SM_FTH + 16; SM_MISC = SM_FPH + 16; SM_DZB = SM_MISC + 8; SM_DXN = SM_DZB + nz;
         SM_TB = SM_DXN + ns; SM_XB = SM_TB + ncp; SM_DINV = SM_XB + ncp; SM_PR = SM_DINV + ncp; SM_CS = SM_PR + ns; SM_DS = SM_CS + 2 * Nr; SM_MUU = (SM_DS + 5 * Nr + 1) & ~1;
@@ -493,6 +492,8 @@ struct BlockSolver {
         for (int k = N - 1; k >= 0; k--) {
             const double *Pn = Pall + (long long)(k + 1) * ns * ns;
             double *Pk = Pall + (long long)k * ns * ns, *Yk = Yall + (long long)k * nc * ldy, *Lk = Lall + (long long)k * ncp * ncp;
+            double *const Bm = Yk;   // [M_ux | m_u] is assembled in the place of Y_k: it is consumed (bulk copy into shared memory) before Y_k is written back,
+                                     // and a separate buffer would cost 200 KB of L2 footprint and of DRAM write-back per stage
             const double *cf = row(R_COEF, k), *cf2 = row(R_COEF2, k);
             const int lds = ncp + 4;   // shared-memory leading dimension of M_uu / L: 4 mod 16, so the 8 x 4 DMMA fragment loads are conflict-free
             // A. pr = p_{k+1} - P_{k+1} rc_{k+1}   (one warp per row)
