@@ -60,6 +60,18 @@ def test_block_path_matches_oracle(pkg, torch_cuda, Nr, N, T, box):
     assert np.abs(out["iters"].cpu().numpy() - ref["iters"]).max() <= 5
 
 
+@pytest.mark.parametrize("Nr,N,box", [(17, 4, 3.5), (32, 3, 5.0), (33, 3, 5.5), (49, 2, 6.5), (63, 2, 7.5)])
+def test_block_path_at_the_block_size_boundaries(pkg, torch_cuda, Nr, N, box):
+    """Robot counts either side of the 32-row block boundaries of the control matrix (2 Nr = 34, 64, 66, 98, 126): the panel
+    Cholesky, the tile maps of the tensor-instruction contractions and the identity padding change shape there."""
+    P = synthetic_instances(3, Nr=Nr, seed=100 + Nr, box=box)
+    prob, out, ref, (lbx, ubx, lbg, ubg) = _solve_both(pkg, torch_cuda, Nr, N, 0.3, P)
+    du, df = _check(out, ref, Nr, N, lbg, P, 0.3)
+    same = (du <= 1e-4) & (df <= 1e-6)
+    assert same.all(), (du, df, out["iters"].cpu().numpy(), ref["iters"])
+    assert np.abs(out["iters"].cpu().numpy() - ref["iters"]).max() <= 5
+
+
 def test_block_path_64_robot_swarm(pkg, torch_cuda):
     """BASELINE.json configs[4]: 64-robot centralized swarm, 2016 pairwise constraints per stage, N = 20
     (SURVEY.md 8d recipe: starts / goals uniform in [-8, 8]^2, separation >= 0.5).  The CPU oracle needs ~7 minutes for
