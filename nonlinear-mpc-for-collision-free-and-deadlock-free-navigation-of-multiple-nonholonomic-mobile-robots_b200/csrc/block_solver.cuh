@@ -313,21 +313,26 @@ struct BlockSolver {
         // ---- inequality rows ----
         for (int idx = tid; idx < S * M; idx += nt) {
             const int b = idx / M, q = idx - b * M;
+            // every load of the row is issued before the first branch on its bounds: behind the branch they are a second dependent
+            // L2 / DRAM round trip per row (the compiler may not speculate them)
             const double lo = DL[b * W + q], hi = DU[b * W + q];
-            const bool hl = lo > -NMPC_INF, hu = hi < NMPC_INF;
-            if (!(hl || hu)) continue;
+            const double s = row(rs, b)[q];
+            const double yd_ = full ? row(R_YD, b)[q] : 0.0, vl_ = full ? row(R_VL, b)[q] : 0.0, vu_ = full ? row(R_VU, b)[q] : 0.0;
+            const double dsoc_ = socacc ? row(R_DSOC, b)[q] : 0.0;
             double dv = NMPC_DUMMY_ROW_VALUE;
             if (b > 0) dv = rowgeom(row(rz, b - 1), q, Mp, nobs, pairs, obs).dv;
-            const double s = row(rs, b)[q], dms = dv - s;
+            const bool hl = lo > -NMPC_INF, hu = hi < NMPC_INF;
+            if (!(hl || hu)) continue;
+            const double dms = dv - s;
             pinf = fmax(pinf, fabs(dms)); th += fabs(dms);
             viol = fmax(viol, fmax(lo - dv, dv - hi));
-            if (socacc) row(R_DSOC, b)[q] = asoc * row(R_DSOC, b)[q] + dms;
+            if (socacc) row(R_DSOC, b)[q] = asoc * dsoc_ + dms;
             if (hl) slog += log(s - lo);
             if (hu) slog += log(hi - s);
             if (hl && !hu) sdamp += s - lo;
             if (hu && !hl) sdamp += hi - s;
             if (full) {
-                const double yd = row(R_YD, b)[q], vl = row(R_VL, b)[q], vu = row(R_VU, b)[q];
+                const double yd = yd_, vl = vl_, vu = vu_;
                 ysum += fabs(yd);
                 double t = -yd - vl + vu;
                 if (hl && !hu) t += kd * mu;
@@ -460,19 +465,21 @@ struct BlockSolver {
         for (int idx = tid; idx < S * M; idx += nt) {
             const int b = idx / M, q = idx - b * M;
             double pxx = 0, pyy = 0, pxy = 0, phx = 0, phy = 0, gxq = 0, gyq = 0, rd = 0, Dq = 0, gs = 0;
+            // (all loads of the row before the branch on its bounds, see eval)
             const double lo = DL[b * W + q], hi = DU[b * W + q];
+            const double s = row(R_S, b)[q], vl_ = row(R_VL, b)[q], vu_ = row(R_VU, b)[q];
+            const double dsoc_ = (soc && mode != 1) ? row(R_DSOC, b)[q] : 0.0, yd_ = mode == 0 ? row(R_YD, b)[q] : 0.0;
+            RowG rg;
+            rg.gx = rg.gy = rg.hxx = rg.hyy = rg.hxy = 0.0; rg.dv = NMPC_DUMMY_ROW_VALUE;
+            if (b > 0) rg = rowgeom(row(R_Z, b - 1), q, Mp, nobs, pairs, obs);
             if (lo > -NMPC_INF || hi < NMPC_INF) {
-                double dv = NMPC_DUMMY_ROW_VALUE, hxx = 0.0, hyy = 0.0, hxy = 0.0;
-                if (b > 0) {
-                    const RowG rg = rowgeom(row(R_Z, b - 1), q, Mp, nobs, pairs, obs);
-                    gxq = rg.gx; gyq = rg.gy; dv = rg.dv; hxx = rg.hxx; hyy = rg.hyy; hxy = rg.hxy;
-                }
-                const double s = row(R_S, b)[q];
+                const double dv = rg.dv, hxx = rg.hxx, hyy = rg.hyy, hxy = rg.hxy;
+                gxq = rg.gx; gyq = rg.gy;
                 double sigs;
-                sig_g(mode, kd, s, lo, hi, row(R_VL, b)[q], row(R_VU, b)[q], mu, 0.0, sigs, gs);
-                rd = mode == 1 ? 0.0 : (soc ? row(R_DSOC, b)[q] : dv - s);
+                sig_g(mode, kd, s, lo, hi, vl_, vu_, mu, 0.0, sigs, gs);
+                rd = mode == 1 ? 0.0 : (soc ? dsoc_ : dv - s);
                 Dq = sigs + delta;
-                const double hq = Dq * rd + gs, yq = mode == 0 ? row(R_YD, b)[q] : 0.0;   // multiplier times the row's own curvature
+                const double hq = Dq * rd + gs, yq = yd_;   // multiplier times the row's own curvature
                 pxx = Dq * gxq * gxq + yq * hxx; pyy = Dq * gyq * gyq + yq * hyy; pxy = Dq * gxq * gyq + yq * hxy;
                 phx = gxq * hq; phy = gyq * hq;
             }
@@ -1020,18 +1027,19 @@ struct BlockSolver {
                 }
                 const int b = k + 1;
                 for (int q = tid; q < M; q += nt) {
+                    // (all loads of the row before the branch on its bounds, see eval)
                     const double lo = DL[b * W + q], hi = DU[b * W + q];
+                    const double gs = row(R_GS, b)[q], gxq_ = row(R_GXQ, b)[q], gyq_ = row(R_GYQ, b)[q], rd_ = row(R_RD, b)[q], dq_ = row(R_DQ, b)[q];
+                    const double s = row(R_S, b)[q], vl_ = row(R_VL, b)[q], vu_ = row(R_VU, b)[q];
+                    double ddx, ddy;
+                    if (q < Mp) { const int pi = pairs[2 * q], pj = pairs[2 * q + 1]; ddx = dzb[3 * pi] - dzb[3 * pj]; ddy = dzb[3 * pi + 1] - dzb[3 * pj + 1]; }
+                    else { const int pi = (q - Mp) / nobs; ddx = dzb[3 * pi]; ddy = dzb[3 * pi + 1]; }
                     const bool act = lo > -NMPC_INF || hi < NMPC_INF;
                     double ds = 0.0, ytd = 0.0;
                     if (act) {
-                        const double gs = row(R_GS, b)[q];
-                        double ddx, ddy;
-                        if (q < Mp) { const int pi = pairs[2 * q], pj = pairs[2 * q + 1]; ddx = dzb[3 * pi] - dzb[3 * pj]; ddy = dzb[3 * pi + 1] - dzb[3 * pj + 1]; }
-                        else { const int pi = (q - Mp) / nobs; ddx = dzb[3 * pi]; ddy = dzb[3 * pi + 1]; }
-                        ds = row(R_GXQ, b)[q] * ddx + row(R_GYQ, b)[q] * ddy + row(R_RD, b)[q];
-                        ytd = row(R_DQ, b)[q] * ds + gs;
-                        const double s = row(R_S, b)[q];
-                        WS::slack_step_terms(s, ds, lo, hi, row(R_VL, b)[q], row(R_VU, b)[q], mu, ap, az);
+                        ds = gxq_ * ddx + gyq_ * ddy + rd_;
+                        ytd = dq_ * ds + gs;
+                        WS::slack_step_terms(s, ds, lo, hi, vl_, vu_, mu, ap, az);
                         gbd += gs * ds; tiny = fmax(tiny, fabs(ds) / (1.0 + fabs(s)));
                     }
                     row(rds, b)[q] = ds; row(rytd, b)[q] = ytd;
@@ -1060,23 +1068,26 @@ struct BlockSolver {
         };
         for (int idx = tid; idx < S * W; idx += nt) {
             const int k = idx / W, l = idx - k * W;
+            // (all loads of an entry before the branches on its bounds, see eval)
             if (l < nvalid(k)) {
                 const double z = row(R_Z, k)[l], dz = row(rdz, k)[l], lo = BL[k * W + l], hi = BU[k * W + l];
+                const double zl_ = row(R_ZL, k)[l], zu_ = row(R_ZU, k)[l];
                 const double zn = z + alpha * dz;
-                if (lo > -NMPC_INF) row(R_ZL, k)[l] = mult(row(R_ZL, k)[l], z - lo, zn - lo, -dz);
-                if (hi < NMPC_INF) row(R_ZU, k)[l] = mult(row(R_ZU, k)[l], hi - z, hi - zn, dz);
+                if (lo > -NMPC_INF) row(R_ZL, k)[l] = mult(zl_, z - lo, zn - lo, -dz);
+                if (hi < NMPC_INF) row(R_ZU, k)[l] = mult(zu_, hi - z, hi - zn, dz);
                 row(R_Z, k)[l] = zn;
             }
             if (l < ns) { const double yc = row(R_YC, k)[l]; row(R_YC, k)[l] = yc + alpha * (row(rytc, k)[l] - yc); }
             if (l < M) {
                 const double lo = DL[k * W + l], hi = DU[k * W + l];
+                const double s = row(R_S, k)[l], ds = row(rds, k)[l], vl_ = row(R_VL, k)[l], vu_ = row(R_VU, k)[l];
+                const double yd = row(R_YD, k)[l], ytd_ = row(rytd, k)[l];
                 if (lo > -NMPC_INF || hi < NMPC_INF) {
-                    const double s = row(R_S, k)[l], ds = row(rds, k)[l], sn_ = s + alpha * ds;
-                    if (lo > -NMPC_INF) row(R_VL, k)[l] = mult(row(R_VL, k)[l], s - lo, sn_ - lo, -ds);
-                    if (hi < NMPC_INF) row(R_VU, k)[l] = mult(row(R_VU, k)[l], hi - s, hi - sn_, ds);
+                    const double sn_ = s + alpha * ds;
+                    if (lo > -NMPC_INF) row(R_VL, k)[l] = mult(vl_, s - lo, sn_ - lo, -ds);
+                    if (hi < NMPC_INF) row(R_VU, k)[l] = mult(vu_, hi - s, hi - sn_, ds);
                     row(R_S, k)[l] = sn_;
-                    const double yd = row(R_YD, k)[l];
-                    row(R_YD, k)[l] = yd + alpha * (row(rytd, k)[l] - yd);
+                    row(R_YD, k)[l] = yd + alpha * (ytd_ - yd);
                 }
             }
         }
